@@ -1,0 +1,131 @@
+// Shared device/host helpers for the RVIP hot path (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace rvip {
+
+// ---------------------------------------------------------------- error plumbing
+void set_error(const char* fmt, ...);
+#define RVIP_CUDA(expr)                                                                   \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      rvip::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return 1;                                                                           \
+    }                                                                                     \
+  } while (0)
+#define RVIP_LAUNCH_CHECK() RVIP_CUDA(cudaGetLastError())
+#define RVIP_REQUIRE(cond, ...)        \
+  do {                                 \
+    if (!(cond)) {                     \
+      rvip::set_error(__VA_ARGS__);    \
+      return 1;                        \
+    }                                  \
+  } while (0)
+
+constexpr int kNumSMs = 148;
+
+// ---------------------------------------------------------------- storage-type traits
+// Activations are NHWC in T = float ("fp32 mode") or __nv_bfloat16 ("bf16 mode").
+// All element-wise kernels move 8 channels per thread (16 B for bf16, 32 B for fp32).
+struct alignas(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+struct alignas(16) f32x8 {
+  float4 lo, hi;
+};
+
+template <typename T>
+struct Vec8;
+template <>
+struct Vec8<float> {
+  __device__ static __forceinline__ void load(const float* p, float (&o)[8]) {
+    float4 a = *reinterpret_cast<const float4*>(p);
+    float4 b = *reinterpret_cast<const float4*>(p + 4);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+    o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+  }
+  __device__ static __forceinline__ void store(float* p, const float (&o)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(o[4], o[5], o[6], o[7]);
+  }
+};
+template <>
+struct Vec8<__nv_bfloat16> {
+  __device__ static __forceinline__ void load(const __nv_bfloat16* p, float (&o)[8]) {
+    uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __bfloat1622float2(h[i]);
+      o[2 * i] = f.x;
+      o[2 * i + 1] = f.y;
+    }
+  }
+  __device__ static __forceinline__ void store(__nv_bfloat16* p, const float (&o)[8]) {
+    uint4 raw;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = raw;
+  }
+};
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// Rounds through the storage type: statistics and masks are computed on the values that
+// are actually stored, so forward and backward see identical numbers.
+template <typename T>
+__device__ __forceinline__ float round_to(float v) { return to_f32<T>(from_f32<T>(v)); }
+
+// ---------------------------------------------------------------- Philox4x32-10 (dropout)
+struct Philox {
+  __device__ static __forceinline__ uint4 gen(uint64_t seed, uint64_t ctr, uint32_t stream) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = stream, c3 = 0x5eed5eedu;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+};
+// keep decision for the 8 channels of vector `vec_idx` of dropout site `site`: 16 random bits
+// per element, keep iff bits >= thr16 (thr16 = round(rate * 65536)).
+__device__ __forceinline__ void dropout_keep8(uint64_t seed, uint32_t site, uint64_t vec_idx, uint32_t thr16,
+                                              bool (&keep)[8]) {
+  uint4 r = Philox::gen(seed, vec_idx, site);
+  uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    keep[2 * i] = (w[i] & 0xffffu) >= thr16;
+    keep[2 * i + 1] = (w[i] >> 16) >= thr16;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace rvip

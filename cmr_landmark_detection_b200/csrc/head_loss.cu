@@ -1,0 +1,163 @@
+// Head (1x1 conv -> sigmoid, src/models/Unets.py:128) fused with the heat-map loss and its gradient:
+//   mse ...................... tf.keras.losses.mse (src/models/Loss_and_metrics.py:6): mean over every element
+//   masked / weighted ........ loss_with_zero_mask (src/models/Loss_and_metrics.py:40-89)
+// One pass reads y (and the target), writes the fp32 heat map, dL/dy for the last decoder block, and
+// reduces the loss, dW_head and db_head with warp shuffles -> shared atomics -> one global atomic per
+// block and output.  G = Cin/8 adjacent lanes share a pixel, so all global traffic is coalesced.
+#include "kernels.cuh"
+
+namespace rvip {
+
+constexpr int kMaxNC = 4;
+
+template <typename T, bool TRAIN>
+__global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
+  extern __shared__ float sm[];            // w [Cin*NC], b [NC], then (TRAIN) dw acc [Cin*NC], db acc [NC]
+  const int NC = a.NC, Cin = a.Cin, G = Cin >> 3;
+  float* w_s = sm;
+  float* b_s = w_s + Cin * NC;
+  float* dw_s = b_s + NC;
+  float* db_s = dw_s + Cin * NC;
+  __shared__ double loss_s;
+  for (int k = threadIdx.x; k < Cin * NC; k += 256) {
+    w_s[k] = a.w[k];
+    if (TRAIN) dw_s[k] = 0.f;
+  }
+  if (threadIdx.x < NC) {
+    b_s[threadIdx.x] = a.b[threadIdx.x];
+    if (TRAIN) db_s[threadIdx.x] = 0.f;
+  }
+  if (threadIdx.x == 0) loss_s = 0.0;
+  __syncthreads();
+
+  const size_t P = (size_t)a.B * a.H * a.W;
+  const size_t n_items = P * G;
+  const size_t i0 = (size_t)blockIdx.x * 256 + threadIdx.x;
+  const int cg = (int)(i0 % G), c = cg * 8;
+  const T* y = static_cast<const T*>(a.y);
+  T* dy = static_cast<T*>(a.dy);
+  float wreg[8][kMaxNC];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int k = 0; k < kMaxNC; ++k) wreg[j][k] = k < NC ? w_s[(c + j) * NC + k] : 0.f;
+  float dw_acc[8][kMaxNC], db_acc[kMaxNC];
+#pragma unroll
+  for (int k = 0; k < kMaxNC; ++k) {
+    db_acc[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dw_acc[j][k] = 0.f;
+  }
+  float loss_acc = 0.f;
+  const float inv_n = 1.f / ((float)P * (float)NC);
+  // all lanes of a warp run the same trip count (n_items and the stride are multiples of 32)
+  const size_t n_round = (n_items + 31) / 32 * 32;
+  for (size_t i = i0; i < n_round; i += (size_t)gridDim.x * 256) {
+    const bool live = i < n_items;
+    const size_t p = live ? i / G : 0;
+    float v[8];
+    if (live)
+      Vec8<T>::load(y + p * Cin + c, v);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    }
+    float logit[kMaxNC];
+#pragma unroll
+    for (int k = 0; k < kMaxNC; ++k) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s = fmaf(v[j], wreg[j][k], s);
+      for (int o = 1; o < G; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      logit[k] = s + (k < NC ? b_s[k] : 0.f);
+    }
+    if (!live) continue;
+    float prob[kMaxNC];
+#pragma unroll
+    for (int k = 0; k < kMaxNC; ++k) prob[k] = 1.f / (1.f + expf(-logit[k]));
+    if (cg == 0) {
+#pragma unroll
+      for (int k = 0; k < kMaxNC; ++k)
+        if (k < NC) a.heat[p * NC + k] = prob[k];
+    }
+    if (TRAIN) {
+      float tgt[kMaxNC], wpx = 1.f;
+      bool any = false;
+#pragma unroll
+      for (int k = 0; k < kMaxNC; ++k) {
+        tgt[k] = k < NC ? a.target[p * NC + k] : 0.f;
+        any = any || (k < NC && tgt[k] > a.mask_thr);
+      }
+      if (a.loss_kind != LOSS_MSE) wpx = any ? 1.f : 0.f;
+      if (a.loss_kind == LOSS_WEIGHTED) wpx *= a.inplane[p % ((size_t)a.H * a.W)];
+      float dl[kMaxNC], se = 0.f;
+#pragma unroll
+      for (int k = 0; k < kMaxNC; ++k) {
+        const float d = k < NC ? prob[k] - tgt[k] : 0.f;
+        se = fmaf(d, d, se);
+        dl[k] = 2.f * d * wpx * inv_n * prob[k] * (1.f - prob[k]);
+      }
+      if (cg == 0) {
+        loss_acc += se / (float)NC * wpx + (a.loss_kind == LOSS_WEIGHTED ? a.eps : 0.f);
+#pragma unroll
+        for (int k = 0; k < kMaxNC; ++k) db_acc[k] += dl[k];
+      }
+      float g[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < kMaxNC; ++k) {
+          s = fmaf(wreg[j][k], dl[k], s);
+          dw_acc[j][k] = fmaf(v[j], dl[k], dw_acc[j][k]);
+        }
+        g[j] = s;
+      }
+      Vec8<T>::store(dy + p * Cin + c, g);
+    }
+  }
+  if (TRAIN) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int k = 0; k < kMaxNC; ++k)
+        if (k < NC) atomicAdd(&dw_s[(c + j) * NC + k], dw_acc[j][k]);
+    if (cg == 0) {
+#pragma unroll
+      for (int k = 0; k < kMaxNC; ++k)
+        if (k < NC) atomicAdd(&db_s[k], db_acc[k]);
+    }
+    float l = warp_sum(loss_acc);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&loss_s, (double)l);
+    __syncthreads();
+    for (int k = threadIdx.x; k < Cin * NC; k += 256) atomicAdd(&a.dw[k], dw_s[k]);
+    if (threadIdx.x < NC) atomicAdd(&a.db[threadIdx.x], db_s[threadIdx.x]);
+    if (threadIdx.x == 0) atomicAdd(a.loss_acc, loss_s / (double)P);  // mean over B*H*W
+  }
+}
+
+int head_launch(const HeadArgs& a, int training, int is_bf16, cudaStream_t st) {
+  const int G = a.Cin / 8;
+  RVIP_REQUIRE(a.Cin % 8 == 0 && G <= 32 && (G & (G - 1)) == 0, "head: Cin=%d must be 8 * power of two <= 256", a.Cin);
+  RVIP_REQUIRE(a.NC >= 1 && a.NC <= kMaxNC, "head: MASK_CLASSES=%d not in [1,%d]", a.NC, kMaxNC);
+  const size_t n = (size_t)a.B * a.H * a.W * G;
+  size_t g = (n + 255) / 256;
+  const size_t cap = (size_t)kNumSMs * 8;
+  const int grid = (int)(g < cap ? (g ? g : 1) : cap);
+  const size_t smem = (size_t)(2 * (a.Cin * a.NC + a.NC)) * sizeof(float);
+  if (training) {
+    if (is_bf16)
+      head_kernel<__nv_bfloat16, true><<<grid, 256, smem, st>>>(a);
+    else
+      head_kernel<float, true><<<grid, 256, smem, st>>>(a);
+  } else {
+    if (is_bf16)
+      head_kernel<__nv_bfloat16, false><<<grid, 256, smem, st>>>(a);
+    else
+      head_kernel<float, false><<<grid, 256, smem, st>>>(a);
+  }
+  RVIP_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace rvip

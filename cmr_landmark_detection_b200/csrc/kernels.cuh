@@ -1,0 +1,109 @@
+// Launchers of the CUDA-core kernels (memory-bound passes, CUDA-core convs, head/loss, extraction, Adam).
+#pragma once
+#include "common.cuh"
+#include "conv_tc.cuh"
+
+namespace rvip {
+
+// ------------------------------------------------------------------ CUDA-core convs (conv_simt.cu)
+struct ConvSimtArgs {
+  const void* in0;
+  const void* in1;      // second concat source (channels C0..Ctot) or nullptr
+  const float* w;       // [9][Ctot][Cout] fp32 (Keras HWIO; rotated copy for dgrad)
+  const float* bias;
+  void* out0;
+  void* out1;           // EPI_LINEAR: channels >= out_split
+  double* stats;        // [2][Cout]
+  int B, H, W, C0, Ctot, Cout, mode, out_split;
+};
+int conv_simt_launch(const ConvSimtArgs& a, int in_is_bf16, int out_is_bf16, cudaStream_t st);
+
+struct WgradSimtArgs {
+  const void* in0;
+  const void* in1;
+  const void* dz;
+  float* dw;            // [9][Ctot][Cout] fp32, accumulated
+  int B, H, W, C0, Ctot, Cout;
+};
+int wgrad_simt_launch(const WgradSimtArgs& a, int in_is_bf16, int dz_is_bf16, cudaStream_t st);
+
+// ------------------------------------------------------------------ BatchNorm passes (bn.cu)
+enum PostOp { POST_NONE = 0, POST_DROPOUT = 1, POST_POOL = 2, POST_UPSAMPLE = 3 };
+
+struct BnArgs {
+  int B, H, W, C;          // geometry of the conv output `a`
+  int post;
+  const void* a;           // relu(conv) [B,H,W,C]
+  const float* gamma;
+  const float* beta;
+  const float* mean;       // batch mean (training) or moving mean (inference)
+  const float* rstd;
+  // forward outputs
+  void* y;                 // [B,H,W,C]        (NONE / DROPOUT / POOL)
+  void* y2;                // POOL: [B,H/2,W/2,C]; UPSAMPLE: [B,2H,2W,C]
+  // dropout
+  uint64_t seed;
+  uint32_t site, thr16;
+  float keep_scale;        // 1 / (1 - rate)
+  // backward inputs
+  const void* g0;          // NONE/DROPOUT: dL/d(y after dropout) [B,H,W,C]; POOL: d skip; UPSAMPLE: d(up) [B,2H,2W,C]
+  const void* g1;          // POOL: d pooled [B,H/2,W/2,C]
+  double* red;             // [2][C]: sum dy, sum dy*ahat
+  void* dz;                // [B,H,W,C]
+  float* dgamma;
+  float* dbeta;
+  float* dbias;            // conv bias gradient = sum dz
+};
+int bn_finalize_launch(const double* stats, double count, float* mean, float* rstd, float* mov_mean, float* mov_var,
+                       int C, float momentum, float eps, cudaStream_t st);
+int bn_eval_prepare_launch(const float* mov_mean, const float* mov_var, float* mean, float* rstd, int n, float eps,
+                           cudaStream_t st);
+int bn_apply_launch(const BnArgs& a, int is_bf16, cudaStream_t st);
+int bn_bwd_reduce_launch(const BnArgs& a, int is_bf16, cudaStream_t st);
+int bn_bwd_apply_launch(const BnArgs& a, int is_bf16, cudaStream_t st);
+// conv + ReLU without BN (decoder up-conv): dz = du * [u > 0], dbias = sum dz
+int relu_bwd_launch(const void* u, const void* du, void* dz, float* dbias, size_t pixels, int C, int is_bf16,
+                    cudaStream_t st);
+int dropout_mask_launch(uint64_t seed, uint32_t site, uint32_t thr16, size_t n_vec8, uint8_t* keep, cudaStream_t st);
+
+// ------------------------------------------------------------------ head + loss (head_loss.cu)
+enum LossKind { LOSS_MSE = 0, LOSS_MASKED = 1, LOSS_WEIGHTED = 2 };
+struct HeadArgs {
+  int B, H, W, Cin, NC;
+  const void* y;           // [B,H,W,Cin]
+  const float* w;          // [Cin][NC]
+  const float* b;          // [NC]
+  float* heat;             // [B,H,W,NC] fp32 sigmoid output
+  // training
+  const float* target;     // [B,H,W,NC]
+  const float* inplane;    // [H,W] or nullptr
+  int loss_kind;
+  float mask_thr, eps;
+  void* dy;                // [B,H,W,Cin]
+  float* dw;
+  float* db;
+  double* loss_acc;        // scalar accumulator (sum of per-pixel losses)
+};
+int head_launch(const HeadArgs& a, int training, int is_bf16, cudaStream_t st);
+
+// ------------------------------------------------------------------ landmark extraction (extract.cu)
+int extract_launch(const float* heat, int Z, int H, int W, int C, float thr, double* yx, int* count, int* argmax,
+                   float* maxv, unsigned long long* scratch, cudaStream_t st);
+size_t extract_scratch_bytes(int Z, int C);
+int label_map_launch(const float* heat, size_t n_pix, int C, float thr, uint8_t* out, cudaStream_t st);
+
+// ------------------------------------------------------------------ optimizer / weight packing (optim.cu)
+int adam_launch(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float b1, float b2, float eps,
+                float grad_scale, cudaStream_t st);
+struct PackEntry {
+  long long src;      // float offset of the HWIO kernel in the parameter buffer
+  long long dst_f;    // element offset in the packed buffer: forward  [Cout][9][Ctot]
+  long long dst_d;    // element offset in the packed buffer: dgrad    [Ctot][9][Cout] (taps rotated), -1 = none
+  int Ctot, Cout;
+};
+// bf16 packs for the tensor-core kernels (packed = __nv_bfloat16*) or fp32 rotated copies for the
+// CUDA-core dgrad (packed = float*, only dst_d is written, layout [9][Cout][Ctot] rotated)
+int pack_weights_launch(const float* params, void* packed, const PackEntry* table_dev, int n_entries, int to_bf16,
+                        cudaStream_t st);
+
+}  // namespace rvip

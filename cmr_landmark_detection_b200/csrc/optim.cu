@@ -1,0 +1,84 @@
+// Adam (tf.keras.optimizers.Adam defaults, src/models/ModelUtils.py:107) over the flat fp32
+// parameter / gradient / moment buffers, and the re-pack of the fp32 master weights (Keras HWIO)
+// into the K-major bf16 operand layouts the tensor-core kernels read.
+#include "kernels.cuh"
+
+namespace rvip {
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, size_t n, float lr_t,
+                                                   float b1, float b2, float eps, float gs) {
+  const size_t n4 = n / 4;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+#define RVIP_ADAM(x)                              \
+  {                                               \
+    const float gr = gg.x * gs;                   \
+    mm.x = b1 * mm.x + (1.f - b1) * gr;           \
+    vv.x = b2 * vv.x + (1.f - b2) * gr * gr;      \
+    pp.x -= lr_t * mm.x / (sqrtf(vv.x) + eps);    \
+  }
+    RVIP_ADAM(x) RVIP_ADAM(y) RVIP_ADAM(z) RVIP_ADAM(w)
+#undef RVIP_ADAM
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  if (blockIdx.x == 0) {
+    for (size_t i = n4 * 4 + threadIdx.x; i < n; i += 256) {
+      const float gr = g[i] * gs;
+      m[i] = b1 * m[i] + (1.f - b1) * gr;
+      v[i] = b2 * v[i] + (1.f - b2) * gr * gr;
+      p[i] -= lr_t * m[i] / (sqrtf(v[i]) + eps);
+    }
+  }
+}
+int adam_launch(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float b1, float b2, float eps,
+                float grad_scale, cudaStream_t st) {
+  size_t blocks = (n / 4 + 255) / 256;
+  if (blocks > (size_t)kNumSMs * 8) blocks = (size_t)kNumSMs * 8;
+  if (blocks < 1) blocks = 1;
+  adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, n, lr_t, b1, b2, eps, grad_scale);
+  RVIP_LAUNCH_CHECK();
+  return 0;
+}
+
+// packed forward  operand: Wf[n][tap][c]  = W[tap][c][n]           (rows = output channels, K-major)
+// packed dgrad    operand: Wd[c][tap'][n] = W[8 - tap'][c][n]      (rows = input channels, taps rotated)
+// fp32 dgrad copy (CUDA-core path): Wr[tap'][n][c] = W[8 - tap'][c][n]
+template <typename TO, bool BF16>
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ params, TO* __restrict__ packed,
+                                                           const PackEntry* __restrict__ table) {
+  const PackEntry e = table[blockIdx.y];
+  const long long n = 9LL * e.Ctot * e.Cout;
+  const float* W = params + e.src;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const int co = (int)(i % e.Cout);
+    const int c = (int)((i / e.Cout) % e.Ctot);
+    const int tap = (int)(i / ((long long)e.Cout * e.Ctot));
+    const float v = W[i];
+    if (BF16) {
+      packed[e.dst_f + ((long long)co * 9 + tap) * e.Ctot + c] = from_f32<TO>(v);
+      if (e.dst_d >= 0) packed[e.dst_d + ((long long)c * 9 + (8 - tap)) * e.Cout + co] = from_f32<TO>(v);
+    } else {
+      if (e.dst_d >= 0) packed[e.dst_d + ((long long)(8 - tap) * e.Cout + co) * e.Ctot + c] = from_f32<TO>(v);
+    }
+  }
+}
+int pack_weights_launch(const float* params, void* packed, const PackEntry* table_dev, int n_entries, int to_bf16,
+                        cudaStream_t st) {
+  if (n_entries == 0) return 0;
+  dim3 grid(64, n_entries);
+  if (to_bf16)
+    pack_weights_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>(params, static_cast<__nv_bfloat16*>(packed),
+                                                                    table_dev);
+  else
+    pack_weights_kernel<float, false><<<grid, 256, 0, st>>>(params, static_cast<float*>(packed), table_dev);
+  RVIP_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace rvip

@@ -1,0 +1,877 @@
+// C ABI (include/rvip.h): network plan, workspace layout, TMA descriptors and the launch sequences of
+// the forward / backward / optimizer passes.  Host code only; every FLOP and byte moves in the kernels.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "../../include/rvip.h"
+#include "kernels.cuh"
+
+namespace rvip {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------- TMA descriptors
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+static int swizzle_for(int inner_bytes, CUtensorMapSwizzle* sw) {
+  if (inner_bytes == 128) *sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  else if (inner_bytes == 64) *sw = CU_TENSOR_MAP_SWIZZLE_64B;
+  else {
+    set_error("tensor map: inner box of %d bytes has no matching swizzle mode", inner_bytes);
+    return 1;
+  }
+  return 0;
+}
+// NHWC bf16 activation viewed as (C, W, H, B); box = {boxC, TW, TH, NB}
+static int make_act_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int boxC, const TileGeom& g) {
+  EncodeTiledFn enc = get_encode();
+  RVIP_REQUIRE(enc, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  CUtensorMapSwizzle sw;
+  if (swizzle_for(boxC * 2, &sw)) return 1;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)boxC, (cuuint32_t)g.TW, (cuuint32_t)g.TH, (cuuint32_t)g.NB};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RVIP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(act %dx%dx%dx%d box %d,%d,%d,%d) failed: %d", B, H, W, C,
+               boxC, g.TW, g.TH, g.NB, (int)r);
+  return 0;
+}
+// packed weights [rows][K] bf16; box = {boxK, boxRows}
+static int make_w_map(CUtensorMap* m, const void* ptr, int rows, int K, int boxK, int boxRows) {
+  EncodeTiledFn enc = get_encode();
+  RVIP_REQUIRE(enc, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  CUtensorMapSwizzle sw;
+  if (swizzle_for(boxK * 2, &sw)) return 1;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)boxK, (cuuint32_t)boxRows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RVIP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights %dx%d box %d,%d) failed: %d", rows, K, boxK,
+               boxRows, (int)r);
+  return 0;
+}
+
+static int pick_kc(int C0, int C1) { return (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32; }
+
+// fills the geometry / tiling fields of a forward-style launch (also used by the single-op entry point)
+static int setup_conv_tc(ConvTcArgs* a, int* KC, int* BN, const void* in0, const void* in1, int C0, int C1,
+                         const void* wpk, void* out0, void* out1, int out_split, int B, int H, int W, int Cout,
+                         int mode, const float* bias, double* stats) {
+  const int Ctot = C0 + C1;
+  RVIP_REQUIRE(C0 % 32 == 0 && C1 % 32 == 0 && Cout % 32 == 0, "conv_tc: channels must be multiples of 32 (%d+%d->%d)",
+               C0, C1, Cout);
+  *KC = pick_kc(C0, C1);
+  int bn = std::min(Cout, 256);
+  if (mode == EPI_LINEAR && out_split < Cout) bn = std::min(bn, out_split);
+  while (Cout % bn != 0 || (mode == EPI_LINEAR && out_split < Cout && out_split % bn != 0)) bn /= 2;
+  RVIP_REQUIRE(bn >= 32, "conv_tc: no valid N tile for Cout=%d split=%d", Cout, out_split);
+  *BN = bn;
+  a->g = make_tile_geom(B, H, W, 128);
+  a->B = B; a->H = H; a->W = W;
+  a->C0 = C0; a->Ctot = Ctot; a->Cout = Cout;
+  a->n_ntiles = Cout / bn;
+  a->total_tiles = a->n_ntiles * a->g.tiles_x * a->g.tiles_y * a->g.tiles_b;
+  a->mode = mode;
+  a->out_split = (mode == EPI_LINEAR) ? out_split : Cout;
+  a->bias = bias;
+  a->stats = stats;
+  if (make_act_map(&a->in0, in0, B, H, W, C0, *KC, a->g)) return 1;
+  if (C1 > 0) {
+    if (make_act_map(&a->in1, in1, B, H, W, C1, *KC, a->g)) return 1;
+  } else {
+    a->in1 = a->in0;
+  }
+  if (make_w_map(&a->w, wpk, Cout, 9 * Ctot, *KC, bn)) return 1;
+  const int och = bn >= 64 ? 64 : 32;
+  const int c_out0 = (mode == EPI_LINEAR) ? a->out_split : Cout;
+  if (make_act_map(&a->out0, out0, B, H, W, c_out0, och, a->g)) return 1;
+  if (mode == EPI_LINEAR && out_split < Cout) {
+    if (make_act_map(&a->out1, out1, B, H, W, Cout - out_split, och, a->g)) return 1;
+  } else {
+    a->out1 = a->out0;
+  }
+  return 0;
+}
+
+static int setup_wgrad_tc(WgradTcArgs* a, int* CBA, int* CBB, const void* x0, const void* x1, int C0, int C1,
+                          const void* dz, float* dw, int B, int H, int W, int Cout) {
+  const int Ctot = C0 + C1;
+  RVIP_REQUIRE(C0 % 32 == 0 && C1 % 32 == 0 && Cout % 32 == 0,
+               "wgrad_tc: channels must be multiples of 32 (%d+%d->%d)", C0, C1, Cout);
+  *CBA = pick_kc(C0, C1);
+  *CBB = (Cout % 64 == 0) ? 64 : 32;
+  a->g = make_tile_geom(B, H, W, 64);
+  a->B = B; a->H = H; a->W = W;
+  a->C0 = C0; a->Ctot = Ctot; a->Cout = Cout;
+  a->BN = std::min(Cout, 128);
+  const int cpt = 128 / *CBA;
+  const int nchunk = 9 * Ctot / *CBA;
+  a->n_mtiles = (nchunk + cpt - 1) / cpt;
+  int mt = (57344 - 128 * a->BN) / 16384;
+  mt = std::max(1, std::min(mt, std::min(a->n_mtiles, 512 / a->BN)));
+  a->MT = mt;
+  a->n_mgroups = (a->n_mtiles + mt - 1) / mt;
+  a->n_ntiles = Cout / a->BN;
+  a->k_tiles = a->g.tiles_x * a->g.tiles_y * a->g.tiles_b;
+  const int units = a->n_mgroups * a->n_ntiles;
+  int split = (2 * kNumSMs + units - 1) / units;
+  split = std::max(1, std::min(split, std::max(1, a->k_tiles / 4)));
+  a->n_split = split;
+  a->dw = dw;
+  if (make_act_map(&a->x0, x0, B, H, W, C0, *CBA, a->g)) return 1;
+  if (C1 > 0) {
+    if (make_act_map(&a->x1, x1, B, H, W, C1, *CBA, a->g)) return 1;
+  } else {
+    a->x1 = a->x0;
+  }
+  if (make_act_map(&a->dz, dz, B, H, W, Cout, *CBB, a->g)) return 1;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------- plan
+enum KClass { KC_CONV_FWD_TC = 0, KC_CONV_DGRAD_TC, KC_CONV_WGRAD_TC, KC_CONV_SIMT, KC_BN_FWD, KC_BN_BWD, KC_HEAD,
+              KC_OPTIM, KC_EXTRACT, KC_MISC };
+static const char* kClassNames[RVIP_NUM_KERNEL_CLASSES] = {"conv_fwd_tcgen05", "conv_dgrad_tcgen05", "conv_wgrad_tcgen05",
+                                                           "conv_cuda_core",   "bn_forward",         "bn_backward",
+                                                           "head_loss",        "adam_pack",          "extract",
+                                                           "memset_misc"};
+
+struct Layer {
+  std::string name;
+  int C0 = 0, C1 = 0, Cout = 0, H = 0, W = 0;
+  bool bn = false, first = false;
+  int post = POST_NONE;
+  float drop = 0.f;
+  uint32_t site = 0;
+  // producers / consumers (indices into layers, -1 = none)
+  int in0_layer = -1, in0_which = 1;   // which buffer of the producer feeds in0 (1 = y, 2 = y2, 0 = a)
+  int in1_layer = -1;                  // skip connection (producer's y)
+  int g0_layer = -1, g0_which = 3;     // gradient source(s) for this layer's output (3 = dx0, 4 = dx1)
+  int g1_layer = -1;
+  // offsets (floats) in params / state
+  long long off_k = 0, off_b = 0, off_g = 0, off_be = 0, off_mm = 0, off_mv = 0;
+  long long off_stat = 0;              // per-channel offset into mean/rstd/stats/red arrays
+  long long pk_f = -1, pk_d = -1;      // element offsets in the packed-weight buffer
+  // bound buffers
+  void *a = nullptr, *y = nullptr, *y2 = nullptr, *dx0 = nullptr, *dx1 = nullptr;
+  // tensor-core launch descriptors (bf16 mode, non-first layers)
+  ConvTcArgs fwd, dgrad;
+  WgradTcArgs wg;
+  int fKC = 0, fBN = 0, dKC = 0, dBN = 0, wCBA = 0, wCBB = 0;
+};
+
+struct TensorInfo {
+  std::string name;
+  int is_state;
+  long long offset;
+  int ndim;
+  int dims[4];
+};
+
+struct ProfRec {
+  int cls;
+  cudaEvent_t e0, e1;
+};
+
+}  // namespace rvip
+
+struct rvip_handle {
+  rvip_cfg cfg;
+  std::vector<rvip::Layer> L;     // 3x3 conv layers in Keras creation order
+  int head_in = -1;               // layer feeding the head
+  long long head_k = 0, head_b = 0;
+  std::vector<rvip::TensorInfo> tensors;
+  long long n_params = 0, n_state = 0, n_stat_ch = 0, n_packed = 0;
+  // binding
+  int batch = 0, training = 0, bound = 0;
+  float *params = nullptr, *grads = nullptr, *bn_state = nullptr;
+  uint8_t* ws = nullptr;
+  float *mean = nullptr, *rstd = nullptr;
+  double *stats = nullptr, *red = nullptr;
+  void *packed = nullptr, *dz = nullptr, *head_dy = nullptr;
+  rvip::PackEntry* pack_table_dev = nullptr;
+  int n_pack = 0;
+  std::vector<std::pair<long long, long long>> buckets;   // (offset, count) in grads
+  std::vector<int> bucket_after_layer;                    // bucket i completes after backward of this layer index
+  std::vector<cudaEvent_t> bucket_events;
+  // profiling
+  int profile = 0;
+  std::vector<rvip::ProfRec> prof;
+  long long launches = 0;
+};
+
+namespace rvip {
+
+static bool is_bf16(const rvip_handle* h) { return h->cfg.precision == 1; }
+static size_t esize(const rvip_handle* h) { return is_bf16(h) ? 2 : 4; }
+
+template <typename F>
+static int timed(rvip_handle* h, int cls, int n_launch, cudaStream_t st, F&& f) {
+  h->launches += n_launch;
+  if (!h->profile) return f();
+  ProfRec r;
+  r.cls = cls;
+  RVIP_CUDA(cudaEventCreate(&r.e0));
+  RVIP_CUDA(cudaEventCreate(&r.e1));
+  RVIP_CUDA(cudaEventRecord(r.e0, st));
+  int rc = f();
+  RVIP_CUDA(cudaEventRecord(r.e1, st));
+  h->prof.push_back(r);
+  return rc;
+}
+
+static int build_plan(rvip_handle* h) {
+  const rvip_cfg& c = h->cfg;
+  RVIP_REQUIRE(c.depth >= 1 && c.depth <= RVIP_MAX_DEPTH, "DEPTH=%d not in [1,%d]", c.depth, RVIP_MAX_DEPTH);
+  RVIP_REQUIRE(c.batch_norm == 1, "BATCH_NORMALISATION=false is not implemented (every shipped config enables it)");
+  RVIP_REQUIRE(c.bn_first == 0, "BN_FIRST=true (Conv->BN->ReLU) is not implemented (SURVEY row N5)");
+  RVIP_REQUIRE(c.use_upsample == 1, "USE_UPSAMPLE=false (Conv2DTranspose decoder) is not implemented (SURVEY row N5)");
+  RVIP_REQUIRE(c.H % (1 << c.depth) == 0 && c.W % (1 << c.depth) == 0, "DIM %dx%d must be divisible by 2^DEPTH=%d",
+               c.H, c.W, 1 << c.depth);
+  RVIP_REQUIRE(c.filters % 32 == 0 && c.filters >= 32, "FILTERS=%d must be a multiple of 32", c.filters);
+  RVIP_REQUIRE(c.classes >= 1 && c.classes <= 4, "MASK_CLASSES=%d not in [1,4]", c.classes);
+  RVIP_REQUIRE(c.in_ch >= 1 && c.in_ch < 32, "IMG_CHANNELS=%d not in [1,31]", c.in_ch);
+  const int d = c.depth;
+  auto add = [&](const std::string& name, int C0, int C1, int Cout, int H, int W, bool bn, int post, float drop) {
+    Layer l;
+    l.name = name; l.C0 = C0; l.C1 = C1; l.Cout = Cout; l.H = H; l.W = W; l.bn = bn;
+    l.post = post; l.drop = drop;
+    if (post == POST_DROPOUT && !(drop > 0.f)) l.post = POST_NONE;
+    l.site = (uint32_t)h->L.size();
+    h->L.push_back(l);
+    return (int)h->L.size() - 1;
+  };
+  std::vector<int> enc_b(d);
+  int f = c.filters, H = c.H, W = c.W, cin = c.in_ch, prev = -1;
+  for (int l = 0; l < d; ++l) {
+    const int ia = add("enc" + std::to_string(l) + ".conv_a", cin, 0, f, H, W, true, POST_DROPOUT, c.dropout[l]);
+    h->L[ia].first = (l == 0);
+    h->L[ia].in0_layer = prev; h->L[ia].in0_which = 2;
+    const int ib = add("enc" + std::to_string(l) + ".conv_b", f, 0, f, H, W, true, POST_POOL, 0.f);
+    h->L[ib].in0_layer = ia; h->L[ib].in0_which = 1;
+    h->L[ia].g0_layer = ib; h->L[ia].g0_which = 3;
+    enc_b[l] = ib;
+    prev = ib; cin = f; f *= 2; H /= 2; W /= 2;
+  }
+  const int ma = add("mid.conv_a", cin, 0, f, H, W, true, POST_DROPOUT, c.dropout_mid);
+  h->L[ma].in0_layer = prev; h->L[ma].in0_which = 2;
+  h->L[prev].g1_layer = ma;               // pooled gradient of the deepest encoder block
+  const int mb = add("mid.conv_b", f, 0, f, H, W, true, POST_UPSAMPLE, 0.f);
+  h->L[mb].in0_layer = ma; h->L[mb].in0_which = 1;
+  h->L[ma].g0_layer = mb;
+  for (int l = 1; l < d; ++l) h->L[enc_b[l - 1]].g1_layer = enc_b[l] - 1;   // pooled gradient <- next conv_a
+  int low = mb, clow = f;
+  for (int l = 0; l < d; ++l) {
+    f /= 2; H *= 2; W *= 2;
+    const std::string p = "dec" + std::to_string(l);
+    const int iu = add(p + ".upconv", clow, 0, f, H, W, false, POST_NONE, 0.f);
+    h->L[iu].in0_layer = low; h->L[iu].in0_which = 2;
+    h->L[low].g0_layer = iu; h->L[low].g0_which = 3;
+    const int skip = enc_b[d - 1 - l];
+    const int ia = add(p + ".conv_a", f, f, f, H, W, true, POST_DROPOUT, c.dropout[d - 1 - l]);
+    h->L[ia].in0_layer = iu; h->L[ia].in0_which = 0;
+    h->L[ia].in1_layer = skip;
+    h->L[iu].g0_layer = ia; h->L[iu].g0_which = 3;
+    h->L[skip].g0_layer = ia; h->L[skip].g0_which = 4;
+    const int ib = add(p + ".conv_b", f, 0, f, H, W, true, l < d - 1 ? POST_UPSAMPLE : POST_NONE, 0.f);
+    h->L[ib].in0_layer = ia; h->L[ib].in0_which = 1;
+    h->L[ia].g0_layer = ib; h->L[ia].g0_which = 3;
+    low = ib; clow = f;
+  }
+  h->head_in = low;
+  // flat offsets + tensor table in model.get_weights() order
+  long long po = 0, so = 0, ch = 0;
+  auto push = [&](const std::string& n, int is_state, long long off, std::initializer_list<int> dims) {
+    TensorInfo t;
+    t.name = n; t.is_state = is_state; t.offset = off; t.ndim = (int)dims.size();
+    int i = 0;
+    for (int v : dims) t.dims[i++] = v;
+    for (; i < 4; ++i) t.dims[i] = 1;
+    h->tensors.push_back(t);
+  };
+  for (Layer& l : h->L) {
+    const int Ct = l.C0 + l.C1;
+    l.off_k = po; push(l.name + "/kernel", 0, po, {3, 3, Ct, l.Cout}); po += 9LL * Ct * l.Cout;
+    l.off_b = po; push(l.name + "/bias", 0, po, {l.Cout}); po += l.Cout;
+    if (l.bn) {
+      l.off_g = po; push(l.name + "/bn/gamma", 0, po, {l.Cout}); po += l.Cout;
+      l.off_be = po; push(l.name + "/bn/beta", 0, po, {l.Cout}); po += l.Cout;
+      l.off_mm = so; push(l.name + "/bn/moving_mean", 1, so, {l.Cout}); so += l.Cout;
+      l.off_mv = so; push(l.name + "/bn/moving_variance", 1, so, {l.Cout}); so += l.Cout;
+      l.off_stat = ch; ch += l.Cout;
+    }
+  }
+  const int hc = h->L[h->head_in].Cout;
+  h->head_k = po; push("head/kernel", 0, po, {1, 1, hc, c.classes}); po += (long long)hc * c.classes;
+  h->head_b = po; push("head/bias", 0, po, {c.classes}); po += c.classes;
+  h->n_params = po; h->n_state = so; h->n_stat_ch = ch;
+  // packed operand copies
+  long long pk = 0;
+  for (Layer& l : h->L) {
+    const long long n = 9LL * (l.C0 + l.C1) * l.Cout;
+    if (is_bf16(h)) {
+      if (l.first) continue;
+      l.pk_f = pk; pk += n;
+      l.pk_d = pk; pk += n;
+    } else {
+      if (l.first) continue;
+      l.pk_d = pk; pk += n;
+    }
+  }
+  h->n_packed = pk;
+  // gradient buckets: contiguous suffixes of the flat buffer in backward order, ~4 buckets
+  const long long target = std::max<long long>(1, h->n_params / 4);
+  long long end = h->n_params;
+  for (int i = (int)h->L.size() - 1; i >= 0; --i) {
+    const long long begin = h->L[i].off_k;
+    if (end - begin >= target || i == 0) {
+      h->buckets.push_back({begin, end - begin});
+      h->bucket_after_layer.push_back(i);
+      end = begin;
+    }
+  }
+  h->bucket_events.assign(h->buckets.size(), nullptr);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------- workspace
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Carver(uint8_t* b) : base(b) {}
+  void* take(size_t bytes) {
+    off = (off + 1023) & ~size_t(1023);
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+static size_t carve(rvip_handle* h, uint8_t* base, int B, int training, bool assign) {
+  Carver cv(base);
+  const size_t es = esize(h);
+  auto T = [&](void** dst, size_t elems) {
+    void* p = cv.take(elems * es);
+    if (assign) *dst = p;
+  };
+  void* tmp;
+  void** sink = &tmp;
+  {
+    void* p = cv.take(sizeof(float) * h->n_stat_ch);
+    if (assign) h->mean = (float*)p;
+    p = cv.take(sizeof(float) * h->n_stat_ch);
+    if (assign) h->rstd = (float*)p;
+    p = cv.take(sizeof(double) * 2 * h->n_stat_ch);
+    if (assign) h->stats = (double*)p;
+    p = cv.take(sizeof(double) * 2 * h->n_stat_ch);
+    if (assign) h->red = (double*)p;
+    p = cv.take((is_bf16(h) ? 2 : 4) * (size_t)std::max<long long>(h->n_packed, 1));
+    if (assign) h->packed = p;
+  }
+  size_t max_dz = 0;
+  for (Layer& l : h->L) {
+    const size_t P = (size_t)B * l.H * l.W;
+    T(assign ? &l.a : sink, P * l.Cout);
+    if (l.bn) {
+      if (l.post == POST_UPSAMPLE) {
+        T(assign ? &l.y2 : sink, 4 * P * l.Cout);
+        if (assign) l.y = nullptr;
+      } else {
+        T(assign ? &l.y : sink, P * l.Cout);
+        if (l.post == POST_POOL) T(assign ? &l.y2 : sink, P / 4 * l.Cout);
+      }
+    } else if (assign) {
+      l.y = l.a;   // conv + ReLU without BN: the conv output is the block output
+    }
+    if (training) {
+      max_dz = std::max(max_dz, P * l.Cout);
+      if (!l.first) {
+        T(assign ? &l.dx0 : sink, P * l.C0);
+        if (l.C1) T(assign ? &l.dx1 : sink, P * l.C1);
+      }
+    }
+  }
+  if (training) {
+    void* p = cv.take(max_dz * es);
+    if (assign) h->dz = p;
+    const Layer& hl = h->L[h->head_in];
+    p = cv.take((size_t)B * hl.H * hl.W * hl.Cout * es);
+    if (assign) h->head_dy = p;
+  }
+  return cv.off + 1024;
+}
+
+static const void* buffer_of(const rvip_handle* h, int layer, int which) {
+  const Layer& l = h->L[layer];
+  switch (which) {
+    case 0: return l.a;
+    case 1: return l.y;
+    case 2: return l.y2;
+    case 3: return l.dx0;
+    default: return l.dx1;
+  }
+}
+
+static int build_descriptors(rvip_handle* h) {
+  const int B = h->batch;
+  for (size_t i = 0; i < h->L.size(); ++i) {
+    Layer& l = h->L[i];
+    if (l.first || !is_bf16(h)) continue;
+    const void* in0 = buffer_of(h, l.in0_layer, l.in0_which);
+    const void* in1 = l.in1_layer >= 0 ? buffer_of(h, l.in1_layer, 1) : nullptr;
+    const __nv_bfloat16* pk = static_cast<const __nv_bfloat16*>(h->packed);
+    const int mode = (l.bn && h->training) ? EPI_RELU_STATS : EPI_RELU;
+    if (setup_conv_tc(&l.fwd, &l.fKC, &l.fBN, in0, in1, l.C0, l.C1, pk + l.pk_f, l.a, nullptr, l.Cout, B, l.H, l.W,
+                      l.Cout, mode, h->params + l.off_b, h->stats + 2 * l.off_stat))
+      return 1;
+    if (h->training) {
+      if (setup_conv_tc(&l.dgrad, &l.dKC, &l.dBN, h->dz, nullptr, l.Cout, 0, pk + l.pk_d, l.dx0, l.dx1,
+                        l.C1 ? l.C0 : l.C0 + l.C1, B, l.H, l.W, l.C0 + l.C1, EPI_LINEAR, nullptr, nullptr))
+        return 1;
+      if (setup_wgrad_tc(&l.wg, &l.wCBA, &l.wCBB, in0, in1, l.C0, l.C1, h->dz, h->grads + l.off_k, B, l.H, l.W,
+                         l.Cout))
+        return 1;
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------- passes
+static int conv_forward(rvip_handle* h, Layer& l, const float* x, bool training, cudaStream_t st) {
+  const int mode = (l.bn && training) ? EPI_RELU_STATS : EPI_RELU;
+  if (is_bf16(h) && !l.first) {
+    l.fwd.mode = mode;
+    return timed(h, KC_CONV_FWD_TC, 1, st, [&] { return conv_tc_launch(l.fwd, l.fKC, l.fBN, st); });
+  }
+  ConvSimtArgs a;
+  a.in0 = l.first ? (const void*)x : buffer_of(h, l.in0_layer, l.in0_which);
+  a.in1 = l.in1_layer >= 0 ? buffer_of(h, l.in1_layer, 1) : nullptr;
+  a.w = h->params + l.off_k;
+  a.bias = h->params + l.off_b;
+  a.out0 = l.a; a.out1 = nullptr;
+  a.stats = h->stats + 2 * l.off_stat;
+  a.B = h->batch; a.H = l.H; a.W = l.W; a.C0 = l.C0; a.Ctot = l.C0 + l.C1; a.Cout = l.Cout;
+  a.mode = mode; a.out_split = l.Cout;
+  const int in_bf16 = l.first ? 0 : is_bf16(h);
+  return timed(h, KC_CONV_SIMT, 1, st, [&] { return conv_simt_launch(a, in_bf16, is_bf16(h), st); });
+}
+
+static void fill_bn(const rvip_handle* h, const Layer& l, BnArgs* a, bool training, uint64_t seed) {
+  memset(a, 0, sizeof(*a));
+  a->B = h->batch; a->H = l.H; a->W = l.W; a->C = l.Cout;
+  a->post = l.post;
+  if (!training && l.post == POST_DROPOUT) a->post = POST_NONE;
+  a->a = l.a;
+  a->gamma = h->params + l.off_g;
+  a->beta = h->params + l.off_be;
+  a->mean = h->mean + l.off_stat;
+  a->rstd = h->rstd + l.off_stat;
+  a->y = l.y; a->y2 = l.y2;
+  a->seed = seed; a->site = l.site;
+  a->thr16 = (uint32_t)std::lround((double)l.drop * 65536.0);
+  a->keep_scale = 1.f / (1.f - l.drop);
+}
+
+static int forward_body(rvip_handle* h, const float* x, bool training, uint64_t seed, cudaStream_t st) {
+  if (training) {
+    if (timed(h, KC_MISC, 1, st, [&] {
+          RVIP_CUDA(cudaMemsetAsync(h->stats, 0, sizeof(double) * 2 * h->n_stat_ch, st));
+          return 0;
+        }))
+      return 1;
+  } else {
+    int n_bn = 0;
+    for (Layer& l : h->L) n_bn += l.bn ? 1 : 0;
+    if (timed(h, KC_BN_FWD, n_bn, st, [&] {
+          // moving_mean / moving_variance are interleaved per layer in bn_state; prepare per layer
+          for (Layer& l : h->L)
+            if (l.bn && bn_eval_prepare_launch(h->bn_state + l.off_mm, h->bn_state + l.off_mv, h->mean + l.off_stat,
+                                               h->rstd + l.off_stat, l.Cout, h->cfg.bn_eps, st))
+              return 1;
+          return 0;
+        }))
+      return 1;
+  }
+  for (Layer& l : h->L) {
+    if (conv_forward(h, l, x, training, st)) return 1;
+    if (!l.bn) continue;
+    BnArgs a;
+    fill_bn(h, l, &a, training, seed);
+    if (training) {
+      const double cnt = (double)h->batch * l.H * l.W;
+      if (timed(h, KC_BN_FWD, 1, st, [&] {
+            return bn_finalize_launch(h->stats + 2 * l.off_stat, cnt, h->mean + l.off_stat, h->rstd + l.off_stat,
+                                      h->bn_state + l.off_mm, h->bn_state + l.off_mv, l.Cout, h->cfg.bn_momentum,
+                                      h->cfg.bn_eps, st);
+          }))
+        return 1;
+    }
+    if (timed(h, KC_BN_FWD, 1, st, [&] { return bn_apply_launch(a, is_bf16(h), st); })) return 1;
+  }
+  return 0;
+}
+
+static void fill_head(const rvip_handle* h, HeadArgs* a, float* heat) {
+  memset(a, 0, sizeof(*a));
+  const Layer& l = h->L[h->head_in];
+  a->B = h->batch; a->H = l.H; a->W = l.W; a->Cin = l.Cout; a->NC = h->cfg.classes;
+  a->y = l.y;
+  a->w = h->params + h->head_k;
+  a->b = h->params + h->head_b;
+  a->heat = heat;
+}
+
+static int backward_body(rvip_handle* h, const float* x, uint64_t seed, cudaStream_t st) {
+  const int bf = is_bf16(h);
+  size_t next_bucket = 0;
+  for (int i = (int)h->L.size() - 1; i >= 0; --i) {
+    Layer& l = h->L[i];
+    const size_t P = (size_t)h->batch * l.H * l.W;
+    if (l.bn) {
+      BnArgs a;
+      fill_bn(h, l, &a, true, seed);
+      if (i == h->head_in) {
+        a.g0 = h->head_dy;
+      } else {
+        a.g0 = buffer_of(h, l.g0_layer, l.g0_which);
+        if (l.post == POST_POOL) a.g1 = buffer_of(h, l.g1_layer, 3);
+      }
+      a.red = h->red + 2 * l.off_stat;
+      a.dz = h->dz;
+      a.dgamma = h->grads + l.off_g;
+      a.dbeta = h->grads + l.off_be;
+      a.dbias = h->grads + l.off_b;
+      if (timed(h, KC_BN_BWD, 2, st, [&] {
+            if (bn_bwd_reduce_launch(a, bf, st)) return 1;
+            return bn_bwd_apply_launch(a, bf, st);
+          }))
+        return 1;
+    } else {
+      const void* du = buffer_of(h, l.g0_layer, l.g0_which);
+      if (timed(h, KC_BN_BWD, 1, st,
+                [&] { return relu_bwd_launch(l.a, du, h->dz, h->grads + l.off_b, P, l.Cout, bf, st); }))
+        return 1;
+    }
+    if (bf && !l.first) {
+      if (timed(h, KC_CONV_WGRAD_TC, 1, st, [&] { return wgrad_tc_launch(l.wg, l.wCBA, l.wCBB, st); })) return 1;
+      if (timed(h, KC_CONV_DGRAD_TC, 1, st, [&] { return conv_tc_launch(l.dgrad, l.dKC, l.dBN, st); })) return 1;
+    } else {
+      WgradSimtArgs w;
+      w.in0 = l.first ? (const void*)x : buffer_of(h, l.in0_layer, l.in0_which);
+      w.in1 = l.in1_layer >= 0 ? buffer_of(h, l.in1_layer, 1) : nullptr;
+      w.dz = h->dz;
+      w.dw = h->grads + l.off_k;
+      w.B = h->batch; w.H = l.H; w.W = l.W; w.C0 = l.C0; w.Ctot = l.C0 + l.C1; w.Cout = l.Cout;
+      const int in_bf16 = l.first ? 0 : bf;
+      if (timed(h, KC_CONV_SIMT, 1, st, [&] { return wgrad_simt_launch(w, in_bf16, bf, st); })) return 1;
+      if (!l.first) {
+        ConvSimtArgs a;
+        a.in0 = h->dz; a.in1 = nullptr;
+        a.w = static_cast<const float*>(h->packed) + l.pk_d;
+        a.bias = nullptr;
+        a.out0 = l.dx0; a.out1 = l.dx1;
+        a.stats = nullptr;
+        a.B = h->batch; a.H = l.H; a.W = l.W; a.C0 = l.Cout; a.Ctot = l.Cout; a.Cout = l.C0 + l.C1;
+        a.mode = EPI_LINEAR;
+        a.out_split = l.C1 ? l.C0 : l.C0 + l.C1;
+        if (timed(h, KC_CONV_SIMT, 1, st, [&] { return conv_simt_launch(a, bf, bf, st); })) return 1;
+      }
+    }
+    if (next_bucket < h->buckets.size() && h->bucket_after_layer[next_bucket] == i) {
+      if (h->bucket_events[next_bucket]) RVIP_CUDA(cudaEventRecord(h->bucket_events[next_bucket], st));
+      ++next_bucket;
+    }
+  }
+  return 0;
+}
+
+static int pack_weights(rvip_handle* h, cudaStream_t st) {
+  return timed(h, KC_OPTIM, 1, st, [&] {
+    return pack_weights_launch(h->params, h->packed, h->pack_table_dev, h->n_pack, is_bf16(h), st);
+  });
+}
+
+}  // namespace rvip
+
+// =====================================================================================
+// extern "C"
+// =====================================================================================
+using namespace rvip;
+
+extern "C" {
+
+const char* rvip_last_error(void) { return g_err; }
+int rvip_abi_version(void) { return 1; }
+
+int rvip_create(const rvip_cfg* cfg, rvip_handle** out) {
+  RVIP_REQUIRE(cfg && out, "rvip_create: null argument");
+  rvip_handle* h = new rvip_handle();
+  h->cfg = *cfg;
+  if (build_plan(h)) {
+    delete h;
+    return 1;
+  }
+  *out = h;
+  return 0;
+}
+
+void rvip_destroy(rvip_handle* h) {
+  if (!h) return;
+  if (h->pack_table_dev) cudaFree(h->pack_table_dev);
+  for (auto& r : h->prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  delete h;
+}
+
+long long rvip_param_count(const rvip_handle* h) { return h->n_params; }
+long long rvip_state_count(const rvip_handle* h) { return h->n_state; }
+int rvip_num_tensors(const rvip_handle* h) { return (int)h->tensors.size(); }
+int rvip_tensor_info(const rvip_handle* h, int index, char* name, int name_cap, int* is_state, long long* offset,
+                     int* ndim, int dims[4]) {
+  RVIP_REQUIRE(index >= 0 && index < (int)h->tensors.size(), "rvip_tensor_info: index %d out of range", index);
+  const TensorInfo& t = h->tensors[index];
+  if (name && name_cap > 0) {
+    strncpy(name, t.name.c_str(), name_cap - 1);
+    name[name_cap - 1] = 0;
+  }
+  if (is_state) *is_state = t.is_state;
+  if (offset) *offset = t.offset;
+  if (ndim) *ndim = t.ndim;
+  if (dims) memcpy(dims, t.dims, sizeof(int) * 4);
+  return 0;
+}
+
+size_t rvip_workspace_bytes(const rvip_handle* h, int batch, int training) {
+  return carve(const_cast<rvip_handle*>(h), nullptr, batch, training, false);
+}
+
+int rvip_bind(rvip_handle* h, float* params, float* grads, float* bn_state, void* workspace, size_t workspace_bytes,
+              int batch, int training) {
+  RVIP_REQUIRE(h && params && bn_state && workspace && batch > 0, "rvip_bind: null/invalid argument");
+  RVIP_REQUIRE(!training || grads, "rvip_bind: training needs a gradient buffer");
+  const size_t need = carve(h, nullptr, batch, training, false);
+  RVIP_REQUIRE(workspace_bytes >= need, "rvip_bind: workspace too small (%zu < %zu)", workspace_bytes, need);
+  int dev_count = 0;
+  RVIP_CUDA(cudaGetDeviceCount(&dev_count));
+  RVIP_REQUIRE(dev_count > 0, "rvip_bind: no CUDA device (this library has no CPU fallback)");
+  h->params = params; h->grads = grads; h->bn_state = bn_state;
+  h->ws = static_cast<uint8_t*>(workspace);
+  h->batch = batch; h->training = training;
+  carve(h, h->ws, batch, training, true);
+  // pack table
+  std::vector<PackEntry> tab;
+  for (const Layer& l : h->L) {
+    if (l.first) continue;
+    PackEntry e;
+    e.src = l.off_k; e.dst_f = l.pk_f; e.dst_d = l.pk_d; e.Ctot = l.C0 + l.C1; e.Cout = l.Cout;
+    tab.push_back(e);
+  }
+  h->n_pack = (int)tab.size();
+  if (h->pack_table_dev) cudaFree(h->pack_table_dev);
+  h->pack_table_dev = nullptr;
+  if (!tab.empty()) {
+    RVIP_CUDA(cudaMalloc(&h->pack_table_dev, sizeof(PackEntry) * tab.size()));
+    RVIP_CUDA(cudaMemcpy(h->pack_table_dev, tab.data(), sizeof(PackEntry) * tab.size(), cudaMemcpyHostToDevice));
+  }
+  if (build_descriptors(h)) return 1;
+  h->bound = 1;
+  return 0;
+}
+
+int rvip_pack_weights(rvip_handle* h, void* stream) {
+  RVIP_REQUIRE(h && h->bound, "rvip_pack_weights: handle not bound");
+  return pack_weights(h, (cudaStream_t)stream);
+}
+
+int rvip_predict(rvip_handle* h, const float* x, float* heat, void* stream) {
+  RVIP_REQUIRE(h && h->bound, "rvip_predict: handle not bound");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (forward_body(h, x, false, 0, st)) return 1;
+  HeadArgs a;
+  fill_head(h, &a, heat);
+  return timed(h, KC_HEAD, 1, st, [&] { return head_launch(a, 0, is_bf16(h), st); });
+}
+
+int rvip_train_step(rvip_handle* h, const float* x, const float* target, const float* inplane, int loss_kind,
+                    float mask_thr, uint64_t seed, float* heat, double* loss_out, void* stream) {
+  RVIP_REQUIRE(h && h->bound && h->training, "rvip_train_step: handle not bound for training");
+  RVIP_REQUIRE(loss_kind != RVIP_LOSS_WEIGHTED || inplane, "rvip_train_step: weighted loss needs in-plane weights");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (timed(h, KC_MISC, 3, st, [&] {
+        RVIP_CUDA(cudaMemsetAsync(h->grads, 0, sizeof(float) * h->n_params, st));
+        RVIP_CUDA(cudaMemsetAsync(h->red, 0, sizeof(double) * 2 * h->n_stat_ch, st));
+        RVIP_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(double), st));
+        return 0;
+      }))
+    return 1;
+  if (forward_body(h, x, true, seed, st)) return 1;
+  HeadArgs a;
+  fill_head(h, &a, heat);
+  a.target = target; a.inplane = inplane; a.loss_kind = loss_kind; a.mask_thr = mask_thr; a.eps = 1e-7f;
+  a.dy = h->head_dy;
+  a.dw = h->grads + h->head_k; a.db = h->grads + h->head_b;
+  a.loss_acc = loss_out;
+  if (timed(h, KC_HEAD, 1, st, [&] { return head_launch(a, 1, is_bf16(h), st); })) return 1;
+  return backward_body(h, x, seed, st);
+}
+
+int rvip_adam_step(rvip_handle* h, float* m, float* v, float lr, float beta1, float beta2, float eps, long long step,
+                   float grad_scale, void* stream) {
+  RVIP_REQUIRE(h && h->bound && h->training && step >= 1, "rvip_adam_step: handle not bound for training");
+  cudaStream_t st = (cudaStream_t)stream;
+  const double lr_t = (double)lr * std::sqrt(1.0 - std::pow((double)beta2, (double)step)) /
+                      (1.0 - std::pow((double)beta1, (double)step));
+  if (timed(h, KC_OPTIM, 1, st, [&] {
+        return adam_launch(h->params, h->grads, m, v, (size_t)h->n_params, (float)lr_t, beta1, beta2, eps, grad_scale,
+                           st);
+      }))
+    return 1;
+  return pack_weights(h, st);
+}
+
+int rvip_num_buckets(const rvip_handle* h) { return (int)h->buckets.size(); }
+int rvip_bucket(const rvip_handle* h, int index, long long* offset, long long* count) {
+  RVIP_REQUIRE(index >= 0 && index < (int)h->buckets.size(), "rvip_bucket: index out of range");
+  *offset = h->buckets[index].first;
+  *count = h->buckets[index].second;
+  return 0;
+}
+int rvip_set_bucket_event(rvip_handle* h, int index, void* ev) {
+  RVIP_REQUIRE(index >= 0 && index < (int)h->buckets.size(), "rvip_set_bucket_event: index out of range");
+  h->bucket_events[index] = (cudaEvent_t)ev;
+  return 0;
+}
+
+size_t rvip_extract_scratch_bytes(int Z, int C) { return extract_scratch_bytes(Z, C); }
+int rvip_extract(const float* heat, int Z, int H, int W, int C, float thr, double* yx, int* count, int* argmax,
+                 float* maxv, void* scratch, void* stream) {
+  RVIP_REQUIRE(heat && yx && count && argmax && maxv && scratch, "rvip_extract: null argument");
+  return extract_launch(heat, Z, H, W, C, thr, yx, count, argmax, maxv, static_cast<unsigned long long*>(scratch),
+                        (cudaStream_t)stream);
+}
+
+int rvip_label_map(const float* heat, long long n_pixels, int C, float thr, uint8_t* labels, void* stream) {
+  RVIP_REQUIRE(heat && labels && n_pixels >= 0 && C >= 1, "rvip_label_map: bad argument");
+  return label_map_launch(heat, (size_t)n_pixels, C, thr, labels, (cudaStream_t)stream);
+}
+
+int rvip_debug_buffer(const rvip_handle* h, const char* name, int which, void** ptr, long long* count,
+                      int* elem_bytes) {
+  RVIP_REQUIRE(h && h->bound, "rvip_debug_buffer: handle not bound");
+  for (size_t i = 0; i < h->L.size(); ++i) {
+    const Layer& l = h->L[i];
+    if (l.name != name) continue;
+    const long long P = (long long)h->batch * l.H * l.W;
+    long long n = 0;
+    switch (which) {
+      case 0: n = P * l.Cout; break;
+      case 1: n = l.y ? P * l.Cout : 0; break;
+      case 2: n = l.post == POST_POOL ? P / 4 * l.Cout : (l.post == POST_UPSAMPLE ? 4 * P * l.Cout : 0); break;
+      case 3: n = l.dx0 ? P * l.C0 : 0; break;
+      case 4: n = l.dx1 ? P * l.C1 : 0; break;
+      default: set_error("rvip_debug_buffer: bad selector %d", which); return 1;
+    }
+    *ptr = const_cast<void*>(buffer_of(h, (int)i, which));
+    *count = *ptr ? n : 0;
+    *elem_bytes = (int)esize(h);
+    return 0;
+  }
+  set_error("rvip_debug_buffer: unknown layer '%s'", name);
+  return 1;
+}
+
+int rvip_dropout_mask(uint64_t seed, uint32_t site, float rate, long long n_elems, uint8_t* keep, void* stream) {
+  RVIP_REQUIRE(n_elems % 8 == 0, "rvip_dropout_mask: element count must be a multiple of 8");
+  return dropout_mask_launch(seed, site, (uint32_t)std::lround((double)rate * 65536.0), (size_t)(n_elems / 8), keep,
+                             (cudaStream_t)stream);
+}
+int rvip_dropout_site(const rvip_handle* h, const char* name, uint32_t* site, float* rate) {
+  for (const Layer& l : h->L)
+    if (l.name == name) {
+      *site = l.site;
+      *rate = l.post == POST_DROPOUT ? l.drop : 0.f;
+      return 0;
+    }
+  set_error("rvip_dropout_site: unknown layer '%s'", name);
+  return 1;
+}
+
+int rvip_profile(rvip_handle* h, int enable) {
+  h->profile = enable;
+  return 0;
+}
+int rvip_profile_read(rvip_handle* h, float ms[RVIP_NUM_KERNEL_CLASSES], long long launches[RVIP_NUM_KERNEL_CLASSES]) {
+  for (int i = 0; i < RVIP_NUM_KERNEL_CLASSES; ++i) {
+    ms[i] = 0.f;
+    launches[i] = 0;
+  }
+  for (auto& r : h->prof) {
+    RVIP_CUDA(cudaEventSynchronize(r.e1));
+    float t = 0.f;
+    RVIP_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    ms[r.cls] += t;
+    launches[r.cls] += 1;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  h->prof.clear();
+  return 0;
+}
+const char* rvip_kernel_class_name(int cls) {
+  return (cls >= 0 && cls < RVIP_NUM_KERNEL_CLASSES) ? kClassNames[cls] : "?";
+}
+long long rvip_launch_count(const rvip_handle* h) { return h->launches; }
+
+int rvip_conv3x3_tc(const void* in0, const void* in1, int C0, int C1, const void* w_packed, const float* bias,
+                    void* out0, void* out1, int out_split, double* stats, int B, int H, int W, int Cout, int mode,
+                    void* stream) {
+  ConvTcArgs a;
+  int KC, BN;
+  if (setup_conv_tc(&a, &KC, &BN, in0, in1, C0, C1, w_packed, out0, out1, out_split, B, H, W, Cout, mode, bias, stats))
+    return 1;
+  return conv_tc_launch(a, KC, BN, (cudaStream_t)stream);
+}
+
+int rvip_wgrad3x3_tc(const void* x0, const void* x1, int C0, int C1, const void* dz, float* dw, int B, int H, int W,
+                     int Cout, void* stream) {
+  WgradTcArgs a;
+  int CBA, CBB;
+  if (setup_wgrad_tc(&a, &CBA, &CBB, x0, x1, C0, C1, dz, dw, B, H, W, Cout)) return 1;
+  return wgrad_tc_launch(a, CBA, CBB, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,65 @@
+"""Heat map -> landmarks on the device.  Replaces the host loops of
+src/models/predict_model.py:149-156 (threshold -> label map) and src/models/evaluate_cv.py:389-442
+(get_ip_from_rvip_mask_3d / get_mean_rvip_2d) and adds the argmax/max of SURVEY row E3.  The return
+structures are the reference's: two lists (anterior, inferior) of [y, x] float64 points or None."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .runtime import ffi
+
+
+def extract_device(heat: torch.Tensor, thr: float = 0.5) -> Dict[str, torch.Tensor]:
+    """heat [Z,H,W,C] fp32 CUDA tensor -> device tensors: yx [Z,C,2] f64 (NaN = label absent),
+    count [Z,C] i32, argmax [Z,C] i32 (flat row-major index), maxv [Z,C] f32."""
+    if not heat.is_cuda or heat.dtype != torch.float32 or heat.dim() != 4:
+        raise ValueError('extract_device expects a CUDA float32 [Z,H,W,C] tensor')
+    heat = heat.contiguous()
+    Z, H, W, Cc = heat.shape
+    dev = heat.device
+    L = ffi.lib()
+    yx = torch.empty((Z, Cc, 2), dtype=torch.float64, device=dev)
+    count = torch.empty((Z, Cc), dtype=torch.int32, device=dev)
+    argmax = torch.empty((Z, Cc), dtype=torch.int32, device=dev)
+    maxv = torch.empty((Z, Cc), dtype=torch.float32, device=dev)
+    scratch = torch.empty(max(int(L.rvip_extract_scratch_bytes(Z, Cc)), 8), dtype=torch.uint8, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    ffi.check(L.rvip_extract(ffi.ptr(heat), Z, H, W, Cc, float(thr), ffi.ptr(yx), ffi.ptr(count), ffi.ptr(argmax),
+                             ffi.ptr(maxv), ffi.ptr(scratch), st))
+    return {'yx': yx, 'count': count, 'argmax': argmax, 'maxv': maxv}
+
+
+def label_map_device(heat: torch.Tensor, thr: float = 0.5) -> torch.Tensor:
+    """predict_model.py:153-156 on the device: [.., C] fp32 -> [..] uint8."""
+    heat = heat.contiguous()
+    out = torch.empty(heat.shape[:-1], dtype=torch.uint8, device=heat.device)
+    st = C.c_void_p(torch.cuda.current_stream(heat.device).cuda_stream)
+    ffi.check(ffi.lib().rvip_label_map(ffi.ptr(heat), out.numel(), heat.shape[-1], float(thr), ffi.ptr(out), st))
+    return out
+
+
+def points_from_stats(yx: np.ndarray, count: np.ndarray, keepdim: bool = False, both_only: bool = True):
+    """(yx, count) -> the reference's (first_ips, second_ips) lists (evaluate_cv.py:389-442)."""
+    first, second = [], []
+    for z in range(yx.shape[0]):
+        pts = [None if count[z, c] == 0 else [float(yx[z, c, 0]), float(yx[z, c, 1])] for c in range(2)]
+        if both_only and (pts[0] is None or pts[1] is None):
+            pts = [None, None]
+        if (pts[0] is not None and pts[1] is not None) or keepdim:
+            first.append(pts[0])
+            second.append(pts[1])
+    return first, second
+
+
+def get_ip_from_heatmaps(preds, thr: float = 0.5, keepdim: bool = False, both_only: bool = True, device=None):
+    """model.predict output [Z,H,W,2] (ndarray or CUDA tensor) -> (anterior list, inferior list):
+    == get_ip_from_rvip_mask_3d(label_map(preds)) of the reference, fused on the device."""
+    if isinstance(preds, np.ndarray):
+        dev = device or torch.device('cuda', torch.cuda.current_device())
+        preds = torch.from_numpy(np.ascontiguousarray(preds, dtype=np.float32)).to(dev)
+    r = extract_device(preds, thr)
+    return points_from_stats(r['yx'].cpu().numpy(), r['count'].cpu().numpy(), keepdim=keepdim, both_only=both_only)

@@ -1,0 +1,571 @@
+"""RvipUNet -- the object create_unet() returns in place of the compiled tf.keras.Model
+(src/models/Unets.py:61-133).  It mirrors the slice of the Keras Model API the reference's callers
+touch: fit (train_model.py:105-112), predict (predict_model.py:143, predict_4d_on_seg.py:86,
+utils/KerasCallbacks.py:481), load_weights / save_weights (predict_model.py:76,
+KerasCallbacks.py:54-61), get_weights / set_weights, summary, count_params, optimizer.lr,
+stop_training.
+
+PyTorch is used for device memory, streams, pinned host buffers and torch.distributed only; all
+arithmetic of the hot path runs in librvip_b200.so through runtime/ffi.py.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import time
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import ffi
+from .dist import DataParallel
+
+
+def _np_round1(v: float) -> float:
+    # Unets.py:105-106 rounds np.float64 values, i.e. numpy's round (x*10, rint, /10)
+    return float(np.round(np.float64(v), 1))
+
+
+def dropout_schedule(config: dict) -> Tuple[List[float], float]:
+    depth = config.get('DEPTH', 4)
+    d1 = config.get('DROPOUT_MIN', 0.3)
+    d3 = config.get('DROPOUT_MAX', 0.5)
+    return [_np_round1(v) for v in np.linspace(d1, d3, depth)], float(d3)
+
+
+class Adam:
+    """tf.keras.optimizers.Adam(lr) as get_optimizer builds it (ModelUtils.py:107): beta_1 0.9,
+    beta_2 0.999, epsilon 1e-7. `lr` is read and written by ReduceLROnPlateau / LRTensorBoard
+    (utils/KerasCallbacks.py:63-70, 173)."""
+
+    def __init__(self, lr: float = 0.001, beta_1: float = 0.9, beta_2: float = 0.999, epsilon: float = 1e-7,
+                 name: str = 'adam'):
+        self.lr = float(lr)
+        self.beta_1, self.beta_2, self.epsilon = float(beta_1), float(beta_2), float(epsilon)
+        self.iterations = 0
+        self.name = name
+        self.m = None
+        self.v = None
+
+    @property
+    def learning_rate(self):
+        return self.lr
+
+    @learning_rate.setter
+    def learning_rate(self, v):
+        self.lr = float(v)
+
+    def get_config(self):
+        return {'name': self.name, 'learning_rate': self.lr, 'beta_1': self.beta_1, 'beta_2': self.beta_2,
+                'epsilon': self.epsilon}
+
+
+class History:
+    def __init__(self):
+        self.history: Dict[str, List[float]] = {}
+        self.epoch: List[int] = []
+
+
+class _Binding:
+    """One (batch, training) instantiation of the C handle with its workspace."""
+
+    def __init__(self, model: 'RvipUNet', batch: int, training: bool):
+        L = ffi.lib()
+        self.batch, self.training = batch, training
+        self.h = C.c_void_p()
+        ffi.check(L.rvip_create(C.byref(model._cfg), C.byref(self.h)))
+        nbytes = L.rvip_workspace_bytes(self.h, batch, int(training))
+        self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=model.device)
+        ffi.check(L.rvip_bind(self.h, ffi.ptr(model.params), ffi.ptr(model.grads) if training else None,
+                              ffi.ptr(model.bn_state), ffi.ptr(self.workspace), nbytes, batch, int(training)))
+        self.packed_version = -1
+        self.events: List[torch.cuda.Event] = []
+        if training:
+            for i in range(L.rvip_num_buckets(self.h)):
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(model.device))   # materialise the cudaEvent_t
+                self.events.append(ev)
+                ffi.check(L.rvip_set_bucket_event(self.h, i, C.c_void_p(ev.cuda_event)))
+
+    def close(self):
+        if self.h:
+            ffi.lib().rvip_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class RvipUNet:
+    def __init__(self, config: dict, name: str = 'unet', device: Optional[torch.device] = None):
+        L = ffi.lib()                                   # raises if the CUDA library is not built
+        if not torch.cuda.is_available():
+            raise ffi.RvipError('RvipUNet needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+        self.name = name
+        self.config = dict(config)
+        if device is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+        self.device = torch.device(device)
+        dim = config.get('DIM', [224, 224])
+        if len(dim) != 2:
+            raise NotImplementedError('only 2D DIM is implemented (the RVIP path); got %r' % (dim,))
+        for key, want in (('ACTIVATION', 'relu'), ('PAD', 'same')):
+            got = config.get(key, want if key == 'PAD' else 'elu')
+            if got != want:
+                raise NotImplementedError('%s=%r is not implemented (shipped configs use %r)' % (key, got, want))
+        if list(config.get('F_SIZE', (3, 3, 3))[-2:]) != [3, 3] or list(config.get('M_POOL', (1, 2, 2))[-2:]) != [2, 2]:
+            raise NotImplementedError('only F_SIZE 3x3 and M_POOL 2x2 are implemented')
+        drops, dmid = dropout_schedule(config)
+        precision = str(config.get('PRECISION', 'bf16')).lower()
+        if precision not in ('bf16', 'fp32'):
+            raise ValueError('PRECISION must be bf16 or fp32')
+        self.precision = precision
+        cfg = ffi.rvip_cfg()
+        cfg.H, cfg.W = int(dim[0]), int(dim[1])
+        cfg.in_ch = int(config.get('IMG_CHANNELS', 1))
+        cfg.classes = int(config.get('MASK_CLASSES', 3))
+        cfg.depth = int(config.get('DEPTH', 4))
+        cfg.filters = int(config.get('FILTERS', 16))
+        cfg.batch_norm = int(bool(config.get('BATCH_NORMALISATION', False)))
+        cfg.bn_first = int(bool(config.get('BN_FIRST', False)))
+        cfg.use_upsample = int(bool(config.get('USE_UPSAMPLE', 'False')))    # string default is truthy (Unets.py:86)
+        cfg.precision = 1 if precision == 'bf16' else 0
+        for i, d in enumerate(drops):
+            cfg.dropout[i] = d
+        cfg.dropout_mid = dmid
+        cfg.bn_momentum, cfg.bn_eps = 0.99, 1e-3
+        self._cfg = cfg
+        self.input_shape = (None, cfg.H, cfg.W, cfg.in_ch)
+        self.output_shape = (None, cfg.H, cfg.W, cfg.classes)
+
+        # a throw-away handle gives the tensor table (plan only, no device work)
+        h = C.c_void_p()
+        ffi.check(L.rvip_create(C.byref(cfg), C.byref(h)))
+        self.n_params = L.rvip_param_count(h)
+        self.n_state = L.rvip_state_count(h)
+        self.tensors = []
+        for i in range(L.rvip_num_tensors(h)):
+            nm = C.create_string_buffer(128)
+            is_state, off, nd, dims = C.c_int(), C.c_longlong(), C.c_int(), (C.c_int * 4)()
+            ffi.check(L.rvip_tensor_info(h, i, nm, 128, C.byref(is_state), C.byref(off), C.byref(nd), C.byref(dims)))
+            self.tensors.append((nm.value.decode(), bool(is_state.value), off.value, tuple(dims[k] for k in range(nd.value))))
+        L.rvip_destroy(h)
+
+        self.params = torch.zeros(self.n_params, dtype=torch.float32, device=self.device)
+        self.grads = torch.zeros(self.n_params, dtype=torch.float32, device=self.device)
+        self.bn_state = torch.zeros(self.n_state, dtype=torch.float32, device=self.device)
+        self._version = 0
+        self._bindings: Dict[Tuple[int, bool], _Binding] = {}
+        self._pinned: Dict[Tuple[str, Tuple[int, ...]], torch.Tensor] = {}
+        self.optimizer: Optional[Adam] = None
+        self.loss_kind = 'mse'
+        self.loss_args = {'mask_smaller_than': 0.01}
+        self._inplane = None
+        self.metrics = []
+        self.stop_training = False
+        self._step = 0
+        self._seed = int(config.get('SEED', 42))
+        self._loss_dev = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self.dp = DataParallel(self.device)
+        self.set_weights(self._initial_weights(self._seed))
+
+    # ------------------------------------------------------------------ weights
+    def _initial_weights(self, seed: int) -> List[np.ndarray]:
+        """KERNEL_INIT he_normal for the 3x3 convs (truncated normal, stddev sqrt(2/fan_in)/0.8796),
+        glorot_uniform head (Unets.py:128 passes no initializer), zero biases, BN (1, 0, 0, 1)."""
+        rng = np.random.default_rng(seed)
+        out = []
+        for name, is_state, off, shape in self.tensors:
+            leaf = name.rsplit('/', 1)[-1]
+            if leaf == 'kernel':
+                kh, kw, cin, cout = shape
+                if name.startswith('head/'):
+                    lim = math.sqrt(6.0 / (kh * kw * cin + kh * kw * cout))
+                    w = rng.uniform(-lim, lim, size=shape)
+                else:
+                    std = math.sqrt(2.0 / (kh * kw * cin)) / 0.87962566103423978
+                    w = rng.standard_normal(size=shape)
+                    bad = np.abs(w) > 2.0
+                    while bad.any():
+                        w[bad] = rng.standard_normal(size=int(bad.sum()))
+                        bad = np.abs(w) > 2.0
+                    w *= std
+                out.append(w.astype(np.float32))
+            elif leaf in ('gamma', 'moving_variance'):
+                out.append(np.ones(shape, np.float32))
+            else:
+                out.append(np.zeros(shape, np.float32))
+        return out
+
+    def get_weights(self) -> List[np.ndarray]:
+        p = self.params.detach().cpu().numpy()
+        s = self._synced_state().cpu().numpy()
+        out = []
+        for name, is_state, off, shape in self.tensors:
+            n = int(np.prod(shape))
+            out.append((s if is_state else p)[off:off + n].reshape(shape).copy())
+        return out
+
+    def set_weights(self, weights: Sequence[np.ndarray]):
+        if len(weights) != len(self.tensors):
+            raise ValueError('expected %d weight tensors, got %d' % (len(self.tensors), len(weights)))
+        p = np.zeros(self.n_params, np.float32)
+        s = np.zeros(self.n_state, np.float32)
+        for (name, is_state, off, shape), w in zip(self.tensors, weights):
+            w = np.asarray(w, dtype=np.float32)
+            if tuple(w.shape) != tuple(shape):
+                raise ValueError('weight %s: expected shape %s, got %s' % (name, shape, w.shape))
+            (s if is_state else p)[off:off + w.size] = w.ravel()
+        self.params.copy_(torch.from_numpy(p))
+        self.bn_state.copy_(torch.from_numpy(s))
+        self._version += 1
+
+    def _synced_state(self) -> torch.Tensor:
+        """MirroredStrategy keeps BN moving statistics per replica and averages them on read
+        (synchronization=ON_READ, aggregation=MEAN)."""
+        return self.dp.mean(self.bn_state.clone()) if self.dp.world > 1 else self.bn_state
+
+    def keras_layer_names(self) -> List[Tuple[str, List[int]]]:
+        """[(keras layer name, indices into self.tensors)] in creation order."""
+        out, n_conv, n_bn, i = [], 0, 0, 0
+        while i < len(self.tensors):
+            name = self.tensors[i][0]
+            if name.endswith('/kernel'):
+                if name.startswith('head/'):
+                    lname = self.name if self.name else 'unet'
+                    lname = 'unet'
+                else:
+                    lname = 'conv2d' if n_conv == 0 else 'conv2d_%d' % n_conv
+                    n_conv += 1
+                out.append((lname, [i, i + 1]))
+                i += 2
+            else:
+                lname = 'batch_normalization' if n_bn == 0 else 'batch_normalization_%d' % n_bn
+                n_bn += 1
+                out.append((lname, [i, i + 1, i + 2, i + 3]))
+                i += 4
+        return out
+
+    _LEAF = {'kernel': 'kernel:0', 'bias': 'bias:0', 'gamma': 'gamma:0', 'beta': 'beta:0',
+             'moving_mean': 'moving_mean:0', 'moving_variance': 'moving_variance:0'}
+
+    def save_weights(self, filepath: str, overwrite: bool = True):
+        """Weights keyed like Keras' HDF5 layout (<layer>/<layer>/<var>:0). h5py is not available in
+        this image, so the container is .npz; a path ending in .h5 is written as <path>.npz."""
+        ws = self.get_weights()
+        blob = {}
+        names = []
+        for lname, idxs in self.keras_layer_names():
+            names.append(lname)
+            for i in idxs:
+                leaf = self._LEAF[self.tensors[i][0].rsplit('/', 1)[-1]]
+                blob['%s/%s/%s' % (lname, lname, leaf)] = ws[i]
+        blob['layer_names'] = np.array(names)
+        path = filepath if filepath.endswith('.npz') else filepath + '.npz'
+        if self.dp.rank == 0:
+            os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+            np.savez(path, **blob)
+
+    def load_weights(self, filepath: str):
+        path = filepath if filepath.endswith('.npz') else filepath + '.npz'
+        if not os.path.exists(path) and filepath.endswith(('.h5', '.hdf5')) and os.path.exists(filepath):
+            raise NotImplementedError('HDF5 weight files need h5py, which is not installed in this image '
+                                      '(SURVEY row N1); convert to .npz with the same keys')
+        z = np.load(path, allow_pickle=False)
+        ws = [None] * len(self.tensors)
+        # key by position (Keras auto-numbering depends on process history), verify shapes
+        file_layers = [str(s) for s in z['layer_names']]
+        mine = self.keras_layer_names()
+        if len(file_layers) != len(mine):
+            raise ValueError('weight file has %d layers, model has %d' % (len(file_layers), len(mine)))
+        for fl, (lname, idxs) in zip(file_layers, mine):
+            for i in idxs:
+                leaf = self._LEAF[self.tensors[i][0].rsplit('/', 1)[-1]]
+                ws[i] = z['%s/%s/%s' % (fl, fl, leaf)]
+        self.set_weights(ws)
+
+    def count_params(self) -> int:
+        return int(self.n_params + self.n_state)
+
+    def summary(self, print_fn=None, line_length=None):
+        print_fn = print_fn or print
+        print_fn('Model: "%s"  (B200-native, precision=%s)' % (self.name, self.precision))
+        print_fn('%-28s %-22s %12s' % ('Layer', 'Weights shape', 'Param #'))
+        for lname, idxs in self.keras_layer_names():
+            n = sum(int(np.prod(self.tensors[i][3])) for i in idxs)
+            print_fn('%-28s %-22s %12d' % (lname, str(self.tensors[idxs[0]][3]), n))
+        print_fn('Total params: {:,}'.format(self.count_params()))
+        print_fn('Trainable params: {:,}'.format(self.n_params))
+        print_fn('Non-trainable params: {:,}'.format(self.n_state))
+
+    # ------------------------------------------------------------------ compile
+    def compile(self, optimizer=None, loss=None, metrics=None, **kw):
+        if optimizer is not None:
+            if not isinstance(optimizer, Adam):
+                raise NotImplementedError('only the Adam optimizer of the shipped configs is implemented')
+            self.optimizer = optimizer
+        if isinstance(loss, dict):
+            loss = loss.get('unet', next(iter(loss.values())))
+        if loss is not None:
+            kind = getattr(loss, 'rvip_kind', loss if isinstance(loss, str) else None)
+            if isinstance(kind, str):
+                kind = kind.lower().replace('mean_squared_error', 'mse')
+            if kind not in ffi.LOSS_KINDS:
+                raise NotImplementedError('loss %r is not implemented on the device path (MSE / masked / weighted '
+                                          'MSE are; BCE+Dice is SURVEY row N2)' % (loss,))
+            self.loss_kind = kind
+            self.loss_args = dict(getattr(loss, 'rvip_args', {'mask_smaller_than': 0.01}))
+        self.metrics = list(metrics or [])
+        if self.loss_kind == 'weighted':
+            H, W = self._cfg.H, self._cfg.W
+            yy, xx = np.mgrid[0:H, 0:W]
+            d = np.minimum(np.minimum(yy, xx), np.minimum(H - 1 - yy, W - 1 - xx))
+            ramp = np.linspace(0, 100, H // 2)                      # Loss_and_metrics.py:62-69
+            w = ramp[np.minimum(d, H // 2 - 1)].astype(np.float32)
+            w[d == 0] = 0.0
+            self._inplane = torch.from_numpy(w).to(self.device)
+        return self
+
+    # ------------------------------------------------------------------ plumbing
+    def _binding(self, batch: int, training: bool) -> _Binding:
+        key = (batch, training)
+        b = self._bindings.get(key)
+        if b is None:
+            b = _Binding(self, batch, training)
+            self._bindings[key] = b
+        if b.packed_version != self._version:
+            ffi.check(ffi.lib().rvip_pack_weights(b.h, self._stream()))
+            b.packed_version = self._version
+        return b
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _pin(self, tag: str, shape, dtype=torch.float32) -> torch.Tensor:
+        key = (tag, tuple(shape))
+        t = self._pinned.get(key)
+        if t is None:
+            t = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
+            self._pinned[key] = t
+        return t
+
+    def _check_x(self, x: np.ndarray):
+        if x.ndim != 4 or tuple(x.shape[1:]) != (self._cfg.H, self._cfg.W, self._cfg.in_ch):
+            raise ValueError('expected input [N,%d,%d,%d], got %s' % (self._cfg.H, self._cfg.W, self._cfg.in_ch,
+                                                                        tuple(x.shape)))
+
+    # ------------------------------------------------------------------ inference
+    def predict_device(self, x_dev: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x_dev [B,H,W,in_ch] fp32 on the device -> heat [B,H,W,classes] fp32 (device)."""
+        B = x_dev.shape[0]
+        b = self._binding(B, False)
+        if out is None:
+            out = torch.empty((B, self._cfg.H, self._cfg.W, self._cfg.classes), dtype=torch.float32, device=self.device)
+        ffi.check(ffi.lib().rvip_predict(b.h, ffi.ptr(x_dev), ffi.ptr(out), self._stream()))
+        return out
+
+    def predict(self, x, batch_size: Optional[int] = None, verbose=0, steps=None, **kw) -> np.ndarray:
+        """model.predict: ndarray [N,H,W,C] (default batch 32) or a Sequence whose items are x or (x, y)."""
+        outs = []
+        if isinstance(x, np.ndarray):
+            self._check_x(x)
+            bs = int(batch_size or 32)
+            batches = (x[i:i + bs] for i in range(0, x.shape[0], bs))
+        else:
+            n = len(x) if steps is None else steps
+            batches = ((x[i][0] if isinstance(x[i], (tuple, list)) else x[i]) for i in range(n))
+        with torch.cuda.device(self.device):
+            for xb in batches:
+                xb = np.ascontiguousarray(xb, dtype=np.float32)
+                self._check_x(xb)
+                hp = self._pin('px', xb.shape)
+                hp.copy_(torch.from_numpy(xb))
+                xd = hp.to(self.device, non_blocking=True)
+                heat = self.predict_device(xd)
+                op = self._pin('ph', heat.shape)
+                op.copy_(heat, non_blocking=True)
+                torch.cuda.current_stream(self.device).synchronize()
+                outs.append(op.numpy().copy())
+        if not outs:
+            return np.zeros((0, self._cfg.H, self._cfg.W, self._cfg.classes), np.float32)
+        return np.concatenate(outs, axis=0)
+
+    def __call__(self, x, training=False):
+        return self.predict(np.asarray(x))
+
+    # ------------------------------------------------------------------ training
+    def train_step_device(self, x_dev: torch.Tensor, y_dev: torch.Tensor, heat: Optional[torch.Tensor] = None,
+                          apply_optimizer: bool = True) -> torch.Tensor:
+        """One optimisation step on device-resident data. Returns the (device, float64) mean loss."""
+        if self.optimizer is None:
+            raise RuntimeError('compile(optimizer=...) first')
+        L = ffi.lib()
+        B = x_dev.shape[0]
+        b = self._binding(B, True)
+        if heat is None:
+            heat = self._heat_buf(B)
+        self._step += 1
+        seed = (self._seed * 1000003 + self._step) ^ (self.dp.rank << 40)
+        thr = float(self.loss_args.get('mask_smaller_than', 0.01))
+        ffi.check(L.rvip_train_step(b.h, ffi.ptr(x_dev), ffi.ptr(y_dev), ffi.ptr(self._inplane),
+                                    ffi.LOSS_KINDS[self.loss_kind], thr, C.c_uint64(seed & (2 ** 64 - 1)),
+                                    ffi.ptr(heat), ffi.ptr(self._loss_dev), self._stream()))
+        if self.dp.world > 1:
+            self.dp.allreduce_buckets(self.grads, self._buckets(b), b.events)
+        if apply_optimizer:
+            self.apply_gradients(b)
+        return self._loss_dev
+
+    def apply_gradients(self, b: Optional[_Binding] = None):
+        opt = self.optimizer
+        if opt.m is None:
+            opt.m = torch.zeros_like(self.params)
+            opt.v = torch.zeros_like(self.params)
+        if b is None:
+            b = next(v for k, v in self._bindings.items() if k[1])
+        opt.iterations += 1
+        ffi.check(ffi.lib().rvip_adam_step(b.h, ffi.ptr(opt.m), ffi.ptr(opt.v), opt.lr, opt.beta_1, opt.beta_2,
+                                           opt.epsilon, opt.iterations, 1.0 / self.dp.world, self._stream()))
+        self._version += 1
+        b.packed_version = self._version      # rvip_adam_step re-packs this binding's operand copies
+
+    def _buckets(self, b: _Binding):
+        if not hasattr(b, 'bucket_ranges'):
+            L = ffi.lib()
+            r = []
+            for i in range(L.rvip_num_buckets(b.h)):
+                o, c = C.c_longlong(), C.c_longlong()
+                ffi.check(L.rvip_bucket(b.h, i, C.byref(o), C.byref(c)))
+                r.append((o.value, c.value))
+            b.bucket_ranges = r
+        return b.bucket_ranges
+
+    def _heat_buf(self, B):
+        key = ('heat', B)
+        if key not in self._pinned:
+            self._pinned[key] = torch.empty((B, self._cfg.H, self._cfg.W, self._cfg.classes), dtype=torch.float32,
+                                            device=self.device)
+        return self._pinned[key]
+
+    def train_on_batch(self, x: np.ndarray, y: np.ndarray) -> float:
+        """Host-facing step: pinned staging + H2D of (x, y), device step, D2H of the loss."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        y = np.ascontiguousarray(y, dtype=np.float32)
+        self._check_x(x)
+        with torch.cuda.device(self.device):
+            hx = self._pin('tx', x.shape)
+            hy = self._pin('ty', y.shape)
+            hx.copy_(torch.from_numpy(x))
+            hy.copy_(torch.from_numpy(y))
+            xd = hx.to(self.device, non_blocking=True)
+            yd = hy.to(self.device, non_blocking=True)
+            loss = self.train_step_device(xd, yd)
+            return float(loss.item())
+
+    def evaluate(self, x, y=None, batch_size=32, verbose=0) -> float:
+        """Validation loss (inference mode) -- reduction on the device with torch ops (not the hot path)."""
+        tot, n = 0.0, 0
+        if isinstance(x, np.ndarray):
+            items = ((x[i:i + batch_size], y[i:i + batch_size]) for i in range(0, len(x), batch_size))
+        else:
+            items = (x[i] for i in range(len(x)))
+        for xb, yb in items:
+            p = torch.from_numpy(self.predict(np.asarray(xb, np.float32), batch_size=len(xb)))
+            t = torch.from_numpy(np.asarray(yb, np.float32))
+            per = ((p - t) ** 2).mean(dim=-1)
+            if self.loss_kind != 'mse':
+                per = per * (t > self.loss_args.get('mask_smaller_than', 0.01)).any(dim=-1).float()
+                if self.loss_kind == 'weighted':
+                    per = per * self._inplane.cpu()[None] + 1e-7
+            tot += float(per.mean()) * len(xb)
+            n += len(xb)
+        return tot / max(n, 1)
+
+    def fit(self, x=None, y=None, batch_size=None, epochs=1, verbose=1, callbacks=None, validation_data=None,
+            shuffle=True, initial_epoch=0, steps_per_epoch=None, max_queue_size=10, workers=1,
+            use_multiprocessing=False, **kw) -> History:
+        """Epoch/step loop with the Keras callback protocol (train_model.py:105-112). `x` is an ndarray
+        (with `y`) or a keras.utils.Sequence-like object (len / getitem -> (x, y) / on_epoch_end)."""
+        hist = History()
+        callbacks = list(callbacks or [])
+        for cb in callbacks:
+            if hasattr(cb, 'set_model'):
+                cb.set_model(self)
+        self.stop_training = False
+        for cb in callbacks:
+            if hasattr(cb, 'on_train_begin'):
+                cb.on_train_begin({})
+        is_seq = not isinstance(x, np.ndarray)
+        bs = int(batch_size or 32)
+        rng = np.random.default_rng(self._seed)
+        for epoch in range(initial_epoch, epochs):
+            for cb in callbacks:
+                if hasattr(cb, 'on_epoch_begin'):
+                    cb.on_epoch_begin(epoch, {})
+            t0 = time.time()
+            losses = []
+            if is_seq:
+                n_steps = len(x) if steps_per_epoch is None else steps_per_epoch
+                for i in range(n_steps):
+                    xb, yb = x[i][:2]
+                    losses.append(self.train_on_batch(xb, yb))
+            else:
+                order = rng.permutation(len(x)) if shuffle else np.arange(len(x))
+                n_steps = len(x) // bs if steps_per_epoch is None else steps_per_epoch
+                for i in range(max(n_steps, 1)):
+                    idx = order[i * bs:(i + 1) * bs]
+                    losses.append(self.train_on_batch(x[idx], y[idx]))
+            logs = {'loss': float(np.mean(losses)) if losses else float('nan'), 'lr': self.optimizer.lr}
+            if validation_data is not None:
+                if isinstance(validation_data, (tuple, list)):
+                    logs['val_loss'] = self.evaluate(validation_data[0], validation_data[1], batch_size=bs)
+                else:
+                    logs['val_loss'] = self.evaluate(validation_data)
+            if is_seq and hasattr(x, 'on_epoch_end'):
+                x.on_epoch_end()
+            hist.epoch.append(epoch)
+            for k, v in logs.items():
+                hist.history.setdefault(k, []).append(v)
+            if verbose and self.dp.rank == 0:
+                print('Epoch %d/%d - %.1fs - %s' % (epoch + 1, epochs, time.time() - t0,
+                                                    ' - '.join('%s: %.6g' % kv for kv in logs.items())))
+            for cb in callbacks:
+                if hasattr(cb, 'on_epoch_end'):
+                    cb.on_epoch_end(epoch, logs)
+            if self.stop_training:
+                break
+        for cb in callbacks:
+            if hasattr(cb, 'on_train_end'):
+                cb.on_train_end({})
+        self.history = hist
+        return hist
+
+    # ------------------------------------------------------------------ introspection (tests / bench)
+    def debug_buffer(self, layer: str, which: int, batch: int, training: bool) -> Optional[torch.Tensor]:
+        b = self._bindings[(batch, training)]
+        p, n, es = C.c_void_p(), C.c_longlong(), C.c_int()
+        ffi.check(ffi.lib().rvip_debug_buffer(b.h, layer.encode(), which, C.byref(p), C.byref(n), C.byref(es)))
+        if not p.value or n.value == 0:
+            return None
+        dt = torch.bfloat16 if es.value == 2 else torch.float32
+        off = p.value - b.workspace.data_ptr()          # every buffer lives inside the bound workspace
+        torch.cuda.current_stream(self.device).synchronize()
+        return b.workspace[off:off + n.value * es.value].view(dt).clone()
+
+    def profile(self, batch: int, training: bool, enable: bool):
+        ffi.check(ffi.lib().rvip_profile(self._bindings[(batch, training)].h, int(enable)))
+
+    def profile_read(self, batch: int, training: bool) -> Dict[str, Tuple[float, int]]:
+        L = ffi.lib()
+        ms = (C.c_float * ffi.NUM_KERNEL_CLASSES)()
+        n = (C.c_longlong * ffi.NUM_KERNEL_CLASSES)()
+        ffi.check(L.rvip_profile_read(self._bindings[(batch, training)].h, C.byref(ms), C.byref(n)))
+        return {L.rvip_kernel_class_name(i).decode(): (float(ms[i]), int(n[i])) for i in range(ffi.NUM_KERNEL_CLASSES)}
+
+    def launch_count(self) -> int:
+        return int(sum(ffi.lib().rvip_launch_count(b.h) for b in self._bindings.values()))

@@ -1,0 +1,130 @@
+/* rvip.h -- C ABI of the B200-native RVIP heat-map U-Net hot path (librvip_b200.so).
+ *
+ * The reference (Cardio-AI/cmr-landmark-detection) has no FFI layer of its own: its hot path is
+ * reached through the tf.keras object returned by create_unet().  Each entry point below names
+ * the reference interface it stands in for; INTEGRATION.md shows the ctypes binding a maintainer
+ * adds behind src/models/Unets.py:create_unet.
+ *
+ * Conventions: all pointers are DEVICE pointers unless the name ends in _host; tensors are NHWC;
+ * every call is asynchronous on the caller's cudaStream_t (passed as void*); functions return 0
+ * on success, non-zero on failure with a message in rvip_last_error().  A handle is owned by one
+ * host thread and one GPU.  There is no CPU fallback anywhere in this library.
+ */
+#ifndef RVIP_H_
+#define RVIP_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RVIP_MAX_DEPTH 8
+
+/* Network description == the config keys create_unet() reads (src/models/Unets.py:77-106). */
+typedef struct rvip_cfg {
+  int H, W;              /* DIM */
+  int in_ch;             /* IMG_CHANNELS */
+  int classes;           /* MASK_CLASSES */
+  int depth;             /* DEPTH */
+  int filters;           /* FILTERS */
+  int batch_norm;        /* BATCH_NORMALISATION (only 1 is implemented) */
+  int bn_first;          /* BN_FIRST (only 0 is implemented: Conv -> ReLU -> BN, KerasLayers.py:687-691) */
+  int use_upsample;      /* USE_UPSAMPLE truthiness (only 1: UpSampling2D + Conv, KerasLayers.py:753-759) */
+  int precision;         /* 0 = fp32 storage, CUDA-core convs; 1 = bf16 storage, tcgen05 convs */
+  float dropout[RVIP_MAX_DEPTH]; /* encoder level l; decoder pops from the back (Unets.py:105-106, :832) */
+  float dropout_mid;     /* DROPOUT_MAX at the bottleneck (Unets.py:813) */
+  float bn_momentum;     /* 0.99  (Keras BatchNormalization default) */
+  float bn_eps;          /* 1e-3 */
+} rvip_cfg;
+
+typedef struct rvip_handle rvip_handle;
+
+enum { RVIP_LOSS_MSE = 0, RVIP_LOSS_MASKED = 1, RVIP_LOSS_WEIGHTED = 2 };
+
+const char* rvip_last_error(void);
+int rvip_abi_version(void);
+
+/* ---- model construction: replaces unet()/create_unet() graph building (Unets.py:61-133, 755-869) */
+int rvip_create(const rvip_cfg* cfg, rvip_handle** out);
+void rvip_destroy(rvip_handle* h);
+
+/* Flat buffers: `params`/`grads` hold the trainable tensors, `bn_state` the BN moving statistics.
+ * The tensor table lists model.get_weights() order (Conv: kernel HWIO, bias; BN: gamma, beta,
+ * moving_mean, moving_variance) with the offset of each tensor in its flat buffer. */
+long long rvip_param_count(const rvip_handle* h);
+long long rvip_state_count(const rvip_handle* h);
+int rvip_num_tensors(const rvip_handle* h);
+int rvip_tensor_info(const rvip_handle* h, int index, char* name, int name_cap, int* is_state, long long* offset,
+                     int* ndim, int dims[4]);
+
+/* Workspace (activations, gradients of activations, packed weights, tensor maps are host side). */
+size_t rvip_workspace_bytes(const rvip_handle* h, int batch, int training);
+int rvip_bind(rvip_handle* h, float* params, float* grads, float* bn_state, void* workspace, size_t workspace_bytes,
+              int batch, int training);
+/* Re-derive the tensor-core operand copies after `params` changed (set_weights / load_weights). */
+int rvip_pack_weights(rvip_handle* h, void* stream);
+
+/* ---- model.predict (predict_model.py:143): inference forward, BN moving stats, no dropout.
+ * x [B,H,W,in_ch] fp32 -> heat [B,H,W,classes] fp32 */
+int rvip_predict(rvip_handle* h, const float* x, float* heat, void* stream);
+
+/* ---- one model.fit step minus the optimizer (train_model.py:105): forward with batch statistics and
+ * dropout(seed), loss, full backward.  grads (bound buffer) receive d(mean loss)/d(param);
+ * loss_out is a device double.  inplane [H,W] is only read for RVIP_LOSS_WEIGHTED. */
+int rvip_train_step(rvip_handle* h, const float* x, const float* target, const float* inplane, int loss_kind,
+                    float mask_thr, uint64_t seed, float* heat, double* loss_out, void* stream);
+
+/* ---- Adam apply (ModelUtils.py:107; Keras epsilon-hat form) + operand re-pack.
+ * grad_scale folds the data-parallel 1/world into the update. step counts from 1. */
+int rvip_adam_step(rvip_handle* h, float* m, float* v, float lr, float beta1, float beta2, float eps, long long step,
+                   float grad_scale, void* stream);
+
+/* ---- data-parallel plumbing (MirroredStrategy, Unets.py:70-75): gradient buckets are contiguous
+ * ranges of `grads` in backward-completion order; each records a cudaEvent_t when complete so the
+ * caller can start that bucket's all-reduce while the rest of backward still runs. */
+int rvip_num_buckets(const rvip_handle* h);
+int rvip_bucket(const rvip_handle* h, int index, long long* offset, long long* count);
+int rvip_set_bucket_event(rvip_handle* h, int index, void* cuda_event);
+
+/* ---- landmark extraction: threshold/label map (predict_model.py:153-156) + per-slice centroid
+ * (evaluate_cv.py:418-442) + argmax/max.
+ * heat [Z,H,W,C] fp32 -> yx [Z,C,2] float64 (NaN when the label is absent), count [Z,C] int32,
+ * argmax [Z,C] int32 flat index, maxv [Z,C] fp32.  scratch: rvip_extract_scratch_bytes(Z,C) bytes. */
+size_t rvip_extract_scratch_bytes(int Z, int C);
+int rvip_extract(const float* heat, int Z, int H, int W, int C, float thr, double* yx, int* count, int* argmax,
+                 float* maxv, void* scratch, void* stream);
+
+/* threshold -> uint8 label map exactly as predict_model.py:153-156 (0 background, c+1 for the LAST channel
+ * whose value is > thr); heat [n_pixels, C] fp32 -> labels [n_pixels] */
+int rvip_label_map(const float* heat, long long n_pixels, int C, float thr, uint8_t* labels, void* stream);
+
+/* ---- introspection for parity tests and profiling */
+/* which: 0 = relu(conv) output `a`, 1 = block output `y`, 2 = pooled / up-sampled output, 3 = dL/d(in0),
+ * 4 = dL/d(in1). Returns the device pointer, element count and element size of layer `name`. */
+int rvip_debug_buffer(const rvip_handle* h, const char* name, int which, void** ptr, long long* count,
+                      int* elem_bytes);
+int rvip_dropout_mask(uint64_t seed, uint32_t site, float rate, long long n_elems, uint8_t* keep, void* stream);
+int rvip_dropout_site(const rvip_handle* h, const char* name, uint32_t* site, float* rate);
+/* Per-kernel-class device timing: after rvip_profile(h, 1) every launch group is bracketed with CUDA
+ * events; rvip_profile_read sums them (ms) and the launch counts per class and clears the log. */
+#define RVIP_NUM_KERNEL_CLASSES 10
+int rvip_profile(rvip_handle* h, int enable);
+int rvip_profile_read(rvip_handle* h, float ms[RVIP_NUM_KERNEL_CLASSES], long long launches[RVIP_NUM_KERNEL_CLASSES]);
+const char* rvip_kernel_class_name(int cls);
+long long rvip_launch_count(const rvip_handle* h); /* kernels launched by this handle so far */
+
+/* ---- single-op entry points (unit tests drive the tensor-core kernels directly).
+ * tcgen05 implicit-GEMM conv: in0/in1 NHWC bf16 (C0 + C1 channels), w_packed [Cout][9][C0+C1] bf16,
+ * out NHWC bf16; mode 0 = bias+ReLU+stats, 1 = bias+ReLU, 2 = linear (dgrad; out1 gets channels >= out_split) */
+int rvip_conv3x3_tc(const void* in0, const void* in1, int C0, int C1, const void* w_packed, const float* bias,
+                    void* out0, void* out1, int out_split, double* stats, int B, int H, int W, int Cout, int mode,
+                    void* stream);
+/* tcgen05 wgrad: dw [9][C0+C1][Cout] fp32 += sum_p x[p+tap] * dz[p] */
+int rvip_wgrad3x3_tc(const void* x0, const void* x1, int C0, int C1, const void* dz, float* dw, int B, int H, int W,
+                     int Cout, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RVIP_H_ */

@@ -1,0 +1,75 @@
+"""Helpers shared by the GPU parity tests: call the single-op C-ABI entry points on torch tensors and
+build torch fp32 references of the same ops (the oracle for the floating-point kernels)."""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from cmr_landmark_detection_b200.runtime import ffi
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def pack_fwd(w_hwio: torch.Tensor) -> torch.Tensor:
+    """[3,3,C,N] -> Wf [N][9][C] bf16."""
+    kh, kw, c, n = w_hwio.shape
+    return w_hwio.permute(3, 0, 1, 2).reshape(n, 9 * c).contiguous().to(torch.bfloat16)
+
+
+def pack_dgrad(w_hwio: torch.Tensor) -> torch.Tensor:
+    """[3,3,C,N] -> Wd [C][9 (rotated)][N] bf16."""
+    kh, kw, c, n = w_hwio.shape
+    rot = torch.flip(w_hwio, dims=(0, 1))
+    return rot.permute(2, 0, 1, 3).reshape(c, 9 * n).contiguous().to(torch.bfloat16)
+
+
+def conv_tc(in0, in1, w_packed, bias, cout, mode, out_split=None, want_stats=False):
+    B, H, W, C0 = in0.shape
+    C1 = in1.shape[3] if in1 is not None else 0
+    dev = in0.device
+    if out_split is None:
+        out_split = cout
+    out0 = torch.full((B, H, W, out_split if mode == 2 else cout), float('nan'), dtype=torch.bfloat16, device=dev)
+    out1 = None
+    if mode == 2 and out_split < cout:
+        out1 = torch.full((B, H, W, cout - out_split), float('nan'), dtype=torch.bfloat16, device=dev)
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device=dev) if want_stats else None
+    ffi.check(ffi.lib().rvip_conv3x3_tc(ffi.ptr(in0), ffi.ptr(in1), C0, C1, ffi.ptr(w_packed), ffi.ptr(bias),
+                                        ffi.ptr(out0), ffi.ptr(out1), out_split, ffi.ptr(stats), B, H, W, cout, mode,
+                                        stream()))
+    torch.cuda.synchronize()
+    return out0, out1, stats
+
+
+def wgrad_tc(x0, x1, dz):
+    B, H, W, C0 = x0.shape
+    C1 = x1.shape[3] if x1 is not None else 0
+    cout = dz.shape[3]
+    dw = torch.zeros((3, 3, C0 + C1, cout), dtype=torch.float32, device=x0.device)
+    ffi.check(ffi.lib().rvip_wgrad3x3_tc(ffi.ptr(x0), ffi.ptr(x1), C0, C1, ffi.ptr(dz), ffi.ptr(dw), B, H, W, cout,
+                                         stream()))
+    torch.cuda.synchronize()
+    return dw
+
+
+def ref_conv(x_nhwc: torch.Tensor, w_hwio: torch.Tensor, bias=None, relu=False):
+    """fp32 reference on the bf16-rounded operands (what the tensor cores see), fp32 accumulate."""
+    x = x_nhwc.float().permute(0, 3, 1, 2)
+    w = w_hwio.to(torch.bfloat16).float().permute(3, 2, 0, 1)
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        y = F.conv2d(x, w, bias, padding=1)
+    if relu:
+        y = torch.relu(y)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def max_err(a, b) -> float:
+    return float((a.double() - b.double()).abs().max())

@@ -1,0 +1,138 @@
+"""GPU parity tests of the individual kernels, called through the C ABI (librvip_b200.so)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+CONV_SHAPES = [  # B, H, W, C0, C1, Cout
+    (2, 16, 16, 64, 0, 64),
+    (2, 32, 32, 32, 0, 32),
+    (1, 16, 16, 32, 32, 64),      # concat, KC=32
+    (2, 8, 8, 128, 0, 256),
+    (3, 4, 4, 64, 0, 512),        # several images per tile, batch not a multiple of NB, two N tiles
+    (1, 24, 40, 64, 0, 32),       # non power-of-two image: partial tiles
+    (2, 16, 16, 64, 64, 128),     # concat, KC=64
+    (1, 128, 128, 32, 0, 32),     # row tiles of 128 pixels
+]
+
+
+def _rand_bf16(shape, gen, scale=1.0):
+    return (torch.randn(shape, generator=gen, device='cuda') * scale).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize('shape', CONV_SHAPES)
+def test_conv_tc_forward_bias_relu_stats(shape):
+    from tests import gpu_util as U
+    B, H, W, C0, C1, N = shape
+    g = torch.Generator(device='cuda').manual_seed(1 + sum(shape))
+    x0 = _rand_bf16((B, H, W, C0), g)
+    x1 = _rand_bf16((B, H, W, C1), g) if C1 else None
+    w = torch.randn((3, 3, C0 + C1, N), generator=g, device='cuda') * (2.0 / (9 * (C0 + C1))) ** 0.5
+    bias = torch.randn(N, generator=g, device='cuda') * 0.1
+    out, _, stats = U.conv_tc(x0, x1, U.pack_fwd(w), bias, N, mode=0, want_stats=True)
+    xin = x0 if x1 is None else torch.cat([x0, x1], dim=3)
+    ref = U.ref_conv(xin, w, bias, relu=True)
+    assert torch.isfinite(out.float()).all()
+    # bf16 output rounding: <= 2^-8 relative per element
+    assert U.max_err(out, ref) <= 1e-2 * float(ref.abs().max()) + 1e-3
+    assert U.rel_err(out, ref) < 4e-3
+    rb = out.double()
+    assert torch.allclose(stats[:N], rb.sum(dim=(0, 1, 2)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(stats[N:], (rb * rb).sum(dim=(0, 1, 2)), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize('shape', CONV_SHAPES)
+def test_conv_tc_dgrad(shape):
+    from tests import gpu_util as U
+    B, H, W, C0, C1, N = shape
+    g = torch.Generator(device='cuda').manual_seed(2 + sum(shape))
+    dz = _rand_bf16((B, H, W, N), g)
+    w = torch.randn((3, 3, C0 + C1, N), generator=g, device='cuda') * (2.0 / (9 * N)) ** 0.5
+    dx0, dx1, _ = U.conv_tc(dz, None, U.pack_dgrad(w), None, C0 + C1, mode=2, out_split=C0 if C1 else C0 + C1)
+    x = torch.zeros((B, C0 + C1, H, W), device='cuda', requires_grad=True)
+    wt = w.to(torch.bfloat16).float().permute(3, 2, 0, 1)
+    y = torch.nn.functional.conv2d(x, wt, padding=1)
+    y.backward(dz.float().permute(0, 3, 1, 2))
+    ref = x.grad.permute(0, 2, 3, 1)
+    got = dx0 if dx1 is None else torch.cat([dx0, dx1], dim=3)
+    assert U.rel_err(got, ref) < 4e-3
+
+
+@pytest.mark.parametrize('shape', CONV_SHAPES)
+def test_wgrad_tc(shape):
+    from tests import gpu_util as U
+    B, H, W, C0, C1, N = shape
+    g = torch.Generator(device='cuda').manual_seed(3 + sum(shape))
+    x0 = _rand_bf16((B, H, W, C0), g)
+    x1 = _rand_bf16((B, H, W, C1), g) if C1 else None
+    dz = _rand_bf16((B, H, W, N), g)
+    dw = U.wgrad_tc(x0, x1, dz)
+    xin = (x0 if x1 is None else torch.cat([x0, x1], dim=3)).float().permute(0, 3, 1, 2)
+    w = torch.zeros((N, C0 + C1, 3, 3), device='cuda', requires_grad=True)
+    y = torch.nn.functional.conv2d(xin, w, padding=1)
+    y.backward(dz.float().permute(0, 3, 1, 2))
+    ref = w.grad.permute(2, 3, 1, 0)
+    assert U.rel_err(dw, ref) < 2e-3
+
+
+def test_extract_matches_reference_golden(golden_dir):
+    """Device kernel vs outputs of the reference's own get_ip_from_rvip_mask_3d (golden) and vs the oracle."""
+    from cmr_landmark_detection_b200.extract import extract_device, label_map_device, points_from_stats
+    from oracle import extract_ref as ex
+    gold = np.load(os.path.join(golden_dir, 'extract_golden.npz'))
+    for key in gold['names']:
+        heat = gold[key + '/heat']
+        r = extract_device(torch.from_numpy(heat).cuda())
+        yx, cnt = r['yx'].cpu().numpy(), r['count'].cpu().numpy()
+        lab = label_map_device(torch.from_numpy(heat).cuda()).cpu().numpy()
+        assert np.array_equal(lab, gold[key + '/labels']), key
+        for both in (True, False):
+            a, b = points_from_stats(yx, cnt, keepdim=True, both_only=both)
+            for got, want in ((a, gold[key + '/ant_both%d' % both]), (b, gold[key + '/inf_both%d' % both])):
+                for p, q in zip(got, want):
+                    if np.isnan(q[0]):
+                        assert p is None
+                    else:
+                        assert abs(p[0] - q[0]) <= 1e-4 and abs(p[1] - q[1]) <= 1e-4     # tolerance: 1e-4 px
+        count, srow, scol, amax, vmax = ex.extract_stats(heat)
+        assert np.array_equal(cnt, count)
+        finite = ~np.isnan(heat).any(axis=(1, 2))
+        assert np.array_equal(r['argmax'].cpu().numpy()[finite], amax[finite])       # bit-exact
+        assert np.array_equal(r['maxv'].cpu().numpy()[finite], vmax[finite])
+
+
+def test_extract_full_size_properties():
+    """BASELINE config 4 size (16 x 256 x 256 x 2): argmax bit-exact vs numpy, centroid of a shifted volume
+    shifts by exactly the shift, empty volume -> all absent."""
+    from cmr_landmark_detection_b200 import synth
+    from cmr_landmark_detection_b200.extract import extract_device
+    vol = synth.make_volume_heat(16, 256, 256, seed=3)
+    r = extract_device(torch.from_numpy(vol).cuda())
+    am = vol.reshape(16, -1, 2).argmax(axis=1)
+    assert np.array_equal(r['argmax'].cpu().numpy(), am)
+    rolled = np.roll(vol, shift=(3, -5), axis=(1, 2))
+    r2 = extract_device(torch.from_numpy(rolled).cuda())
+    d = (r2['yx'] - r['yx']).cpu().numpy()
+    ok = np.isfinite(d[..., 0])
+    inside = ok & (np.abs(r['yx'].cpu().numpy()[..., 0] - 128) < 90) & (np.abs(r['yx'].cpu().numpy()[..., 1] - 128) < 90)
+    # noise pixels never exceed thr, so a blob away from the border translates rigidly
+    assert np.allclose(d[inside][:, 0], 3.0, atol=1e-9) and np.allclose(d[inside][:, 1], -5.0, atol=1e-9)
+    z = extract_device(torch.zeros((2, 256, 256, 2), device='cuda'))
+    assert int(z['count'].sum()) == 0 and bool(torch.isnan(z['yx']).all())
+    assert np.array_equal(z['argmax'].cpu().numpy(), np.zeros((2, 2), np.int32))
+
+
+def test_reference_signature_wrappers():
+    from src.models.evaluate_cv import get_ip_from_rvip_mask_3d, get_mean_rvip_2d
+    m = np.zeros((32, 32), np.uint8)
+    m[5:8, 10:13] = 1
+    m[20:22, 4:9] = 2
+    assert get_mean_rvip_2d(m) == ([6.0, 11.0], [20.5, 6.0])        # SURVEY 8c hand-checkable example
+    vol = np.stack([m, np.zeros_like(m), m])
+    a, b = get_ip_from_rvip_mask_3d(vol, keepdim=True)
+    assert a == [[6.0, 11.0], None, [6.0, 11.0]] and b[1] is None
+    a, b = get_ip_from_rvip_mask_3d(vol)
+    assert len(a) == 2

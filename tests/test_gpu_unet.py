@@ -1,0 +1,200 @@
+"""End-to-end parity of the device U-Net path (through create_unet -> C ABI) against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BASE = {'DEPTH': 2, 'FILTERS': 32, 'IMG_CHANNELS': 1, 'MASK_CLASSES': 2, 'BATCH_NORMALISATION': True,
+        'BN_FIRST': False, 'ACTIVATION': 'relu', 'PAD': 'same', 'DROPOUT_MIN': 0.0, 'DROPOUT_MAX': 0.0,
+        'LEARNING_RATE': 1e-3, 'M_POOL': [2, 2], 'F_SIZE': [3, 3], 'SEED': 7}
+
+# tolerances: heat max-abs / loss rel / gradient cosine + rel-L2 / Adam update rel
+TOL = {'fp32': dict(heat=1e-4, loss=1e-5, cos=0.99999, rl2=2e-4, upd=1e-3),
+       'bf16': dict(heat=2e-2, loss=1e-2, cos=0.999, rl2=3e-2, upd=5e-2)}
+
+
+def _setup(precision, dim, depth, batch, randomize_bn=True, seed=0):
+    from cmr_landmark_detection_b200 import synth
+    from cmr_landmark_detection_b200.models.Unets import create_unet
+    from oracle import unet_ref as R
+    config = dict(BASE, DIM=[dim, dim], DEPTH=depth, PRECISION=precision)
+    model = create_unet(config)
+    cfg = R.cfg_from_config(config)
+    ws = R.init_weights(cfg, seed=11 + seed, randomize_bn=randomize_bn)
+    model.set_weights(ws)
+    x, y = synth.make_batch(batch, dim, dim, seed=5 + seed)
+    return model, cfg, ws, x, y
+
+
+@pytest.mark.parametrize('precision,dim,depth,batch', [('fp32', 32, 2, 3), ('bf16', 32, 2, 3), ('fp32', 64, 4, 2),
+                                                       ('bf16', 64, 4, 4), ('bf16', 256, 4, 2)])
+def test_predict_matches_oracle(precision, dim, depth, batch):
+    from oracle import unet_ref as R
+    model, cfg, ws, x, y = _setup(precision, dim, depth, batch)
+    heat = model.predict(x, batch_size=batch)
+    ref = R.predict(cfg, ws, x)
+    assert heat.shape == ref.shape and heat.dtype == np.float32
+    t = TOL[precision]
+    assert np.abs(heat - ref).max() <= t['heat'], np.abs(heat - ref).max()
+    if precision == 'bf16':
+        assert np.abs(heat - ref).mean() <= 2e-3
+
+
+@pytest.mark.parametrize('precision,dim,depth,batch', [('fp32', 32, 2, 3), ('bf16', 32, 2, 4), ('fp32', 64, 4, 2),
+                                                       ('bf16', 64, 4, 4), ('bf16', 128, 4, 2)])
+def test_train_step_matches_oracle(precision, dim, depth, batch):
+    from oracle import unet_ref as R
+    model, cfg, ws, x, y = _setup(precision, dim, depth, batch, randomize_bn=False)
+    t = TOL[precision]
+    ref = R.train_grads(cfg, ws, x, y)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    loss = float(model.train_step_device(xd, yd, apply_optimizer=False).item())
+    assert abs(loss - ref['loss']) <= t['loss'] * abs(ref['loss']), (loss, ref['loss'])
+    g = model.grads.cpu().numpy()
+    worst = []
+    for (name, is_state, off, shape), rg in zip(model.tensors, ref['grads']):
+        if is_state:
+            continue
+        n = int(np.prod(shape))
+        mine = g[off:off + n].reshape(shape).astype(np.float64)
+        rg = rg.astype(np.float64)
+        nr = np.linalg.norm(rg)
+        if nr < 1e-12:
+            continue
+        cos = float((mine * rg).sum() / (np.linalg.norm(mine) * nr + 1e-300))
+        rl2 = float(np.linalg.norm(mine - rg) / nr)
+        worst.append((cos, rl2, name))
+        assert cos >= t['cos'] and rl2 <= t['rl2'], (name, cos, rl2)
+    # BN moving statistics after one step
+    new = R.apply_new_stats(cfg, ws, ref['new_stats'])
+    mine = model.get_weights()
+    for (name, is_state, off, shape), a, b in zip(model.tensors, mine, new):
+        if is_state:
+            assert np.allclose(a, b, rtol=1e-2 if precision == 'bf16' else 1e-5, atol=1e-5), name
+    # Adam step
+    opt = R.Adam(lr=1e-3)
+    stepped = opt.step(ws, ref['grads'])
+    model.apply_gradients()
+    after = model.get_weights()
+    for (name, is_state, off, shape), a, b, w0, rg in zip(model.tensors, after, stepped, ws, ref['grads']):
+        if is_state:
+            continue
+        big = np.abs(rg) > 1e-3 * np.abs(rg).max()
+        assert np.allclose((a - w0)[big], (b - w0)[big], rtol=t['upd'], atol=1e-7), name
+
+
+def test_fp32_argmax_bit_exact_and_landmarks_within_half_pixel():
+    """north_star: integer argmax bit-exact in fp32 mode (when the oracle's top-2 differ by > 1e-3) and
+    landmark coordinates within 0.5 px in both modes."""
+    from cmr_landmark_detection_b200.extract import extract_device
+    from oracle import extract_ref as ex
+    from oracle import unet_ref as R
+    for precision in ('fp32', 'bf16'):
+        model, cfg, ws, x, y = _setup(precision, 64, 4, 4, seed=3)
+        # bias the head so both channels cross the 0.5 threshold somewhere
+        heat = model.predict(x, batch_size=4)
+        ref = R.predict(cfg, ws, x)
+        thr = float(np.quantile(ref, 0.97))
+        r = extract_device(torch.from_numpy(heat).cuda(), thr)
+        cnt, sr, sc, am, vm = ex.extract_stats(ref, thr)
+        yx = r['yx'].cpu().numpy()
+        for z in range(ref.shape[0]):
+            for c in range(2):
+                flat = np.sort(ref[z, :, :, c].ravel())
+                if precision == 'fp32' and flat[-1] - flat[-2] > 1e-3:
+                    assert int(r['argmax'][z, c]) == int(am[z, c])
+                # centroid parity only where the thresholded set is not sitting on the decision boundary
+                margin = np.abs(ref[z, :, :, c] - thr).min()
+                if cnt[z, c] > 0 and margin > (1e-4 if precision == 'fp32' else 2e-2):
+                    assert abs(yx[z, c, 0] - sr[z, c] / cnt[z, c]) <= 0.5
+                    assert abs(yx[z, c, 1] - sc[z, c] / cnt[z, c]) <= 0.5
+
+
+def test_dropout_masks_replayed_in_oracle():
+    """Dropout on: export the Philox keep-masks the kernels used and feed them to the oracle."""
+    import ctypes as C
+    from cmr_landmark_detection_b200 import synth
+    from cmr_landmark_detection_b200.models.Unets import create_unet
+    from cmr_landmark_detection_b200.runtime import ffi
+    from oracle import unet_ref as R
+    config = dict(BASE, DIM=[32, 32], DEPTH=2, PRECISION='fp32', DROPOUT_MIN=0.3, DROPOUT_MAX=0.5)
+    model = create_unet(config)
+    cfg = R.cfg_from_config(config)
+    ws = R.init_weights(cfg, seed=21)
+    model.set_weights(ws)
+    x, y = synth.make_batch(4, 32, 32, seed=9)
+    loss = float(model.train_step_device(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(),
+                                         apply_optimizer=False).item())
+    seed = (model._seed * 1000003 + model._step) & (2 ** 64 - 1)
+    b = model._bindings[(4, True)]
+    masks = {}
+    shapes = {'enc0.conv_a': (4, 32, 32, 32), 'enc1.conv_a': (4, 16, 16, 64), 'mid.conv_a': (4, 8, 8, 128),
+              'dec0.conv_a': (4, 16, 16, 64), 'dec1.conv_a': (4, 32, 32, 32)}
+    names = {'enc0.conv_a': 'enc0', 'enc1.conv_a': 'enc1', 'mid.conv_a': 'mid', 'dec0.conv_a': 'dec0',
+             'dec1.conv_a': 'dec1'}
+    for lname, shp in shapes.items():
+        site, rate = C.c_uint32(), C.c_float()
+        ffi.check(ffi.lib().rvip_dropout_site(b.h, lname.encode(), C.byref(site), C.byref(rate)))
+        n = int(np.prod(shp))
+        keep = torch.empty(n, dtype=torch.uint8, device='cuda')
+        ffi.check(ffi.lib().rvip_dropout_mask(C.c_uint64(seed), site.value, rate.value, n, ffi.ptr(keep), None))
+        torch.cuda.synchronize()
+        masks[names[lname]] = keep.cpu().numpy().reshape(shp)
+        assert abs(masks[names[lname]].mean() - (1 - rate.value)) < 0.02
+    ref = R.train_grads(cfg, ws, x, y, dropout_masks=masks)
+    assert abs(loss - ref['loss']) <= 1e-5 * abs(ref['loss'])
+    g = model.grads.cpu().numpy()
+    name, is_state, off, shape = model.tensors[0]
+    mine = g[off:off + int(np.prod(shape))].reshape(shape)
+    assert np.linalg.norm(mine - ref['grads'][0]) <= 2e-4 * np.linalg.norm(ref['grads'][0])
+
+
+def test_weights_roundtrip_and_summary(tmp_path):
+    from cmr_landmark_detection_b200.models.Unets import create_unet
+    model = create_unet(dict(BASE, DIM=[128, 128], DEPTH=4, PRECISION='bf16'))
+    assert model.count_params() == 8641730 and model.n_params == 8635842 and model.n_state == 5888
+    ws = model.get_weights()
+    assert len(ws) == 118
+    p = str(tmp_path / 'model.h5')
+    model.save_weights(p)
+    m2 = create_unet(dict(BASE, DIM=[128, 128], DEPTH=4, PRECISION='bf16', SEED=99))
+    m2.load_weights(p)
+    for a, b in zip(ws, m2.get_weights()):
+        assert np.array_equal(a, b)
+    lines = []
+    model.summary(print_fn=lines.append)
+    assert any('8,641,730' in l for l in lines)
+
+
+def test_fit_reduces_loss_and_callbacks_run():
+    from cmr_landmark_detection_b200 import synth
+    from cmr_landmark_detection_b200.models.Unets import create_unet
+    model = create_unet(dict(BASE, DIM=[32, 32], DEPTH=2, PRECISION='bf16', LEARNING_RATE=2e-3))
+    x, y = synth.make_batch(16, 32, 32, seed=4)
+
+    class Seq:
+        def __len__(self):
+            return 4
+
+        def __getitem__(self, i):
+            return x[4 * i:4 * i + 4], y[4 * i:4 * i + 4]
+
+        def on_epoch_end(self):
+            pass
+
+    seen = []
+
+    class CB:
+        def set_model(self, m):
+            self.model = m
+
+        def on_epoch_end(self, epoch, logs):
+            seen.append(logs['loss'])
+            if epoch == 5:
+                self.model.stop_training = True
+
+    h = model.fit(x=Seq(), validation_data=Seq(), epochs=20, callbacks=[CB()], initial_epoch=0, max_queue_size=12,
+                  verbose=0)
+    assert len(seen) == 6 and h.history['loss'][-1] < h.history['loss'][0]
+    assert 'val_loss' in h.history

@@ -136,8 +136,9 @@ def test_adam_keras_form_and_dp_equivalence():
     g = dp['grads'][0]
     # first Adam step moves every coordinate by ~lr * sign(g)
     step = new[0] - ws[0]
-    big = np.abs(g) > 1e-4
-    assert np.allclose(step[big], -1e-3 * np.sign(g[big]), rtol=2e-3)
+    # epsilon-hat form, t=1: step = -lr * g / (|g| + eps / sqrt(1 - b2))
+    expect = -1e-3 * g / (np.abs(g) + 1e-7 / np.sqrt(1 - 0.999))
+    assert np.allclose(step, expect, rtol=1e-4, atol=1e-9)
 
 
 def test_inplane_weights_match_reference_loop():
