@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path's headline measurement (BASELINE.json: "U-Net train slices/s @256^2").
+
+  python bench.py --gpus N --steps K --warmup W            # B200 arm (one process per GPU under torchrun for N>1)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle restatement of the reference's
+                                                          # TF2 path on all host threads (TF is not installable)
+
+A step = one fit step of the 4-level / 32-filter U-Net on a batch of 32 synthetic 256x256 SAX slices per GPU:
+forward (batch-stat BN, dropout on) + MSE heat-map loss + full backward + gradient all-reduce (N>1) + Adam.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CONFIG = {'DIM': [256, 256], 'DEPTH': 4, 'FILTERS': 32, 'IMG_CHANNELS': 1, 'MASK_CLASSES': 2,
+          'BATCH_NORMALISATION': True, 'BN_FIRST': False, 'ACTIVATION': 'relu', 'PAD': 'same', 'KERNEL_INIT': 'he_normal',
+          'M_POOL': [2, 2], 'F_SIZE': [3, 3], 'DROPOUT_MIN': 0.3, 'DROPOUT_MAX': 0.5, 'OPTIMIZER': 'adam',
+          'LEARNING_RATE': 1e-4, 'SEED': 42, 'PRECISION': 'bf16'}
+BATCH_PER_GPU = 32
+WORKLOAD = 'C2: U-Net d4 f32 fwd+bwd+MSE+Adam, batch 32/GPU, 256x256x1 -> 2 RVIP heat maps, bf16 storage / fp32 accumulate'
+
+
+def conv_flops_per_slice(cfg=CONFIG):
+    """Algorithmic conv FLOPs (2*MACs) per slice: forward, and forward+dgrad+wgrad (first layer has no dgrad)."""
+    H, W = cfg['DIM']
+    f, cin, d = cfg['FILTERS'], cfg['IMG_CHANNELS'], cfg['DEPTH']
+    layers = []
+    h, w = H, W
+    for l in range(d):
+        layers += [(cin, f, h, w), (f, f, h, w)]
+        cin, f, h, w = f, f * 2, h // 2, w // 2
+    layers += [(cin, f, h, w), (f, f, h, w)]
+    low = f
+    for l in range(d):
+        f //= 2
+        h, w = h * 2, w * 2
+        layers += [(low, f, h, w), (2 * f, f, h, w), (f, f, h, w)]
+        low = f
+    fwd = sum(2 * 9 * ci * co * hh * ww for ci, co, hh, ww in layers)
+    first = 2 * 9 * layers[0][0] * layers[0][1] * layers[0][2] * layers[0][3]
+    tc_fwd = fwd - first                  # tensor-core share (everything but the Cin=1 layer)
+    return dict(fwd=fwd, train=3 * fwd - first, tc_fwd=tc_fwd, tc_dgrad=tc_fwd, tc_wgrad=tc_fwd)
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) > 8 and r[1].replace('.', '').isdigit())
+        mx = [int(float(r[2])) for r in self.rows if len(r) > 8 and r[2].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows if len(r) > 8 for n, v in zip(names, r[5:9]) if v.lower().startswith('active')})
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(self.rows)}
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('bf16_tflops_sustained', 1377.3), d.get('hbm_gbs', 6548.2), 'measured (MEASURED_PEAKS.json, sustained bf16)'
+    return 1400.0, 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def oracle_train_rate(n_slices=4, steps=3, warmup=1, threads=None):
+    """Times the CPU oracle (torch CPU ops, fp32) on the same net / synthetic data: slices per second."""
+    import torch
+    from cmr_landmark_detection_b200 import synth
+    from oracle import unet_ref as R
+    if threads:
+        torch.set_num_threads(threads)
+    cfg = R.cfg_from_config(CONFIG)
+    ws = R.init_weights(cfg, seed=1234)
+    x, y = synth.make_batch(n_slices, 256, 256, seed=42)
+    # dropout on in the GPU arm; the oracle needs explicit masks -> Bernoulli masks of the same rates
+    import numpy as np
+    rng = np.random.default_rng(0)
+    masks, f, h = {}, CONFIG['FILTERS'], 256
+    for l in range(4):
+        masks['enc%d' % l] = (rng.random((n_slices, h, h, f)) >= cfg.dropouts[l]).astype(np.float32)
+        masks['dec%d' % (3 - l)] = (rng.random((n_slices, h, h, f)) >= cfg.dropouts[l]).astype(np.float32)
+        f, h = f * 2, h // 2
+    masks['mid'] = (rng.random((n_slices, h, h, f)) >= cfg.drop_mid).astype(np.float32)
+    opt = R.Adam(lr=1e-4)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = R.train_grads(cfg, ws, x, y, dropout_masks=masks)
+        ws = opt.step(R.apply_new_stats(cfg, ws, out['new_stats']), out['grads'])
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return n_slices * len(times) / sum(times), torch.get_num_threads(), sum(times) / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    n_slices = 4
+    rate, cores, spt = oracle_train_rate(n_slices=n_slices, steps=args.steps, warmup=min(args.warmup, 2))
+    line = {'impl': 'reference', 'metric': 'unet_train_slices_per_s_256', 'value': rate, 'unit': 'slices/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': min(args.warmup, 2), 'ms_per_step': spt * 1e3,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'note': 'CPU restatement (torch/oneDNN) of the reference TF2 path; TF is not '
+                       'installable here. Each step = %d slices (bounded sample of the 32-slice batch)' % n_slices},
+            'cpu_baseline': {'value': rate, 'unit': 'slices/s', 'cores': cores, 'kind': 'port',
+                             'sample': '%d-slice fwd+bwd+Adam step x %d' % (n_slices, args.steps)},
+            'e2e': {'value': rate, 'unit': 'slices/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import numpy as np
+    import torch
+    from cmr_landmark_detection_b200 import synth
+    from cmr_landmark_detection_b200.models.Unets import create_unet
+    from cmr_landmark_detection_b200.runtime import dist as rdist
+    rank, local, world = rdist.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    model = create_unet(dict(CONFIG))
+    B = BATCH_PER_GPU
+    # two different synthetic batches alternate so no step sees cache-warm inputs; the per-step working set
+    # (~4.4 GB of activations + gradients) is far larger than the 126 MB L2 anyway
+    data = [synth.make_batch(B, 256, 256, seed=42 + 7 * rank + i) for i in range(2)]
+    dev_data = [(torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev)) for x, y in data]
+    K, Wm = args.steps, max(args.warmup, 3)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput
+    for i in range(Wm):
+        model.train_step_device(*dev_data[i % 2])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = model.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        loss = model.train_step_device(*dev_data[i % 2])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = model.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = model.dp.max_float(ms)
+    value = world * B * K / (ms * 1e-3)
+    final_loss = float(loss.item())
+
+    # ---- end to end through the public API: host buffers in, loss out, copies inside the timed region
+    for i in range(2):
+        model.train_on_batch(*data[i % 2])
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(K):
+        model.train_on_batch(*data[i % 2])
+    e1.record()
+    barrier()
+    ms_e2e = model.dp.max_float(e0.elapsed_time(e1))
+    e2e = world * B * K / (ms_e2e * 1e-3)
+    h2d = int(data[0][0].nbytes + data[0][1].nbytes)
+
+    # ---- per-kernel-class device time (CUDA events around every launch group) for the roofline
+    model.profile(B, True, True)
+    for i in range(K):
+        model.train_step_device(*dev_data[i % 2])
+    torch.cuda.synchronize()
+    prof = model.profile_read(B, True)
+    model.profile(B, True, False)
+
+    line = None
+    if rank == 0:
+        peak_tf, peak_gbs, peak_src = peaks()
+        fl = conv_flops_per_slice()
+        per_step = {k: v[0] / K for k, v in prof.items()}
+        tot = sum(per_step.values())
+        cls_flops = {'conv_fwd_tcgen05': fl['tc_fwd'] * B, 'conv_dgrad_tcgen05': fl['tc_dgrad'] * B,
+                     'conv_wgrad_tcgen05': fl['tc_wgrad'] * B}
+        kern = {}
+        for k, t in per_step.items():
+            if t <= 0:
+                continue
+            kern[k] = {'ms_per_step': round(t, 4), 'share': round(t / tot, 4), 'launches_per_step': prof[k][1] // K}
+            if k in cls_flops:
+                kern[k]['tflops'] = round(cls_flops[k] / (t * 1e-3) / 1e12, 1)
+        dom = max(cls_flops, key=lambda k: per_step.get(k, 0.0))
+        ach = cls_flops[dom] / (per_step[dom] * 1e-3) / 1e12
+        conv_t = sum(per_step.get(k, 0.0) for k in cls_flops)
+        conv_tf = sum(cls_flops.values()) / (conv_t * 1e-3) / 1e12
+        roof = {'bound': 'tensor', 'kernel': dom, 'achieved': round(ach, 1), 'peak': peak_tf, 'unit': 'TFLOP/s',
+                'frac': round(ach / peak_tf, 4), 'traffic': None, 'peak_source': peak_src,
+                'all_conv_tcgen05_tflops': round(conv_tf, 1), 'all_conv_frac': round(conv_tf / peak_tf, 4),
+                'step_tensor_frac': round(fl['train'] * B / (ms / K * 1e-3) / 1e12 / peak_tf, 4),
+                'kernels': kern}
+        cpu_rate, cores, spt = oracle_train_rate(n_slices=4, steps=2, warmup=1)
+        line = {'metric': 'unet_train_slices_per_s_256', 'value': round(value, 1), 'unit': 'slices/s', 'n_gpus': world,
+                'steps': K, 'warmup': Wm, 'ms_per_step': round(ms / K, 4), 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+                'config': {'workload': WORKLOAD, 'global_batch': world * B, 'parallelism': 'dp%d' % world,
+                           'l2': 'per-step working set ~4.4 GB >> 126 MB L2; two input batches alternate',
+                           'final_loss': final_loss, 'gflop_per_slice_train': round(fl['train'] / 1e9, 2)},
+                'clocks': clocks, 'gpu_launches': int(launches),
+                'e2e': {'value': round(e2e, 1), 'unit': 'slices/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 8,
+                        'ms_per_step': round(ms_e2e / K, 4)},
+                'roofline': roof,
+                'cpu_baseline': {'value': round(cpu_rate, 3), 'unit': 'slices/s', 'cores': cores, 'kind': 'port',
+                                 'sample': '4-slice fwd+bwd+Adam step x 2 (oracle, torch CPU fp32), %.2f s/step' % spt}}
+        if args.extra:
+            line['extra'] = extra_measurements(model, dev)
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def extra_measurements(model, dev):
+    """Secondary BASELINE metrics: volume inference (C4: 16 x 256 x 256) with fused extraction, and the
+    extraction kernel alone against the HBM roofline."""
+    import torch
+    from cmr_landmark_detection_b200 import synth
+    from cmr_landmark_detection_b200.extract import extract_device
+    out = {}
+    x, _ = synth.make_batch(16, 256, 256, seed=3)
+    xd = torch.from_numpy(x).to(dev)
+    for _ in range(3):
+        extract_device(model.predict_device(xd))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 20
+    e0.record()
+    for _ in range(n):
+        r = extract_device(model.predict_device(xd))
+    e1.record()
+    torch.cuda.synchronize()
+    out['infer_vols_per_s'] = round(n / (e0.elapsed_time(e1) * 1e-3), 1)
+    heat = torch.from_numpy(synth.make_volume_heat(16 * 64, 256, 256, seed=1)[:, :, :, :]).to(dev)   # 537 MB > L2
+    for _ in range(3):
+        extract_device(heat)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n):
+        extract_device(heat)
+    e1.record()
+    torch.cuda.synchronize()
+    gbs = heat.numel() * 4 * n / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    out['extract_gbs'] = round(gbs, 1)
+    out['extract_frac_of_hbm_peak'] = round(gbs / peaks()[1], 4)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--extra', action='store_true', help='also measure volume inference + extraction')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,346 @@
+// Row-tiled tcgen05 3x3 convolution for the wide, few-channel layers (W % 128 == 0: the full- and
+// half-resolution levels of the U-Net), forward and dgrad.
+//
+// The generic kernel (conv_tc.cu) fetches one shifted input box per tap, i.e. reads the activation nine
+// times through L2; these layers are HBM/L2-bound (arithmetic intensity 144..384 FLOP/B), so here the
+// input is staged ONCE per tile with its halo:  TMA box {32 ch, 130 px, R+2 rows} -> smem as a dense
+// [pixel][32 ch] (64 B, SWIZZLE_64B) array.  Output row i of the tile is one M=128 accumulator; for tap
+// (dy, dx) its A operand is simply the same smem block read from pixel (i+dy+1)*130 + (dx+1) on: 128
+// consecutive pixels = 16 core-matrix groups at a uniform 512 B stride, so a K-major descriptor whose
+// start address is shifted by whole pixels addresses it directly (the 64B swizzle is a function of the
+// absolute smem address, identical for the TMA write and the MMA read).  Input traffic drops from 9x
+// to (R+2)/R x.  Small weight sets stay resident in shared memory for the whole kernel.
+#include "conv_row.cuh"
+
+#include "common.cuh"
+#include "tc_prims.cuh"
+
+namespace rvip {
+using namespace tc;
+
+constexpr int kMaxDynSmemRow = 227 * 1024;
+constexpr int kRowStagesMax = 4;
+constexpr int kHaloW = 130;           // 128 output columns + 1 halo column each side
+constexpr int kPixB = 64;             // bytes per pixel of a 32-channel chunk
+
+__device__ __forceinline__ void row_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+struct RowCtl {
+  uint64_t full[kRowStagesMax];
+  uint64_t empty[kRowStagesMax];
+  uint64_t tfull[2];
+  uint64_t tempty[2];
+  uint64_t wfull;
+  uint32_t tmem_base;
+};
+
+__host__ __device__ constexpr int row_a_bytes(int R) { return (R + 2) * kHaloW * kPixB; }
+__host__ __device__ constexpr int round1k(int v) { return (v + 1023) & ~1023; }
+
+template <int BN, int R>
+__global__ void __launch_bounds__(256, 1) conv3x3_row_kernel(const __grid_constant__ ConvRowArgs a, int nst) {
+  constexpr int A_TX = row_a_bytes(R);
+  constexpr int A_ST = round1k(A_TX);
+  constexpr int W_TILE = BN * kPixB;           // one (chunk, tap) weight tile: BN rows x 64 B
+  constexpr int OCH = BN >= 64 ? 64 : 32;
+  constexpr int OROWB = OCH * 2;
+  constexpr int OCHUNK = R * 128 * OROWB;
+  constexpr int STAGING = R * 128 * BN * 2;
+  constexpr int ACC_COLS = R * BN;
+  constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM budget");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int nchunks = a.Ctot / 32;
+  const int wres_bytes = a.wres ? nchunks * 9 * a.Cout * kPixB : 0;
+  const int stage_bytes = A_ST + (a.wres ? 0 : 9 * W_TILE);
+  uint8_t* wres = smem;
+  uint8_t* stages = smem + round1k(wres_bytes);
+  uint8_t* staging = stages + (size_t)nst * stage_bytes;
+  float* s_sum = reinterpret_cast<float*>(staging + STAGING);
+  float* s_sq = s_sum + a.Cout;
+  RowCtl* ctl = reinterpret_cast<RowCtl*>((reinterpret_cast<uintptr_t>(s_sq + a.Cout) + 15) & ~uintptr_t(15));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&a.in0);
+    prefetch_tmap(&a.in1);
+    prefetch_tmap(&a.w);
+    prefetch_tmap(&a.out0);
+    prefetch_tmap(&a.out1);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < nst; ++i) {
+      mbar_init(&ctl->full[i], 1);
+      mbar_init(&ctl->empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctl->tfull[i], 1);
+      mbar_init(&ctl->tempty[i], 4);
+    }
+    mbar_init(&ctl->wfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&ctl->tmem_base, TMEM_COLS);
+    tmem_relinquish();
+  }
+  if (warp >= 4)
+    for (int c = threadIdx.x - 128; c < 2 * a.Cout; c += 128) s_sum[c] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      if (a.wres) {
+        mbar_expect_tx(&ctl->wfull, wres_bytes);
+        for (int nt = 0; nt < a.n_ntiles; ++nt)
+          for (int c = 0; c < nchunks; ++c)
+            for (int tap = 0; tap < 9; ++tap)
+              tma_load_2d(wres + ((nt * nchunks + c) * 9 + tap) * W_TILE, &a.w, &ctl->wfull, tap * a.Ctot + c * 32,
+                          nt * BN);
+      }
+      int stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const int nt = tile % a.n_ntiles, pt = tile / a.n_ntiles;
+        const int x0 = (pt % a.tiles_x) * 128;
+        const int y0 = ((pt / a.tiles_x) % a.tiles_y) * R;
+        const int b = pt / (a.tiles_x * a.tiles_y);
+        for (int c = 0; c < nchunks; ++c) {
+          mbar_wait(&ctl->empty[stage], phase ^ 1);
+          mbar_expect_tx(&ctl->full[stage], A_TX + (a.wres ? 0 : 9 * W_TILE));
+          uint8_t* A = stages + (size_t)stage * stage_bytes;
+          const int cc = c * 32;
+          if (cc < a.C0)
+            tma_load_4d(A, &a.in0, &ctl->full[stage], cc, x0 - 1, y0 - 1, b);
+          else
+            tma_load_4d(A, &a.in1, &ctl->full[stage], cc - a.C0, x0 - 1, y0 - 1, b);
+          if (!a.wres)
+            for (int tap = 0; tap < 9; ++tap)
+              tma_load_2d(A + A_ST + tap * W_TILE, &a.w, &ctl->full[stage], tap * a.Ctot + cc, nt * BN);
+          if (++stage == nst) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      int stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      if (a.wres) mbar_wait(&ctl->wfull, 0);
+      const uint64_t bo = (uint64_t)a.base_offset_mode;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const int nt = tile % a.n_ntiles;
+        mbar_wait(&ctl->tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + acc * ACC_COLS;
+        for (int c = 0; c < nchunks; ++c) {
+          mbar_wait(&ctl->full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(stages + (size_t)stage * stage_bytes);
+          const uint32_t w_base = a.wres ? smem_u32(wres) + ((nt * nchunks + c) * 9) * W_TILE : a_base + A_ST;
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap % 3;   // already offset by +1
+            const uint64_t bdesc = make_smem_desc(w_base + tap * W_TILE, 16, 512, kLayoutSW64);
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+              const uint32_t a_addr = a_base + ((i + dy) * kHaloW + dx) * kPixB;
+              uint64_t adesc = make_smem_desc(a_addr, 16, 512, kLayoutSW64);
+              if (bo) adesc |= (uint64_t)((a_addr >> 7) & 3u) << 49;
+#pragma unroll
+              for (int kk = 0; kk < 2; ++kk)
+                mma_bf16_ss(d0 + i * BN, adesc + 2 * kk, bdesc + 2 * kk, idesc, (c | tap | kk) != 0);
+            }
+          }
+          mma_commit(&ctl->empty[stage]);
+          if (++stage == nst) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        mma_commit(&ctl->tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int ew = warp - 4;
+    const int r = ew * 32 + lane;   // pixel column inside the tile
+    const int et = threadIdx.x - 128;
+    int acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      const int nt = tile % a.n_ntiles, pt = tile / a.n_ntiles;
+      const int x0 = (pt % a.tiles_x) * 128;
+      const int y0 = ((pt / a.tiles_x) % a.tiles_y) * R;
+      const int b = pt / (a.tiles_x * a.tiles_y);
+      const int n0 = nt * BN;
+      if (et == 0) tma_store_wait_read0();
+      row_bar_sync(1, 128);
+      mbar_wait(&ctl->tfull[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int i = 0; i < R; ++i) {
+        const uint32_t row = i * 128 + r;
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * ACC_COLS + i * BN + ch * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              f[j] = __uint_as_float(v[q * 8 + j]);
+              if (a.mode != EPI_LINEAR) f[j] = fmaxf(f[j] + __ldg(a.bias + n0 + ch * 32 + q * 8 + j), 0.f);
+            }
+            uint4 pk;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            const int col = ch * 32 + q * 8;
+            const int oc = col / OCH, cidx = (col % OCH) / 8;
+            *reinterpret_cast<uint4*>(staging + oc * OCHUNK + swz_off<OROWB>(row, cidx)) = pk;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->tempty[acc]);
+      fence_proxy_async_smem();
+      row_bar_sync(1, 128);
+      if (et == 0) {
+#pragma unroll 1
+        for (int oc = 0; oc < BN / OCH; ++oc) {
+          const int n = n0 + oc * OCH;
+          if (a.mode == EPI_LINEAR && n >= a.out_split)
+            tma_store_4d(&a.out1, staging + oc * OCHUNK, n - a.out_split, x0, y0, b);
+          else
+            tma_store_4d(&a.out0, staging + oc * OCHUNK, n, x0, y0, b);
+        }
+        tma_store_commit();
+      }
+      if (a.mode == EPI_RELU_STATS) {
+        constexpr int G8 = BN / 8;
+        constexpr int RT = 128 / G8;
+        const int cg = et % G8, rt = et / G8;
+        float s[8], q2[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] = q2[j] = 0.f;
+        const int col = cg * 8;
+        const int oc = col / OCH, cidx = (col % OCH) / 8;
+#pragma unroll 1
+        for (int k = 0; k < R * G8; ++k) {
+          const uint32_t row = rt + k * RT;
+          uint4 raw = *reinterpret_cast<const uint4*>(staging + oc * OCHUNK + swz_off<OROWB>(row, cidx));
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float2 f = __bfloat1622float2(h[j]);
+            s[2 * j] += f.x;
+            s[2 * j + 1] += f.y;
+            q2[2 * j] = fmaf(f.x, f.x, q2[2 * j]);
+            q2[2 * j + 1] = fmaf(f.y, f.y, q2[2 * j + 1]);
+          }
+        }
+#pragma unroll
+        for (int o = 16; o >= G8; o >>= 1) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+            q2[j] += __shfl_xor_sync(0xffffffffu, q2[j], o);
+          }
+        }
+        if (lane < G8) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            atomicAdd(&s_sum[n0 + col + j], s[j]);
+            atomicAdd(&s_sq[n0 + col + j], q2[j]);
+          }
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (et == 0) tma_store_wait_all0();
+    if (a.mode == EPI_RELU_STATS) {
+      row_bar_sync(1, 128);
+      for (int c = et; c < a.Cout; c += 128) {
+        atomicAdd(&a.stats[c], (double)s_sum[c]);
+        atomicAdd(&a.stats[a.Cout + c], (double)s_sq[c]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------- host
+static size_t row_fixed_bytes(int BN, int R, int Cout, int wres_bytes) {
+  return 1024 + (size_t)round1k(wres_bytes) + (size_t)R * 128 * BN * 2 + 2 * (size_t)Cout * sizeof(float) +
+         sizeof(RowCtl) + 64;
+}
+static size_t row_stage_bytes(int BN, int R, int wres) { return round1k(row_a_bytes(R)) + (wres ? 0 : 9 * BN * kPixB); }
+
+bool conv_row_plan(int H, int W, int C0, int C1, int Cout, int mode, int out_split, int* BN, int* R, int* wres,
+                   int* nst) {
+  if (W % 128 != 0 || C0 % 32 != 0 || C1 % 32 != 0 || Cout % 32 != 0) return false;
+  int bn = (Cout % 64 == 0) ? 64 : 32;
+  if (mode == EPI_LINEAR && out_split < Cout && out_split % bn != 0) bn = 32;
+  if (mode == EPI_LINEAR && out_split < Cout && out_split % bn != 0) return false;
+  const int nchunks = (C0 + C1) / 32;
+  const int wbytes = nchunks * 9 * Cout * kPixB;
+  const int wr = wbytes <= 40960 ? 1 : 0;
+  for (int r : {4, 2}) {
+    if (H % r != 0) continue;
+    const size_t fixed = row_fixed_bytes(bn, r, Cout, wr ? wbytes : 0);
+    if (fixed >= (size_t)kMaxDynSmemRow) continue;
+    int n = (int)((kMaxDynSmemRow - fixed) / row_stage_bytes(bn, r, wr));
+    if (n > kRowStagesMax) n = kRowStagesMax;
+    if (n >= 2) {
+      *BN = bn; *R = r; *wres = wr; *nst = n;
+      return true;
+    }
+  }
+  return false;
+}
+
+template <int BN, int R>
+static int launch_row(const ConvRowArgs& a, int nst, cudaStream_t st) {
+  const int nchunks = a.Ctot / 32;
+  const int wres_bytes = a.wres ? nchunks * 9 * a.Cout * kPixB : 0;
+  const size_t smem = row_fixed_bytes(BN, R, a.Cout, wres_bytes) + (size_t)nst * row_stage_bytes(BN, R, a.wres);
+  RVIP_REQUIRE(smem <= (size_t)kMaxDynSmemRow, "conv_row: %zu bytes of shared memory needed", smem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    RVIP_CUDA(cudaFuncSetAttribute(conv3x3_row_kernel<BN, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kMaxDynSmemRow));
+    attr_set = true;
+  }
+  const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
+  conv3x3_row_kernel<BN, R><<<grid, 256, smem, st>>>(a, nst);
+  RVIP_LAUNCH_CHECK();
+  return 0;
+}
+
+int conv_row_launch(const ConvRowArgs& a, int BN, int R, int nst, cudaStream_t st) {
+  if (BN == 32 && R == 4) return launch_row<32, 4>(a, nst, st);
+  if (BN == 32 && R == 2) return launch_row<32, 2>(a, nst, st);
+  if (BN == 64 && R == 4) return launch_row<64, 4>(a, nst, st);
+  if (BN == 64 && R == 2) return launch_row<64, 2>(a, nst, st);
+  set_error("conv_row: unsupported tile BN=%d R=%d", BN, R);
+  return 1;
+}
+
+}  // namespace rvip

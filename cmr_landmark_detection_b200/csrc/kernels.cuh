@@ -27,6 +27,12 @@ struct WgradSimtArgs {
 };
 int wgrad_simt_launch(const WgradSimtArgs& a, int in_is_bf16, int dz_is_bf16, cudaStream_t st);
 
+// Cin == 1 first layer (x fp32 [B,H,W], w [9][Cout] fp32)
+int conv_c1_fwd_launch(const float* x, const float* w, const float* bias, void* out, double* stats, int B, int H, int W,
+                       int Cout, int want_stats, int out_is_bf16, cudaStream_t st);
+int wgrad_c1_launch(const float* x, const void* dz, float* dw, int B, int H, int W, int Cout, int dz_is_bf16,
+                    cudaStream_t st);
+
 // ------------------------------------------------------------------ BatchNorm passes (bn.cu)
 enum PostOp { POST_NONE = 0, POST_DROPOUT = 1, POST_POOL = 2, POST_UPSAMPLE = 3 };
 

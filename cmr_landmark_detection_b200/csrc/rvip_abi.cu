@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -11,6 +12,7 @@
 #include <vector>
 
 #include "../../include/rvip.h"
+#include "conv_row.cuh"
 #include "kernels.cuh"
 
 namespace rvip {
@@ -80,6 +82,63 @@ static int make_w_map(CUtensorMap* m, const void* ptr, int rows, int K, int boxK
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   RVIP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights %dx%d box %d,%d) failed: %d", rows, K, boxK,
                boxRows, (int)r);
+  return 0;
+}
+
+// NHWC bf16 activation with an explicit box {boxC, bw, bh, bb}
+static int make_act_map_box(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int boxC, int bw, int bh,
+                            int bb) {
+  TileGeom g;
+  g.TW = bw; g.TH = bh; g.NB = bb;
+  g.tiles_x = g.tiles_y = g.tiles_b = 0; g.full = 0;
+  return make_act_map(m, ptr, B, H, W, C, boxC, g);
+}
+
+static int setup_conv_row(ConvRowArgs* a, int BN, int R, int wres, const void* in0, const void* in1, int C0, int C1,
+                          const void* wpk, void* out0, void* out1, int out_split, int B, int H, int W, int Cout, int mode,
+                          const float* bias, double* stats) {
+  const int Ctot = C0 + C1;
+  a->B = B; a->H = H; a->W = W; a->C0 = C0; a->Ctot = Ctot; a->Cout = Cout;
+  a->n_ntiles = Cout / BN;
+  a->tiles_x = W / 128; a->tiles_y = H / R;
+  a->total_tiles = a->n_ntiles * a->tiles_x * a->tiles_y * B;
+  a->mode = mode;
+  a->out_split = (mode == EPI_LINEAR) ? out_split : Cout;
+  a->wres = wres;
+  a->base_offset_mode = 0;
+  a->bias = bias; a->stats = stats;
+  if (make_act_map_box(&a->in0, in0, B, H, W, C0, 32, 130, R + 2, 1)) return 1;
+  if (C1 > 0) {
+    if (make_act_map_box(&a->in1, in1, B, H, W, C1, 32, 130, R + 2, 1)) return 1;
+  } else {
+    a->in1 = a->in0;
+  }
+  if (make_w_map(&a->w, wpk, Cout, 9 * Ctot, 32, BN)) return 1;
+  const int och = BN >= 64 ? 64 : 32;
+  const int c_out0 = (mode == EPI_LINEAR) ? a->out_split : Cout;
+  if (make_act_map_box(&a->out0, out0, B, H, W, c_out0, och, 128, R, 1)) return 1;
+  if (mode == EPI_LINEAR && out_split < Cout) {
+    if (make_act_map_box(&a->out1, out1, B, H, W, Cout - out_split, och, 128, R, 1)) return 1;
+  } else {
+    a->out1 = a->out0;
+  }
+  return 0;
+}
+
+static int setup_wgrad_row(WgradRowArgs* a, int BN, int R, const void* x0, const void* x1, int C0, int C1,
+                           const void* dz, float* dw, int B, int H, int W, int Cout) {
+  a->B = B; a->H = H; a->W = W; a->C0 = C0; a->Ctot = C0 + C1; a->Cout = Cout;
+  a->n_ntiles = Cout / BN;
+  a->tiles_x = W / 128; a->tiles_y = H / R;
+  a->pixel_tiles = a->tiles_x * a->tiles_y * B;
+  a->dw = dw;
+  if (make_act_map_box(&a->x0, x0, B, H, W, C0, 32, 130, R + 2, 1)) return 1;
+  if (C1 > 0) {
+    if (make_act_map_box(&a->x1, x1, B, H, W, C1, 32, 130, R + 2, 1)) return 1;
+  } else {
+    a->x1 = a->x0;
+  }
+  if (make_act_map_box(&a->dz, dz, B, H, W, Cout, BN, 128, R, 1)) return 1;
   return 0;
 }
 
@@ -190,6 +249,11 @@ struct Layer {
   ConvTcArgs fwd, dgrad;
   WgradTcArgs wg;
   int fKC = 0, fBN = 0, dKC = 0, dBN = 0, wCBA = 0, wCBB = 0;
+  // row-tiled variants for W % 128 == 0 layers
+  ConvRowArgs rfwd, rdgrad;
+  WgradRowArgs rwg;
+  int use_rfwd = 0, use_rdgrad = 0, use_rwg = 0;
+  int rfBN = 0, rfR = 0, rfNst = 0, rdBN = 0, rdR = 0, rdNst = 0, rwBN = 0, rwR = 0, rwNst = 0;
 };
 
 struct TensorInfo {
@@ -456,7 +520,24 @@ static int build_descriptors(rvip_handle* h) {
     if (setup_conv_tc(&l.fwd, &l.fKC, &l.fBN, in0, in1, l.C0, l.C1, pk + l.pk_f, l.a, nullptr, l.Cout, B, l.H, l.W,
                       l.Cout, mode, h->params + l.off_b, h->stats + 2 * l.off_stat))
       return 1;
+    const bool allow_row = getenv("RVIP_NO_ROW") == nullptr;
+    int wres = 0;
+    l.use_rfwd = allow_row && conv_row_plan(l.H, l.W, l.C0, l.C1, l.Cout, mode, l.Cout, &l.rfBN, &l.rfR, &wres, &l.rfNst);
+    if (l.use_rfwd && setup_conv_row(&l.rfwd, l.rfBN, l.rfR, wres, in0, in1, l.C0, l.C1, pk + l.pk_f, l.a, nullptr,
+                                     l.Cout, B, l.H, l.W, l.Cout, mode, h->params + l.off_b, h->stats + 2 * l.off_stat))
+      return 1;
     if (h->training) {
+      const int dsplit = l.C1 ? l.C0 : l.C0 + l.C1;
+      l.use_rdgrad = allow_row && conv_row_plan(l.H, l.W, l.Cout, 0, l.C0 + l.C1, EPI_LINEAR, dsplit, &l.rdBN, &l.rdR,
+                                                &wres, &l.rdNst);
+      if (l.use_rdgrad && setup_conv_row(&l.rdgrad, l.rdBN, l.rdR, wres, h->dz, nullptr, l.Cout, 0, pk + l.pk_d, l.dx0,
+                                         l.dx1, dsplit, B, l.H, l.W, l.C0 + l.C1, EPI_LINEAR, nullptr, nullptr))
+        return 1;
+      l.use_rwg = allow_row && getenv("RVIP_NO_ROW_WGRAD") == nullptr &&
+                  wgrad_row_plan(l.H, l.W, l.C0, l.C1, l.Cout, &l.rwBN, &l.rwR, &l.rwNst);
+      if (l.use_rwg && setup_wgrad_row(&l.rwg, l.rwBN, l.rwR, in0, in1, l.C0, l.C1, h->dz, h->grads + l.off_k, B, l.H,
+                                       l.W, l.Cout))
+        return 1;
       if (setup_conv_tc(&l.dgrad, &l.dKC, &l.dBN, h->dz, nullptr, l.Cout, 0, pk + l.pk_d, l.dx0, l.dx1,
                         l.C1 ? l.C0 : l.C0 + l.C1, B, l.H, l.W, l.C0 + l.C1, EPI_LINEAR, nullptr, nullptr))
         return 1;
@@ -472,8 +553,18 @@ static int build_descriptors(rvip_handle* h) {
 static int conv_forward(rvip_handle* h, Layer& l, const float* x, bool training, cudaStream_t st) {
   const int mode = (l.bn && training) ? EPI_RELU_STATS : EPI_RELU;
   if (is_bf16(h) && !l.first) {
+    if (l.use_rfwd) {
+      l.rfwd.mode = mode;
+      return timed(h, KC_CONV_FWD_TC, 1, st, [&] { return conv_row_launch(l.rfwd, l.rfBN, l.rfR, l.rfNst, st); });
+    }
     l.fwd.mode = mode;
     return timed(h, KC_CONV_FWD_TC, 1, st, [&] { return conv_tc_launch(l.fwd, l.fKC, l.fBN, st); });
+  }
+  if (l.first && l.C0 == 1 && l.Cout <= 256) {
+    return timed(h, KC_CONV_SIMT, 1, st, [&] {
+      return conv_c1_fwd_launch(x, h->params + l.off_k, h->params + l.off_b, l.a, h->stats + 2 * l.off_stat, h->batch,
+                                l.H, l.W, l.Cout, mode == EPI_RELU_STATS, is_bf16(h), st);
+    });
   }
   ConvSimtArgs a;
   a.in0 = l.first ? (const void*)x : buffer_of(h, l.in0_layer, l.in0_which);
@@ -585,8 +676,21 @@ static int backward_body(rvip_handle* h, const float* x, uint64_t seed, cudaStre
         return 1;
     }
     if (bf && !l.first) {
-      if (timed(h, KC_CONV_WGRAD_TC, 1, st, [&] { return wgrad_tc_launch(l.wg, l.wCBA, l.wCBB, st); })) return 1;
-      if (timed(h, KC_CONV_DGRAD_TC, 1, st, [&] { return conv_tc_launch(l.dgrad, l.dKC, l.dBN, st); })) return 1;
+      if (timed(h, KC_CONV_WGRAD_TC, 1, st, [&] {
+            return l.use_rwg ? wgrad_row_launch(l.rwg, l.rwBN, l.rwR, l.rwNst, st)
+                             : wgrad_tc_launch(l.wg, l.wCBA, l.wCBB, st);
+          }))
+        return 1;
+      if (timed(h, KC_CONV_DGRAD_TC, 1, st, [&] {
+            return l.use_rdgrad ? conv_row_launch(l.rdgrad, l.rdBN, l.rdR, l.rdNst, st)
+                                : conv_tc_launch(l.dgrad, l.dKC, l.dBN, st);
+          }))
+        return 1;
+    } else if (l.first && l.C0 == 1 && l.Cout <= 256) {
+      if (timed(h, KC_CONV_SIMT, 1, st, [&] {
+            return wgrad_c1_launch(x, h->dz, h->grads + l.off_k, h->batch, l.H, l.W, l.Cout, bf, st);
+          }))
+        return 1;
     } else {
       WgradSimtArgs w;
       w.in0 = l.first ? (const void*)x : buffer_of(h, l.in0_layer, l.in0_which);
@@ -872,6 +976,30 @@ int rvip_wgrad3x3_tc(const void* x0, const void* x1, int C0, int C1, const void*
   int CBA, CBB;
   if (setup_wgrad_tc(&a, &CBA, &CBB, x0, x1, C0, C1, dz, dw, B, H, W, Cout)) return 1;
   return wgrad_tc_launch(a, CBA, CBB, (cudaStream_t)stream);
+}
+
+int rvip_conv3x3_row(const void* in0, const void* in1, int C0, int C1, const void* w_packed, const float* bias,
+                     void* out0, void* out1, int out_split, double* stats, int B, int H, int W, int Cout, int mode,
+                     int base_offset_mode, void* stream) {
+  ConvRowArgs a;
+  int BN, R, wres, nst;
+  RVIP_REQUIRE(conv_row_plan(H, W, C0, C1, Cout, mode, out_split, &BN, &R, &wres, &nst),
+               "rvip_conv3x3_row: shape not eligible for the row-tiled kernel");
+  if (setup_conv_row(&a, BN, R, wres, in0, in1, C0, C1, w_packed, out0, out1, out_split, B, H, W, Cout, mode, bias,
+                     stats))
+    return 1;
+  a.base_offset_mode = base_offset_mode;
+  return conv_row_launch(a, BN, R, nst, (cudaStream_t)stream);
+}
+
+int rvip_wgrad3x3_row(const void* x0, const void* x1, int C0, int C1, const void* dz, float* dw, int B, int H, int W,
+                      int Cout, void* stream) {
+  WgradRowArgs a;
+  int BN, R, nst;
+  RVIP_REQUIRE(wgrad_row_plan(H, W, C0, C1, Cout, &BN, &R, &nst),
+               "rvip_wgrad3x3_row: shape not eligible for the row-tiled kernel");
+  if (setup_wgrad_row(&a, BN, R, x0, x1, C0, C1, dz, dw, B, H, W, Cout)) return 1;
+  return wgrad_row_launch(a, BN, R, nst, (cudaStream_t)stream);
 }
 
 }  // extern "C"

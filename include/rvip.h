@@ -124,6 +124,14 @@ int rvip_conv3x3_tc(const void* in0, const void* in1, int C0, int C1, const void
 int rvip_wgrad3x3_tc(const void* x0, const void* x1, int C0, int C1, const void* dz, float* dw, int B, int H, int W,
                      int Cout, void* stream);
 
+/* Row-tiled variants (W % 128 == 0): the input tile is staged once with its halo and all nine taps are
+ * issued from shifted shared-memory descriptors. Same contracts as the two entry points above. */
+int rvip_conv3x3_row(const void* in0, const void* in1, int C0, int C1, const void* w_packed, const float* bias,
+                     void* out0, void* out1, int out_split, double* stats, int B, int H, int W, int Cout, int mode,
+                     int base_offset_mode, void* stream);
+int rvip_wgrad3x3_row(const void* x0, const void* x1, int C0, int C1, const void* dz, float* dw, int B, int H, int W,
+                      int Cout, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

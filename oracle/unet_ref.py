@@ -209,7 +209,36 @@ def _bn(x, gamma, beta, mm, mv, training, new_stats, name):
     return (x - mean[None, :, None, None]) * (inv * gamma)[None, :, None, None] + beta[None, :, None, None]
 
 
+class _RoundFwd(torch.autograd.Function):
+    """bf16-storage emulation: round a stored activation, straight-through gradient."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _RoundBwd(torch.autograd.Function):
+    """bf16-storage emulation: identity forward, round the gradient flowing back (a stored dz / dx)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+_STORAGE = {'mode': 'fp32'}
+
+
 def _block(x, p: _Params, spec: ConvSpec, cfg: NetCfg, training, new_stats, acts):
+    if _STORAGE['mode'] == 'bf16':
+        return _block_bf16(x, p, spec, cfg, training, new_stats, acts)
     k, b = p.take(2)
     z = _conv(x, k, b)
     if spec.bn:
@@ -224,6 +253,30 @@ def _block(x, p: _Params, spec: ConvSpec, cfg: NetCfg, training, new_stats, acts
     else:
         y = torch.relu(z)
         acts[spec.name + '/a'] = y
+    acts[spec.name + '/y'] = y
+    return y
+
+
+def _block_bf16(x, p: _Params, spec: ConvSpec, cfg: NetCfg, training, new_stats, acts):
+    """Same block with the device path's bf16 storage points restated: tensor-core operands (weights of
+    every conv but the Cin=in_ch first layer), the stored relu(conv) `a`, the stored block output `y`,
+    and in backward the stored dz (gradient at the conv output) and dx (gradient at the conv input).
+    Accumulation stays fp32, as in TMEM. Used only to CALIBRATE what bf16 storage itself does to the
+    gradients of this ill-conditioned (BatchNorm, random init) problem; the fp32 oracle stays the spec."""
+    assert not cfg.bn_first
+    k, b = p.take(2)
+    first = spec.cin == cfg.in_ch and spec.name == 'enc0.conv_a'
+    if not first:
+        k = _RoundFwd.apply(k)
+        x = _RoundBwd.apply(x)
+    z = _RoundBwd.apply(_conv(x, k, b))
+    a = _RoundFwd.apply(torch.relu(z))
+    acts[spec.name + '/a'] = a
+    if spec.bn:
+        g, be, mm, mv = p.take(4)
+        y = _RoundFwd.apply(_bn(a, g, be, mm, mv, training, new_stats, spec.name))
+    else:
+        y = a
     acts[spec.name + '/y'] = y
     return y
 
@@ -268,6 +321,8 @@ def forward_torch(cfg: NetCfg, params: Sequence[torch.Tensor], x_nchw: torch.Ten
         h = _dropout(h, drops.pop(), training, dropout_masks, f'dec{l}')
         h = _block(h, p, specs[f'dec{l}.conv_b'], cfg, training, new_stats, acts)
     k, b = p.take(2)
+    if _STORAGE['mode'] == 'bf16':
+        h = _RoundBwd.apply(h)
     logits = _conv(h, k, b)
     acts['head/logits'] = logits
     heat = torch.sigmoid(logits)                      # Unets.py:128
@@ -336,9 +391,18 @@ def loss_torch(heat_nchw, target_nchw, kind='mse', mask_smaller_than=0.01, weigh
 # training step (fwd, loss, bwd) and Adam
 # --------------------------------------------------------------------------------------
 def train_grads(cfg: NetCfg, weights: Sequence[np.ndarray], x_nhwc, t_nhwc, dtype=torch.float32,
-                loss_kind='mse', dropout_masks=None, return_acts=False, weights_hw=None):
+                loss_kind='mse', dropout_masks=None, return_acts=False, weights_hw=None, storage='fp32'):
     """One replica's forward + loss + backward. Returns dict(loss, heat, grads (Keras order,
-    None for non-trainable), new_stats, [acts, act_grads])."""
+    None for non-trainable), new_stats, [acts, act_grads]). storage='bf16' restates the device path's
+    bf16 storage points (see _block_bf16)."""
+    _STORAGE['mode'] = storage
+    try:
+        return _train_grads(cfg, weights, x_nhwc, t_nhwc, dtype, loss_kind, dropout_masks, return_acts, weights_hw)
+    finally:
+        _STORAGE['mode'] = 'fp32'
+
+
+def _train_grads(cfg, weights, x_nhwc, t_nhwc, dtype, loss_kind, dropout_masks, return_acts, weights_hw):
     ps = _to_params(weights, dtype)
     tm = trainable_mask(cfg)
     for p_, t_ in zip(ps, tm):

@@ -22,14 +22,21 @@ def case_conv(kind, shape):
     w = torch.randn((3, 3, C0 + C1, N), generator=g, device='cuda') * (2.0 / (9 * (C0 + C1))) ** 0.5
     bias = torch.randn(N, generator=g, device='cuda') * 0.1
     xin = x0 if x1 is None else torch.cat([x0, x1], dim=3)
+    bo = 1 if kind.endswith('_bo') else 0
+    row = kind.startswith('r')
+    kind = kind.replace('_bo', '')
+    if row:
+        kind = kind[1:]
+    conv = (lambda *a, **k: U.conv_row(*a, base_offset_mode=bo, **k)) if row else U.conv_tc
+    wg = U.wgrad_row if row else U.wgrad_tc
     if kind == 'fwd':
-        out, _, stats = U.conv_tc(x0, x1, U.pack_fwd(w), bias, N, mode=0, want_stats=True)
+        out, _, stats = conv(x0, x1, U.pack_fwd(w), bias, N, mode=0, want_stats=True)
         ref = U.ref_conv(xin, w, bias, relu=True)
         s_err = float((stats[:N] - out.double().sum(dim=(0, 1, 2))).abs().max())
         print('  stats max abs err', s_err)
     elif kind == 'dgrad':
         dz = rb((B, H, W, N))
-        dx0, dx1, _ = U.conv_tc(dz, None, U.pack_dgrad(w), None, C0 + C1, mode=2, out_split=C0 if C1 else C0 + C1)
+        dx0, dx1, _ = conv(dz, None, U.pack_dgrad(w), None, C0 + C1, mode=2, out_split=C0 if C1 else C0 + C1)
         x = torch.zeros((B, C0 + C1, H, W), device='cuda', requires_grad=True)
         y = torch.nn.functional.conv2d(x, w.to(torch.bfloat16).float().permute(3, 2, 0, 1), padding=1)
         y.backward(dz.float().permute(0, 3, 1, 2))
@@ -37,7 +44,7 @@ def case_conv(kind, shape):
         out = dx0 if dx1 is None else torch.cat([dx0, dx1], dim=3)
     else:
         dz = rb((B, H, W, N))
-        out = U.wgrad_tc(x0, x1, dz)
+        out = wg(x0, x1, dz)
         wv = torch.zeros((N, C0 + C1, 3, 3), device='cuda', requires_grad=True)
         y = torch.nn.functional.conv2d(xin.float().permute(0, 3, 1, 2), wv, padding=1)
         y.backward(dz.float().permute(0, 3, 1, 2))
@@ -117,6 +124,13 @@ def main():
         for kind in ('fwd', 'dgrad', 'wgrad'):
             for s in CONV_SHAPES:
                 cases.append((kind, s))
+    if what in ('row', 'all'):
+        ROW_SHAPES = [(1, 8, 128, 32, 0, 32), (2, 8, 256, 64, 0, 32), (1, 8, 128, 32, 32, 32), (1, 8, 128, 64, 0, 64),
+                      (1, 4, 128, 128, 0, 64), (1, 6, 128, 32, 0, 32), (2, 16, 128, 64, 64, 64)]
+        cases.append(('rfwd_bo', ROW_SHAPES[0]))
+        for kind in ('rfwd', 'rdgrad', 'rwgrad'):
+            for s_ in ROW_SHAPES:
+                cases.append((kind, s_))
     if what in ('unet', 'all'):
         cases += [('unet', ('fp32', 32, 2, 3)), ('unet', ('bf16', 32, 2, 4)), ('unet', ('fp32', 64, 4, 2)),
                   ('unet', ('bf16', 64, 4, 4))]
@@ -125,7 +139,7 @@ def main():
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), 'case', kind, repr(args)], cwd=ROOT, timeout=120,
                                capture_output=True, text=True)
-            print(r.stdout[-3000:], end='')
+            print(r.stdout[-12000:], end="")
             if r.returncode != 0:
                 print('  EXIT', r.returncode, r.stderr[-1500:])
         except subprocess.TimeoutExpired:
