@@ -65,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -168,12 +168,13 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput
-    for i in range(Wm):
-        model.train_step_device(*dev_data[i % 2])
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for i in range(Wm):
+        model.train_step_device(*dev_data[i % 2])
+    barrier()
+    n_warm_rows = len(sampler.rows)
     l0 = model.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -183,6 +184,8 @@ def run_b200(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = model.launch_count() - l0
+    if rank == 0 and len(sampler.rows) > n_warm_rows + 2:
+        sampler.rows = sampler.rows[n_warm_rows:]      # keep the samples taken during the timed region
     clocks = sampler.stop() if rank == 0 else None
     ms = model.dp.max_float(ms)
     value = world * B * K / (ms * 1e-3)

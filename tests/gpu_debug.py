@@ -127,7 +127,6 @@ def main():
     if what in ('row', 'all'):
         ROW_SHAPES = [(1, 8, 128, 32, 0, 32), (2, 8, 256, 64, 0, 32), (1, 8, 128, 32, 32, 32), (1, 8, 128, 64, 0, 64),
                       (1, 4, 128, 128, 0, 64), (1, 6, 128, 32, 0, 32), (2, 16, 128, 64, 64, 64)]
-        cases.append(('rfwd_bo', ROW_SHAPES[0]))
         for kind in ('rfwd', 'rdgrad', 'rwgrad'):
             for s_ in ROW_SHAPES:
                 cases.append((kind, s_))

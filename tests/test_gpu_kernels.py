@@ -19,20 +19,33 @@ CONV_SHAPES = [  # B, H, W, C0, C1, Cout
 ]
 
 
+ROW_SHAPES = [  # W % 128 == 0: eligible for the row-tiled kernels
+    (1, 8, 128, 32, 0, 32),
+    (2, 8, 256, 64, 0, 32),
+    (1, 8, 128, 32, 32, 32),
+    (1, 8, 128, 64, 0, 64),
+    (1, 4, 128, 128, 0, 64),      # weights streamed per stage (not resident)
+    (1, 6, 128, 32, 0, 32),       # H % 4 != 0 -> R = 2
+    (2, 16, 128, 64, 64, 64),
+]
+ALL_CASES = [('tc', s) for s in CONV_SHAPES] + [('row', s) for s in ROW_SHAPES]
+
+
 def _rand_bf16(shape, gen, scale=1.0):
     return (torch.randn(shape, generator=gen, device='cuda') * scale).to(torch.bfloat16)
 
 
-@pytest.mark.parametrize('shape', CONV_SHAPES)
-def test_conv_tc_forward_bias_relu_stats(shape):
+@pytest.mark.parametrize('variant,shape', ALL_CASES)
+def test_conv_tc_forward_bias_relu_stats(variant, shape):
     from tests import gpu_util as U
+    conv = U.conv_tc if variant == 'tc' else U.conv_row
     B, H, W, C0, C1, N = shape
     g = torch.Generator(device='cuda').manual_seed(1 + sum(shape))
     x0 = _rand_bf16((B, H, W, C0), g)
     x1 = _rand_bf16((B, H, W, C1), g) if C1 else None
     w = torch.randn((3, 3, C0 + C1, N), generator=g, device='cuda') * (2.0 / (9 * (C0 + C1))) ** 0.5
     bias = torch.randn(N, generator=g, device='cuda') * 0.1
-    out, _, stats = U.conv_tc(x0, x1, U.pack_fwd(w), bias, N, mode=0, want_stats=True)
+    out, _, stats = conv(x0, x1, U.pack_fwd(w), bias, N, mode=0, want_stats=True)
     xin = x0 if x1 is None else torch.cat([x0, x1], dim=3)
     ref = U.ref_conv(xin, w, bias, relu=True)
     assert torch.isfinite(out.float()).all()
@@ -44,14 +57,15 @@ def test_conv_tc_forward_bias_relu_stats(shape):
     assert torch.allclose(stats[N:], (rb * rb).sum(dim=(0, 1, 2)), rtol=1e-4, atol=1e-2)
 
 
-@pytest.mark.parametrize('shape', CONV_SHAPES)
-def test_conv_tc_dgrad(shape):
+@pytest.mark.parametrize('variant,shape', ALL_CASES)
+def test_conv_tc_dgrad(variant, shape):
     from tests import gpu_util as U
+    conv = U.conv_tc if variant == 'tc' else U.conv_row
     B, H, W, C0, C1, N = shape
     g = torch.Generator(device='cuda').manual_seed(2 + sum(shape))
     dz = _rand_bf16((B, H, W, N), g)
     w = torch.randn((3, 3, C0 + C1, N), generator=g, device='cuda') * (2.0 / (9 * N)) ** 0.5
-    dx0, dx1, _ = U.conv_tc(dz, None, U.pack_dgrad(w), None, C0 + C1, mode=2, out_split=C0 if C1 else C0 + C1)
+    dx0, dx1, _ = conv(dz, None, U.pack_dgrad(w), None, C0 + C1, mode=2, out_split=C0 if C1 else C0 + C1)
     x = torch.zeros((B, C0 + C1, H, W), device='cuda', requires_grad=True)
     wt = w.to(torch.bfloat16).float().permute(3, 2, 0, 1)
     y = torch.nn.functional.conv2d(x, wt, padding=1)
@@ -61,15 +75,15 @@ def test_conv_tc_dgrad(shape):
     assert U.rel_err(got, ref) < 4e-3
 
 
-@pytest.mark.parametrize('shape', CONV_SHAPES)
-def test_wgrad_tc(shape):
+@pytest.mark.parametrize('variant,shape', ALL_CASES)
+def test_wgrad_tc(variant, shape):
     from tests import gpu_util as U
     B, H, W, C0, C1, N = shape
     g = torch.Generator(device='cuda').manual_seed(3 + sum(shape))
     x0 = _rand_bf16((B, H, W, C0), g)
     x1 = _rand_bf16((B, H, W, C1), g) if C1 else None
     dz = _rand_bf16((B, H, W, N), g)
-    dw = U.wgrad_tc(x0, x1, dz)
+    dw = (U.wgrad_tc if variant == 'tc' else U.wgrad_row)(x0, x1, dz)
     xin = (x0 if x1 is None else torch.cat([x0, x1], dim=3)).float().permute(0, 3, 1, 2)
     w = torch.zeros((N, C0 + C1, 3, 3), device='cuda', requires_grad=True)
     y = torch.nn.functional.conv2d(xin, w, padding=1)
