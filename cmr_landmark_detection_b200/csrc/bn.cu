@@ -220,7 +220,7 @@ struct Gather {
 };
 
 template <typename T, int POST>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnArgs a) {
+__global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(BnArgs a) {
   extern __shared__ float red_s[];  // [2][C]
   constexpr int K = Gather<T, POST>::K;
   const int G = a.C >> 3;
@@ -239,17 +239,30 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnArgs a) {
       mean[j] = a.mean[c + j];
       rstd[j] = a.rstd[c + j];
     }
-    for (size_t i = i0; i < n_items; i += (size_t)gridDim.x * 256) {
-      size_t pix[K];
-      float av[K][8], dy[K][8];
-      Gather<T, POST>::run(a, i, G, c, sc, sh, pix, av, dy);
+    // U independent work items per iteration keep 2U..9U 16-byte loads in flight per thread
+    constexpr int U = K == 1 ? 2 : 1;
+    const size_t stride = (size_t)gridDim.x * 256;
+    for (size_t i = i0; i < n_items; i += U * stride) {
+      size_t pix[U][K];
+      float av[U][K][8], dy[U][K][8];
+      bool live[U];
 #pragma unroll
-      for (int k = 0; k < K; ++k)
+      for (int u = 0; u < U; ++u) {
+        const size_t iu = i + u * stride;
+        live[u] = iu < n_items;
+        Gather<T, POST>::run(a, live[u] ? iu : i, G, c, sc, sh, pix[u], av[u], dy[u]);
+      }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          s1[j] += dy[k][j];
-          s2[j] = fmaf(dy[k][j], (av[k][j] - mean[j]) * rstd[j], s2[j]);
-        }
+      for (int u = 0; u < U; ++u) {
+        if (!live[u]) continue;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            s1[j] += dy[u][k][j];
+            s2[j] = fmaf(dy[u][k][j], (av[u][k][j] - mean[j]) * rstd[j], s2[j]);
+          }
+      }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -262,7 +275,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnArgs a) {
 }
 
 template <typename T, int POST>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnArgs a) {
+__global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(BnArgs a) {
   extern __shared__ float red_s[];  // [C] bias-gradient partials
   constexpr int K = Gather<T, POST>::K;
   const int G = a.C >> 3;
@@ -291,21 +304,33 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnArgs a) {
       db[j] = 0.f;
     }
     T* dzp = static_cast<T*>(a.dz);
-    for (size_t i = i0; i < n_items; i += (size_t)gridDim.x * 256) {
-      size_t pix[K];
-      float av[K][8], dy[K][8];
-      Gather<T, POST>::run(a, i, G, c, sc, sh, pix, av, dy);
+    constexpr int U = K == 1 ? 2 : 1;
+    const size_t stride = (size_t)gridDim.x * 256;
+    for (size_t i = i0; i < n_items; i += U * stride) {
+      size_t pix[U][K];
+      float av[U][K][8], dy[U][K][8];
+      bool live[U];
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        float dz[8];
+      for (int u = 0; u < U; ++u) {
+        const size_t iu = i + u * stride;
+        live[u] = iu < n_items;
+        Gather<T, POST>::run(a, live[u] ? iu : i, G, c, sc, sh, pix[u], av[u], dy[u]);
+      }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float ahat = (av[k][j] - mean[j]) * rstd[j];
-          const float da = sc[j] * (dy[k][j] - m1[j] - ahat * m2[j]);
-          dz[j] = av[k][j] > 0.f ? da : 0.f;
-          db[j] += round_to<T>(dz[j]);
+      for (int u = 0; u < U; ++u) {
+        if (!live[u]) continue;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          float dz[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float ahat = (av[u][k][j] - mean[j]) * rstd[j];
+            const float da = sc[j] * (dy[u][k][j] - m1[j] - ahat * m2[j]);
+            dz[j] = av[u][k][j] > 0.f ? da : 0.f;
+            db[j] += round_to<T>(dz[j]);
+          }
+          Vec8<T>::store(dzp + pix[u][k] * a.C + c, dz);
         }
-        Vec8<T>::store(dzp + pix[k] * a.C + c, dz);
       }
     }
 #pragma unroll

@@ -39,8 +39,51 @@ struct RowCtl {
 __host__ __device__ constexpr int row_a_bytes(int R) { return (R + 2) * kHaloW * kPixB; }
 __host__ __device__ constexpr int round1k(int v) { return (v + 1023) & ~1023; }
 
+template <int BN, int R, bool ZERO_BASE>
+__device__ __forceinline__ void row_mma_loop(const ConvRowArgs& a, RowCtl* ctl, uint8_t* stages, uint8_t* wres,
+                                             int stage_bytes, int nst, int nchunks, uint32_t tmem_base_rt) {
+  constexpr int A_ST = round1k(row_a_bytes(R));
+  constexpr int W_TILE = BN * kPixB;
+  constexpr int ACC_COLS = R * BN;
+  constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+  const uint32_t tmem_base = ZERO_BASE ? 0u : tmem_base_rt;
+  int stage = 0, phase = 0, acc = 0, acc_phase = 0;
+  if (a.wres) mbar_wait(&ctl->wfull, 0);
+  for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+    const int nt = tile % a.n_ntiles;
+    mbar_wait(&ctl->tempty[acc], acc_phase ^ 1);
+    tc_fence_after();
+    const uint32_t d0 = tmem_base + acc * ACC_COLS;
+    for (int c = 0; c < nchunks; ++c) {
+      mbar_wait(&ctl->full[stage], phase);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(stages + (size_t)stage * stage_bytes);
+      const uint32_t w_base = a.wres ? smem_u32(wres) + ((nt * nchunks + c) * 9) * W_TILE : a_base + A_ST;
+      // one descriptor per operand block; every tap / row / k-half is a compile-time offset of its start field
+      const uint64_t adesc0 = make_smem_desc(a_base, 16, 512, kLayoutSW64);
+      const uint64_t bdesc0 = make_smem_desc(w_base, 16, 512, kLayoutSW64);
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int dy = tap / 3, dx = tap % 3;   // halo coordinates (already +1)
+        // R rows x 2 K-halves in one statement: row i adds one halo row (130 px) to A and BN columns to D
+        mma_bf16_ss_tap<R, BN, ((kHaloW * kPixB) >> 4)>(d0, adesc0 + (uint64_t)(((dy * kHaloW + dx) * kPixB) >> 4),
+                                                      bdesc0 + (uint64_t)((tap * W_TILE) >> 4), idesc,
+                                                      tap != 0 ? 1u : (uint32_t)(c != 0));
+      }
+      mma_commit(&ctl->empty[stage]);
+      if (++stage == nst) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    mma_commit(&ctl->tfull[acc]);
+    acc ^= 1;
+    if (acc == 0) acc_phase ^= 1;
+  }
+}
+
 template <int BN, int R>
-__global__ void __launch_bounds__(256, 1) conv3x3_row_kernel(const __grid_constant__ ConvRowArgs a, int nst) {
+__global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_constant__ ConvRowArgs a, int nst) {
   constexpr int A_TX = row_a_bytes(R);
   constexpr int A_ST = round1k(A_TX);
   constexpr int W_TILE = BN * kPixB;           // one (chunk, tap) weight tile: BN rows x 64 B
@@ -59,9 +102,9 @@ __global__ void __launch_bounds__(256, 1) conv3x3_row_kernel(const __grid_consta
   uint8_t* wres = smem;
   uint8_t* stages = smem + round1k(wres_bytes);
   uint8_t* staging = stages + (size_t)nst * stage_bytes;
-  float* s_sum = reinterpret_cast<float*>(staging + STAGING);
-  float* s_sq = s_sum + a.Cout;
-  RowCtl* ctl = reinterpret_cast<RowCtl*>((reinterpret_cast<uintptr_t>(s_sq + a.Cout) + 15) & ~uintptr_t(15));
+  float* s_bias = reinterpret_cast<float*>(staging + STAGING);     // [Cout]
+  float* s_slot = s_bias + a.Cout;                                  // [8 warps][2][Cout] sum / sum^2 partials
+  RowCtl* ctl = reinterpret_cast<RowCtl*>((reinterpret_cast<uintptr_t>(s_slot + 16 * a.Cout) + 15) & ~uintptr_t(15));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -78,7 +121,7 @@ __global__ void __launch_bounds__(256, 1) conv3x3_row_kernel(const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ctl->tfull[i], 1);
-      mbar_init(&ctl->tempty[i], 4);
+      mbar_init(&ctl->tempty[i], 8);
     }
     mbar_init(&ctl->wfull, 1);
     fence_barrier_init();
@@ -87,8 +130,10 @@ __global__ void __launch_bounds__(256, 1) conv3x3_row_kernel(const __grid_consta
     tmem_alloc(&ctl->tmem_base, TMEM_COLS);
     tmem_relinquish();
   }
-  if (warp >= 4)
-    for (int c = threadIdx.x - 128; c < 2 * a.Cout; c += 128) s_sum[c] = 0.f;
+  if (warp >= 4) {
+    for (int c = threadIdx.x - 128; c < 16 * a.Cout; c += 256) s_slot[c] = 0.f;
+    for (int c = threadIdx.x - 128; c < a.Cout; c += 256) s_bias[c] = a.mode != EPI_LINEAR ? a.bias[c] : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -133,50 +178,23 @@ __global__ void __launch_bounds__(256, 1) conv3x3_row_kernel(const __grid_consta
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
-      int stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      if (a.wres) mbar_wait(&ctl->wfull, 0);
-      const uint64_t bo = (uint64_t)a.base_offset_mode;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-        const int nt = tile % a.n_ntiles;
-        mbar_wait(&ctl->tempty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d0 = tmem_base + acc * ACC_COLS;
-        for (int c = 0; c < nchunks; ++c) {
-          mbar_wait(&ctl->full[stage], phase);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(stages + (size_t)stage * stage_bytes);
-          const uint32_t w_base = a.wres ? smem_u32(wres) + ((nt * nchunks + c) * 9) * W_TILE : a_base + A_ST;
-#pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap) {
-            const int dy = tap / 3, dx = tap % 3;   // already offset by +1
-            const uint64_t bdesc = make_smem_desc(w_base + tap * W_TILE, 16, 512, kLayoutSW64);
-#pragma unroll
-            for (int i = 0; i < R; ++i) {
-              const uint32_t a_addr = a_base + ((i + dy) * kHaloW + dx) * kPixB;
-              uint64_t adesc = make_smem_desc(a_addr, 16, 512, kLayoutSW64);
-              if (bo) adesc |= (uint64_t)((a_addr >> 7) & 3u) << 49;
-#pragma unroll
-              for (int kk = 0; kk < 2; ++kk)
-                mma_bf16_ss(d0 + i * BN, adesc + 2 * kk, bdesc + 2 * kk, idesc, (c | tap | kk) != 0);
-            }
-          }
-          mma_commit(&ctl->empty[stage]);
-          if (++stage == nst) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-        mma_commit(&ctl->tfull[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-      }
+      // The first (and only) TMEM allocation of an SM-exclusive CTA starts at column 0; with the base a literal
+      // every tcgen05.mma operand lives in uniform registers (no per-instruction R2UR/ELECT loop).
+      if (tmem_base == 0)
+        row_mma_loop<BN, R, true>(a, ctl, stages, wres, stage_bytes, nst, nchunks, 0u);
+      else
+        row_mma_loop<BN, R, false>(a, ctl, stages, wres, stage_bytes, nst, nchunks, tmem_base);
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue
-    const int ew = warp - 4;
-    const int r = ew * 32 + lane;   // pixel column inside the tile
-    const int et = threadIdx.x - 128;
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    // Two warps per TMEM lane quarter: warp (4+q) takes rows [0, R/2), warp (8+q) rows [R/2, R) of the tile.
+    // Per 32-column chunk a thread keeps its pixel's values in registers: bias + ReLU, bf16 pack into the
+    // swizzled staging tile, and running per-channel sum / sum-of-squares that are folded across the warp
+    // with a 31-shuffle transpose-reduce (lane j ends up owning channel j) into a per-warp smem slot.
+    const int q = (warp - 4) & 3, eh = (warp - 4) >> 2;
+    const int r = q * 32 + lane;            // pixel column inside the tile == TMEM lane
+    const int et = threadIdx.x - 128;       // 0..255
+    float* slot = s_slot + (size_t)(warp - 4) * 2 * a.Cout;
     int acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
       const int nt = tile % a.n_ntiles, pt = tile / a.n_ntiles;
@@ -184,41 +202,72 @@ __global__ void __launch_bounds__(256, 1) conv3x3_row_kernel(const __grid_consta
       const int y0 = ((pt / a.tiles_x) % a.tiles_y) * R;
       const int b = pt / (a.tiles_x * a.tiles_y);
       const int n0 = nt * BN;
-      if (et == 0) tma_store_wait_read0();
-      row_bar_sync(1, 128);
+      if (et == 0) tma_store_wait_read0();   // previous tile's TMA store has drained the staging buffer
+      row_bar_sync(1, 256);
       mbar_wait(&ctl->tfull[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int i = 0; i < R; ++i) {
-        const uint32_t row = i * 128 + r;
-#pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        float bias[32], s1[32], s2[32];
+        if (a.mode != EPI_LINEAR) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 t = *reinterpret_cast<const float4*>(s_bias + n0 + ch * 32 + j * 4);
+            bias[4 * j] = t.x; bias[4 * j + 1] = t.y; bias[4 * j + 2] = t.z; bias[4 * j + 3] = t.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s1[j] = s2[j] = 0.f;
+#pragma unroll
+        for (int ii = 0; ii < R / 2; ++ii) {
+          const int i = eh * (R / 2) + ii;
+          const uint32_t row = i * 128 + r;
           uint32_t v[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * ACC_COLS + i * BN + ch * 32, v);
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS + i * BN + ch * 32, v);
           tmem_ld_wait();
+          float f[32];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              f[j] = __uint_as_float(v[q * 8 + j]);
-              if (a.mode != EPI_LINEAR) f[j] = fmaxf(f[j] + __ldg(a.bias + n0 + ch * 32 + q * 8 + j), 0.f);
+          for (int j = 0; j < 32; ++j) {
+            f[j] = __uint_as_float(v[j]);
+            if (a.mode != EPI_LINEAR) f[j] = fmaxf(f[j] + bias[j], 0.f);
+            if (a.mode == EPI_RELU_STATS) {
+              s1[j] += f[j];
+              s2[j] = fmaf(f[j], f[j], s2[j]);
             }
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
             uint4 pk;
             __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-            const int col = ch * 32 + q * 8;
+            for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[g * 8 + 2 * j], f[g * 8 + 2 * j + 1]);
+            const int col = ch * 32 + g * 8;
             const int oc = col / OCH, cidx = (col % OCH) / 8;
             *reinterpret_cast<uint4*>(staging + oc * OCHUNK + swz_off<OROWB>(row, cidx)) = pk;
           }
+        }
+        if (a.mode == EPI_RELU_STATS) {
+          // transpose-reduce: after the 5 steps lane j holds the sum over the warp's 32 pixels of channel j
+#pragma unroll
+          for (int S = 16; S >= 1; S >>= 1) {
+            const bool up = (lane & S) != 0;
+#pragma unroll
+            for (int k = 0; k < S; ++k) {
+              const float send1 = up ? s1[k] : s1[k + S], keep1 = up ? s1[k + S] : s1[k];
+              const float send2 = up ? s2[k] : s2[k + S], keep2 = up ? s2[k + S] : s2[k];
+              s1[k] = keep1 + __shfl_xor_sync(0xffffffffu, send1, S);
+              s2[k] = keep2 + __shfl_xor_sync(0xffffffffu, send2, S);
+            }
+          }
+          slot[n0 + ch * 32 + lane] += s1[0];
+          slot[a.Cout + n0 + ch * 32 + lane] += s2[0];
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->tempty[acc]);
       fence_proxy_async_smem();
-      row_bar_sync(1, 128);
+      row_bar_sync(1, 256);
       if (et == 0) {
 #pragma unroll 1
         for (int oc = 0; oc < BN / OCH; ++oc) {
@@ -230,54 +279,17 @@ __global__ void __launch_bounds__(256, 1) conv3x3_row_kernel(const __grid_consta
         }
         tma_store_commit();
       }
-      if (a.mode == EPI_RELU_STATS) {
-        constexpr int G8 = BN / 8;
-        constexpr int RT = 128 / G8;
-        const int cg = et % G8, rt = et / G8;
-        float s[8], q2[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s[j] = q2[j] = 0.f;
-        const int col = cg * 8;
-        const int oc = col / OCH, cidx = (col % OCH) / 8;
-#pragma unroll 1
-        for (int k = 0; k < R * G8; ++k) {
-          const uint32_t row = rt + k * RT;
-          uint4 raw = *reinterpret_cast<const uint4*>(staging + oc * OCHUNK + swz_off<OROWB>(row, cidx));
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float2 f = __bfloat1622float2(h[j]);
-            s[2 * j] += f.x;
-            s[2 * j + 1] += f.y;
-            q2[2 * j] = fmaf(f.x, f.x, q2[2 * j]);
-            q2[2 * j + 1] = fmaf(f.y, f.y, q2[2 * j + 1]);
-          }
-        }
-#pragma unroll
-        for (int o = 16; o >= G8; o >>= 1) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
-            q2[j] += __shfl_xor_sync(0xffffffffu, q2[j], o);
-          }
-        }
-        if (lane < G8) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            atomicAdd(&s_sum[n0 + col + j], s[j]);
-            atomicAdd(&s_sq[n0 + col + j], q2[j]);
-          }
-        }
-      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
     if (et == 0) tma_store_wait_all0();
     if (a.mode == EPI_RELU_STATS) {
-      row_bar_sync(1, 128);
-      for (int c = et; c < a.Cout; c += 128) {
-        atomicAdd(&a.stats[c], (double)s_sum[c]);
-        atomicAdd(&a.stats[a.Cout + c], (double)s_sq[c]);
+      row_bar_sync(1, 256);
+      for (int c = et; c < 2 * a.Cout; c += 256) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s_slot[(size_t)w * 2 * a.Cout + c];
+        atomicAdd(&a.stats[c], (double)t);
       }
     }
   }
@@ -288,7 +300,7 @@ __global__ void __launch_bounds__(256, 1) conv3x3_row_kernel(const __grid_consta
 
 // ------------------------------------------------------------------------------------- host
 static size_t row_fixed_bytes(int BN, int R, int Cout, int wres_bytes) {
-  return 1024 + (size_t)round1k(wres_bytes) + (size_t)R * 128 * BN * 2 + 2 * (size_t)Cout * sizeof(float) +
+  return 1024 + (size_t)round1k(wres_bytes) + (size_t)R * 128 * BN * 2 + 17 * (size_t)Cout * sizeof(float) +
          sizeof(RowCtl) + 64;
 }
 static size_t row_stage_bytes(int BN, int R, int wres) { return round1k(row_a_bytes(R)) + (wres ? 0 : 9 * BN * kPixB); }
@@ -329,7 +341,7 @@ static int launch_row(const ConvRowArgs& a, int nst, cudaStream_t st) {
     attr_set = true;
   }
   const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
-  conv3x3_row_kernel<BN, R><<<grid, 256, smem, st>>>(a, nst);
+  conv3x3_row_kernel<BN, R><<<grid, 384, smem, st>>>(a, nst);
   RVIP_LAUNCH_CHECK();
   return 0;
 }

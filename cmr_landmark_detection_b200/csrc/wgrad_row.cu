@@ -40,6 +40,50 @@ __device__ __forceinline__ void wg_red_add_v4(float* addr, float a, float b, flo
                : "memory");
 }
 
+template <int BN, int R, bool ZERO_BASE>
+__device__ __forceinline__ void wg_mma_loop(const WgradRowArgs& a, WgCtl* ctl, uint8_t* dzbuf, uint8_t* stages, int nst,
+                                            int nchunks, uint32_t tmem_base_rt) {
+  constexpr int X_ST = wg_round1k(wg_x_bytes(R));
+  constexpr int DZ_ROWB = BN * 2;
+  constexpr int DZ_BYTES = R * 128 * DZ_ROWB;
+  constexpr uint64_t LAYB = BN == 64 ? kLayoutSW128 : kLayoutSW64;
+  constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+  const uint32_t tmem_base = ZERO_BASE ? 0u : tmem_base_rt;
+  int stage = 0, phase = 0, db = 0, dphase = 0;
+  uint32_t not_first = 0;
+  for (int pt = blockIdx.x; pt < a.pixel_tiles; pt += gridDim.x) {
+    mbar_wait(&ctl->dfull[db], dphase);
+    tc_fence_after();
+    // B: dz rows, MN-major; 8-pixel groups 8*DZ_ROWB apart
+    const uint64_t bdesc0 = make_smem_desc(smem_u32(dzbuf + db * DZ_BYTES), 16, 8 * DZ_ROWB, LAYB);
+    for (int c = 0; c < nchunks; ++c) {
+      mbar_wait(&ctl->full[stage], phase);
+      tc_fence_after();
+      // A: MN-major, 32-channel chunks one pixel (64 B) apart (the dx taps), 8-pixel groups 512 B apart
+      const uint64_t adesc0 = make_smem_desc(smem_u32(stages + (size_t)stage * X_ST), kWgPixB, 8 * kWgPixB, kLayoutSW64);
+      const uint32_t dc = tmem_base + c * 3 * BN;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+        for (int i = 0; i < R; ++i)   // 8 MMAs of 16 pixels each = one dz row, issued as one statement
+          mma_bf16_ss_k8<((16 * kWgPixB) >> 4), ((16 * DZ_ROWB) >> 4)>(
+              dc + dy * BN, adesc0 + (uint64_t)((((i + dy) * kWgHaloW) * kWgPixB) >> 4),
+              bdesc0 + (uint64_t)(((i * 128) * DZ_ROWB) >> 4), idesc, i != 0 ? 1u : not_first);
+      }
+      mma_commit(&ctl->empty[stage]);
+      if (++stage == nst) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    mma_commit(&ctl->dempty[db]);
+    db ^= 1;
+    if (db == 0) dphase ^= 1;
+    not_first = 1;
+  }
+  mma_commit(&ctl->done);
+}
+
 template <int BN, int R>
 __global__ void __launch_bounds__(256, 1) wgrad3x3_row_kernel(const __grid_constant__ WgradRowArgs a, int nst,
                                                               int tmem_cols) {
@@ -114,45 +158,10 @@ __global__ void __launch_bounds__(256, 1) wgrad3x3_row_kernel(const __grid_const
     }
   } else if (warp == 1) {
     if (lane == 0 && has_work) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
-      int stage = 0, phase = 0, db = 0, dphase = 0;
-      bool first_tile = true;
-      for (int pt = blockIdx.x; pt < a.pixel_tiles; pt += gridDim.x) {
-        mbar_wait(&ctl->dfull[db], dphase);
-        tc_fence_after();
-        const uint32_t dz_addr = smem_u32(dzbuf + db * DZ_BYTES);
-        for (int c = 0; c < nchunks; ++c) {
-          mbar_wait(&ctl->full[stage], phase);
-          tc_fence_after();
-          const uint32_t x_addr = smem_u32(stages + (size_t)stage * X_ST);
-#pragma unroll 1
-          for (int dy = 0; dy < 3; ++dy) {
-            const uint32_t d = tmem_base + (c * 3 + dy) * BN;
-#pragma unroll 1
-            for (int i = 0; i < R; ++i) {
-#pragma unroll
-              for (int kk = 0; kk < 8; ++kk) {   // 16 pixels per MMA
-                // A: MN-major, 32-channel chunks one pixel (64 B) apart (the dx taps), 8-pixel groups 512 B apart
-                const uint64_t adesc =
-                    make_smem_desc(x_addr + ((i + dy) * kWgHaloW + kk * 16) * kWgPixB, kWgPixB, 8 * kWgPixB, kLayoutSW64);
-                const uint64_t bdesc =
-                    make_smem_desc(dz_addr + (i * 128 + kk * 16) * DZ_ROWB, 16, 8 * DZ_ROWB, LAYB);
-                mma_bf16_ss(d, adesc, bdesc, idesc, (!first_tile || i > 0 || kk > 0) ? 1u : 0u);
-              }
-            }
-          }
-          mma_commit(&ctl->empty[stage]);
-          if (++stage == nst) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-        mma_commit(&ctl->dempty[db]);
-        db ^= 1;
-        if (db == 0) dphase ^= 1;
-        first_tile = false;
-      }
-      mma_commit(&ctl->done);
+      if (tmem_base == 0)
+        wg_mma_loop<BN, R, true>(a, ctl, dzbuf, stages, nst, nchunks, 0u);
+      else
+        wg_mma_loop<BN, R, false>(a, ctl, dzbuf, stages, nst, nchunks, tmem_base);
     }
   } else if (warp >= 4 && has_work) {
     const int ew = warp - 4;

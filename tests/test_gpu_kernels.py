@@ -53,8 +53,8 @@ def test_conv_tc_forward_bias_relu_stats(variant, shape):
     assert U.max_err(out, ref) <= 1e-2 * float(ref.abs().max()) + 1e-3
     assert U.rel_err(out, ref) < 4e-3
     rb = out.double()
-    assert torch.allclose(stats[:N], rb.sum(dim=(0, 1, 2)), rtol=1e-4, atol=1e-2)
-    assert torch.allclose(stats[N:], (rb * rb).sum(dim=(0, 1, 2)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(stats[:N], rb.sum(dim=(0, 1, 2)), rtol=2e-3, atol=1e-2)
+    assert torch.allclose(stats[N:], (rb * rb).sum(dim=(0, 1, 2)), rtol=2e-3, atol=1e-2)
 
 
 @pytest.mark.parametrize('variant,shape', ALL_CASES)
