@@ -5,6 +5,10 @@
 //   BatchNormalization(axis=-1) :684,691   Dropout :718,772 (Unets.py:813)   MaxPooling2D :714,721
 //   UpSampling2D :756-757   and their gradients.  Block order is Conv -> ReLU -> BN (BN_FIRST false).
 // Every thread moves 8 channels (16 B bf16 / 32 B fp32) of one pixel: fully coalesced NHWC traffic.
+// These passes were issue-bound before they were HBM-bound, so the per-element instruction count is
+// kept minimal: 32-bit index math with shifts (C/8 is a power of two), a 7-op counter hash for the
+// dropout mask, and the backward formula folded into two FMAs per element:
+//   dz = [a>0] * ( sc*dy - k1*a + c0 ),  sc = gamma*rstd, k1 = sc*rstd*mean(dy*ahat), c0 = k1*mu - sc*mean(dy)
 #include "kernels.cuh"
 
 namespace rvip {
@@ -51,73 +55,97 @@ int bn_eval_prepare_launch(const float* mm, const float* mv, float* mean, float*
   return 0;
 }
 
+// item index -> pixel coordinates (32-bit; all tensors of this path have < 2^31 16-byte vectors)
+struct Geo {
+  uint32_t lg;       // log2(C / 8)
+  uint32_t n_items;  // (#pixels or #pooling windows) * C/8
+  uint32_t stride;   // gridDim.x * 256
+};
+__device__ __forceinline__ Geo make_geo(const BnArgs& a, bool pool) {
+  Geo g;
+  g.lg = 31 - __clz(a.C >> 3);
+  const uint32_t P = (uint32_t)a.B * a.H * a.W;
+  g.n_items = (pool ? P / 4 : P) << g.lg;
+  g.stride = gridDim.x * 256;
+  return g;
+}
+// pixel indices of the 2x2 window `win` (row-major order) of a [B,H,W] tensor
+__device__ __forceinline__ void window_pixels(const BnArgs& a, uint32_t win, uint32_t (&p)[4]) {
+  const uint32_t Wo = a.W >> 1, Ho = a.H >> 1;
+  const uint32_t xo = win % Wo, t = win / Wo;
+  const uint32_t yo = t % Ho, b = t / Ho;
+  const uint32_t base = (b * a.H + 2 * yo) * a.W + 2 * xo;
+  p[0] = base; p[1] = base + 1; p[2] = base + a.W; p[3] = base + a.W + 1;
+}
+// the four pixels of the x2 up-sampled tensor [B,2H,2W] that replicate pixel p of [B,H,W]
+__device__ __forceinline__ void upsampled_pixels(const BnArgs& a, uint32_t p, uint32_t (&q)[4]) {
+  const uint32_t xx = p % a.W, t = p / a.W;
+  const uint32_t yy = t % a.H, b = t / a.H;
+  const uint32_t base = (b * 2 * a.H + 2 * yy) * (2 * a.W) + 2 * xx;
+  q[0] = base; q[1] = base + 1; q[2] = base + 2 * a.W; q[3] = base + 2 * a.W + 1;
+}
+
 // ------------------------------------------------------------------------------------- forward apply
 template <typename T, int POST>
 __global__ void __launch_bounds__(256) bn_apply_kernel(BnArgs a) {
-  const int G = a.C >> 3;
-  const size_t P = (size_t)a.B * a.H * a.W;
-  const size_t n_items = (POST == POST_POOL ? P / 4 : P) * G;
-  const size_t i0 = (size_t)blockIdx.x * 256 + threadIdx.x;
-  if (i0 >= n_items) return;
-  const int c = (int)(i0 % G) * 8;
+  const Geo g = make_geo(a, POST == POST_POOL);
+  const uint32_t i0 = blockIdx.x * 256 + threadIdx.x;
+  if (i0 >= g.n_items) return;
+  const int c = (int)(i0 & ((1u << g.lg) - 1)) * 8;
   float sc[8], sh[8];
   scale_shift8(a, c, sc, sh);
-  const T* av = static_cast<const T*>(a.a);
-  T* y = static_cast<T*>(a.y);
-  T* y2 = static_cast<T*>(a.y2);
-  for (size_t i = i0; i < n_items; i += (size_t)gridDim.x * 256) {
+  const T* av = static_cast<const T*>(a.a) + c;
+  T* y = static_cast<T*>(a.y) + c;
+  T* y2 = static_cast<T*>(a.y2) + c;
+  const DropKey key = dropout_key(a.seed, a.site);
+  for (uint32_t i = i0; i < g.n_items; i += g.stride) {
     if (POST == POST_NONE || POST == POST_DROPOUT) {
-      const size_t p = i / G;
+      const size_t off = (size_t)(i >> g.lg) * a.C;
       float v[8];
-      Vec8<T>::load(av + p * a.C + c, v);
+      Vec8<T>::load(av + off, v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
       if (POST == POST_DROPOUT) {
         bool keep[8];
-        dropout_keep8(a.seed, a.site, i, a.thr16, keep);
+        dropout_keep8(key, i, a.thr16, keep);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = keep[j] ? v[j] * a.keep_scale : 0.f;
       }
-      Vec8<T>::store(y + p * a.C + c, v);
+      Vec8<T>::store(y + off, v);
     } else if (POST == POST_POOL) {
-      const size_t win = i / G;
-      const int Wo = a.W >> 1, Ho = a.H >> 1;
-      const int xo = (int)(win % Wo), yo = (int)((win / Wo) % Ho);
-      const size_t b = win / ((size_t)Wo * Ho);
+      const uint32_t win = i >> g.lg;
+      uint32_t p[4];
+      window_pixels(a, win, p);
       float mx[8];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const size_t p = (b * a.H + 2 * yo + (k >> 1)) * a.W + 2 * xo + (k & 1);
         float v[8];
-        Vec8<T>::load(av + p * a.C + c, v);
+        Vec8<T>::load(av + (size_t)p[k] * a.C, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           v[j] = fmaf(v[j], sc[j], sh[j]);
           mx[j] = (k == 0) ? v[j] : fmaxf(mx[j], v[j]);
         }
-        Vec8<T>::store(y + p * a.C + c, v);
+        Vec8<T>::store(y + (size_t)p[k] * a.C, v);
       }
-      Vec8<T>::store(y2 + win * a.C + c, mx);
+      Vec8<T>::store(y2 + (size_t)win * a.C, mx);
     } else {  // POST_UPSAMPLE
-      const size_t p = i / G;
-      const int xx = (int)(p % a.W), yy = (int)((p / a.W) % a.H);
-      const size_t b = p / ((size_t)a.W * a.H);
+      const uint32_t p = i >> g.lg;
+      uint32_t q[4];
+      upsampled_pixels(a, p, q);
       float v[8];
-      Vec8<T>::load(av + p * a.C + c, v);
+      Vec8<T>::load(av + (size_t)p * a.C, v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const size_t q = (b * 2 * a.H + 2 * yy + (k >> 1)) * (2 * a.W) + 2 * xx + (k & 1);
-        Vec8<T>::store(y2 + q * a.C + c, v);
-      }
+      for (int k = 0; k < 4; ++k) Vec8<T>::store(y2 + (size_t)q[k] * a.C, v);
     }
   }
 }
 
-static int ew_grid(size_t n_items) {
+static int ew_grid(size_t n_items, int per_sm) {
   size_t g = (n_items + 255) / 256;
-  const size_t cap = (size_t)kNumSMs * 16;
+  const size_t cap = (size_t)kNumSMs * per_sm;
   return (int)(g < cap ? (g ? g : 1) : cap);
 }
 
@@ -126,7 +154,7 @@ static int bn_apply_t(const BnArgs& a, cudaStream_t st) {
   const size_t P = (size_t)a.B * a.H * a.W;
   const int G = a.C / 8;
   const size_t n = (a.post == POST_POOL ? P / 4 : P) * G;
-  const int grid = ew_grid(n);
+  const int grid = ew_grid(n, 16);
   switch (a.post) {
     case POST_NONE: bn_apply_kernel<T, POST_NONE><<<grid, 256, 0, st>>>(a); break;
     case POST_DROPOUT: bn_apply_kernel<T, POST_DROPOUT><<<grid, 256, 0, st>>>(a); break;
@@ -141,6 +169,7 @@ static int check_bn(const BnArgs& a) {
   RVIP_REQUIRE(a.C % 8 == 0 && G <= 256 && (G & (G - 1)) == 0, "bn: C=%d must be 8 * power of two (<= 2048)", a.C);
   RVIP_REQUIRE(a.post != POST_POOL || (a.H % 2 == 0 && a.W % 2 == 0), "bn: max-pool needs even H, W (got %dx%d)", a.H,
                a.W);
+  RVIP_REQUIRE((size_t)a.B * a.H * a.W * 4 * G < 0x7fffffffULL, "bn: tensor too large for 32-bit vector indexing");
   return 0;
 }
 int bn_apply_launch(const BnArgs& a, int is_bf16, cudaStream_t st) {
@@ -154,53 +183,47 @@ int bn_apply_launch(const BnArgs& a, int is_bf16, cudaStream_t st) {
 template <typename T, int POST>
 struct Gather {
   static constexpr int K = POST == POST_POOL ? 4 : 1;
-  __device__ static __forceinline__ void run(const BnArgs& a, size_t i, int G, int c, const float (&sc)[8],
-                                             const float (&sh)[8], size_t (&pix)[K], float (&av)[K][8],
-                                             float (&dy)[K][8]) {
-    const T* A = static_cast<const T*>(a.a);
-    const T* g0 = static_cast<const T*>(a.g0);
-    if (POST == POST_NONE || POST == POST_DROPOUT) {
-      const size_t p = i / G;
+  __device__ static __forceinline__ void run(const BnArgs& a, const Geo& g, const DropKey& key, uint32_t i, int c,
+                                             const float (&sc)[8], const float (&sh)[8], uint32_t (&pix)[K],
+                                             float (&av)[K][8], float (&dy)[K][8]) {
+    const T* A = static_cast<const T*>(a.a) + c;
+    const T* g0 = static_cast<const T*>(a.g0) + c;
+    if constexpr (POST == POST_NONE || POST == POST_DROPOUT) {
+      const uint32_t p = i >> g.lg;
       pix[0] = p;
-      Vec8<T>::load(A + p * a.C + c, av[0]);
-      Vec8<T>::load(g0 + p * a.C + c, dy[0]);
+      Vec8<T>::load(A + (size_t)p * a.C, av[0]);
+      Vec8<T>::load(g0 + (size_t)p * a.C, dy[0]);
       if (POST == POST_DROPOUT) {
         bool keep[8];
-        dropout_keep8(a.seed, a.site, i, a.thr16, keep);
+        dropout_keep8(key, i, a.thr16, keep);
 #pragma unroll
         for (int j = 0; j < 8; ++j) dy[0][j] = keep[j] ? dy[0][j] * a.keep_scale : 0.f;
       }
-    } else if (POST == POST_UPSAMPLE) {
-      const size_t p = i / G;
+    } else if constexpr (POST == POST_UPSAMPLE) {
+      const uint32_t p = i >> g.lg;
       pix[0] = p;
-      const int xx = (int)(p % a.W), yy = (int)((p / a.W) % a.H);
-      const size_t b = p / ((size_t)a.W * a.H);
-      Vec8<T>::load(A + p * a.C + c, av[0]);
+      uint32_t q[4];
+      upsampled_pixels(a, p, q);
+      Vec8<T>::load(A + (size_t)p * a.C, av[0]);
+      float t[4][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) dy[0][j] = 0.f;
+      for (int k = 0; k < 4; ++k) Vec8<T>::load(g0 + (size_t)q[k] * a.C, t[k]);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const size_t q = (b * 2 * a.H + 2 * yy + (k >> 1)) * (2 * a.W) + 2 * xx + (k & 1);
-        float t[8];
-        Vec8<T>::load(g0 + q * a.C + c, t);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dy[0][j] += t[j];
-      }
+      for (int j = 0; j < 8; ++j) dy[0][j] = (t[0][j] + t[1][j]) + (t[2][j] + t[3][j]);
     } else {  // POST_POOL: skip gradient + pooled gradient routed to the first maximum (row-major, strict >)
-      const T* g1 = static_cast<const T*>(a.g1);
-      const size_t win = i / G;
-      const int Wo = a.W >> 1, Ho = a.H >> 1;
-      const int xo = (int)(win % Wo), yo = (int)((win / Wo) % Ho);
-      const size_t b = win / ((size_t)Wo * Ho);
+      const T* g1 = static_cast<const T*>(a.g1) + c;
+      const uint32_t win = i >> g.lg;
+      window_pixels(a, win, pix);
       float best[8], dp[8];
       int arg[8];
-      Vec8<T>::load(g1 + win * a.C + c, dp);
+      Vec8<T>::load(g1 + (size_t)win * a.C, dp);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const size_t p = (b * a.H + 2 * yo + (k >> 1)) * a.W + 2 * xo + (k & 1);
-        pix[k] = p;
-        Vec8<T>::load(A + p * a.C + c, av[k]);
-        Vec8<T>::load(g0 + p * a.C + c, dy[k]);
+        Vec8<T>::load(A + (size_t)pix[k] * a.C, av[k]);
+        Vec8<T>::load(g0 + (size_t)pix[k] * a.C, dy[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float yv = fmaf(av[k][j], sc[j], sh[j]);
@@ -209,7 +232,6 @@ struct Gather {
             arg[j] = k;
           }
         }
-      }
 #pragma unroll
       for (int k = 0; k < 4; ++k)
 #pragma unroll
@@ -219,50 +241,33 @@ struct Gather {
   }
 };
 
+// pass 1: red[c] += sum dy, red[C + c] += sum dy * a   (raw a; normalised in pass 2)
 template <typename T, int POST>
-__global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(BnArgs a) {
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnArgs a) {
   extern __shared__ float red_s[];  // [2][C]
   constexpr int K = Gather<T, POST>::K;
-  const int G = a.C >> 3;
-  const size_t P = (size_t)a.B * a.H * a.W;
-  const size_t n_items = (POST == POST_POOL ? P / 4 : P) * G;
+  const Geo g = make_geo(a, POST == POST_POOL);
   for (int k = threadIdx.x; k < 2 * a.C; k += 256) red_s[k] = 0.f;
   __syncthreads();
-  const size_t i0 = (size_t)blockIdx.x * 256 + threadIdx.x;
-  if (i0 < n_items) {
-    const int c = (int)(i0 % G) * 8;
-    float sc[8], sh[8], s1[8], s2[8], mean[8], rstd[8];
-    scale_shift8(a, c, sc, sh);
+  const uint32_t i0 = blockIdx.x * 256 + threadIdx.x;
+  if (i0 < g.n_items) {
+    const int c = (int)(i0 & ((1u << g.lg) - 1)) * 8;
+    float sc[8], sh[8], s1[8], s2[8];
+    if (POST == POST_POOL) scale_shift8(a, c, sc, sh);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s1[j] = s2[j] = 0.f;
-      mean[j] = a.mean[c + j];
-      rstd[j] = a.rstd[c + j];
-    }
-    // U independent work items per iteration keep 2U..9U 16-byte loads in flight per thread
-    constexpr int U = K == 1 ? 2 : 1;
-    const size_t stride = (size_t)gridDim.x * 256;
-    for (size_t i = i0; i < n_items; i += U * stride) {
-      size_t pix[U][K];
-      float av[U][K][8], dy[U][K][8];
-      bool live[U];
+    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+    const DropKey key = dropout_key(a.seed, a.site);
+    for (uint32_t i = i0; i < g.n_items; i += g.stride) {
+      uint32_t pix[K];
+      float av[K][8], dy[K][8];
+      Gather<T, POST>::run(a, g, key, i, c, sc, sh, pix, av, dy);
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const size_t iu = i + u * stride;
-        live[u] = iu < n_items;
-        Gather<T, POST>::run(a, live[u] ? iu : i, G, c, sc, sh, pix[u], av[u], dy[u]);
-      }
+      for (int k = 0; k < K; ++k)
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (!live[u]) continue;
-#pragma unroll
-        for (int k = 0; k < K; ++k)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            s1[j] += dy[u][k][j];
-            s2[j] = fmaf(dy[u][k][j], (av[u][k][j] - mean[j]) * rstd[j], s2[j]);
-          }
-      }
+        for (int j = 0; j < 8; ++j) {
+          s1[j] += dy[k][j];
+          s2[j] = fmaf(dy[k][j], av[k][j], s2[j]);
+        }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -274,63 +279,53 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(BnArgs a) {
   for (int k = threadIdx.x; k < 2 * a.C; k += 256) atomicAdd(&a.red[k], (double)red_s[k]);
 }
 
+// pass 2: dz, conv-bias gradient, and (block 0) dgamma / dbeta
 template <typename T, int POST>
-__global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(BnArgs a) {
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnArgs a) {
   extern __shared__ float red_s[];  // [C] bias-gradient partials
   constexpr int K = Gather<T, POST>::K;
-  const int G = a.C >> 3;
-  const size_t P = (size_t)a.B * a.H * a.W;
-  const size_t n_items = (POST == POST_POOL ? P / 4 : P) * G;
+  const Geo g = make_geo(a, POST == POST_POOL);
+  const double P = (double)a.B * a.H * a.W;
   for (int k = threadIdx.x; k < a.C; k += 256) red_s[k] = 0.f;
   if (blockIdx.x == 0) {
     for (int k = threadIdx.x; k < a.C; k += 256) {
-      a.dbeta[k] = (float)a.red[k];
-      a.dgamma[k] = (float)a.red[a.C + k];
+      const double s1 = a.red[k], s2 = a.red[a.C + k];
+      a.dbeta[k] = (float)s1;
+      a.dgamma[k] = (float)((double)a.rstd[k] * (s2 - (double)a.mean[k] * s1));   // sum dy * ahat
     }
   }
   __syncthreads();
-  const size_t i0 = (size_t)blockIdx.x * 256 + threadIdx.x;
-  if (i0 < n_items) {
-    const int c = (int)(i0 % G) * 8;
-    float sc[8], sh[8], mean[8], rstd[8], m1[8], m2[8], db[8];
+  const uint32_t i0 = blockIdx.x * 256 + threadIdx.x;
+  if (i0 < g.n_items) {
+    const int c = (int)(i0 & ((1u << g.lg) - 1)) * 8;
+    float sc[8], sh[8], k1[8], c0[8], db[8];
     scale_shift8(a, c, sc, sh);
-    const double invP = 1.0 / (double)P;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      mean[j] = a.mean[c + j];
-      rstd[j] = a.rstd[c + j];
-      m1[j] = (float)(a.red[c + j] * invP);
-      m2[j] = (float)(a.red[a.C + c + j] * invP);
+      const double s1 = a.red[c + j], s2 = a.red[a.C + c + j];
+      const double mu = a.mean[c + j], r = a.rstd[c + j];
+      const double m1 = s1 / P, m2 = r * (s2 - mu * s1) / P;   // mean(dy), mean(dy * ahat)
+      const double k = (double)sc[j] * r * m2;
+      k1[j] = (float)k;
+      c0[j] = (float)(k * mu - (double)sc[j] * m1);
       db[j] = 0.f;
     }
-    T* dzp = static_cast<T*>(a.dz);
-    constexpr int U = K == 1 ? 2 : 1;
-    const size_t stride = (size_t)gridDim.x * 256;
-    for (size_t i = i0; i < n_items; i += U * stride) {
-      size_t pix[U][K];
-      float av[U][K][8], dy[U][K][8];
-      bool live[U];
+    T* dzp = static_cast<T*>(a.dz) + c;
+    const DropKey key = dropout_key(a.seed, a.site);
+    for (uint32_t i = i0; i < g.n_items; i += g.stride) {
+      uint32_t pix[K];
+      float av[K][8], dy[K][8];
+      Gather<T, POST>::run(a, g, key, i, c, sc, sh, pix, av, dy);
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const size_t iu = i + u * stride;
-        live[u] = iu < n_items;
-        Gather<T, POST>::run(a, live[u] ? iu : i, G, c, sc, sh, pix[u], av[u], dy[u]);
-      }
+      for (int k = 0; k < K; ++k) {
+        float dz[8];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (!live[u]) continue;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          float dz[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float ahat = (av[u][k][j] - mean[j]) * rstd[j];
-            const float da = sc[j] * (dy[u][k][j] - m1[j] - ahat * m2[j]);
-            dz[j] = av[u][k][j] > 0.f ? da : 0.f;
-            db[j] += round_to<T>(dz[j]);
-          }
-          Vec8<T>::store(dzp + pix[u][k] * a.C + c, dz);
+        for (int j = 0; j < 8; ++j) {
+          const float da = fmaf(sc[j], dy[k][j], fmaf(-k1[j], av[k][j], c0[j]));
+          dz[j] = av[k][j] > 0.f ? da : 0.f;
+          db[j] += dz[j];
         }
+        Vec8<T>::store(dzp + (size_t)pix[k] * a.C, dz);
       }
     }
 #pragma unroll
@@ -345,9 +340,7 @@ static int bn_bwd_t(const BnArgs& a, cudaStream_t st) {
   const size_t P = (size_t)a.B * a.H * a.W;
   const int G = a.C / 8;
   const size_t n = (a.post == POST_POOL ? P / 4 : P) * G;
-  size_t g = (n + 255) / 256;
-  const size_t cap = (size_t)kNumSMs * 8;
-  const int grid = (int)(g < cap ? (g ? g : 1) : cap);
+  const int grid = ew_grid(n, 8);
   const size_t sm = (WHICH == 0 ? 2 : 1) * a.C * sizeof(float);
 #define RVIP_BWD(POSTV)                                                 \
   if (WHICH == 0)                                                       \
@@ -375,30 +368,29 @@ int bn_bwd_apply_launch(const BnArgs& a, int is_bf16, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------- ReLU backward (up-conv)
 template <typename T>
-__global__ void __launch_bounds__(256) relu_bwd_kernel(const T* u, const T* du, T* dz, float* dbias, size_t pixels,
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const T* __restrict__ u, const T* __restrict__ du,
+                                                       T* __restrict__ dz, float* dbias, uint32_t n_items, uint32_t lg,
                                                        int C) {
   extern __shared__ float red_s[];
-  const int G = C >> 3;
-  const size_t n_items = pixels * G;
   for (int k = threadIdx.x; k < C; k += 256) red_s[k] = 0.f;
   __syncthreads();
-  const size_t i0 = (size_t)blockIdx.x * 256 + threadIdx.x;
+  const uint32_t i0 = blockIdx.x * 256 + threadIdx.x;
   if (i0 < n_items) {
-    const int c = (int)(i0 % G) * 8;
+    const int c = (int)(i0 & ((1u << lg) - 1)) * 8;
     float db[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) db[j] = 0.f;
-    for (size_t i = i0; i < n_items; i += (size_t)gridDim.x * 256) {
-      const size_t p = i / G;
-      float uv[8], g[8];
-      Vec8<T>::load(u + p * C + c, uv);
-      Vec8<T>::load(du + p * C + c, g);
+    for (uint32_t i = i0; i < n_items; i += gridDim.x * 256) {
+      const size_t off = (size_t)(i >> lg) * C + c;
+      float uv[8], gv[8];
+      Vec8<T>::load(u + off, uv);
+      Vec8<T>::load(du + off, gv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        g[j] = uv[j] > 0.f ? g[j] : 0.f;
-        db[j] += g[j];
+        gv[j] = uv[j] > 0.f ? gv[j] : 0.f;
+        db[j] += gv[j];
       }
-      Vec8<T>::store(dz + p * C + c, g);
+      Vec8<T>::store(dz + off, gv);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) atomicAdd(&red_s[c + j], db[j]);
@@ -410,17 +402,19 @@ int relu_bwd_launch(const void* u, const void* du, void* dz, float* dbias, size_
                     cudaStream_t st) {
   const int G = C / 8;
   RVIP_REQUIRE(C % 8 == 0 && G <= 256 && (G & (G - 1)) == 0, "relu_bwd: C=%d must be 8 * power of two", C);
-  size_t g = (pixels * G + 255) / 256;
-  const size_t cap = (size_t)kNumSMs * 8;
-  const int grid = (int)(g < cap ? (g ? g : 1) : cap);
+  RVIP_REQUIRE(pixels * G < 0x7fffffffULL, "relu_bwd: tensor too large for 32-bit vector indexing");
+  uint32_t lg = 0;
+  while ((1 << lg) < G) ++lg;
+  const uint32_t n = (uint32_t)(pixels * G);
+  const int grid = ew_grid(n, 8);
   if (is_bf16)
     relu_bwd_kernel<__nv_bfloat16><<<grid, 256, C * sizeof(float), st>>>(
         static_cast<const __nv_bfloat16*>(u), static_cast<const __nv_bfloat16*>(du), static_cast<__nv_bfloat16*>(dz),
-        dbias, pixels, C);
+        dbias, n, lg, C);
   else
     relu_bwd_kernel<float><<<grid, 256, C * sizeof(float), st>>>(static_cast<const float*>(u),
                                                                   static_cast<const float*>(du),
-                                                                  static_cast<float*>(dz), dbias, pixels, C);
+                                                                  static_cast<float*>(dz), dbias, n, lg, C);
   RVIP_LAUNCH_CHECK();
   return 0;
 }

@@ -10,7 +10,7 @@ namespace rvip {
 
 constexpr int kMaxNC = 4;
 
-template <typename T, bool TRAIN>
+template <typename T, bool TRAIN, int NCT>
 __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
   extern __shared__ float sm[];            // w [Cin*NC], b [NC], then (TRAIN) dw acc [Cin*NC], db acc [NC]
   const int NC = a.NC, Cin = a.Cin, G = Cin >> 3;
@@ -30,20 +30,22 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
   if (threadIdx.x == 0) loss_s = 0.0;
   __syncthreads();
 
-  const size_t P = (size_t)a.B * a.H * a.W;
-  const size_t n_items = P * G;
-  const size_t i0 = (size_t)blockIdx.x * 256 + threadIdx.x;
-  const int cg = (int)(i0 % G), c = cg * 8;
+  const uint32_t P = (uint32_t)a.B * a.H * a.W;
+  const uint32_t lg = 31 - __clz(G);
+  const uint32_t n_items = P << lg;
+  const uint32_t i0 = blockIdx.x * 256 + threadIdx.x;
+  const int cg = (int)(i0 & (G - 1)), c = cg * 8;
+  const uint32_t HW = (uint32_t)a.H * a.W;
   const T* y = static_cast<const T*>(a.y);
   T* dy = static_cast<T*>(a.dy);
-  float wreg[8][kMaxNC];
+  float wreg[8][NCT];
 #pragma unroll
   for (int j = 0; j < 8; ++j)
 #pragma unroll
-    for (int k = 0; k < kMaxNC; ++k) wreg[j][k] = k < NC ? w_s[(c + j) * NC + k] : 0.f;
-  float dw_acc[8][kMaxNC], db_acc[kMaxNC];
+    for (int k = 0; k < NCT; ++k) wreg[j][k] = k < NC ? w_s[(c + j) * NC + k] : 0.f;
+  float dw_acc[8][NCT], db_acc[NCT];
 #pragma unroll
-  for (int k = 0; k < kMaxNC; ++k) {
+  for (int k = 0; k < NCT; ++k) {
     db_acc[k] = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) dw_acc[j][k] = 0.f;
@@ -51,10 +53,10 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
   float loss_acc = 0.f;
   const float inv_n = 1.f / ((float)P * (float)NC);
   // all lanes of a warp run the same trip count (n_items and the stride are multiples of 32)
-  const size_t n_round = (n_items + 31) / 32 * 32;
-  for (size_t i = i0; i < n_round; i += (size_t)gridDim.x * 256) {
+  const uint32_t n_round = (n_items + 31) / 32 * 32;
+  for (uint32_t i = i0; i < n_round; i += gridDim.x * 256) {
     const bool live = i < n_items;
-    const size_t p = live ? i / G : 0;
+    const size_t p = live ? (i >> lg) : 0;
     float v[8];
     if (live)
       Vec8<T>::load(y + p * Cin + c, v);
@@ -62,9 +64,9 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = 0.f;
     }
-    float logit[kMaxNC];
+    float logit[NCT];
 #pragma unroll
-    for (int k = 0; k < kMaxNC; ++k) {
+    for (int k = 0; k < NCT; ++k) {
       float s = 0.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) s = fmaf(v[j], wreg[j][k], s);
@@ -72,27 +74,27 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
       logit[k] = s + (k < NC ? b_s[k] : 0.f);
     }
     if (!live) continue;
-    float prob[kMaxNC];
+    float prob[NCT];
 #pragma unroll
-    for (int k = 0; k < kMaxNC; ++k) prob[k] = 1.f / (1.f + expf(-logit[k]));
+    for (int k = 0; k < NCT; ++k) prob[k] = 1.f / (1.f + expf(-logit[k]));
     if (cg == 0) {
 #pragma unroll
-      for (int k = 0; k < kMaxNC; ++k)
+      for (int k = 0; k < NCT; ++k)
         if (k < NC) a.heat[p * NC + k] = prob[k];
     }
     if (TRAIN) {
-      float tgt[kMaxNC], wpx = 1.f;
+      float tgt[NCT], wpx = 1.f;
       bool any = false;
 #pragma unroll
-      for (int k = 0; k < kMaxNC; ++k) {
+      for (int k = 0; k < NCT; ++k) {
         tgt[k] = k < NC ? a.target[p * NC + k] : 0.f;
         any = any || (k < NC && tgt[k] > a.mask_thr);
       }
       if (a.loss_kind != LOSS_MSE) wpx = any ? 1.f : 0.f;
-      if (a.loss_kind == LOSS_WEIGHTED) wpx *= a.inplane[p % ((size_t)a.H * a.W)];
-      float dl[kMaxNC], se = 0.f;
+      if (a.loss_kind == LOSS_WEIGHTED) wpx *= a.inplane[(uint32_t)p % HW];
+      float dl[NCT], se = 0.f;
 #pragma unroll
-      for (int k = 0; k < kMaxNC; ++k) {
+      for (int k = 0; k < NCT; ++k) {
         const float d = k < NC ? prob[k] - tgt[k] : 0.f;
         se = fmaf(d, d, se);
         dl[k] = 2.f * d * wpx * inv_n * prob[k] * (1.f - prob[k]);
@@ -100,14 +102,14 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
       if (cg == 0) {
         loss_acc += se / (float)NC * wpx + (a.loss_kind == LOSS_WEIGHTED ? a.eps : 0.f);
 #pragma unroll
-        for (int k = 0; k < kMaxNC; ++k) db_acc[k] += dl[k];
+        for (int k = 0; k < NCT; ++k) db_acc[k] += dl[k];
       }
       float g[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float s = 0.f;
 #pragma unroll
-        for (int k = 0; k < kMaxNC; ++k) {
+        for (int k = 0; k < NCT; ++k) {
           s = fmaf(wreg[j][k], dl[k], s);
           dw_acc[j][k] = fmaf(v[j], dl[k], dw_acc[j][k]);
         }
@@ -120,11 +122,11 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
 #pragma unroll
     for (int j = 0; j < 8; ++j)
 #pragma unroll
-      for (int k = 0; k < kMaxNC; ++k)
+      for (int k = 0; k < NCT; ++k)
         if (k < NC) atomicAdd(&dw_s[(c + j) * NC + k], dw_acc[j][k]);
     if (cg == 0) {
 #pragma unroll
-      for (int k = 0; k < kMaxNC; ++k)
+      for (int k = 0; k < NCT; ++k)
         if (k < NC) atomicAdd(&db_s[k], db_acc[k]);
     }
     float l = warp_sum(loss_acc);
@@ -139,23 +141,29 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
 int head_launch(const HeadArgs& a, int training, int is_bf16, cudaStream_t st) {
   const int G = a.Cin / 8;
   RVIP_REQUIRE(a.Cin % 8 == 0 && G <= 32 && (G & (G - 1)) == 0, "head: Cin=%d must be 8 * power of two <= 256", a.Cin);
+  RVIP_REQUIRE((size_t)a.B * a.H * a.W * G < 0x7fffffffULL, "head: tensor too large for 32-bit indexing");
   RVIP_REQUIRE(a.NC >= 1 && a.NC <= kMaxNC, "head: MASK_CLASSES=%d not in [1,%d]", a.NC, kMaxNC);
   const size_t n = (size_t)a.B * a.H * a.W * G;
   size_t g = (n + 255) / 256;
   const size_t cap = (size_t)kNumSMs * 8;
   const int grid = (int)(g < cap ? (g ? g : 1) : cap);
   const size_t smem = (size_t)(2 * (a.Cin * a.NC + a.NC)) * sizeof(float);
-  if (training) {
-    if (is_bf16)
-      head_kernel<__nv_bfloat16, true><<<grid, 256, smem, st>>>(a);
-    else
-      head_kernel<float, true><<<grid, 256, smem, st>>>(a);
-  } else {
-    if (is_bf16)
-      head_kernel<__nv_bfloat16, false><<<grid, 256, smem, st>>>(a);
-    else
-      head_kernel<float, false><<<grid, 256, smem, st>>>(a);
+#define RVIP_HEAD(NCV)                                                        \
+  if (a.NC == NCV) {                                                          \
+    if (training) {                                                           \
+      if (is_bf16)                                                            \
+        head_kernel<__nv_bfloat16, true, NCV><<<grid, 256, smem, st>>>(a);    \
+      else                                                                    \
+        head_kernel<float, true, NCV><<<grid, 256, smem, st>>>(a);            \
+    } else {                                                                  \
+      if (is_bf16)                                                            \
+        head_kernel<__nv_bfloat16, false, NCV><<<grid, 256, smem, st>>>(a);   \
+      else                                                                    \
+        head_kernel<float, false, NCV><<<grid, 256, smem, st>>>(a);           \
+    }                                                                         \
   }
+  RVIP_HEAD(1) RVIP_HEAD(2) RVIP_HEAD(3) RVIP_HEAD(4)
+#undef RVIP_HEAD
   RVIP_LAUNCH_CHECK();
   return 0;
 }

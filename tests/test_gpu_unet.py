@@ -76,6 +76,8 @@ def test_train_step_matches_oracle(precision, dim, depth, batch):
             # depth-4 nets at 64x64 normalise over as few as 32 values at the bottleneck: fp32 summation-order
             # noise is amplified ~1e3x there (same effect in the oracle run twice with permuted sums)
             lim_cos, lim_rl2 = (t['cos'], t['rl2']) if depth <= 2 else (0.9999, 2e-2)
+            if name.endswith('/bias'):      # sum of dz under BatchNorm nearly cancels: atomics-order noise shows
+                lim_cos, lim_rl2 = min(lim_cos, 0.9999), max(lim_rl2, 1e-2)
             assert cos >= lim_cos and rl2 <= lim_rl2, (name, cos, rl2)
         else:
             # no worse than what bf16 storage itself does to the fp32 oracle (calibration run `cal`)
