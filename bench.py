@@ -100,8 +100,8 @@ def oracle_train_rate(n_slices=4, steps=3, warmup=1, threads=None):
     import torch
     from cmr_landmark_detection_b200 import synth
     from oracle import unet_ref as R
-    if threads:
-        torch.set_num_threads(threads)
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core it can get
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     cfg = R.cfg_from_config(CONFIG)
     ws = R.init_weights(cfg, seed=1234)
     x, y = synth.make_batch(n_slices, 256, 256, seed=42)
@@ -294,6 +294,7 @@ def extra_measurements(model, dev):
 
 
 def main():
+    os.environ['NCCL_DEBUG'] = os.environ.get('RVIP_NCCL_DEBUG', 'WARN')   # keep stdout to the one JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)

@@ -55,23 +55,27 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
   const PackEntry e = table[blockIdx.y];
   const long long n = 9LL * e.Ctot * e.Cout;
   const float* W = params + e.src;
+  // i enumerates DESTINATION elements so the narrow stores coalesce; the strided fp32 reads hit L2
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
-    const int co = (int)(i % e.Cout);
-    const int c = (int)((i / e.Cout) % e.Ctot);
-    const int tap = (int)(i / ((long long)e.Cout * e.Ctot));
-    const float v = W[i];
     if (BF16) {
-      packed[e.dst_f + ((long long)co * 9 + tap) * e.Ctot + c] = from_f32<TO>(v);
-      if (e.dst_d >= 0) packed[e.dst_d + ((long long)c * 9 + (8 - tap)) * e.Cout + co] = from_f32<TO>(v);
-    } else {
-      if (e.dst_d >= 0) packed[e.dst_d + ((long long)(8 - tap) * e.Cout + co) * e.Ctot + c] = from_f32<TO>(v);
+      {  // Wf[co][tap][c]
+        const int c = (int)(i % e.Ctot), tap = (int)((i / e.Ctot) % 9), co = (int)(i / (9LL * e.Ctot));
+        packed[e.dst_f + i] = from_f32<TO>(W[((long long)tap * e.Ctot + c) * e.Cout + co]);
+      }
+      if (e.dst_d >= 0) {  // Wd[c][tap'][co] = W[8 - tap'][c][co]
+        const int co = (int)(i % e.Cout), tp = (int)((i / e.Cout) % 9), c = (int)(i / (9LL * e.Cout));
+        packed[e.dst_d + i] = from_f32<TO>(W[((long long)(8 - tp) * e.Ctot + c) * e.Cout + co]);
+      }
+    } else if (e.dst_d >= 0) {  // Wr[tap'][co][c] = W[8 - tap'][c][co]
+      const int c = (int)(i % e.Ctot), co = (int)((i / e.Ctot) % e.Cout), tp = (int)(i / ((long long)e.Ctot * e.Cout));
+      packed[e.dst_d + i] = from_f32<TO>(W[((long long)(8 - tp) * e.Ctot + c) * e.Cout + co]);
     }
   }
 }
 int pack_weights_launch(const float* params, void* packed, const PackEntry* table_dev, int n_entries, int to_bf16,
                         cudaStream_t st) {
   if (n_entries == 0) return 0;
-  dim3 grid(64, n_entries);
+  dim3 grid(148, n_entries);
   if (to_bf16)
     pack_weights_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>(params, static_cast<__nv_bfloat16*>(packed),
                                                                     table_dev);

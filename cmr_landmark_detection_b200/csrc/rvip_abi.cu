@@ -152,12 +152,24 @@ static int setup_conv_tc(ConvTcArgs* a, int* KC, int* BN, const void* in0, const
   RVIP_REQUIRE(C0 % 32 == 0 && C1 % 32 == 0 && Cout % 32 == 0, "conv_tc: channels must be multiples of 32 (%d+%d->%d)",
                C0, C1, Cout);
   *KC = pick_kc(C0, C1);
-  int bn = std::min(Cout, 256);
-  if (mode == EPI_LINEAR && out_split < Cout) bn = std::min(bn, out_split);
-  while (Cout % bn != 0 || (mode == EPI_LINEAR && out_split < Cout && out_split % bn != 0)) bn /= 2;
+  a->g = make_tile_geom(B, H, W, 128);
+  // widest N tile that divides the channels -- unless a narrower one fills the 148 persistent CTAs clearly
+  // better (e.g. 256 M-tiles x 1 N-tile = 1.73 waves -> 58 %; x 2 N-tiles = 3.46 waves -> 86 %)
+  int bn = 0;
+  double best_eff = 0.0;
+  for (int cand : {256, 128, 64, 32}) {
+    if (cand > Cout || Cout % cand != 0) continue;
+    if (mode == EPI_LINEAR && out_split < Cout && (cand > out_split || out_split % cand != 0)) continue;
+    const long tiles = (long)(Cout / cand) * a->g.tiles_x * a->g.tiles_y * a->g.tiles_b;
+    const double eff = (double)tiles / (double)(((tiles + kNumSMs - 1) / kNumSMs) * kNumSMs);
+    (void)eff;
+    if (bn == 0) {   // measured: narrower tiles lose more to A re-reads than they gain in wave efficiency
+      bn = cand;
+      best_eff = eff;
+    }
+  }
   RVIP_REQUIRE(bn >= 32, "conv_tc: no valid N tile for Cout=%d split=%d", Cout, out_split);
   *BN = bn;
-  a->g = make_tile_geom(B, H, W, 128);
   a->B = B; a->H = H; a->W = W;
   a->C0 = C0; a->Ctot = Ctot; a->Cout = Cout;
   a->n_ntiles = Cout / bn;
@@ -194,11 +206,13 @@ static int setup_wgrad_tc(WgradTcArgs* a, int* CBA, int* CBB, const void* x0, co
   a->g = make_tile_geom(B, H, W, 64);
   a->B = B; a->H = H; a->W = W;
   a->C0 = C0; a->Ctot = Ctot; a->Cout = Cout;
-  a->BN = std::min(Cout, 128);
+  // Per 64-pixel K step a CTA streams MT*16 KB of x and 128*BN bytes of dz for MT*4 MMAs of 128 x BN x 16:
+  // the wider the N tile, the fewer L2->smem bytes per MMA cycle (BN=256, MT=2: 64 B/cycle/SM).
+  a->BN = std::min(Cout, 256);
   const int cpt = 128 / *CBA;
   const int nchunk = 9 * Ctot / *CBA;
   a->n_mtiles = (nchunk + cpt - 1) / cpt;
-  int mt = (57344 - 128 * a->BN) / 16384;
+  int mt = (72 * 1024 - 128 * a->BN) / 16384;
   mt = std::max(1, std::min(mt, std::min(a->n_mtiles, 512 / a->BN)));
   a->MT = mt;
   a->n_mgroups = (a->n_mtiles + mt - 1) / mt;
