@@ -85,6 +85,41 @@ __device__ __forceinline__ void upsampled_pixels(const BnArgs& a, uint32_t p, ui
   q[0] = base; q[1] = base + 1; q[2] = base + 2 * a.W; q[3] = base + 2 * a.W + 1;
 }
 
+// L2 prefetch of what the block (256 consecutive items starting at item `i`) will read: `a` always, plus the
+// gradient sources when BWD.  Called by thread 0 for the iteration kPrefetchAhead grid-strides ahead.
+template <typename T, int POST, bool BWD>
+__device__ __forceinline__ void prefetch_inputs(const BnArgs& a, const Geo& g, uint32_t i) {
+  if (i >= g.n_items) return;
+  const uint32_t pb = a.C * sizeof(T);                 // bytes per pixel
+  const uint32_t npx = 256u >> g.lg ? 256u >> g.lg : 1u;
+  const uint32_t P = (uint32_t)a.B * a.H * a.W;
+  if (POST == POST_NONE || POST == POST_DROPOUT) {
+    const uint32_t p = i >> g.lg;
+    l2_prefetch_items(a.a, p, npx, P, pb);
+    if (BWD) l2_prefetch_items(a.g0, p, npx, P, pb);
+  } else if (POST == POST_UPSAMPLE) {
+    const uint32_t p = i >> g.lg;
+    l2_prefetch_items(a.a, p, npx, P, pb);
+    if (BWD) {
+      uint32_t q[4];
+      upsampled_pixels(a, p, q);
+      l2_prefetch_items(a.g0, q[0], 2 * npx, 4 * P, pb);
+      l2_prefetch_items(a.g0, q[2], 2 * npx, 4 * P, pb);
+    }
+  } else {
+    const uint32_t win = i >> g.lg;
+    uint32_t p[4];
+    window_pixels(a, win, p);
+    l2_prefetch_items(a.a, p[0], 2 * npx, P, pb);
+    l2_prefetch_items(a.a, p[2], 2 * npx, P, pb);
+    if (BWD) {
+      l2_prefetch_items(a.g0, p[0], 2 * npx, P, pb);
+      l2_prefetch_items(a.g0, p[2], 2 * npx, P, pb);
+      l2_prefetch_items(a.g1, win, npx, P / 4, pb);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------- forward apply
 template <typename T, int POST>
 __global__ void __launch_bounds__(256) bn_apply_kernel(BnArgs a) {
@@ -99,6 +134,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(BnArgs a) {
   T* y2 = static_cast<T*>(a.y2) + c;
   const DropKey key = dropout_key(a.seed, a.site);
   for (uint32_t i = i0; i < g.n_items; i += g.stride) {
+    if (threadIdx.x == 0) prefetch_inputs<T, POST, false>(a, g, i + kPrefetchAhead * g.stride);
     if (POST == POST_NONE || POST == POST_DROPOUT) {
       const size_t off = (size_t)(i >> g.lg) * a.C;
       float v[8];
@@ -243,14 +279,14 @@ struct Gather {
 
 // pass 1: red[c] += sum dy, red[C + c] += sum dy * a   (raw a; normalised in pass 2)
 template <typename T, int POST>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnArgs a) {
+__global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 5) bn_bwd_reduce_kernel(BnArgs a) {
   extern __shared__ float red_s[];  // [2][C]
   constexpr int K = Gather<T, POST>::K;
   const Geo g = make_geo(a, POST == POST_POOL);
   for (int k = threadIdx.x; k < 2 * a.C; k += 256) red_s[k] = 0.f;
   __syncthreads();
   const uint32_t i0 = blockIdx.x * 256 + threadIdx.x;
-  if (i0 < g.n_items) {
+  if ((i0 & ~31u) < g.n_items) {   // warp-uniform: n_items is a multiple of 32 vectors or the warp is partial
     const int c = (int)(i0 & ((1u << g.lg) - 1)) * 8;
     float sc[8], sh[8], s1[8], s2[8];
     if (POST == POST_POOL) scale_shift8(a, c, sc, sh);
@@ -258,6 +294,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnArgs a) {
     for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
     const DropKey key = dropout_key(a.seed, a.site);
     for (uint32_t i = i0; i < g.n_items; i += g.stride) {
+      if (threadIdx.x == 0) prefetch_inputs<T, POST, true>(a, g, i + kPrefetchAhead * g.stride);
       uint32_t pix[K];
       float av[K][8], dy[K][8];
       Gather<T, POST>::run(a, g, key, i, c, sc, sh, pix, av, dy);
@@ -269,11 +306,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnArgs a) {
           s2[j] = fmaf(dy[k][j], av[k][j], s2[j]);
         }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&red_s[c + j], s1[j]);
-      atomicAdd(&red_s[a.C + c + j], s2[j]);
-    }
+    block_accumulate8(red_s, c, s1, 1u << g.lg);
+    block_accumulate8(red_s + a.C, c, s2, 1u << g.lg);
   }
   __syncthreads();
   for (int k = threadIdx.x; k < 2 * a.C; k += 256) atomicAdd(&a.red[k], (double)red_s[k]);
@@ -281,7 +315,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnArgs a) {
 
 // pass 2: dz, conv-bias gradient, and (block 0) dgamma / dbeta
 template <typename T, int POST>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnArgs a) {
+__global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_apply_kernel(BnArgs a) {
   extern __shared__ float red_s[];  // [C] bias-gradient partials
   constexpr int K = Gather<T, POST>::K;
   const Geo g = make_geo(a, POST == POST_POOL);
@@ -296,7 +330,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnArgs a) {
   }
   __syncthreads();
   const uint32_t i0 = blockIdx.x * 256 + threadIdx.x;
-  if (i0 < g.n_items) {
+  if ((i0 & ~31u) < g.n_items) {
     const int c = (int)(i0 & ((1u << g.lg) - 1)) * 8;
     float sc[8], sh[8], k1[8], c0[8], db[8];
     scale_shift8(a, c, sc, sh);
@@ -313,6 +347,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnArgs a) {
     T* dzp = static_cast<T*>(a.dz) + c;
     const DropKey key = dropout_key(a.seed, a.site);
     for (uint32_t i = i0; i < g.n_items; i += g.stride) {
+      if (threadIdx.x == 0) prefetch_inputs<T, POST, true>(a, g, i + kPrefetchAhead * g.stride);
       uint32_t pix[K];
       float av[K][8], dy[K][8];
       Gather<T, POST>::run(a, g, key, i, c, sc, sh, pix, av, dy);
@@ -328,8 +363,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnArgs a) {
         Vec8<T>::store(dzp + (size_t)pix[k] * a.C, dz);
       }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&red_s[c + j], db[j]);
+    block_accumulate8(red_s, c, db, 1u << g.lg);
   }
   __syncthreads();
   for (int k = threadIdx.x; k < a.C; k += 256) atomicAdd(&a.dbias[k], red_s[k]);
@@ -375,12 +409,17 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const T* __restrict__ u, 
   for (int k = threadIdx.x; k < C; k += 256) red_s[k] = 0.f;
   __syncthreads();
   const uint32_t i0 = blockIdx.x * 256 + threadIdx.x;
-  if (i0 < n_items) {
+  if ((i0 & ~31u) < n_items) {
     const int c = (int)(i0 & ((1u << lg) - 1)) * 8;
     float db[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) db[j] = 0.f;
     for (uint32_t i = i0; i < n_items; i += gridDim.x * 256) {
+      if (threadIdx.x == 0) {
+        const uint32_t ip = i + kPrefetchAhead * gridDim.x * 256;
+        l2_prefetch_items(u, ip, 256, n_items, 8 * sizeof(T));
+        l2_prefetch_items(du, ip, 256, n_items, 8 * sizeof(T));
+      }
       const size_t off = (size_t)(i >> lg) * C + c;
       float uv[8], gv[8];
       Vec8<T>::load(u + off, uv);
@@ -392,8 +431,7 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const T* __restrict__ u, 
       }
       Vec8<T>::store(dz + off, gv);
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&red_s[c + j], db[j]);
+    block_accumulate8(red_s, c, db, 1u << lg);
   }
   __syncthreads();
   for (int k = threadIdx.x; k < C; k += 256) atomicAdd(&dbias[k], red_s[k]);

@@ -146,6 +146,38 @@ __device__ __forceinline__ void dropout_keep8(uint64_t seed, uint32_t site, uint
   dropout_keep8(dropout_key(seed, site), (uint32_t)vec_idx, thr16, keep);
 }
 
+// Streaming passes keep few bytes in flight per thread (registers go to per-channel constants), so one thread
+// per block asks the L2 to fetch the block's data a few iterations ahead (bulk prefetch, no smem, no
+// registers); the vector loads that follow then pay L2 instead of HBM latency.
+__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// prefetch `count` items of `item_bytes` starting at item `first` of a tensor holding `n_items`
+__device__ __forceinline__ void l2_prefetch_items(const void* base, uint32_t first, uint32_t count, uint32_t n_items,
+                                                  uint32_t item_bytes) {
+  if (first >= n_items) return;
+  if (first + count > n_items) count = n_items - first;
+  l2_prefetch(static_cast<const char*>(base) + (size_t)first * item_bytes, count * item_bytes);
+}
+constexpr uint32_t kPrefetchAhead = 4;   // grid-stride iterations
+
+// Per-channel block reduction used by the streaming passes: thread t owns channels [c, c+8) with
+// c = (t % G) * 8, so lanes l, l+G, l+2G, ... of a warp hold the same channels.  Fold those with shuffles and
+// let one lane per channel group touch shared memory (float atomicAdd on smem is a CAS loop).
+__device__ __forceinline__ void block_accumulate8(float* smem_acc, int c, const float (&v)[8], uint32_t G) {
+  float r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = v[j];
+  for (uint32_t o = 16; o >= G && o > 0; o >>= 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] += __shfl_xor_sync(0xffffffffu, r[j], o);
+  }
+  if ((threadIdx.x & 31) < G || G >= 32) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&smem_acc[c + j], r[j]);
+  }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -211,158 +211,3 @@ int wgrad_simt_launch(const WgradSimtArgs& a, int in_is_bf16, int dz_is_bf16, cu
 }
 
 }  // namespace rvip
-
-// =====================================================================================
-// Cin == 1 first layer (enc0.conv_a): K = 9, pure HBM streaming.  G = Cout/8 adjacent threads share a pixel,
-// each owns 8 output channels (its 72 weights live in registers), stores 16 B (bf16) / 32 B (fp32).
-// =====================================================================================
-namespace rvip {
-
-template <typename Tout>
-__global__ void __launch_bounds__(256) conv3x3_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                             const float* __restrict__ bias, Tout* __restrict__ out,
-                                                             double* __restrict__ stats, int B, int H, int W, int Cout,
-                                                             int want_stats) {
-  extern __shared__ float red_s[];  // [2][Cout]
-  const int G = Cout >> 3;
-  const size_t P = (size_t)B * H * W, n_items = P * G;
-  for (int k = threadIdx.x; k < 2 * Cout; k += 256) red_s[k] = 0.f;
-  __syncthreads();
-  const size_t i0 = (size_t)blockIdx.x * 256 + threadIdx.x;
-  if (i0 < n_items) {
-    const int c = (int)(i0 % G) * 8;
-    float wr[9][8], br[8], s[8], q[8];
-#pragma unroll
-    for (int t = 0; t < 9; ++t)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) wr[t][j] = w[t * Cout + c + j];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      br[j] = bias[c + j];
-      s[j] = q[j] = 0.f;
-    }
-    for (size_t i = i0; i < n_items; i += (size_t)gridDim.x * 256) {
-      const size_t p = i / G;
-      const int xx = (int)(p % W), yy = (int)((p / W) % H);
-      const float* img = x + (p - (size_t)yy * W - xx);
-      float acc[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = br[j];
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int y2 = yy + t / 3 - 1, x2 = xx + t % 3 - 1;
-        const float v = (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) ? __ldg(img + (size_t)y2 * W + x2) : 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[t][j], acc[j]);
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[j] = fmaxf(acc[j], 0.f);
-        const float r = round_to<Tout>(acc[j]);
-        s[j] += r;
-        q[j] = fmaf(r, r, q[j]);
-      }
-      Vec8<Tout>::store(out + p * Cout + c, acc);
-    }
-    if (want_stats) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        atomicAdd(&red_s[c + j], s[j]);
-        atomicAdd(&red_s[Cout + c + j], q[j]);
-      }
-    }
-  }
-  if (want_stats) {
-    __syncthreads();
-    for (int k = threadIdx.x; k < 2 * Cout; k += 256) atomicAdd(&stats[k], (double)red_s[k]);
-  }
-}
-
-// dW[tap][0][co] = sum_p x[p + off(tap)] * dz[p][co]
-template <typename Tdz>
-__global__ void __launch_bounds__(256) wgrad3x3_c1_kernel(const float* __restrict__ x, const Tdz* __restrict__ dz,
-                                                          float* __restrict__ dw, int B, int H, int W, int Cout) {
-  extern __shared__ float red_s[];  // [9][Cout]
-  const int G = Cout >> 3;
-  const size_t P = (size_t)B * H * W, n_items = P * G;
-  for (int k = threadIdx.x; k < 9 * Cout; k += 256) red_s[k] = 0.f;
-  __syncthreads();
-  const size_t i0 = (size_t)blockIdx.x * 256 + threadIdx.x;
-  if (i0 < n_items) {
-    const int c = (int)(i0 % G) * 8;
-    float acc[9][8];
-#pragma unroll
-    for (int t = 0; t < 9; ++t)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
-    for (size_t i = i0; i < n_items; i += (size_t)gridDim.x * 256) {
-      const size_t p = i / G;
-      const int xx = (int)(p % W), yy = (int)((p / W) % H);
-      const float* img = x + (p - (size_t)yy * W - xx);
-      float g[8];
-      Vec8<Tdz>::load(dz + p * Cout + c, g);
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int y2 = yy + t / 3 - 1, x2 = xx + t % 3 - 1;
-        const float v = (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) ? __ldg(img + (size_t)y2 * W + x2) : 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(v, g[j], acc[t][j]);
-      }
-    }
-    // lanes with equal (lane % G) own the same channels: fold inside the warp first
-#pragma unroll
-    for (int t = 0; t < 9; ++t)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float v = acc[t][j];
-        for (int o = 16; o >= G; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        acc[t][j] = v;
-      }
-    if ((threadIdx.x & 31) < G) {
-#pragma unroll
-      for (int t = 0; t < 9; ++t)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(&red_s[t * Cout + c + j], acc[t][j]);
-    }
-  }
-  __syncthreads();
-  for (int k = threadIdx.x; k < 9 * Cout; k += 256) atomicAdd(&dw[k], red_s[k]);
-}
-
-static int c1_grid(size_t n_items) {
-  size_t g = (n_items + 255) / 256;
-  const size_t cap = (size_t)kNumSMs * 4;
-  return (int)(g < cap ? (g ? g : 1) : cap);
-}
-
-int conv_c1_fwd_launch(const float* x, const float* w, const float* bias, void* out, double* stats, int B, int H, int W,
-                       int Cout, int want_stats, int out_is_bf16, cudaStream_t st) {
-  const int G = Cout / 8;
-  RVIP_REQUIRE(Cout % 8 == 0 && G <= 32 && (G & (G - 1)) == 0, "conv_c1: Cout=%d must be 8 * power of two <= 256", Cout);
-  const int grid = c1_grid((size_t)B * H * W * G);
-  if (out_is_bf16)
-    conv3x3_c1_fwd_kernel<__nv_bfloat16><<<grid, 256, 2 * Cout * sizeof(float), st>>>(
-        x, w, bias, static_cast<__nv_bfloat16*>(out), stats, B, H, W, Cout, want_stats);
-  else
-    conv3x3_c1_fwd_kernel<float><<<grid, 256, 2 * Cout * sizeof(float), st>>>(x, w, bias, static_cast<float*>(out),
-                                                                              stats, B, H, W, Cout, want_stats);
-  RVIP_LAUNCH_CHECK();
-  return 0;
-}
-
-int wgrad_c1_launch(const float* x, const void* dz, float* dw, int B, int H, int W, int Cout, int dz_is_bf16,
-                    cudaStream_t st) {
-  const int G = Cout / 8;
-  RVIP_REQUIRE(Cout % 8 == 0 && G <= 32 && (G & (G - 1)) == 0, "wgrad_c1: Cout=%d must be 8 * power of two <= 256", Cout);
-  const int grid = c1_grid((size_t)B * H * W * G);
-  if (dz_is_bf16)
-    wgrad3x3_c1_kernel<__nv_bfloat16><<<grid, 256, 9 * Cout * sizeof(float), st>>>(
-        x, static_cast<const __nv_bfloat16*>(dz), dw, B, H, W, Cout);
-  else
-    wgrad3x3_c1_kernel<float><<<grid, 256, 9 * Cout * sizeof(float), st>>>(x, static_cast<const float*>(dz), dw, B, H,
-                                                                           W, Cout);
-  RVIP_LAUNCH_CHECK();
-  return 0;
-}
-
-}  // namespace rvip

@@ -574,7 +574,7 @@ static int conv_forward(rvip_handle* h, Layer& l, const float* x, bool training,
     l.fwd.mode = mode;
     return timed(h, KC_CONV_FWD_TC, 1, st, [&] { return conv_tc_launch(l.fwd, l.fKC, l.fBN, st); });
   }
-  if (l.first && l.C0 == 1 && l.Cout <= 256) {
+  if (l.first && l.C0 == 1 && l.Cout <= 256 && l.W % 4 == 0) {
     return timed(h, KC_CONV_SIMT, 1, st, [&] {
       return conv_c1_fwd_launch(x, h->params + l.off_k, h->params + l.off_b, l.a, h->stats + 2 * l.off_stat, h->batch,
                                 l.H, l.W, l.Cout, mode == EPI_RELU_STATS, is_bf16(h), st);
@@ -700,7 +700,7 @@ static int backward_body(rvip_handle* h, const float* x, uint64_t seed, cudaStre
                                 : conv_tc_launch(l.dgrad, l.dKC, l.dBN, st);
           }))
         return 1;
-    } else if (l.first && l.C0 == 1 && l.Cout <= 256) {
+    } else if (l.first && l.C0 == 1 && l.Cout <= 256 && l.W % 4 == 0) {
       if (timed(h, KC_CONV_SIMT, 1, st, [&] {
             return wgrad_c1_launch(x, h->dz, h->grads + l.off_k, h->batch, l.H, l.W, l.Cout, bf, st);
           }))
