@@ -281,6 +281,7 @@ struct TensorInfo {
 struct ProfRec {
   int cls;
   cudaEvent_t e0, e1;
+  std::string tag;   // "<layer>:<op>" of the launch group
 };
 
 }  // namespace rvip
@@ -307,6 +308,8 @@ struct rvip_handle {
   // profiling
   int profile = 0;
   std::vector<rvip::ProfRec> prof;
+  std::string cur_tag;            // label attached to the launch groups recorded next
+  std::string detail;             // per-launch-group CSV of the last rvip_profile_read
   long long launches = 0;
 };
 
@@ -321,6 +324,7 @@ static int timed(rvip_handle* h, int cls, int n_launch, cudaStream_t st, F&& f) 
   if (!h->profile) return f();
   ProfRec r;
   r.cls = cls;
+  r.tag = h->cur_tag;
   RVIP_CUDA(cudaEventCreate(&r.e0));
   RVIP_CUDA(cudaEventCreate(&r.e1));
   RVIP_CUDA(cudaEventRecord(r.e0, st));
@@ -630,8 +634,10 @@ static int forward_body(rvip_handle* h, const float* x, bool training, uint64_t 
       return 1;
   }
   for (Layer& l : h->L) {
+    h->cur_tag = l.name + ":conv_fwd";
     if (conv_forward(h, l, x, training, st)) return 1;
     if (!l.bn) continue;
+    h->cur_tag = l.name + ":bn_fwd";
     BnArgs a;
     fill_bn(h, l, &a, training, seed);
     if (training) {
@@ -664,6 +670,7 @@ static int backward_body(rvip_handle* h, const float* x, uint64_t seed, cudaStre
   for (int i = (int)h->L.size() - 1; i >= 0; --i) {
     Layer& l = h->L[i];
     const size_t P = (size_t)h->batch * l.H * l.W;
+    h->cur_tag = l.name + ":bn_bwd";
     if (l.bn) {
       BnArgs a;
       fill_bn(h, l, &a, true, seed);
@@ -689,6 +696,7 @@ static int backward_body(rvip_handle* h, const float* x, uint64_t seed, cudaStre
                 [&] { return relu_bwd_launch(l.a, du, h->dz, h->grads + l.off_b, P, l.Cout, bf, st); }))
         return 1;
     }
+    h->cur_tag = l.name + ":conv_bwd";
     if (bf && !l.first) {
       if (timed(h, KC_CONV_WGRAD_TC, 1, st, [&] {
             return l.use_rwg ? wgrad_row_launch(l.rwg, l.rwBN, l.rwR, l.rwNst, st)
@@ -849,6 +857,7 @@ int rvip_train_step(rvip_handle* h, const float* x, const float* target, const f
   RVIP_REQUIRE(h && h->bound && h->training, "rvip_train_step: handle not bound for training");
   RVIP_REQUIRE(loss_kind != RVIP_LOSS_WEIGHTED || inplane, "rvip_train_step: weighted loss needs in-plane weights");
   cudaStream_t st = (cudaStream_t)stream;
+  h->cur_tag = "step:memset";
   if (timed(h, KC_MISC, 3, st, [&] {
         RVIP_CUDA(cudaMemsetAsync(h->grads, 0, sizeof(float) * h->n_params, st));
         RVIP_CUDA(cudaMemsetAsync(h->red, 0, sizeof(double) * 2 * h->n_stat_ch, st));
@@ -863,6 +872,7 @@ int rvip_train_step(rvip_handle* h, const float* x, const float* target, const f
   a.dy = h->head_dy;
   a.dw = h->grads + h->head_k; a.db = h->grads + h->head_b;
   a.loss_acc = loss_out;
+  h->cur_tag = "head:loss";
   if (timed(h, KC_HEAD, 1, st, [&] { return head_launch(a, 1, is_bf16(h), st); })) return 1;
   return backward_body(h, x, seed, st);
 }
@@ -871,6 +881,7 @@ int rvip_adam_step(rvip_handle* h, float* m, float* v, float lr, float beta1, fl
                    float grad_scale, void* stream) {
   RVIP_REQUIRE(h && h->bound && h->training && step >= 1, "rvip_adam_step: handle not bound for training");
   cudaStream_t st = (cudaStream_t)stream;
+  h->cur_tag = "step:adam";
   const double lr_t = (double)lr * std::sqrt(1.0 - std::pow((double)beta2, (double)step)) /
                       (1.0 - std::pow((double)beta1, (double)step));
   if (timed(h, KC_OPTIM, 1, st, [&] {
@@ -957,10 +968,14 @@ int rvip_profile_read(rvip_handle* h, float ms[RVIP_NUM_KERNEL_CLASSES], long lo
     ms[i] = 0.f;
     launches[i] = 0;
   }
+  h->detail.clear();
   for (auto& r : h->prof) {
     RVIP_CUDA(cudaEventSynchronize(r.e1));
     float t = 0.f;
     RVIP_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    char line[256];
+    snprintf(line, sizeof(line), "%s,%s,%.5f\n", kClassNames[r.cls], r.tag.c_str(), t);
+    h->detail += line;
     ms[r.cls] += t;
     launches[r.cls] += 1;
     cudaEventDestroy(r.e0);
@@ -969,6 +984,7 @@ int rvip_profile_read(rvip_handle* h, float ms[RVIP_NUM_KERNEL_CLASSES], long lo
   h->prof.clear();
   return 0;
 }
+const char* rvip_profile_detail(const rvip_handle* h) { return h->detail.c_str(); }
 const char* rvip_kernel_class_name(int cls) {
   return (cls >= 0 && cls < RVIP_NUM_KERNEL_CLASSES) ? kClassNames[cls] : "?";
 }

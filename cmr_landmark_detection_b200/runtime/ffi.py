@@ -66,6 +66,7 @@ _SIGS = {
     'rvip_dropout_site': (_I, [_VP, C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(_F)]),
     'rvip_profile': (_I, [_VP, _I]),
     'rvip_profile_read': (_I, [_VP, C.POINTER(_F * NUM_KERNEL_CLASSES), C.POINTER(_LL * NUM_KERNEL_CLASSES)]),
+    'rvip_profile_detail': (C.c_char_p, [_VP]),
     'rvip_kernel_class_name': (C.c_char_p, [_I]),
     'rvip_launch_count': (_LL, [_VP]),
     'rvip_conv3x3_tc': (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _I, _VP, _I, _I, _I, _I, _I, _VP]),

@@ -567,5 +567,11 @@ class RvipUNet:
         ffi.check(L.rvip_profile_read(self._bindings[(batch, training)].h, C.byref(ms), C.byref(n)))
         return {L.rvip_kernel_class_name(i).decode(): (float(ms[i]), int(n[i])) for i in range(ffi.NUM_KERNEL_CLASSES)}
 
+    def profile_detail(self, batch: int, training: bool):
+        """Per launch group (class, 'layer:op', ms) of the log consumed by the last profile_read()."""
+        txt = ffi.lib().rvip_profile_detail(self._bindings[(batch, training)].h).decode()
+        rows = [ln.split(',') for ln in txt.splitlines() if ln]
+        return [(c, tag, float(ms)) for c, tag, ms in rows]
+
     def launch_count(self) -> int:
         return int(sum(ffi.lib().rvip_launch_count(b.h) for b in self._bindings.values()))

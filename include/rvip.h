@@ -111,6 +111,8 @@ int rvip_dropout_site(const rvip_handle* h, const char* name, uint32_t* site, fl
 #define RVIP_NUM_KERNEL_CLASSES 10
 int rvip_profile(rvip_handle* h, int enable);
 int rvip_profile_read(rvip_handle* h, float ms[RVIP_NUM_KERNEL_CLASSES], long long launches[RVIP_NUM_KERNEL_CLASSES]);
+/* "class,layer:op,ms" lines, one per launch group, of the log consumed by the last rvip_profile_read */
+const char* rvip_profile_detail(const rvip_handle* h);
 const char* rvip_kernel_class_name(int cls);
 long long rvip_launch_count(const rvip_handle* h); /* kernels launched by this handle so far */
 

@@ -111,8 +111,19 @@ def test_train_step_matches_oracle(precision, dim, depth, batch):
         for (name, is_state, off, shape), a, b, w0, rg in zip(model.tensors, after, stepped, ws, ref['grads']):
             if is_state:
                 continue
-            big = np.abs(rg) > 1e-3 * np.abs(rg).max()
-            assert np.allclose((a - w0)[big], (b - w0)[big], rtol=5e-3, atol=5e-6), name
+            # first Adam step: upd = lr * g / (|g| + eps'), eps' = eps / sqrt(1 - beta2) = 3.16e-6, so an element's
+            # update moves by lr * eps' * dg / (|g| + eps')^2 when its gradient moves by dg.  The norm-wise checks
+            # above hold the tensor to rel-L2 1e-4; single elements carry fp32 summation-order noise of about
+            # 1e-6 * sum|terms| ~ 1e-4 * max|g| (atomics), which is what dg allows for.
+            eps_h = 1e-7 / np.sqrt(1 - 0.999)
+            gabs = np.abs(rg.astype(np.float64))
+            big = gabs > 1e-3 * gabs.max()
+            dg = 2e-2 * gabs + 2e-4 * gabs.max()
+            tol = 5e-3 * np.abs(b - w0) + 1e-3 * eps_h * dg / (gabs + eps_h) ** 2 + 1e-7
+            viol = (np.abs((a - w0) - (b - w0)) / tol)[big]
+            k = int(np.argmax(viol))
+            assert viol[k] <= 1.0, (name, float(viol[k]), float(gabs[big][k]), float(gabs.max()),
+                                    float((a - w0)[big][k]), float((b - w0)[big][k]))
     if True:
         # Adam on the device gradients themselves (the optimizer kernel is exact given its input)
         gl = [None if st else g[off:off + int(np.prod(shp))].reshape(shp) for (nm, st, off, shp) in model.tensors]
