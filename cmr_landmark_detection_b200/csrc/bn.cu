@@ -85,41 +85,6 @@ __device__ __forceinline__ void upsampled_pixels(const BnArgs& a, uint32_t p, ui
   q[0] = base; q[1] = base + 1; q[2] = base + 2 * a.W; q[3] = base + 2 * a.W + 1;
 }
 
-// L2 prefetch of what the block (256 consecutive items starting at item `i`) will read: `a` always, plus the
-// gradient sources when BWD.  Called by thread 0 for the iteration kPrefetchAhead grid-strides ahead.
-template <typename T, int POST, bool BWD>
-__device__ __forceinline__ void prefetch_inputs(const BnArgs& a, const Geo& g, uint32_t i) {
-  if (i >= g.n_items) return;
-  const uint32_t pb = a.C * sizeof(T);                 // bytes per pixel
-  const uint32_t npx = 256u >> g.lg ? 256u >> g.lg : 1u;
-  const uint32_t P = (uint32_t)a.B * a.H * a.W;
-  if (POST == POST_NONE || POST == POST_DROPOUT) {
-    const uint32_t p = i >> g.lg;
-    l2_prefetch_items(a.a, p, npx, P, pb);
-    if (BWD) l2_prefetch_items(a.g0, p, npx, P, pb);
-  } else if (POST == POST_UPSAMPLE) {
-    const uint32_t p = i >> g.lg;
-    l2_prefetch_items(a.a, p, npx, P, pb);
-    if (BWD) {
-      uint32_t q[4];
-      upsampled_pixels(a, p, q);
-      l2_prefetch_items(a.g0, q[0], 2 * npx, 4 * P, pb);
-      l2_prefetch_items(a.g0, q[2], 2 * npx, 4 * P, pb);
-    }
-  } else {
-    const uint32_t win = i >> g.lg;
-    uint32_t p[4];
-    window_pixels(a, win, p);
-    l2_prefetch_items(a.a, p[0], 2 * npx, P, pb);
-    l2_prefetch_items(a.a, p[2], 2 * npx, P, pb);
-    if (BWD) {
-      l2_prefetch_items(a.g0, p[0], 2 * npx, P, pb);
-      l2_prefetch_items(a.g0, p[2], 2 * npx, P, pb);
-      l2_prefetch_items(a.g1, win, npx, P / 4, pb);
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------- forward apply
 template <typename T, int POST>
 __global__ void __launch_bounds__(256) bn_apply_kernel(BnArgs a) {
@@ -134,7 +99,6 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(BnArgs a) {
   T* y2 = static_cast<T*>(a.y2) + c;
   const DropKey key = dropout_key(a.seed, a.site);
   for (uint32_t i = i0; i < g.n_items; i += g.stride) {
-    if (threadIdx.x == 0) prefetch_inputs<T, POST, false>(a, g, i + kPrefetchAhead * g.stride);
     if (POST == POST_NONE || POST == POST_DROPOUT) {
       const size_t off = (size_t)(i >> g.lg) * a.C;
       float v[8];
@@ -277,9 +241,11 @@ struct Gather {
   }
 };
 
-// pass 1: red[c] += sum dy, red[C + c] += sum dy * a   (raw a; normalised in pass 2)
+// pass 1: red[stripe][c] += sum dy, red[stripe][C + c] += sum dy * a   (raw a; normalised by the finalize kernel).
+// Blocks spread their double atomics over kRedStripes copies: ~1200 blocks adding to ONE copy serialise in the L2
+// atomic unit for ~17 us (profiles/microbench/atomics.cu), 16 copies cost nothing measurable.
 template <typename T, int POST>
-__global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 5) bn_bwd_reduce_kernel(BnArgs a) {
+__global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_reduce_kernel(BnArgs a) {
   extern __shared__ float red_s[];  // [2][C]
   constexpr int K = Gather<T, POST>::K;
   const Geo g = make_geo(a, POST == POST_POOL);
@@ -294,7 +260,6 @@ __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 5) bn_bwd_reduce_
     for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
     const DropKey key = dropout_key(a.seed, a.site);
     for (uint32_t i = i0; i < g.n_items; i += g.stride) {
-      if (threadIdx.x == 0) prefetch_inputs<T, POST, true>(a, g, i + kPrefetchAhead * g.stride);
       uint32_t pix[K];
       float av[K][8], dy[K][8];
       Gather<T, POST>::run(a, g, key, i, c, sc, sh, pix, av, dy);
@@ -310,44 +275,62 @@ __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 5) bn_bwd_reduce_
     block_accumulate8(red_s + a.C, c, s2, 1u << g.lg);
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < 2 * a.C; k += 256) atomicAdd(&a.red[k], (double)red_s[k]);
+  double* dst = a.red + (size_t)(blockIdx.x % kRedStripes) * 2 * a.C;
+  for (int k = threadIdx.x; k < 2 * a.C; k += 256) atomicAdd(&dst[k], (double)red_s[k]);
 }
 
-// pass 2: dz, conv-bias gradient, and (block 0) dgamma / dbeta
+// between the passes: one thread per channel folds the stripes and derives the three coefficients of
+//   dz = [a>0] * ( sc*dy - k1*a + c0 )   plus dgamma / dbeta   (double arithmetic once per channel, not per thread)
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ red, const float* __restrict__ gamma,
+                                       const float* __restrict__ mean, const float* __restrict__ rstd, double P,
+                                       float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                       int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+  for (int s = 0; s < kRedStripes; ++s) {
+    s1 += red[(size_t)s * 2 * C + c];
+    s2 += red[(size_t)s * 2 * C + C + c];
+  }
+  const double mu = mean[c], r = rstd[c], sc = (double)gamma[c] * r;
+  const double sda = r * (s2 - mu * s1);          // sum dy * ahat
+  const double m1 = s1 / P, m2 = sda / P;
+  const double k1 = sc * r * m2;
+  coef[c] = (float)sc;
+  coef[C + c] = (float)k1;
+  coef[2 * C + c] = (float)(k1 * mu - sc * m1);
+  dbeta[c] = (float)s1;
+  dgamma[c] = (float)sda;
+}
+
+// pass 2: dz and the conv-bias gradient
 template <typename T, int POST>
 __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_apply_kernel(BnArgs a) {
   extern __shared__ float red_s[];  // [C] bias-gradient partials
   constexpr int K = Gather<T, POST>::K;
   const Geo g = make_geo(a, POST == POST_POOL);
-  const double P = (double)a.B * a.H * a.W;
   for (int k = threadIdx.x; k < a.C; k += 256) red_s[k] = 0.f;
-  if (blockIdx.x == 0) {
-    for (int k = threadIdx.x; k < a.C; k += 256) {
-      const double s1 = a.red[k], s2 = a.red[a.C + k];
-      a.dbeta[k] = (float)s1;
-      a.dgamma[k] = (float)((double)a.rstd[k] * (s2 - (double)a.mean[k] * s1));   // sum dy * ahat
-    }
-  }
   __syncthreads();
   const uint32_t i0 = blockIdx.x * 256 + threadIdx.x;
   if ((i0 & ~31u) < g.n_items) {
     const int c = (int)(i0 & ((1u << g.lg) - 1)) * 8;
     float sc[8], sh[8], k1[8], c0[8], db[8];
-    scale_shift8(a, c, sc, sh);
+    if (POST == POST_POOL) scale_shift8(a, c, sc, sh);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const double s1 = a.red[c + j], s2 = a.red[a.C + c + j];
-      const double mu = a.mean[c + j], r = a.rstd[c + j];
-      const double m1 = s1 / P, m2 = r * (s2 - mu * s1) / P;   // mean(dy), mean(dy * ahat)
-      const double k = (double)sc[j] * r * m2;
-      k1[j] = (float)k;
-      c0[j] = (float)(k * mu - (double)sc[j] * m1);
-      db[j] = 0.f;
+    for (int h = 0; h < 2; ++h) {
+      const float4 t0 = *reinterpret_cast<const float4*>(a.coef + c + 4 * h);
+      const float4 t1 = *reinterpret_cast<const float4*>(a.coef + a.C + c + 4 * h);
+      const float4 t2 = *reinterpret_cast<const float4*>(a.coef + 2 * a.C + c + 4 * h);
+      if (POST != POST_POOL) { sc[4 * h] = t0.x; sc[4 * h + 1] = t0.y; sc[4 * h + 2] = t0.z; sc[4 * h + 3] = t0.w; }
+      k1[4 * h] = t1.x; k1[4 * h + 1] = t1.y; k1[4 * h + 2] = t1.z; k1[4 * h + 3] = t1.w;
+      c0[4 * h] = t2.x; c0[4 * h + 1] = t2.y; c0[4 * h + 2] = t2.z; c0[4 * h + 3] = t2.w;
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) db[j] = 0.f;
     T* dzp = static_cast<T*>(a.dz) + c;
     const DropKey key = dropout_key(a.seed, a.site);
     for (uint32_t i = i0; i < g.n_items; i += g.stride) {
-      if (threadIdx.x == 0) prefetch_inputs<T, POST, true>(a, g, i + kPrefetchAhead * g.stride);
       uint32_t pix[K];
       float av[K][8], dy[K][8];
       Gather<T, POST>::run(a, g, key, i, c, sc, sh, pix, av, dy);
@@ -374,7 +357,8 @@ static int bn_bwd_t(const BnArgs& a, cudaStream_t st) {
   const size_t P = (size_t)a.B * a.H * a.W;
   const int G = a.C / 8;
   const size_t n = (a.post == POST_POOL ? P / 4 : P) * G;
-  const int grid = ew_grid(n, 8);
+  // persistent grids: every block ends with C global atomics, so few, long-lived blocks
+  const int grid = ew_grid(n, a.post == POST_POOL ? 2 : 4);
   const size_t sm = (WHICH == 0 ? 2 : 1) * a.C * sizeof(float);
 #define RVIP_BWD(POSTV)                                                 \
   if (WHICH == 0)                                                       \
@@ -397,6 +381,10 @@ int bn_bwd_reduce_launch(const BnArgs& a, int is_bf16, cudaStream_t st) {
 }
 int bn_bwd_apply_launch(const BnArgs& a, int is_bf16, cudaStream_t st) {
   if (check_bn(a)) return 1;
+  const double P = (double)a.B * a.H * a.W;
+  bn_bwd_finalize_kernel<<<(a.C + 127) / 128, 128, 0, st>>>(a.red, a.gamma, a.mean, a.rstd, P, a.coef, a.dgamma,
+                                                           a.dbeta, a.C);
+  RVIP_LAUNCH_CHECK();
   return is_bf16 ? bn_bwd_t<__nv_bfloat16, 1>(a, st) : bn_bwd_t<float, 1>(a, st);
 }
 
@@ -415,11 +403,6 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const T* __restrict__ u, 
 #pragma unroll
     for (int j = 0; j < 8; ++j) db[j] = 0.f;
     for (uint32_t i = i0; i < n_items; i += gridDim.x * 256) {
-      if (threadIdx.x == 0) {
-        const uint32_t ip = i + kPrefetchAhead * gridDim.x * 256;
-        l2_prefetch_items(u, ip, 256, n_items, 8 * sizeof(T));
-        l2_prefetch_items(du, ip, 256, n_items, 8 * sizeof(T));
-      }
       const size_t off = (size_t)(i >> lg) * C + c;
       float uv[8], gv[8];
       Vec8<T>::load(u + off, uv);
@@ -444,7 +427,7 @@ int relu_bwd_launch(const void* u, const void* du, void* dz, float* dbias, size_
   uint32_t lg = 0;
   while ((1 << lg) < G) ++lg;
   const uint32_t n = (uint32_t)(pixels * G);
-  const int grid = ew_grid(n, 8);
+  const int grid = ew_grid(n, 4);
   if (is_bf16)
     relu_bwd_kernel<__nv_bfloat16><<<grid, 256, C * sizeof(float), st>>>(
         static_cast<const __nv_bfloat16*>(u), static_cast<const __nv_bfloat16*>(du), static_cast<__nv_bfloat16*>(dz),

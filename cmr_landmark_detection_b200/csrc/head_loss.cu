@@ -119,15 +119,21 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
     }
   }
   if (TRAIN) {
+    // lanes l, l+G, l+2G, ... hold the same channels: fold them with shuffles so that G lanes per warp (not 32)
+    // touch the shared accumulators (float atomicAdd on smem is a CAS loop; 64-way contention cost ~100 us)
+    const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
 #pragma unroll
-      for (int k = 0; k < NCT; ++k)
-        if (k < NC) atomicAdd(&dw_s[(c + j) * NC + k], dw_acc[j][k]);
-    if (cg == 0) {
+      for (int k = 0; k < NCT; ++k) {
+        float v = dw_acc[j][k];
+        for (int o = 16; o >= G; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (k < NC && lane < G) atomicAdd(&dw_s[(c + j) * NC + k], v);
+      }
 #pragma unroll
-      for (int k = 0; k < NCT; ++k)
-        if (k < NC) atomicAdd(&db_s[k], db_acc[k]);
+    for (int k = 0; k < NCT; ++k) {
+      const float v = warp_sum(db_acc[k]);     // only the cg == 0 lanes carry non-zero partials
+      if (k < NC && lane == 0) atomicAdd(&db_s[k], v);
     }
     float l = warp_sum(loss_acc);
     if ((threadIdx.x & 31) == 0) atomicAdd(&loss_s, (double)l);
@@ -145,7 +151,7 @@ int head_launch(const HeadArgs& a, int training, int is_bf16, cudaStream_t st) {
   RVIP_REQUIRE(a.NC >= 1 && a.NC <= kMaxNC, "head: MASK_CLASSES=%d not in [1,%d]", a.NC, kMaxNC);
   const size_t n = (size_t)a.B * a.H * a.W * G;
   size_t g = (n + 255) / 256;
-  const size_t cap = (size_t)kNumSMs * 8;
+  const size_t cap = (size_t)kNumSMs * 4;   // every block ends with Cin*NC + NC + 1 global atomics: keep them few
   const int grid = (int)(g < cap ? (g ? g : 1) : cap);
   const size_t smem = (size_t)(2 * (a.Cin * a.NC + a.NC)) * sizeof(float);
 #define RVIP_HEAD(NCV)                                                        \

@@ -34,6 +34,7 @@ int wgrad_c1_launch(const float* x, const void* dz, float* dw, int B, int H, int
                     cudaStream_t st);
 
 // ------------------------------------------------------------------ BatchNorm passes (bn.cu)
+constexpr int kRedStripes = 16;
 enum PostOp { POST_NONE = 0, POST_DROPOUT = 1, POST_POOL = 2, POST_UPSAMPLE = 3 };
 
 struct BnArgs {
@@ -54,7 +55,8 @@ struct BnArgs {
   // backward inputs
   const void* g0;          // NONE/DROPOUT: dL/d(y after dropout) [B,H,W,C]; POOL: d skip; UPSAMPLE: d(up) [B,2H,2W,C]
   const void* g1;          // POOL: d pooled [B,H/2,W/2,C]
-  double* red;             // [2][C]: sum dy, sum dy*ahat
+  double* red;             // [kRedStripes][2][C]: sum dy, sum dy*a (striped partial sums)
+  float* coef;             // [3][C]: sc, k1, c0 of dz = [a>0](sc*dy - k1*a + c0), written between the passes
   void* dz;                // [B,H,W,C]
   float* dgamma;
   float* dbeta;
@@ -66,7 +68,7 @@ int bn_eval_prepare_launch(const float* mov_mean, const float* mov_var, float* m
                            cudaStream_t st);
 int bn_apply_launch(const BnArgs& a, int is_bf16, cudaStream_t st);
 int bn_bwd_reduce_launch(const BnArgs& a, int is_bf16, cudaStream_t st);
-int bn_bwd_apply_launch(const BnArgs& a, int is_bf16, cudaStream_t st);
+int bn_bwd_apply_launch(const BnArgs& a, int is_bf16, cudaStream_t st);   // finalize (coef, dgamma, dbeta) + apply
 // conv + ReLU without BN (decoder up-conv): dz = du * [u > 0], dbias = sum dz
 int relu_bwd_launch(const void* u, const void* du, void* dz, float* dbias, size_t pixels, int C, int is_bf16,
                     cudaStream_t st);

@@ -297,7 +297,7 @@ struct rvip_handle {
   int batch = 0, training = 0, bound = 0;
   float *params = nullptr, *grads = nullptr, *bn_state = nullptr;
   uint8_t* ws = nullptr;
-  float *mean = nullptr, *rstd = nullptr;
+  float *mean = nullptr, *rstd = nullptr, *coef = nullptr;
   double *stats = nullptr, *red = nullptr;
   void *packed = nullptr, *dz = nullptr, *head_dy = nullptr;
   rvip::PackEntry* pack_table_dev = nullptr;
@@ -477,8 +477,10 @@ static size_t carve(rvip_handle* h, uint8_t* base, int B, int training, bool ass
     if (assign) h->rstd = (float*)p;
     p = cv.take(sizeof(double) * 2 * h->n_stat_ch);
     if (assign) h->stats = (double*)p;
-    p = cv.take(sizeof(double) * 2 * h->n_stat_ch);
+    p = cv.take(sizeof(double) * 2 * kRedStripes * h->n_stat_ch);
     if (assign) h->red = (double*)p;
+    p = cv.take(sizeof(float) * 3 * h->n_stat_ch);
+    if (assign) h->coef = (float*)p;
     p = cv.take((is_bf16(h) ? 2 : 4) * (size_t)std::max<long long>(h->n_packed, 1));
     if (assign) h->packed = p;
   }
@@ -680,12 +682,13 @@ static int backward_body(rvip_handle* h, const float* x, uint64_t seed, cudaStre
         a.g0 = buffer_of(h, l.g0_layer, l.g0_which);
         if (l.post == POST_POOL) a.g1 = buffer_of(h, l.g1_layer, 3);
       }
-      a.red = h->red + 2 * l.off_stat;
+      a.red = h->red + 2 * kRedStripes * l.off_stat;
+      a.coef = h->coef + 3 * l.off_stat;
       a.dz = h->dz;
       a.dgamma = h->grads + l.off_g;
       a.dbeta = h->grads + l.off_be;
       a.dbias = h->grads + l.off_b;
-      if (timed(h, KC_BN_BWD, 2, st, [&] {
+      if (timed(h, KC_BN_BWD, 3, st, [&] {
             if (bn_bwd_reduce_launch(a, bf, st)) return 1;
             return bn_bwd_apply_launch(a, bf, st);
           }))
@@ -860,7 +863,7 @@ int rvip_train_step(rvip_handle* h, const float* x, const float* target, const f
   h->cur_tag = "step:memset";
   if (timed(h, KC_MISC, 3, st, [&] {
         RVIP_CUDA(cudaMemsetAsync(h->grads, 0, sizeof(float) * h->n_params, st));
-        RVIP_CUDA(cudaMemsetAsync(h->red, 0, sizeof(double) * 2 * h->n_stat_ch, st));
+        RVIP_CUDA(cudaMemsetAsync(h->red, 0, sizeof(double) * 2 * kRedStripes * h->n_stat_ch, st));
         RVIP_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(double), st));
         return 0;
       }))
