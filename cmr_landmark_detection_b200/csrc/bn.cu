@@ -21,27 +21,7 @@ __device__ __forceinline__ void scale_shift8(const BnArgs& a, int c, float (&sc)
   }
 }
 
-// ------------------------------------------------------------------------------------- finalize
-__global__ void bn_finalize_kernel(const double* stats, double count, float* mean, float* rstd, float* mm, float* mv,
-                                   int C, float momentum, float eps) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const double m = stats[c] / count;
-  double var = stats[C + c] / count - m * m;   // biased batch variance
-  if (var < 0) var = 0;
-  mean[c] = (float)m;
-  rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
-  // moving statistics: momentum 0.99, unbiased variance (TF fused batch norm)
-  const double unb = count > 1 ? var * count / (count - 1) : var;
-  mm[c] = momentum * mm[c] + (1.f - momentum) * (float)m;
-  mv[c] = momentum * mv[c] + (1.f - momentum) * (float)unb;
-}
-int bn_finalize_launch(const double* stats, double count, float* mean, float* rstd, float* mm, float* mv, int C,
-                       float momentum, float eps, cudaStream_t st) {
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats, count, mean, rstd, mm, mv, C, momentum, eps);
-  RVIP_LAUNCH_CHECK();
-  return 0;
-}
+// ------------------------------------------------------------------------------------- inference statistics
 __global__ void bn_eval_prepare_kernel(const float* mm, const float* mv, float* mean, float* rstd, int n, float eps) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n) return;
@@ -86,14 +66,47 @@ __device__ __forceinline__ void upsampled_pixels(const BnArgs& a, uint32_t p, ui
 }
 
 // ------------------------------------------------------------------------------------- forward apply
+// Training: every block first derives mean / rstd of all C channels from the conv epilogue's sum / sum^2
+// (a.stats, double) into shared memory -- the former one-block bn_finalize launch, folded in; block 0 also
+// publishes mean / rstd for the backward pass and updates the moving statistics (momentum 0.99, unbiased
+// variance: TF fused batch norm).  Inference: mean / rstd were prepared from the moving statistics.
 template <typename T, int POST>
 __global__ void __launch_bounds__(256) bn_apply_kernel(BnArgs a) {
+  extern __shared__ float coef_s[];   // [2][C]: scale, shift
+  for (int k = threadIdx.x; k < a.C; k += 256) {
+    float m, r;
+    if (a.stats) {
+      const double mean = a.stats[k] * a.inv_count;
+      double var = a.stats[a.C + k] * a.inv_count - mean * mean;   // biased batch variance
+      if (var < 0) var = 0;
+      m = (float)mean;
+      r = (float)(1.0 / sqrt(var + (double)a.eps));
+      if (blockIdx.x == 0) {
+        a.mean_out[k] = m;
+        a.rstd_out[k] = r;
+        const double unb = a.count > 1.0 ? var * a.count / (a.count - 1.0) : var;
+        a.mov_mean[k] = a.momentum * a.mov_mean[k] + (1.f - a.momentum) * m;
+        a.mov_var[k] = a.momentum * a.mov_var[k] + (1.f - a.momentum) * (float)unb;
+      }
+    } else {
+      m = a.mean[k];
+      r = a.rstd[k];
+    }
+    const float sck = a.gamma[k] * r;
+    coef_s[k] = sck;
+    coef_s[a.C + k] = fmaf(-m, sck, a.beta[k]);
+  }
+  __syncthreads();
   const Geo g = make_geo(a, POST == POST_POOL);
   const uint32_t i0 = blockIdx.x * 256 + threadIdx.x;
   if (i0 >= g.n_items) return;
   const int c = (int)(i0 & ((1u << g.lg) - 1)) * 8;
   float sc[8], sh[8];
-  scale_shift8(a, c, sc, sh);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = coef_s[c + j];
+    sh[j] = coef_s[a.C + c + j];
+  }
   const T* av = static_cast<const T*>(a.a) + c;
   T* y = static_cast<T*>(a.y) + c;
   T* y2 = static_cast<T*>(a.y2) + c;
@@ -155,11 +168,12 @@ static int bn_apply_t(const BnArgs& a, cudaStream_t st) {
   const int G = a.C / 8;
   const size_t n = (a.post == POST_POOL ? P / 4 : P) * G;
   const int grid = ew_grid(n, 16);
+  const size_t sm = 2 * a.C * sizeof(float);
   switch (a.post) {
-    case POST_NONE: bn_apply_kernel<T, POST_NONE><<<grid, 256, 0, st>>>(a); break;
-    case POST_DROPOUT: bn_apply_kernel<T, POST_DROPOUT><<<grid, 256, 0, st>>>(a); break;
-    case POST_POOL: bn_apply_kernel<T, POST_POOL><<<grid, 256, 0, st>>>(a); break;
-    default: bn_apply_kernel<T, POST_UPSAMPLE><<<grid, 256, 0, st>>>(a); break;
+    case POST_NONE: bn_apply_kernel<T, POST_NONE><<<grid, 256, sm, st>>>(a); break;
+    case POST_DROPOUT: bn_apply_kernel<T, POST_DROPOUT><<<grid, 256, sm, st>>>(a); break;
+    case POST_POOL: bn_apply_kernel<T, POST_POOL><<<grid, 256, sm, st>>>(a); break;
+    default: bn_apply_kernel<T, POST_UPSAMPLE><<<grid, 256, sm, st>>>(a); break;
   }
   RVIP_LAUNCH_CHECK();
   return 0;
@@ -279,52 +293,51 @@ __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_reduce_
   for (int k = threadIdx.x; k < 2 * a.C; k += 256) atomicAdd(&dst[k], (double)red_s[k]);
 }
 
-// between the passes: one thread per channel folds the stripes and derives the three coefficients of
-//   dz = [a>0] * ( sc*dy - k1*a + c0 )   plus dgamma / dbeta   (double arithmetic once per channel, not per thread)
-__global__ void bn_bwd_finalize_kernel(const double* __restrict__ red, const float* __restrict__ gamma,
-                                       const float* __restrict__ mean, const float* __restrict__ rstd, double P,
-                                       float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                       int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s1 = 0.0, s2 = 0.0;
-#pragma unroll
-  for (int s = 0; s < kRedStripes; ++s) {
-    s1 += red[(size_t)s * 2 * C + c];
-    s2 += red[(size_t)s * 2 * C + C + c];
-  }
-  const double mu = mean[c], r = rstd[c], sc = (double)gamma[c] * r;
-  const double sda = r * (s2 - mu * s1);          // sum dy * ahat
-  const double m1 = s1 / P, m2 = sda / P;
-  const double k1 = sc * r * m2;
-  coef[c] = (float)sc;
-  coef[C + c] = (float)k1;
-  coef[2 * C + c] = (float)(k1 * mu - sc * m1);
-  dbeta[c] = (float)s1;
-  dgamma[c] = (float)sda;
-}
-
-// pass 2: dz and the conv-bias gradient
+// pass 2: dz and the conv-bias gradient.  Prologue (every block, one thread per channel): fold the stripes and
+// derive the coefficients of  dz = [a>0] * ( sc*dy - k1*a + c0 )  in double, once per channel; block 0 also
+// writes dgamma / dbeta.
 template <typename T, int POST>
 __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_apply_kernel(BnArgs a) {
-  extern __shared__ float red_s[];  // [C] bias-gradient partials
+  extern __shared__ float red_s[];  // [C] bias-gradient partials, then [4][C] sc, k1, c0, shift
+  float* coef_s = red_s + a.C;
   constexpr int K = Gather<T, POST>::K;
   const Geo g = make_geo(a, POST == POST_POOL);
-  for (int k = threadIdx.x; k < a.C; k += 256) red_s[k] = 0.f;
+  const double P = (double)a.B * a.H * a.W;
+  for (int k = threadIdx.x; k < a.C; k += 256) {
+    red_s[k] = 0.f;
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int s = 0; s < kRedStripes; ++s) {
+      s1 += a.red[(size_t)s * 2 * a.C + k];
+      s2 += a.red[(size_t)s * 2 * a.C + a.C + k];
+    }
+    const double mu = a.mean[k], r = a.rstd[k], sck = (double)a.gamma[k] * r;
+    const double sda = r * (s2 - mu * s1);          // sum dy * ahat
+    const double k1 = sck * r * (sda / P);
+    coef_s[k] = (float)sck;
+    coef_s[a.C + k] = (float)k1;
+    coef_s[2 * a.C + k] = (float)(k1 * mu - sck * (s1 / P));
+    coef_s[3 * a.C + k] = fmaf(-a.mean[k], a.gamma[k] * a.rstd[k], a.beta[k]);
+    if (blockIdx.x == 0) {
+      a.dbeta[k] = (float)s1;
+      a.dgamma[k] = (float)sda;
+    }
+  }
   __syncthreads();
   const uint32_t i0 = blockIdx.x * 256 + threadIdx.x;
   if ((i0 & ~31u) < g.n_items) {
     const int c = (int)(i0 & ((1u << g.lg) - 1)) * 8;
     float sc[8], sh[8], k1[8], c0[8], db[8];
-    if (POST == POST_POOL) scale_shift8(a, c, sc, sh);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const float4 t0 = *reinterpret_cast<const float4*>(a.coef + c + 4 * h);
-      const float4 t1 = *reinterpret_cast<const float4*>(a.coef + a.C + c + 4 * h);
-      const float4 t2 = *reinterpret_cast<const float4*>(a.coef + 2 * a.C + c + 4 * h);
-      if (POST != POST_POOL) { sc[4 * h] = t0.x; sc[4 * h + 1] = t0.y; sc[4 * h + 2] = t0.z; sc[4 * h + 3] = t0.w; }
-      k1[4 * h] = t1.x; k1[4 * h + 1] = t1.y; k1[4 * h + 2] = t1.z; k1[4 * h + 3] = t1.w;
-      c0[4 * h] = t2.x; c0[4 * h + 1] = t2.y; c0[4 * h + 2] = t2.z; c0[4 * h + 3] = t2.w;
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = coef_s[c + j];
+      k1[j] = coef_s[a.C + c + j];
+      c0[j] = coef_s[2 * a.C + c + j];
+      if (POST == POST_POOL) {
+        // the pooling argmax replays the forward values: same float expressions as scale_shift8
+        sc[j] = a.gamma[c + j] * a.rstd[c + j];
+        sh[j] = coef_s[3 * a.C + c + j];
+      }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) db[j] = 0.f;
@@ -359,7 +372,7 @@ static int bn_bwd_t(const BnArgs& a, cudaStream_t st) {
   const size_t n = (a.post == POST_POOL ? P / 4 : P) * G;
   // persistent grids: every block ends with C global atomics, so few, long-lived blocks
   const int grid = ew_grid(n, a.post == POST_POOL ? 2 : 4);
-  const size_t sm = (WHICH == 0 ? 2 : 1) * a.C * sizeof(float);
+  const size_t sm = (WHICH == 0 ? 2 : 5) * a.C * sizeof(float);
 #define RVIP_BWD(POSTV)                                                 \
   if (WHICH == 0)                                                       \
     bn_bwd_reduce_kernel<T, POSTV><<<grid, 256, sm, st>>>(a);           \
@@ -381,10 +394,6 @@ int bn_bwd_reduce_launch(const BnArgs& a, int is_bf16, cudaStream_t st) {
 }
 int bn_bwd_apply_launch(const BnArgs& a, int is_bf16, cudaStream_t st) {
   if (check_bn(a)) return 1;
-  const double P = (double)a.B * a.H * a.W;
-  bn_bwd_finalize_kernel<<<(a.C + 127) / 128, 128, 0, st>>>(a.red, a.gamma, a.mean, a.rstd, P, a.coef, a.dgamma,
-                                                           a.dbeta, a.C);
-  RVIP_LAUNCH_CHECK();
   return is_bf16 ? bn_bwd_t<__nv_bfloat16, 1>(a, st) : bn_bwd_t<float, 1>(a, st);
 }
 

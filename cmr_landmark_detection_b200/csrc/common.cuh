@@ -74,6 +74,40 @@ struct Vec8<__nv_bfloat16> {
   }
 };
 
+// Raw (still packed) 8-channel vectors: a load can be issued iterations ahead and unpacked only when consumed.
+template <typename T>
+struct Raw8;
+template <>
+struct Raw8<float> {
+  float4 lo, hi;
+};
+template <>
+struct Raw8<__nv_bfloat16> {
+  uint4 r;
+};
+__device__ __forceinline__ void load_raw8(const float* p, Raw8<float>& o) {
+  o.lo = *reinterpret_cast<const float4*>(p);
+  o.hi = *reinterpret_cast<const float4*>(p + 4);
+}
+__device__ __forceinline__ void load_raw8(const __nv_bfloat16* p, Raw8<__nv_bfloat16>& o) {
+  o.r = *reinterpret_cast<const uint4*>(p);
+}
+__device__ __forceinline__ void unpack_raw8(const Raw8<float>& r, float (&o)[8]) {
+  o[0] = r.lo.x; o[1] = r.lo.y; o[2] = r.lo.z; o[3] = r.lo.w;
+  o[4] = r.hi.x; o[5] = r.hi.y; o[6] = r.hi.z; o[7] = r.hi.w;
+}
+__device__ __forceinline__ void unpack_raw8(const Raw8<__nv_bfloat16>& r, float (&o)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    o[2 * i] = f.x;
+    o[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void zero_raw8(Raw8<float>& o) { o.lo = o.hi = make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void zero_raw8(Raw8<__nv_bfloat16>& o) { o.r = make_uint4(0u, 0u, 0u, 0u); }
+
 template <typename T>
 __device__ __forceinline__ float to_f32(T v);
 template <>

@@ -27,7 +27,7 @@ __device__ __forceinline__ void load_patch(const float* __restrict__ img, int H,
 }
 
 template <typename Tout>
-__global__ void __launch_bounds__(256) conv3x3_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, 2) conv3x3_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ bias, Tout* __restrict__ out,
                                                              double* __restrict__ stats, int B, int H, int W, int Cout,
                                                              int want_stats) {
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) conv3x3_c1_fwd_kernel(const float* __rest
 
 // dW[tap][0][co] = sum_p x[p + off(tap)] * dz[p][co]
 template <typename Tdz>
-__global__ void __launch_bounds__(256) wgrad3x3_c1_kernel(const float* __restrict__ x, const Tdz* __restrict__ dz,
+__global__ void __launch_bounds__(256, 2) wgrad3x3_c1_kernel(const float* __restrict__ x, const Tdz* __restrict__ dz,
                                                           float* __restrict__ dw, int B, int H, int W, int Cout) {
   extern __shared__ float red_s[];  // [9][Cout]
   const uint32_t G = Cout >> 3, lg = 31 - __clz(G);

@@ -34,7 +34,7 @@ int wgrad_c1_launch(const float* x, const void* dz, float* dw, int B, int H, int
                     cudaStream_t st);
 
 // ------------------------------------------------------------------ BatchNorm passes (bn.cu)
-constexpr int kRedStripes = 16;
+constexpr int kRedStripes = 4;   // copies of the BN-backward partial sums (blocks add to copy blockIdx % 4)
 enum PostOp { POST_NONE = 0, POST_DROPOUT = 1, POST_POOL = 2, POST_UPSAMPLE = 3 };
 
 struct BnArgs {
@@ -45,6 +45,14 @@ struct BnArgs {
   const float* beta;
   const float* mean;       // batch mean (training) or moving mean (inference)
   const float* rstd;
+  // training forward: batch statistics straight from the conv epilogue (nullptr = inference, use mean / rstd)
+  const double* stats;     // [2][C] sum, sum of squares
+  double count, inv_count; // B*H*W
+  float momentum, eps;
+  float* mean_out;         // [C] published by block 0 for the backward pass
+  float* rstd_out;
+  float* mov_mean;
+  float* mov_var;
   // forward outputs
   void* y;                 // [B,H,W,C]        (NONE / DROPOUT / POOL)
   void* y2;                // POOL: [B,H/2,W/2,C]; UPSAMPLE: [B,2H,2W,C]
@@ -56,19 +64,16 @@ struct BnArgs {
   const void* g0;          // NONE/DROPOUT: dL/d(y after dropout) [B,H,W,C]; POOL: d skip; UPSAMPLE: d(up) [B,2H,2W,C]
   const void* g1;          // POOL: d pooled [B,H/2,W/2,C]
   double* red;             // [kRedStripes][2][C]: sum dy, sum dy*a (striped partial sums)
-  float* coef;             // [3][C]: sc, k1, c0 of dz = [a>0](sc*dy - k1*a + c0), written between the passes
   void* dz;                // [B,H,W,C]
   float* dgamma;
   float* dbeta;
   float* dbias;            // conv bias gradient = sum dz
 };
-int bn_finalize_launch(const double* stats, double count, float* mean, float* rstd, float* mov_mean, float* mov_var,
-                       int C, float momentum, float eps, cudaStream_t st);
 int bn_eval_prepare_launch(const float* mov_mean, const float* mov_var, float* mean, float* rstd, int n, float eps,
                            cudaStream_t st);
 int bn_apply_launch(const BnArgs& a, int is_bf16, cudaStream_t st);
 int bn_bwd_reduce_launch(const BnArgs& a, int is_bf16, cudaStream_t st);
-int bn_bwd_apply_launch(const BnArgs& a, int is_bf16, cudaStream_t st);   // finalize (coef, dgamma, dbeta) + apply
+int bn_bwd_apply_launch(const BnArgs& a, int is_bf16, cudaStream_t st);
 // conv + ReLU without BN (decoder up-conv): dz = du * [u > 0], dbias = sum dz
 int relu_bwd_launch(const void* u, const void* du, void* dz, float* dbias, size_t pixels, int C, int is_bf16,
                     cudaStream_t st);

@@ -297,7 +297,7 @@ struct rvip_handle {
   int batch = 0, training = 0, bound = 0;
   float *params = nullptr, *grads = nullptr, *bn_state = nullptr;
   uint8_t* ws = nullptr;
-  float *mean = nullptr, *rstd = nullptr, *coef = nullptr;
+  float *mean = nullptr, *rstd = nullptr;
   double *stats = nullptr, *red = nullptr;
   void *packed = nullptr, *dz = nullptr, *head_dy = nullptr;
   rvip::PackEntry* pack_table_dev = nullptr;
@@ -479,8 +479,7 @@ static size_t carve(rvip_handle* h, uint8_t* base, int B, int training, bool ass
     if (assign) h->stats = (double*)p;
     p = cv.take(sizeof(double) * 2 * kRedStripes * h->n_stat_ch);
     if (assign) h->red = (double*)p;
-    p = cv.take(sizeof(float) * 3 * h->n_stat_ch);
-    if (assign) h->coef = (float*)p;
+
     p = cv.take((is_bf16(h) ? 2 : 4) * (size_t)std::max<long long>(h->n_packed, 1));
     if (assign) h->packed = p;
   }
@@ -643,13 +642,15 @@ static int forward_body(rvip_handle* h, const float* x, bool training, uint64_t 
     BnArgs a;
     fill_bn(h, l, &a, training, seed);
     if (training) {
-      const double cnt = (double)h->batch * l.H * l.W;
-      if (timed(h, KC_BN_FWD, 1, st, [&] {
-            return bn_finalize_launch(h->stats + 2 * l.off_stat, cnt, h->mean + l.off_stat, h->rstd + l.off_stat,
-                                      h->bn_state + l.off_mm, h->bn_state + l.off_mv, l.Cout, h->cfg.bn_momentum,
-                                      h->cfg.bn_eps, st);
-          }))
-        return 1;
+      a.stats = h->stats + 2 * l.off_stat;
+      a.count = (double)h->batch * l.H * l.W;
+      a.inv_count = 1.0 / a.count;
+      a.momentum = h->cfg.bn_momentum;
+      a.eps = h->cfg.bn_eps;
+      a.mean_out = h->mean + l.off_stat;
+      a.rstd_out = h->rstd + l.off_stat;
+      a.mov_mean = h->bn_state + l.off_mm;
+      a.mov_var = h->bn_state + l.off_mv;
     }
     if (timed(h, KC_BN_FWD, 1, st, [&] { return bn_apply_launch(a, is_bf16(h), st); })) return 1;
   }
@@ -683,12 +684,11 @@ static int backward_body(rvip_handle* h, const float* x, uint64_t seed, cudaStre
         if (l.post == POST_POOL) a.g1 = buffer_of(h, l.g1_layer, 3);
       }
       a.red = h->red + 2 * kRedStripes * l.off_stat;
-      a.coef = h->coef + 3 * l.off_stat;
       a.dz = h->dz;
       a.dgamma = h->grads + l.off_g;
       a.dbeta = h->grads + l.off_be;
       a.dbias = h->grads + l.off_b;
-      if (timed(h, KC_BN_BWD, 3, st, [&] {
+      if (timed(h, KC_BN_BWD, 2, st, [&] {
             if (bn_bwd_reduce_launch(a, bf, st)) return 1;
             return bn_bwd_apply_launch(a, bf, st);
           }))
