@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       if (a.wres) {
         mbar_expect_tx(&ctl->wfull, wres_bytes);
         for (int nt = 0; nt < a.n_ntiles; ++nt)
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       // The first (and only) TMEM allocation of an SM-exclusive CTA starts at column 0; with the base a literal
       // every tcgen05.mma operand lives in uniform registers (no per-instruction R2UR/ELECT loop).
       if (tmem_base == 0)

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256, 1) conv3x3_tc_kernel(const __grid_constan
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
         const int nt = tile % a.n_ntiles, pt = tile / a.n_ntiles;
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256, 1) conv3x3_tc_kernel(const __grid_constan
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
       int stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(256, 1) wgrad3x3_tc_kernel(const __grid_consta
 
   if (kt0 < kt1) {
     if (warp == 0) {
-      if (lane == 0) {
+      if (elect_one()) {
         int stage = 0, phase = 0;
         const uint32_t tx_bytes = mcount * A_TILE + KP * BN * 2;
         for (int kt = kt0; kt < kt1; ++kt) {
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(256, 1) wgrad3x3_tc_kernel(const __grid_consta
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
         int stage = 0, phase = 0;
         for (int kt = kt0; kt < kt1; ++kt) {

@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256, 1) wgrad3x3_row_kernel(const __grid_const
   const bool has_work = (int)blockIdx.x < a.pixel_tiles;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0, phase = 0, db = 0, dphase = 0;
       for (int pt = blockIdx.x; pt < a.pixel_tiles; pt += gridDim.x) {
         const int x0 = (pt % a.tiles_x) * 128;
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256, 1) wgrad3x3_row_kernel(const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && has_work) {
+    if (has_work && elect_one()) {
       if (tmem_base == 0)
         wg_mma_loop<BN, R, true>(a, ctl, dzbuf, stages, nst, nchunks, 0u);
       else
