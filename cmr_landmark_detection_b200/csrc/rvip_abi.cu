@@ -13,6 +13,7 @@
 
 #include "../../include/rvip.h"
 #include "conv_row.cuh"
+#include "wgrad_halo.cuh"
 #include "kernels.cuh"
 
 namespace rvip {
@@ -142,6 +143,22 @@ static int setup_wgrad_row(WgradRowArgs* a, int BN, int R, const void* x0, const
   return 0;
 }
 
+static int setup_wgrad_halo(WgradHaloArgs* a, const WgradHaloPlan& p, const void* x0, const void* x1, int C0, int C1,
+                            const void* dz, float* dw, int B, int H, int W, int Cout) {
+  a->B = B; a->H = H; a->W = W; a->C0 = C0; a->Ctot = C0 + C1; a->Cout = Cout;
+  a->TW = p.TW; a->TH = p.TH; a->tiles_x = p.tiles_x; a->tiles_y = p.tiles_y; a->pixel_tiles = p.pixel_tiles;
+  a->n_cchunks = p.n_cchunks; a->n_ntiles = p.n_ntiles; a->k_split = p.k_split;
+  a->dw = dw;
+  if (make_act_map_box(&a->x0, x0, B, H, W, C0, p.CIC, p.TW + 2, p.TH + 2, 1)) return 1;
+  if (C1 > 0) {
+    if (make_act_map_box(&a->x1, x1, B, H, W, C1, p.CIC, p.TW + 2, p.TH + 2, 1)) return 1;
+  } else {
+    a->x1 = a->x0;
+  }
+  if (make_act_map_box(&a->dz, dz, B, H, W, Cout, p.BN >= 64 ? 64 : 32, p.TW, p.TH, 1)) return 1;
+  return 0;
+}
+
 static int pick_kc(int C0, int C1) { return (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32; }
 
 // fills the geometry / tiling fields of a forward-style launch (also used by the single-op entry point)
@@ -266,7 +283,9 @@ struct Layer {
   // row-tiled variants for W % 128 == 0 layers
   ConvRowArgs rfwd, rdgrad;
   WgradRowArgs rwg;
-  int use_rfwd = 0, use_rdgrad = 0, use_rwg = 0;
+  WgradHaloArgs hwg;
+  WgradHaloPlan hwp;
+  int use_rfwd = 0, use_rdgrad = 0, use_rwg = 0, use_hwg = 0;
   int rfBN = 0, rfR = 0, rfNst = 0, rdBN = 0, rdR = 0, rdNst = 0, rwBN = 0, rwR = 0, rwNst = 0;
 };
 
@@ -552,7 +571,13 @@ static int build_descriptors(rvip_handle* h) {
       if (l.use_rdgrad && setup_conv_row(&l.rdgrad, l.rdBN, l.rdR, wres, h->dz, nullptr, l.Cout, 0, pk + l.pk_d, l.dx0,
                                          l.dx1, dsplit, B, l.H, l.W, l.C0 + l.C1, EPI_LINEAR, nullptr, nullptr))
         return 1;
-      l.use_rwg = allow_row && getenv("RVIP_NO_ROW_WGRAD") == nullptr &&
+      // weight gradient: halo-staged kernel wherever it applies (fastest at every level of the bench network),
+      // then the row-tiled kernel (RVIP_NO_HALO_WGRAD=1), then the generic per-tap kernel
+      l.use_hwg = getenv("RVIP_NO_HALO_WGRAD") == nullptr && wgrad_halo_plan(B, l.H, l.W, l.C0, l.C1, l.Cout, &l.hwp);
+      if (l.use_hwg && setup_wgrad_halo(&l.hwg, l.hwp, in0, in1, l.C0, l.C1, h->dz, h->grads + l.off_k, B, l.H, l.W,
+                                        l.Cout))
+        return 1;
+      l.use_rwg = !l.use_hwg && allow_row && getenv("RVIP_NO_ROW_WGRAD") == nullptr &&
                   wgrad_row_plan(l.H, l.W, l.C0, l.C1, l.Cout, &l.rwBN, &l.rwR, &l.rwNst);
       if (l.use_rwg && setup_wgrad_row(&l.rwg, l.rwBN, l.rwR, in0, in1, l.C0, l.C1, h->dz, h->grads + l.off_k, B, l.H,
                                        l.W, l.Cout))
@@ -702,8 +727,9 @@ static int backward_body(rvip_handle* h, const float* x, uint64_t seed, cudaStre
     h->cur_tag = l.name + ":conv_bwd";
     if (bf && !l.first) {
       if (timed(h, KC_CONV_WGRAD_TC, 1, st, [&] {
-            return l.use_rwg ? wgrad_row_launch(l.rwg, l.rwBN, l.rwR, l.rwNst, st)
-                             : wgrad_tc_launch(l.wg, l.wCBA, l.wCBB, st);
+            if (l.use_hwg) return wgrad_halo_launch(l.hwg, l.hwp.CIC, l.hwp.BN, st);
+            if (l.use_rwg) return wgrad_row_launch(l.rwg, l.rwBN, l.rwR, l.rwNst, st);
+            return wgrad_tc_launch(l.wg, l.wCBA, l.wCBB, st);
           }))
         return 1;
       if (timed(h, KC_CONV_DGRAD_TC, 1, st, [&] {
@@ -1009,6 +1035,15 @@ int rvip_wgrad3x3_tc(const void* x0, const void* x1, int C0, int C1, const void*
   int CBA, CBB;
   if (setup_wgrad_tc(&a, &CBA, &CBB, x0, x1, C0, C1, dz, dw, B, H, W, Cout)) return 1;
   return wgrad_tc_launch(a, CBA, CBB, (cudaStream_t)stream);
+}
+
+int rvip_wgrad3x3_halo(const void* x0, const void* x1, int C0, int C1, const void* dz, float* dw, int B, int H, int W,
+                       int Cout, void* stream) {
+  WgradHaloArgs a;
+  WgradHaloPlan p;
+  RVIP_REQUIRE(wgrad_halo_plan(B, H, W, C0, C1, Cout, &p), "rvip_wgrad3x3_halo: shape not eligible for the halo kernel");
+  if (setup_wgrad_halo(&a, p, x0, x1, C0, C1, dz, dw, B, H, W, Cout)) return 1;
+  return wgrad_halo_launch(a, p.CIC, p.BN, (cudaStream_t)stream);
 }
 
 int rvip_conv3x3_row(const void* in0, const void* in1, int C0, int C1, const void* w_packed, const float* bias,

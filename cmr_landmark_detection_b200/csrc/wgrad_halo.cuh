@@ -1,0 +1,29 @@
+// Halo-staged tcgen05 weight gradient (wgrad_halo.cu): host-visible argument block, planner and launcher.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rvip {
+
+struct WgradHaloPlan {
+  int CIC, BN;               // input channels per CTA (32 | 64), output-channel tile (32 | 64 | 128)
+  int TW, TH;                // pixel tile: TW (16 | 32) columns x TH rows, at most 256 pixels
+  int tiles_x, tiles_y, pixel_tiles;
+  int n_cchunks, n_ntiles, k_split;
+};
+
+struct WgradHaloArgs {
+  CUtensorMap x0, x1;        // conv input(s) NHWC bf16, box {CIC, TW+2, TH+2, 1} (halo), swizzle = CIC*2 bytes
+  CUtensorMap dz;            // NHWC bf16, box {min(BN,64), TW, TH, 1}
+  float* dw;                 // [9][Ctot][Cout] fp32, accumulated with red.global.add
+  int B, H, W;
+  int C0, Ctot, Cout;
+  int TW, TH, tiles_x, tiles_y, pixel_tiles;
+  int n_cchunks, n_ntiles, k_split;
+};
+// false if the layer does not fit this kernel (W not a multiple of 16, channels not multiples of 32)
+bool wgrad_halo_plan(int B, int H, int W, int C0, int C1, int Cout, WgradHaloPlan* p);
+int wgrad_halo_launch(const WgradHaloArgs& a, int CIC, int BN, cudaStream_t st);
+
+}  // namespace rvip

@@ -73,6 +73,7 @@ _SIGS = {
     'rvip_conv3x3_row': (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, _VP]),
     'rvip_wgrad3x3_row': (_I, [_VP, _VP, _I, _I, _VP, _VP, _I, _I, _I, _I, _VP]),
     'rvip_wgrad3x3_tc': (_I, [_VP, _VP, _I, _I, _VP, _VP, _I, _I, _I, _I, _VP]),
+    'rvip_wgrad3x3_halo': (_I, [_VP, _VP, _I, _I, _VP, _VP, _I, _I, _I, _I, _VP]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
 

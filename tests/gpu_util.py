@@ -102,3 +102,14 @@ def wgrad_row(x0, x1, dz):
                                           stream()))
     torch.cuda.synchronize()
     return dw
+
+
+def wgrad_halo(x0, x1, dz):
+    B, H, W, C0 = x0.shape
+    C1 = x1.shape[3] if x1 is not None else 0
+    cout = dz.shape[3]
+    dw = torch.zeros((3, 3, C0 + C1, cout), dtype=torch.float32, device=x0.device)
+    ffi.check(ffi.lib().rvip_wgrad3x3_halo(ffi.ptr(x0), ffi.ptr(x1), C0, C1, ffi.ptr(dz), ffi.ptr(dw), B, H, W, cout,
+                                           stream()))
+    torch.cuda.synchronize()
+    return dw

@@ -29,6 +29,18 @@ ROW_SHAPES = [  # W % 128 == 0: eligible for the row-tiled kernels
     (2, 16, 128, 64, 64, 64),
 ]
 ALL_CASES = [('tc', s) for s in CONV_SHAPES] + [('row', s) for s in ROW_SHAPES]
+HALO_SHAPES = [  # W % 16 == 0: eligible for the halo-staged wgrad kernel
+    (2, 16, 16, 64, 0, 128),      # CIC=32, BN=128, TW=16
+    (2, 32, 32, 128, 0, 256),     # two N tiles, TW=32
+    (1, 64, 64, 64, 0, 64),       # CIC=64 (taps paired), BN=64
+    (2, 32, 32, 64, 64, 64),      # concat, CIC=64
+    (1, 32, 32, 32, 32, 64),      # concat on a 32-channel boundary -> CIC=32, BN=64
+    (1, 24, 48, 64, 0, 32),       # H not a multiple of the tile height, BN=32
+    (3, 16, 16, 32, 0, 32),       # CIC=32, BN=32
+    (1, 8, 16, 256, 0, 128),      # image lower than the nominal tile
+    (2, 128, 128, 128, 0, 64),    # level-1 shape of the bench network
+]
+WGRAD_CASES = ALL_CASES + [('halo', s) for s in HALO_SHAPES]
 
 
 def _rand_bf16(shape, gen, scale=1.0):
@@ -75,7 +87,7 @@ def test_conv_tc_dgrad(variant, shape):
     assert U.rel_err(got, ref) < 4e-3
 
 
-@pytest.mark.parametrize('variant,shape', ALL_CASES)
+@pytest.mark.parametrize('variant,shape', WGRAD_CASES)
 def test_wgrad_tc(variant, shape):
     from tests import gpu_util as U
     B, H, W, C0, C1, N = shape
@@ -83,7 +95,7 @@ def test_wgrad_tc(variant, shape):
     x0 = _rand_bf16((B, H, W, C0), g)
     x1 = _rand_bf16((B, H, W, C1), g) if C1 else None
     dz = _rand_bf16((B, H, W, N), g)
-    dw = (U.wgrad_tc if variant == 'tc' else U.wgrad_row)(x0, x1, dz)
+    dw = {'tc': U.wgrad_tc, 'row': U.wgrad_row, 'halo': U.wgrad_halo}[variant](x0, x1, dz)
     xin = (x0 if x1 is None else torch.cat([x0, x1], dim=3)).float().permute(0, 3, 1, 2)
     w = torch.zeros((N, C0 + C1, 3, 3), device='cuda', requires_grad=True)
     y = torch.nn.functional.conv2d(xin, w, padding=1)
