@@ -54,15 +54,34 @@ def conv_flops_per_slice(cfg=CONFIG):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """Samples SM clock, power and throttle reasons DURING the timed region (B200_PROFILING.md recipe) through NVML
+    every few milliseconds; falls back to an `nvidia-smi -lms` child process when pynvml is unavailable."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+    def __init__(self, gpu_index=0, period_s=0.004):
+        self.rows, self.proc, self.gpu, self.period = [], None, gpu_index, period_s
+        self.samples, self._stop, self._thread, self.nvml = [], False, None, None
+        self.max_mhz = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+            idx = self.gpu
+            if vis and all(v.strip().isdigit() for v in vis.split(',')):
+                idx = int(vis.split(',')[self.gpu])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
                                           '--format=csv,noheader,nounits', '-lms', '50'],
@@ -71,19 +90,48 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self._stop:
+            try:
+                mhz = int(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    reasons = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    reasons = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                watts = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                self.samples.append((time.perf_counter(), mhz, reasons, watts))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(',')]))
 
-    def stop(self):
+    def mark(self):
+        return time.perf_counter()
+
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples taken between the wall-clock marks t0 and t1 (all samples if none fall inside)."""
+        self._stop = True
         if self.proc is not None:
             self.proc.terminate()
-        sm = sorted(int(float(r[1])) for r in self.rows if len(r) > 8 and r[1].replace('.', '').isdigit())
-        mx = [int(float(r[2])) for r in self.rows if len(r) > 8 and r[2].replace('.', '').isdigit()]
+        if self.nvml is not None:
+            inside = [s for s in self.samples if (t0 is None or s[0] >= t0) and (t1 is None or s[0] <= t1)] or self.samples
+            sm = sorted(s[1] for s in inside)
+            bits = {'hw_slowdown': 0x8, 'sw_power_cap': 0x4, 'sw_thermal_slowdown': 0x20, 'hw_thermal_slowdown': 0x40}
+            reasons = sorted({k for s in inside for k, b in bits.items() if s[2] & b})
+            return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_min_mhz': sm[0] if sm else None,
+                    'sm_max_mhz': self.max_mhz, 'reasons': reasons, 'samples': len(inside),
+                    'power_w_max': round(max((s[3] for s in inside), default=0.0), 1), 'source': 'nvml'}
+        rows = [r for t, r in self.rows if (t0 is None or t >= t0) and (t1 is None or t <= t1)] or [r for _, r in self.rows]
+        sm = sorted(int(float(r[1])) for r in rows if len(r) > 8 and r[1].replace('.', '').isdigit())
+        mx = [int(float(r[2])) for r in rows if len(r) > 8 and r[2].replace('.', '').isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({n for r in self.rows if len(r) > 8 for n, v in zip(names, r[5:9]) if v.lower().startswith('active')})
+        reasons = sorted({n for r in rows if len(r) > 8 for n, v in zip(names, r[5:9]) if v.lower().startswith('active')})
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
-                'samples': len(self.rows)}
+                'samples': len(rows), 'source': 'nvidia-smi'}
 
 
 def peaks():
@@ -174,7 +222,7 @@ def run_b200(args):
     for i in range(Wm):
         model.train_step_device(*dev_data[i % 2])
     barrier()
-    n_warm_rows = len(sampler.rows)
+    t_mark0 = sampler.mark()
     l0 = model.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -184,9 +232,7 @@ def run_b200(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = model.launch_count() - l0
-    if rank == 0 and len(sampler.rows) > n_warm_rows + 2:
-        sampler.rows = sampler.rows[n_warm_rows:]      # keep the samples taken during the timed region
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_mark0, sampler.mark()) if rank == 0 else None
     ms = model.dp.max_float(ms)
     value = world * B * K / (ms * 1e-3)
     final_loss = float(loss.item())

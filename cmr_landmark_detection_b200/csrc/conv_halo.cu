@@ -1,0 +1,353 @@
+// Halo-staged tcgen05 3x3 convolution (forward and dgrad) for the deep levels of the U-Net
+// (H, W multiples of 16; input channels in chunks of 64; Cout a multiple of 64).
+//
+// The generic kernel (conv_tc.cu) moves one shifted activation box AND one weight tile per (tap, 64-channel
+// chunk) for a 128-pixel tile: (128 + BN) * 128 B per 4 MMAs, i.e. 96 B/cycle at BN = 256 -- more than twice
+// what L2 delivers to one SM (~43 B/cycle), so those layers ran at ~45 % of the tensor pipe.  This kernel cuts
+// the L2 traffic per MMA cycle 2.6x:
+//   * a CTA computes a 16 x 16 pixel block = two 128-row accumulators (left / right 8-pixel-wide halves), so
+//     every weight tile fetched is used for 8 MMAs instead of 4;
+//   * the activation block is staged ONCE per 64-channel chunk with its halo (TMA box {64 ch, 18, 18} ->
+//     [pixel][128 B], SWIZZLE_128B) and all nine taps read it through K-major descriptors whose start address
+//     is shifted by whole pixels: rows of an accumulator are 8-pixel groups (one image row each) at a uniform
+//     18-pixel stride, which is exactly a stride-dimension byte offset of 18 * 128 B.  The swizzle is a function
+//     of the absolute shared-memory address, so shifted views stay consistent with what TMA wrote.
+// Per 64-channel chunk: 41.5 KB of activations + 9 weight tiles for 72 MMAs (36 B/cycle at BN = 256).
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (elected thread, all operand offsets immediates), warp 2
+// TMEM allocator, warps 4-7 / 8-11 epilogue of the left / right half (tcgen05.ld -> bias + ReLU -> bf16 ->
+// swizzled staging -> TMA store per 64-channel slice, plus the BatchNorm sum / sum of squares).
+// Replaces tf.keras Conv2D forward and Conv2DBackpropInput (src/models/KerasLayers.py:683,689,758).
+#include "conv_halo.cuh"
+
+#include "common.cuh"
+#include "tc_prims.cuh"
+
+namespace rvip {
+using namespace tc;
+
+constexpr int kHaloMaxSmem = 227 * 1024;
+constexpr int kHaloMaxB = 6;                 // weight-tile ring slots
+constexpr int kHaloPitch = 18;               // 16 + 2 halo pixels per row
+constexpr int kHaloATx = kHaloPitch * kHaloPitch * 128;       // 41472 B delivered per activation block
+constexpr int kHaloASlot = (kHaloATx + 1023) & ~1023;         // 41984
+
+struct HaloCtl {
+  uint64_t afull[2], aempty[2];
+  uint64_t bfull[kHaloMaxB], bempty[kHaloMaxB];
+  uint64_t tfull[2], tempty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void halo_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int BN>
+struct HaloCfg {
+  static constexpr int NBUF = BN <= 128 ? 2 : 1;              // TMEM accumulator buffers (2 halves x BN columns each)
+  static constexpr int SB = BN <= 128 ? 2 : 1;                // staging buffers per epilogue group
+  static constexpr int B_BYTES = BN * 128;                    // one (tap, chunk) weight tile
+  static constexpr int STG = 128 * 128;                       // one 64-channel slice of a 128-row half, bf16
+  static constexpr int TMEM_COLS = 2 * BN * NBUF;
+  static_assert(TMEM_COLS <= 512, "TMEM budget");
+};
+
+template <int BN>
+__global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_constant__ ConvHaloArgs a, int nbst) {
+  using Cfg = HaloCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* a_ring = smem;                                     // 2 activation blocks
+  uint8_t* b_ring = a_ring + 2 * kHaloASlot;                  // nbst weight tiles
+  uint8_t* staging = b_ring + (size_t)nbst * Cfg::B_BYTES;    // 2 groups x SB slices
+  float* s_sum = reinterpret_cast<float*>(staging + 2 * Cfg::SB * Cfg::STG);
+  float* s_sq = s_sum + a.Cout;
+  HaloCtl* ctl = reinterpret_cast<HaloCtl*>((reinterpret_cast<uintptr_t>(s_sq + a.Cout) + 15) & ~uintptr_t(15));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&a.in0);
+    prefetch_tmap(&a.in1);
+    prefetch_tmap(&a.w);
+    prefetch_tmap(&a.out0);
+    prefetch_tmap(&a.out1);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctl->afull[i], 1);
+      mbar_init(&ctl->aempty[i], 1);
+      mbar_init(&ctl->tfull[i], 1);
+      mbar_init(&ctl->tempty[i], 8);
+    }
+    for (int i = 0; i < nbst; ++i) {
+      mbar_init(&ctl->bfull[i], 1);
+      mbar_init(&ctl->bempty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&ctl->tmem_base, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  if (warp >= 4) {
+    for (int c = threadIdx.x - 128; c < 2 * a.Cout; c += 256) s_sum[c] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+  const int nchunks = a.Ctot / 64;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int as = 0, aphase = 0, bs = 0, bphase = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const int nt = tile % a.n_ntiles, pt = tile / a.n_ntiles;
+        const int x0 = (pt % a.tiles_x) * 16;
+        const int y0 = ((pt / a.tiles_x) % a.tiles_y) * 16;
+        const int b = pt / (a.tiles_x * a.tiles_y);
+        const int n0 = nt * BN;
+        for (int c = 0; c < nchunks; ++c) {
+          const int cc = c * 64;
+          mbar_wait(&ctl->aempty[as], aphase ^ 1);
+          mbar_expect_tx(&ctl->afull[as], kHaloATx);
+          if (cc < a.C0)
+            tma_load_4d(a_ring + as * kHaloASlot, &a.in0, &ctl->afull[as], cc, x0 - 1, y0 - 1, b);
+          else
+            tma_load_4d(a_ring + as * kHaloASlot, &a.in1, &ctl->afull[as], cc - a.C0, x0 - 1, y0 - 1, b);
+          as ^= 1;
+          if (as == 0) aphase ^= 1;
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&ctl->bempty[bs], bphase ^ 1);
+            mbar_expect_tx(&ctl->bfull[bs], Cfg::B_BYTES);
+            tma_load_2d(b_ring + (size_t)bs * Cfg::B_BYTES, &a.w, &ctl->bfull[bs], tap * a.Ctot + cc, n0);
+            if (++bs == nbst) {
+              bs = 0;
+              bphase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      int as = 0, aphase = 0, bs = 0, bphase = 0, buf = 0, tphase = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        mbar_wait(&ctl->tempty[buf], tphase ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + buf * 2 * BN;
+        for (int c = 0; c < nchunks; ++c) {
+          mbar_wait(&ctl->afull[as], aphase);
+          tc_fence_after();
+          // rows = 8-pixel groups (one image row of the half tile each), kHaloPitch pixels apart
+          const uint64_t adesc0 = make_smem_desc(smem_u32(a_ring + as * kHaloASlot), 16, kHaloPitch * 128, kLayoutSW128);
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&ctl->bfull[bs], bphase);
+            tc_fence_after();
+            const uint64_t bdesc0 = make_smem_desc(smem_u32(b_ring + (size_t)bs * Cfg::B_BYTES), 16, 1024, kLayoutSW128);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t a_off = (uint32_t)((((tap / 3) * kHaloPitch + (tap % 3) + 8 * half) * 128 + k * 32) >> 4);
+                mma_bf16_ss(d0 + half * BN, adesc0 + a_off, bdesc0 + 2 * k, idesc, (tap | k) != 0 ? 1u : (uint32_t)(c != 0));
+              }
+            }
+            mma_commit(&ctl->bempty[bs]);
+            if (++bs == nbst) {
+              bs = 0;
+              bphase ^= 1;
+            }
+          }
+          mma_commit(&ctl->aempty[as]);
+          as ^= 1;
+          if (as == 0) aphase ^= 1;
+        }
+        mma_commit(&ctl->tfull[buf]);
+        if (Cfg::NBUF == 2) {
+          buf ^= 1;
+          if (buf == 0) tphase ^= 1;
+        } else {
+          tphase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue: group 0 = left half, 1 = right half
+    const int grp = (warp - 4) >> 2;
+    const int ew = warp & 3;                 // TMEM lane quarter
+    const int r = ew * 32 + lane;            // accumulator row: pixel (y = r / 8, x = r % 8) of the half tile
+    const int gt = threadIdx.x - 128 - grp * 128;   // thread index inside the group
+    uint8_t* stg = staging + (size_t)grp * Cfg::SB * Cfg::STG;
+    int buf = 0, tphase = 0, sb = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      const int nt = tile % a.n_ntiles, pt = tile / a.n_ntiles;
+      const int x0 = (pt % a.tiles_x) * 16 + 8 * grp;
+      const int y0 = ((pt / a.tiles_x) % a.tiles_y) * 16;
+      const int b = pt / (a.tiles_x * a.tiles_y);
+      const int n0 = nt * BN;
+      mbar_wait(&ctl->tfull[buf], tphase);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * 2 * BN + grp * BN;
+#pragma unroll 1
+      for (int sl = 0; sl < BN / 64; ++sl) {
+        uint8_t* sbuf = stg + (size_t)sb * Cfg::STG;
+        // the staging slice must have been drained by the TMA store issued SB slices ago
+        if (gt == 0) {
+          if (Cfg::SB == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else tma_store_wait_read0();
+        }
+        halo_bar_sync(1 + grp, 128);
+#pragma unroll
+        for (int hc = 0; hc < 2; ++hc) {
+          uint32_t v[32];
+          tmem_ld_32x32(acc + sl * 64 + hc * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              f[j] = __uint_as_float(v[q * 8 + j]);
+              if (a.mode != EPI_LINEAR) f[j] = fmaxf(f[j] + __ldg(a.bias + n0 + sl * 64 + hc * 32 + q * 8 + j), 0.f);
+            }
+            uint4 pk;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            *reinterpret_cast<uint4*>(sbuf + swz_off<128>(r, hc * 4 + q)) = pk;
+          }
+        }
+        if (sl == BN / 64 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ctl->tempty[buf]);   // all TMEM reads of this warp for this tile are done
+        }
+        fence_proxy_async_smem();
+        halo_bar_sync(1 + grp, 128);
+        if (gt == 0) {
+          const int n = n0 + sl * 64;
+          if (a.mode == EPI_LINEAR && n >= a.out_split)
+            tma_store_4d(&a.out1, sbuf, n - a.out_split, x0, y0, b);
+          else
+            tma_store_4d(&a.out0, sbuf, n, x0, y0, b);
+          tma_store_commit();
+        }
+        if (a.mode == EPI_RELU_STATS) {
+          // per-channel sum / sum^2 of the slice from the bf16 values just staged: 8 column groups x 16 threads
+          const int cg = gt & 7, rt = gt >> 3;
+          float s[8], q2[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s[j] = q2[j] = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int row = rt + k * 16;
+            const uint4 raw = *reinterpret_cast<const uint4*>(sbuf + swz_off<128>(row, cg));
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __bfloat1622float2(h[j]);
+              s[2 * j] += f.x;
+              s[2 * j + 1] += f.y;
+              q2[2 * j] = fmaf(f.x, f.x, q2[2 * j]);
+              q2[2 * j + 1] = fmaf(f.y, f.y, q2[2 * j + 1]);
+            }
+          }
+          // lanes with equal (lane & 7) hold the same channels
+#pragma unroll
+          for (int o = 16; o >= 8; o >>= 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+              q2[j] += __shfl_xor_sync(0xffffffffu, q2[j], o);
+            }
+          }
+          if (lane < 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              atomicAdd(&s_sum[n0 + sl * 64 + cg * 8 + j], s[j]);
+              atomicAdd(&s_sq[n0 + sl * 64 + cg * 8 + j], q2[j]);
+            }
+          }
+        }
+        if (Cfg::SB == 2) sb ^= 1;
+      }
+      if (Cfg::NBUF == 2) {
+        buf ^= 1;
+        if (buf == 0) tphase ^= 1;
+      } else {
+        tphase ^= 1;
+      }
+    }
+    if (gt == 0) tma_store_wait_all0();
+    if (a.mode == EPI_RELU_STATS) {
+      halo_bar_sync(3, 256);
+      for (int c = threadIdx.x - 128; c < a.Cout; c += 256) {
+        atomicAdd(&a.stats[c], (double)s_sum[c]);
+        atomicAdd(&a.stats[a.Cout + c], (double)s_sq[c]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------- host
+static size_t halo_fixed_bytes(int BN, int Cout) {
+  const int sb = BN <= 128 ? 2 : 1;
+  return 1024 + 2 * (size_t)kHaloASlot + 2 * (size_t)sb * 128 * 128 + 2 * (size_t)Cout * sizeof(float) + sizeof(HaloCtl) + 64;
+}
+
+bool conv_halo_plan(int B, int H, int W, int C0, int C1, int Cout, int mode, int out_split, int* BN, int* nbst) {
+  if (H % 16 != 0 || W % 16 != 0 || C0 % 64 != 0 || C1 % 64 != 0 || Cout % 64 != 0) return false;
+  if (mode == EPI_LINEAR && out_split < Cout && out_split % 64 != 0) return false;
+  int bn = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  // a wider N tile halves the activation re-reads, a narrower one fills the 148 SMs: take the narrower tile when
+  // the wide one would leave more than a third of the SMs idle in the last wave
+  const long mtiles = (long)B * (H / 16) * (W / 16);
+  auto waves_eff = [&](int n) {
+    const long t = mtiles * (Cout / n);
+    return (double)t / (double)(((t + kNumSMs - 1) / kNumSMs) * kNumSMs);
+  };
+  if (bn == 256 && waves_eff(256) < 0.67 && waves_eff(128) > waves_eff(256)) bn = 128;
+  const size_t fixed = halo_fixed_bytes(bn, Cout);
+  if (fixed >= (size_t)kHaloMaxSmem) return false;
+  int n = (int)((kHaloMaxSmem - fixed) / ((size_t)bn * 128));
+  if (n > kHaloMaxB) n = kHaloMaxB;
+  if (n < 3) return false;
+  *BN = bn; *nbst = n;
+  (void)mode;
+  return true;
+}
+
+template <int BN>
+static int launch_halo(const ConvHaloArgs& a, int nbst, cudaStream_t st) {
+  const size_t smem = halo_fixed_bytes(BN, a.Cout) + (size_t)nbst * BN * 128;
+  RVIP_REQUIRE(smem <= (size_t)kHaloMaxSmem, "conv_halo: %zu bytes of shared memory needed", smem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    RVIP_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloMaxSmem));
+    attr_set = true;
+  }
+  const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
+  conv3x3_halo_kernel<BN><<<grid, 384, smem, st>>>(a, nbst);
+  RVIP_LAUNCH_CHECK();
+  return 0;
+}
+
+int conv_halo_launch(const ConvHaloArgs& a, int BN, int nbst, cudaStream_t st) {
+  RVIP_REQUIRE(a.C0 % 64 == 0 && a.Ctot % 64 == 0 && a.Cout % BN == 0 && a.H % 16 == 0 && a.W % 16 == 0,
+               "conv_halo: bad shape %dx%d C0=%d Ctot=%d Cout=%d BN=%d", a.H, a.W, a.C0, a.Ctot, a.Cout, BN);
+  if (BN == 256) return launch_halo<256>(a, nbst, st);
+  if (BN == 128) return launch_halo<128>(a, nbst, st);
+  if (BN == 64) return launch_halo<64>(a, nbst, st);
+  set_error("conv_halo: unsupported N tile %d", BN);
+  return 1;
+}
+
+}  // namespace rvip

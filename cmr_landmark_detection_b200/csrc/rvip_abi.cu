@@ -14,6 +14,7 @@
 #include "../../include/rvip.h"
 #include "conv_row.cuh"
 #include "wgrad_halo.cuh"
+#include "conv_halo.cuh"
 #include "kernels.cuh"
 
 namespace rvip {
@@ -140,6 +141,34 @@ static int setup_wgrad_row(WgradRowArgs* a, int BN, int R, const void* x0, const
     a->x1 = a->x0;
   }
   if (make_act_map_box(&a->dz, dz, B, H, W, Cout, BN, 128, R, 1)) return 1;
+  return 0;
+}
+
+static int setup_conv_halo(ConvHaloArgs* a, int BN, const void* in0, const void* in1, int C0, int C1, const void* wpk,
+                           void* out0, void* out1, int out_split, int B, int H, int W, int Cout, int mode,
+                           const float* bias, double* stats) {
+  const int Ctot = C0 + C1;
+  a->B = B; a->H = H; a->W = W; a->C0 = C0; a->Ctot = Ctot; a->Cout = Cout;
+  a->n_ntiles = Cout / BN;
+  a->tiles_x = W / 16; a->tiles_y = H / 16;
+  a->total_tiles = a->n_ntiles * a->tiles_x * a->tiles_y * B;
+  a->mode = mode;
+  a->out_split = (mode == EPI_LINEAR) ? out_split : Cout;
+  a->bias = bias; a->stats = stats;
+  if (make_act_map_box(&a->in0, in0, B, H, W, C0, 64, 18, 18, 1)) return 1;
+  if (C1 > 0) {
+    if (make_act_map_box(&a->in1, in1, B, H, W, C1, 64, 18, 18, 1)) return 1;
+  } else {
+    a->in1 = a->in0;
+  }
+  if (make_w_map(&a->w, wpk, Cout, 9 * Ctot, 64, BN)) return 1;
+  const int c_out0 = (mode == EPI_LINEAR) ? a->out_split : Cout;
+  if (make_act_map_box(&a->out0, out0, B, H, W, c_out0, 64, 8, 16, 1)) return 1;
+  if (mode == EPI_LINEAR && out_split < Cout) {
+    if (make_act_map_box(&a->out1, out1, B, H, W, Cout - out_split, 64, 8, 16, 1)) return 1;
+  } else {
+    a->out1 = a->out0;
+  }
   return 0;
 }
 
@@ -285,6 +314,8 @@ struct Layer {
   WgradRowArgs rwg;
   WgradHaloArgs hwg;
   WgradHaloPlan hwp;
+  ConvHaloArgs hfwd, hdgrad;
+  int use_hfwd = 0, use_hdgrad = 0, hfBN = 0, hfNb = 0, hdBN = 0, hdNb = 0;
   int use_rfwd = 0, use_rdgrad = 0, use_rwg = 0, use_hwg = 0;
   int rfBN = 0, rfR = 0, rfNst = 0, rdBN = 0, rdR = 0, rdNst = 0, rwBN = 0, rwR = 0, rwNst = 0;
 };
@@ -564,12 +595,22 @@ static int build_descriptors(rvip_handle* h) {
     if (l.use_rfwd && setup_conv_row(&l.rfwd, l.rfBN, l.rfR, wres, in0, in1, l.C0, l.C1, pk + l.pk_f, l.a, nullptr,
                                      l.Cout, B, l.H, l.W, l.Cout, mode, h->params + l.off_b, h->stats + 2 * l.off_stat))
       return 1;
+    const bool allow_halo = getenv("RVIP_NO_HALO_CONV") == nullptr;
+    l.use_hfwd = !l.use_rfwd && allow_halo && conv_halo_plan(B, l.H, l.W, l.C0, l.C1, l.Cout, mode, l.Cout, &l.hfBN, &l.hfNb);
+    if (l.use_hfwd && setup_conv_halo(&l.hfwd, l.hfBN, in0, in1, l.C0, l.C1, pk + l.pk_f, l.a, nullptr, l.Cout, B, l.H,
+                                      l.W, l.Cout, mode, h->params + l.off_b, h->stats + 2 * l.off_stat))
+      return 1;
     if (h->training) {
       const int dsplit = l.C1 ? l.C0 : l.C0 + l.C1;
       l.use_rdgrad = allow_row && conv_row_plan(l.H, l.W, l.Cout, 0, l.C0 + l.C1, EPI_LINEAR, dsplit, &l.rdBN, &l.rdR,
                                                 &wres, &l.rdNst);
       if (l.use_rdgrad && setup_conv_row(&l.rdgrad, l.rdBN, l.rdR, wres, h->dz, nullptr, l.Cout, 0, pk + l.pk_d, l.dx0,
                                          l.dx1, dsplit, B, l.H, l.W, l.C0 + l.C1, EPI_LINEAR, nullptr, nullptr))
+        return 1;
+      l.use_hdgrad = !l.use_rdgrad && allow_halo &&
+                     conv_halo_plan(B, l.H, l.W, l.Cout, 0, l.C0 + l.C1, EPI_LINEAR, dsplit, &l.hdBN, &l.hdNb);
+      if (l.use_hdgrad && setup_conv_halo(&l.hdgrad, l.hdBN, h->dz, nullptr, l.Cout, 0, pk + l.pk_d, l.dx0, l.dx1, dsplit,
+                                          B, l.H, l.W, l.C0 + l.C1, EPI_LINEAR, nullptr, nullptr))
         return 1;
       // weight gradient: halo-staged kernel wherever it applies (fastest at every level of the bench network),
       // then the row-tiled kernel (RVIP_NO_HALO_WGRAD=1), then the generic per-tap kernel
@@ -600,6 +641,10 @@ static int conv_forward(rvip_handle* h, Layer& l, const float* x, bool training,
     if (l.use_rfwd) {
       l.rfwd.mode = mode;
       return timed(h, KC_CONV_FWD_TC, 1, st, [&] { return conv_row_launch(l.rfwd, l.rfBN, l.rfR, l.rfNst, st); });
+    }
+    if (l.use_hfwd) {
+      l.hfwd.mode = mode;
+      return timed(h, KC_CONV_FWD_TC, 1, st, [&] { return conv_halo_launch(l.hfwd, l.hfBN, l.hfNb, st); });
     }
     l.fwd.mode = mode;
     return timed(h, KC_CONV_FWD_TC, 1, st, [&] { return conv_tc_launch(l.fwd, l.fKC, l.fBN, st); });
@@ -733,8 +778,9 @@ static int backward_body(rvip_handle* h, const float* x, uint64_t seed, cudaStre
           }))
         return 1;
       if (timed(h, KC_CONV_DGRAD_TC, 1, st, [&] {
-            return l.use_rdgrad ? conv_row_launch(l.rdgrad, l.rdBN, l.rdR, l.rdNst, st)
-                                : conv_tc_launch(l.dgrad, l.dKC, l.dBN, st);
+            if (l.use_rdgrad) return conv_row_launch(l.rdgrad, l.rdBN, l.rdR, l.rdNst, st);
+            if (l.use_hdgrad) return conv_halo_launch(l.hdgrad, l.hdBN, l.hdNb, st);
+            return conv_tc_launch(l.dgrad, l.dKC, l.dBN, st);
           }))
         return 1;
     } else if (l.first && l.C0 == 1 && l.Cout <= 256 && l.W % 4 == 0) {
@@ -1035,6 +1081,18 @@ int rvip_wgrad3x3_tc(const void* x0, const void* x1, int C0, int C1, const void*
   int CBA, CBB;
   if (setup_wgrad_tc(&a, &CBA, &CBB, x0, x1, C0, C1, dz, dw, B, H, W, Cout)) return 1;
   return wgrad_tc_launch(a, CBA, CBB, (cudaStream_t)stream);
+}
+
+int rvip_conv3x3_halo(const void* in0, const void* in1, int C0, int C1, const void* w_packed, const float* bias,
+                      void* out0, void* out1, int out_split, double* stats, int B, int H, int W, int Cout, int mode,
+                      void* stream) {
+  ConvHaloArgs a;
+  int BN, nb;
+  RVIP_REQUIRE(conv_halo_plan(B, H, W, C0, C1, Cout, mode, out_split, &BN, &nb),
+               "rvip_conv3x3_halo: shape not eligible for the halo kernel");
+  if (setup_conv_halo(&a, BN, in0, in1, C0, C1, w_packed, out0, out1, out_split, B, H, W, Cout, mode, bias, stats))
+    return 1;
+  return conv_halo_launch(a, BN, nb, (cudaStream_t)stream);
 }
 
 int rvip_wgrad3x3_halo(const void* x0, const void* x1, int C0, int C1, const void* dz, float* dw, int B, int H, int W,

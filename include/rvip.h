@@ -134,6 +134,11 @@ int rvip_conv3x3_row(const void* in0, const void* in1, int C0, int C1, const voi
 int rvip_wgrad3x3_row(const void* x0, const void* x1, int C0, int C1, const void* dz, float* dw, int B, int H, int W,
                       int Cout, void* stream);
 
+/* Halo-staged conv for the deep levels (H, W % 16 == 0, channels % 64 == 0): 16 x 16 pixel blocks staged once with
+ * their halo, two 128-row accumulators per CTA share every weight tile. Same contract as rvip_conv3x3_tc. */
+int rvip_conv3x3_halo(const void* in0, const void* in1, int C0, int C1, const void* w_packed, const float* bias,
+                      void* out0, void* out1, int out_split, double* stats, int B, int H, int W, int Cout, int mode,
+                      void* stream);
 /* Halo-staged wgrad for the deep levels (W % 16 == 0): one input-channel chunk per CTA, the x tile staged once
  * with its halo, all nine taps accumulated in TMEM. Same contract as rvip_wgrad3x3_tc. */
 int rvip_wgrad3x3_halo(const void* x0, const void* x1, int C0, int C1, const void* dz, float* dw, int B, int H, int W,

@@ -113,3 +113,21 @@ def wgrad_halo(x0, x1, dz):
                                            stream()))
     torch.cuda.synchronize()
     return dw
+
+
+def conv_halo(in0, in1, w_packed, bias, cout, mode, out_split=None, want_stats=False):
+    B, H, W, C0 = in0.shape
+    C1 = in1.shape[3] if in1 is not None else 0
+    dev = in0.device
+    if out_split is None:
+        out_split = cout
+    out0 = torch.full((B, H, W, out_split if mode == 2 else cout), float('nan'), dtype=torch.bfloat16, device=dev)
+    out1 = None
+    if mode == 2 and out_split < cout:
+        out1 = torch.full((B, H, W, cout - out_split), float('nan'), dtype=torch.bfloat16, device=dev)
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device=dev) if want_stats else None
+    ffi.check(ffi.lib().rvip_conv3x3_halo(ffi.ptr(in0), ffi.ptr(in1), C0, C1, ffi.ptr(w_packed), ffi.ptr(bias),
+                                          ffi.ptr(out0), ffi.ptr(out1), out_split, ffi.ptr(stats), B, H, W, cout, mode,
+                                          stream()))
+    torch.cuda.synchronize()
+    return out0, out1, stats
