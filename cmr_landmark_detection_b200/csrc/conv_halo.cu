@@ -19,6 +19,8 @@
 // Replaces tf.keras Conv2D forward and Conv2DBackpropInput (src/models/KerasLayers.py:683,689,758).
 #include "conv_halo.cuh"
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_prims.cuh"
 
@@ -60,11 +62,13 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
   uint8_t* a_ring = smem;                                     // 2 activation blocks
   uint8_t* b_ring = a_ring + 2 * kHaloASlot;                  // nbst weight tiles
   uint8_t* staging = b_ring + (size_t)nbst * Cfg::B_BYTES;    // 2 groups x SB slices
-  float* s_sum = reinterpret_cast<float*>(staging + 2 * Cfg::SB * Cfg::STG);
-  float* s_sq = s_sum + a.Cout;
-  HaloCtl* ctl = reinterpret_cast<HaloCtl*>((reinterpret_cast<uintptr_t>(s_sq + a.Cout) + 15) & ~uintptr_t(15));
+  float* s_part = reinterpret_cast<float*>(staging + 2 * Cfg::SB * Cfg::STG);   // [2 groups][2][Cout] sum, sum^2
+  float* s_scr = s_part + 4 * a.Cout;                                            // [2 groups][4 warps][8][16]
+  float* s_bias = s_scr + 2 * 4 * 8 * 16;                                        // [Cout]
+  HaloCtl* ctl = reinterpret_cast<HaloCtl*>((reinterpret_cast<uintptr_t>(s_bias + a.Cout) + 15) & ~uintptr_t(15));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t_kernel = a.dbg ? clock64() : 0;
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&a.in0);
     prefetch_tmap(&a.in1);
@@ -90,7 +94,9 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
     tmem_relinquish();
   }
   if (warp >= 4) {
-    for (int c = threadIdx.x - 128; c < 2 * a.Cout; c += 256) s_sum[c] = 0.f;
+    for (int c = threadIdx.x - 128; c < 4 * a.Cout; c += 256) s_part[c] = 0.f;
+    // the bias lives in shared memory: per-element __ldg in the epilogue exposed one L2 latency per 8 channels
+    for (int c = threadIdx.x - 128; c < a.Cout; c += 256) s_bias[c] = a.mode != EPI_LINEAR ? a.bias[c] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -102,23 +108,34 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       int as = 0, aphase = 0, bs = 0, bphase = 0;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-        const int nt = tile % a.n_ntiles, pt = tile / a.n_ntiles;
+      // activation block of (tile, chunk c): issued one chunk AHEAD, in the middle of the previous chunk's weight
+      // tiles -- late enough that its ring slot has been released (no stall of the weight stream), early enough
+      // that the ~3000-cycle load lands before the chunk starts
+      auto load_act = [&](int tile, int c) {
+        const int pt = tile / a.n_ntiles;
         const int x0 = (pt % a.tiles_x) * 16;
         const int y0 = ((pt / a.tiles_x) % a.tiles_y) * 16;
         const int b = pt / (a.tiles_x * a.tiles_y);
-        const int n0 = nt * BN;
+        const int cc = c * 64;
+        mbar_wait(&ctl->aempty[as], aphase ^ 1);
+        mbar_expect_tx(&ctl->afull[as], kHaloATx);
+        if (cc < a.C0)
+          tma_load_4d(a_ring + as * kHaloASlot, &a.in0, &ctl->afull[as], cc, x0 - 1, y0 - 1, b);
+        else
+          tma_load_4d(a_ring + as * kHaloASlot, &a.in1, &ctl->afull[as], cc - a.C0, x0 - 1, y0 - 1, b);
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      };
+      if ((int)blockIdx.x < a.total_tiles) load_act(blockIdx.x, 0);
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % a.n_ntiles) * BN;
         for (int c = 0; c < nchunks; ++c) {
           const int cc = c * 64;
-          mbar_wait(&ctl->aempty[as], aphase ^ 1);
-          mbar_expect_tx(&ctl->afull[as], kHaloATx);
-          if (cc < a.C0)
-            tma_load_4d(a_ring + as * kHaloASlot, &a.in0, &ctl->afull[as], cc, x0 - 1, y0 - 1, b);
-          else
-            tma_load_4d(a_ring + as * kHaloASlot, &a.in1, &ctl->afull[as], cc - a.C0, x0 - 1, y0 - 1, b);
-          as ^= 1;
-          if (as == 0) aphase ^= 1;
           for (int tap = 0; tap < 9; ++tap) {
+            if (tap == (nbst < 6 ? nbst : 6)) {   // the MMA pipe is then inside this chunk: the slot of chunk c-1 is free
+              if (c + 1 < nchunks) load_act(tile, c + 1);
+              else if (tile + (int)gridDim.x < a.total_tiles) load_act(tile + gridDim.x, 0);
+            }
             mbar_wait(&ctl->bempty[bs], bphase ^ 1);
             mbar_expect_tx(&ctl->bfull[bs], Cfg::B_BYTES);
             tma_load_2d(b_ring + (size_t)bs * Cfg::B_BYTES, &a.w, &ctl->bfull[bs], tap * a.Ctot + cc, n0);
@@ -135,18 +152,26 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
       int as = 0, aphase = 0, bs = 0, bphase = 0, buf = 0, tphase = 0;
+      // optional wait-time accounting of the issuing thread (a.dbg != nullptr): where does the main loop stall?
+      long long w_t = 0, w_a = 0, w_b = 0, t_begin = a.dbg ? clock64() : 0;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        long long t0 = a.dbg ? clock64() : 0;
         mbar_wait(&ctl->tempty[buf], tphase ^ 1);
+        if (a.dbg) w_t += clock64() - t0;
         tc_fence_after();
         const uint32_t d0 = tmem_base + buf * 2 * BN;
         for (int c = 0; c < nchunks; ++c) {
+          t0 = a.dbg ? clock64() : 0;
           mbar_wait(&ctl->afull[as], aphase);
+          if (a.dbg) w_a += clock64() - t0;
           tc_fence_after();
           // rows = 8-pixel groups (one image row of the half tile each), kHaloPitch pixels apart
           const uint64_t adesc0 = make_smem_desc(smem_u32(a_ring + as * kHaloASlot), 16, kHaloPitch * 128, kLayoutSW128);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
+            t0 = a.dbg ? clock64() : 0;
             mbar_wait(&ctl->bfull[bs], bphase);
+            if (a.dbg) w_b += clock64() - t0;
             tc_fence_after();
             const uint64_t bdesc0 = make_smem_desc(smem_u32(b_ring + (size_t)bs * Cfg::B_BYTES), 16, 1024, kLayoutSW128);
 #pragma unroll
@@ -175,6 +200,12 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
           tphase ^= 1;
         }
       }
+      if (a.dbg) {
+        a.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin;
+        a.dbg[blockIdx.x * 8 + 1] = w_t;
+        a.dbg[blockIdx.x * 8 + 2] = w_a;
+        a.dbg[blockIdx.x * 8 + 3] = w_b;
+      }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue: group 0 = left half, 1 = right half
@@ -184,6 +215,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
     const int gt = threadIdx.x - 128 - grp * 128;   // thread index inside the group
     uint8_t* stg = staging + (size_t)grp * Cfg::SB * Cfg::STG;
     int buf = 0, tphase = 0, sb = 0;
+    long long t_epi = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
       const int nt = tile % a.n_ntiles, pt = tile / a.n_ntiles;
       const int x0 = (pt % a.tiles_x) * 16 + 8 * grp;
@@ -192,6 +224,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
       const int n0 = nt * BN;
       mbar_wait(&ctl->tfull[buf], tphase);
       tc_fence_after();
+      const long long t_e0 = a.dbg ? clock64() : 0;
       const uint32_t acc = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * 2 * BN + grp * BN;
 #pragma unroll 1
       for (int sl = 0; sl < BN / 64; ++sl) {
@@ -211,9 +244,14 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
           for (int q = 0; q < 4; ++q) {
             float f[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              f[j] = __uint_as_float(v[q * 8 + j]);
-              if (a.mode != EPI_LINEAR) f[j] = fmaxf(f[j] + __ldg(a.bias + n0 + sl * 64 + hc * 32 + q * 8 + j), 0.f);
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]);
+            if (a.mode != EPI_LINEAR) {
+              const float4 b0 = *reinterpret_cast<const float4*>(s_bias + n0 + sl * 64 + hc * 32 + q * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(s_bias + n0 + sl * 64 + hc * 32 + q * 8 + 4);
+              f[0] = fmaxf(f[0] + b0.x, 0.f); f[1] = fmaxf(f[1] + b0.y, 0.f);
+              f[2] = fmaxf(f[2] + b0.z, 0.f); f[3] = fmaxf(f[3] + b0.w, 0.f);
+              f[4] = fmaxf(f[4] + b1.x, 0.f); f[5] = fmaxf(f[5] + b1.y, 0.f);
+              f[6] = fmaxf(f[6] + b1.z, 0.f); f[7] = fmaxf(f[7] + b1.w, 0.f);
             }
             uint4 pk;
             __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
@@ -266,12 +304,23 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
               q2[j] += __shfl_xor_sync(0xffffffffu, q2[j], o);
             }
           }
+          // fold the group's four warps through a small scratch tile; channel ch of the slice is then owned by
+          // exactly one thread of the group (plain +=, no shared-memory float atomics = CAS loops)
+          float* scr = s_scr + (size_t)grp * 4 * 8 * 16;
           if (lane < 8) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              atomicAdd(&s_sum[n0 + sl * 64 + cg * 8 + j], s[j]);
-              atomicAdd(&s_sq[n0 + sl * 64 + cg * 8 + j], q2[j]);
+              scr[(ew * 8 + cg) * 16 + j] = s[j];
+              scr[(ew * 8 + cg) * 16 + 8 + j] = q2[j];
             }
+          }
+          halo_bar_sync(1 + grp, 128);
+          {
+            const int ch = gt & 63, which = gt >> 6;
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) v += scr[(w * 8 + (ch >> 3)) * 16 + which * 8 + (ch & 7)];
+            s_part[(size_t)(grp * 2 + which) * a.Cout + n0 + sl * 64 + ch] += v;
           }
         }
         if (Cfg::SB == 2) sb ^= 1;
@@ -282,25 +331,26 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
       } else {
         tphase ^= 1;
       }
+      if (a.dbg) t_epi += clock64() - t_e0;
     }
+    if (a.dbg && threadIdx.x == 128) a.dbg[blockIdx.x * 8 + 5] = t_epi;
     if (gt == 0) tma_store_wait_all0();
     if (a.mode == EPI_RELU_STATS) {
       halo_bar_sync(3, 256);
-      for (int c = threadIdx.x - 128; c < a.Cout; c += 256) {
-        atomicAdd(&a.stats[c], (double)s_sum[c]);
-        atomicAdd(&a.stats[a.Cout + c], (double)s_sq[c]);
-      }
+      for (int c = threadIdx.x - 128; c < 2 * a.Cout; c += 256)
+        atomicAdd(&a.stats[c], (double)s_part[c] + (double)s_part[2 * a.Cout + c]);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (a.dbg && threadIdx.x == 0) a.dbg[blockIdx.x * 8 + 4] = clock64() - t_kernel;
 }
 
 // ------------------------------------------------------------------------------------- host
 static size_t halo_fixed_bytes(int BN, int Cout) {
   const int sb = BN <= 128 ? 2 : 1;
-  return 1024 + 2 * (size_t)kHaloASlot + 2 * (size_t)sb * 128 * 128 + 2 * (size_t)Cout * sizeof(float) + sizeof(HaloCtl) + 64;
+  return 1024 + 2 * (size_t)kHaloASlot + 2 * (size_t)sb * 128 * 128 + (5 * (size_t)Cout + 2 * 4 * 8 * 16) * sizeof(float) + sizeof(HaloCtl) + 64;
 }
 
 bool conv_halo_plan(int B, int H, int W, int C0, int C1, int Cout, int mode, int out_split, int* BN, int* nbst) {
@@ -315,6 +365,8 @@ bool conv_halo_plan(int B, int H, int W, int C0, int C1, int Cout, int mode, int
     return (double)t / (double)(((t + kNumSMs - 1) / kNumSMs) * kNumSMs);
   };
   if (bn == 256 && waves_eff(256) < 0.67 && waves_eff(128) > waves_eff(256)) bn = 128;
+  // BN = 256 fills TMEM with one tile (no double buffering): with several tiles per CTA every epilogue is exposed
+  if (bn == 256 && mtiles * (Cout / 256) > kNumSMs && getenv("RVIP_HALO_BN256") == nullptr) bn = 128;
   const size_t fixed = halo_fixed_bytes(bn, Cout);
   if (fixed >= (size_t)kHaloMaxSmem) return false;
   int n = (int)((kHaloMaxSmem - fixed) / ((size_t)bn * 128));

@@ -93,7 +93,7 @@ struct FwdCfg {
 
 size_t conv_tc_smem_bytes(int KC, int BN, int Cout) {
   // stages are added by the launcher; this is the fixed part
-  return 1024 + (size_t)128 * BN * 2 + (size_t)2 * Cout * sizeof(float) + sizeof(SmemCtl) + 64;
+  return 1024 + (size_t)128 * BN * 2 + (size_t)3 * Cout * sizeof(float) + sizeof(SmemCtl) + 64;
 }
 
 template <int KC, int BN>
@@ -104,7 +104,8 @@ __global__ void __launch_bounds__(256, 1) conv3x3_tc_kernel(const __grid_constan
   uint8_t* staging = smem + (size_t)nst * Cfg::STAGE;
   float* s_sum = reinterpret_cast<float*>(staging + Cfg::STAGING);
   float* s_sq = s_sum + a.Cout;
-  SmemCtl* ctl = reinterpret_cast<SmemCtl*>((reinterpret_cast<uintptr_t>(s_sq + a.Cout) + 15) & ~uintptr_t(15));
+  float* s_bias = s_sq + a.Cout;
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>((reinterpret_cast<uintptr_t>(s_bias + a.Cout) + 15) & ~uintptr_t(15));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const TileGeom g = a.g;
@@ -133,6 +134,8 @@ __global__ void __launch_bounds__(256, 1) conv3x3_tc_kernel(const __grid_constan
   }
   if (warp >= 4) {
     for (int c = threadIdx.x - 128; c < 2 * a.Cout; c += 128) s_sum[c] = 0.f;
+    // bias in shared memory: a per-element __ldg in the epilogue exposes an L2 latency per 8 channels
+    for (int c = threadIdx.x - 128; c < a.Cout; c += 128) s_bias[c] = a.mode != EPI_LINEAR ? a.bias[c] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(256, 1) conv3x3_tc_kernel(const __grid_constan
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             f[j] = __uint_as_float(v[q * 8 + j]);
-            if (a.mode != EPI_LINEAR) f[j] = fmaxf(f[j] + __ldg(a.bias + n0 + ch * 32 + q * 8 + j), 0.f);
+            if (a.mode != EPI_LINEAR) f[j] = fmaxf(f[j] + s_bias[n0 + ch * 32 + q * 8 + j], 0.f);
           }
           uint4 pk;
           __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);

@@ -155,6 +155,7 @@ static int setup_conv_halo(ConvHaloArgs* a, int BN, const void* in0, const void*
   a->mode = mode;
   a->out_split = (mode == EPI_LINEAR) ? out_split : Cout;
   a->bias = bias; a->stats = stats;
+  a->dbg = nullptr;
   if (make_act_map_box(&a->in0, in0, B, H, W, C0, 64, 18, 18, 1)) return 1;
   if (C1 > 0) {
     if (make_act_map_box(&a->in1, in1, B, H, W, C1, 64, 18, 18, 1)) return 1;
@@ -1083,6 +1084,13 @@ int rvip_wgrad3x3_tc(const void* x0, const void* x1, int C0, int C1, const void*
   return wgrad_tc_launch(a, CBA, CBB, (cudaStream_t)stream);
 }
 
+/* debug: device buffer [148][4] of long long receiving the issue-loop wait accounting of rvip_conv3x3_halo */
+static long long* g_halo_dbg = nullptr;
+int rvip_conv3x3_halo_debug(long long* dbg) {
+  g_halo_dbg = dbg;
+  return 0;
+}
+
 int rvip_conv3x3_halo(const void* in0, const void* in1, int C0, int C1, const void* w_packed, const float* bias,
                       void* out0, void* out1, int out_split, double* stats, int B, int H, int W, int Cout, int mode,
                       void* stream) {
@@ -1092,6 +1100,7 @@ int rvip_conv3x3_halo(const void* in0, const void* in1, int C0, int C1, const vo
                "rvip_conv3x3_halo: shape not eligible for the halo kernel");
   if (setup_conv_halo(&a, BN, in0, in1, C0, C1, w_packed, out0, out1, out_split, B, H, W, Cout, mode, bias, stats))
     return 1;
+  a.dbg = g_halo_dbg;
   return conv_halo_launch(a, BN, nb, (cudaStream_t)stream);
 }
 

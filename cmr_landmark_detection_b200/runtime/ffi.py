@@ -71,6 +71,7 @@ _SIGS = {
     'rvip_launch_count': (_LL, [_VP]),
     'rvip_conv3x3_tc': (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _I, _VP, _I, _I, _I, _I, _I, _VP]),
     'rvip_conv3x3_halo': (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _I, _VP, _I, _I, _I, _I, _I, _VP]),
+    'rvip_conv3x3_halo_debug': (_I, [_VP]),
     'rvip_conv3x3_row': (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, _VP]),
     'rvip_wgrad3x3_row': (_I, [_VP, _VP, _I, _I, _VP, _VP, _I, _I, _I, _I, _VP]),
     'rvip_wgrad3x3_tc': (_I, [_VP, _VP, _I, _I, _VP, _VP, _I, _I, _I, _I, _VP]),

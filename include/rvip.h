@@ -139,6 +139,9 @@ int rvip_wgrad3x3_row(const void* x0, const void* x1, int C0, int C1, const void
 int rvip_conv3x3_halo(const void* in0, const void* in1, int C0, int C1, const void* w_packed, const float* bias,
                       void* out0, void* out1, int out_split, double* stats, int B, int H, int W, int Cout, int mode,
                       void* stream);
+/* profiling aid: dbg (device, [148][8] int64) receives per CTA {issue-loop cycles, cycles waiting for a free
+ * accumulator, for the activation block, for a weight tile, whole-kernel cycles, epilogue cycles} of subsequent rvip_conv3x3_halo calls; NULL = off */
+int rvip_conv3x3_halo_debug(long long* dbg);
 /* Halo-staged wgrad for the deep levels (W % 16 == 0): one input-channel chunk per CTA, the x tile staged once
  * with its halo, all nine taps accumulated in TMEM. Same contract as rvip_wgrad3x3_tc. */
 int rvip_wgrad3x3_halo(const void* x0, const void* x1, int C0, int C1, const void* dz, float* dw, int B, int H, int W,
