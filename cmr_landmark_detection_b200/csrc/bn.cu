@@ -73,6 +73,7 @@ __device__ __forceinline__ void upsampled_pixels(const BnArgs& a, uint32_t p, ui
 template <typename T, int POST>
 __global__ void __launch_bounds__(256) bn_apply_kernel(BnArgs a) {
   extern __shared__ float coef_s[];   // [2][C]: scale, shift
+  pdl_wait();
   for (int k = threadIdx.x; k < a.C; k += 256) {
     float m, r;
     if (a.stats) {
@@ -80,7 +81,9 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(BnArgs a) {
       double var = a.stats[a.C + k] * a.inv_count - mean * mean;   // biased batch variance
       if (var < 0) var = 0;
       m = (float)mean;
-      r = (float)(1.0 / sqrt(var + (double)a.eps));
+      // only the variance needs double (cancellation); 1/sqrt in fp32 is exact to ~1e-7 and 50x cheaper -- this
+      // prologue runs in every block
+      r = rsqrtf((float)var + a.eps);
       if (blockIdx.x == 0) {
         a.mean_out[k] = m;
         a.rstd_out[k] = r;
@@ -154,6 +157,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(BnArgs a) {
       for (int k = 0; k < 4; ++k) Vec8<T>::store(y2 + (size_t)q[k] * a.C, v);
     }
   }
+  pdl_launch_dependents();
 }
 
 static int ew_grid(size_t n_items, int per_sm) {
@@ -167,13 +171,13 @@ static int bn_apply_t(const BnArgs& a, cudaStream_t st) {
   const size_t P = (size_t)a.B * a.H * a.W;
   const int G = a.C / 8;
   const size_t n = (a.post == POST_POOL ? P / 4 : P) * G;
-  const int grid = ew_grid(n, 16);
+  const int grid = ew_grid(n, 6);   // persistent blocks: the per-block coefficient prologue is amortised
   const size_t sm = 2 * a.C * sizeof(float);
   switch (a.post) {
-    case POST_NONE: bn_apply_kernel<T, POST_NONE><<<grid, 256, sm, st>>>(a); break;
-    case POST_DROPOUT: bn_apply_kernel<T, POST_DROPOUT><<<grid, 256, sm, st>>>(a); break;
-    case POST_POOL: bn_apply_kernel<T, POST_POOL><<<grid, 256, sm, st>>>(a); break;
-    default: bn_apply_kernel<T, POST_UPSAMPLE><<<grid, 256, sm, st>>>(a); break;
+    case POST_NONE: launch_kernel(bn_apply_kernel<T, POST_NONE>, grid, 256, sm, st, a); break;
+    case POST_DROPOUT: launch_kernel(bn_apply_kernel<T, POST_DROPOUT>, grid, 256, sm, st, a); break;
+    case POST_POOL: launch_kernel(bn_apply_kernel<T, POST_POOL>, grid, 256, sm, st, a); break;
+    default: launch_kernel(bn_apply_kernel<T, POST_UPSAMPLE>, grid, 256, sm, st, a); break;
   }
   RVIP_LAUNCH_CHECK();
   return 0;
@@ -261,6 +265,7 @@ struct Gather {
 template <typename T, int POST>
 __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_reduce_kernel(BnArgs a) {
   extern __shared__ float red_s[];  // [2][C]
+  pdl_wait();
   constexpr int K = Gather<T, POST>::K;
   const Geo g = make_geo(a, POST == POST_POOL);
   for (int k = threadIdx.x; k < 2 * a.C; k += 256) red_s[k] = 0.f;
@@ -285,6 +290,7 @@ __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_reduce_
           s2[j] = fmaf(dy[k][j], av[k][j], s2[j]);
         }
     }
+    pdl_launch_dependents();
     block_accumulate8(red_s, c, s1, 1u << g.lg);
     block_accumulate8(red_s + a.C, c, s2, 1u << g.lg);
   }
@@ -299,10 +305,11 @@ __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_reduce_
 template <typename T, int POST>
 __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_apply_kernel(BnArgs a) {
   extern __shared__ float red_s[];  // [C] bias-gradient partials, then [4][C] sc, k1, c0, shift
+  pdl_wait();
   float* coef_s = red_s + a.C;
   constexpr int K = Gather<T, POST>::K;
   const Geo g = make_geo(a, POST == POST_POOL);
-  const double P = (double)a.B * a.H * a.W;
+  const double inv_P = 1.0 / ((double)a.B * a.H * a.W);
   for (int k = threadIdx.x; k < a.C; k += 256) {
     red_s[k] = 0.f;
     double s1 = 0.0, s2 = 0.0;
@@ -313,10 +320,10 @@ __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_apply_k
     }
     const double mu = a.mean[k], r = a.rstd[k], sck = (double)a.gamma[k] * r;
     const double sda = r * (s2 - mu * s1);          // sum dy * ahat
-    const double k1 = sck * r * (sda / P);
+    const double k1 = sck * r * (sda * inv_P);
     coef_s[k] = (float)sck;
     coef_s[a.C + k] = (float)k1;
-    coef_s[2 * a.C + k] = (float)(k1 * mu - sck * (s1 / P));
+    coef_s[2 * a.C + k] = (float)(k1 * mu - sck * (s1 * inv_P));
     coef_s[3 * a.C + k] = fmaf(-a.mean[k], a.gamma[k] * a.rstd[k], a.beta[k]);
     if (blockIdx.x == 0) {
       a.dbeta[k] = (float)s1;
@@ -359,6 +366,7 @@ __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_apply_k
         Vec8<T>::store(dzp + (size_t)pix[k] * a.C, dz);
       }
     }
+    pdl_launch_dependents();
     block_accumulate8(red_s, c, db, 1u << g.lg);
   }
   __syncthreads();
@@ -375,9 +383,9 @@ static int bn_bwd_t(const BnArgs& a, cudaStream_t st) {
   const size_t sm = (WHICH == 0 ? 2 : 5) * a.C * sizeof(float);
 #define RVIP_BWD(POSTV)                                                 \
   if (WHICH == 0)                                                       \
-    bn_bwd_reduce_kernel<T, POSTV><<<grid, 256, sm, st>>>(a);           \
+    launch_kernel(bn_bwd_reduce_kernel<T, POSTV>, grid, 256, sm, st, a); \
   else                                                                  \
-    bn_bwd_apply_kernel<T, POSTV><<<grid, 256, sm, st>>>(a);
+    launch_kernel(bn_bwd_apply_kernel<T, POSTV>, grid, 256, sm, st, a);
   switch (a.post) {
     case POST_NONE: RVIP_BWD(POST_NONE) break;
     case POST_DROPOUT: RVIP_BWD(POST_DROPOUT) break;
@@ -403,6 +411,7 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const T* __restrict__ u, 
                                                        T* __restrict__ dz, float* dbias, uint32_t n_items, uint32_t lg,
                                                        int C) {
   extern __shared__ float red_s[];
+  pdl_wait();
   for (int k = threadIdx.x; k < C; k += 256) red_s[k] = 0.f;
   __syncthreads();
   const uint32_t i0 = blockIdx.x * 256 + threadIdx.x;
@@ -423,6 +432,7 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const T* __restrict__ u, 
       }
       Vec8<T>::store(dz + off, gv);
     }
+    pdl_launch_dependents();
     block_accumulate8(red_s, c, db, 1u << lg);
   }
   __syncthreads();
@@ -438,13 +448,11 @@ int relu_bwd_launch(const void* u, const void* du, void* dz, float* dbias, size_
   const uint32_t n = (uint32_t)(pixels * G);
   const int grid = ew_grid(n, 4);
   if (is_bf16)
-    relu_bwd_kernel<__nv_bfloat16><<<grid, 256, C * sizeof(float), st>>>(
-        static_cast<const __nv_bfloat16*>(u), static_cast<const __nv_bfloat16*>(du), static_cast<__nv_bfloat16*>(dz),
-        dbias, n, lg, C);
+    launch_kernel(relu_bwd_kernel<__nv_bfloat16>, grid, 256, C * sizeof(float), st, static_cast<const __nv_bfloat16*>(u),
+                  static_cast<const __nv_bfloat16*>(du), static_cast<__nv_bfloat16*>(dz), dbias, n, lg, C);
   else
-    relu_bwd_kernel<float><<<grid, 256, C * sizeof(float), st>>>(static_cast<const float*>(u),
-                                                                  static_cast<const float*>(du),
-                                                                  static_cast<float*>(dz), dbias, n, lg, C);
+    launch_kernel(relu_bwd_kernel<float>, grid, 256, C * sizeof(float), st, static_cast<const float*>(u),
+                  static_cast<const float*>(du), static_cast<float*>(dz), dbias, n, lg, C);
   RVIP_LAUNCH_CHECK();
   return 0;
 }

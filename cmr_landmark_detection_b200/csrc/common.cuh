@@ -28,6 +28,34 @@ void set_error(const char* fmt, ...);
 
 constexpr int kNumSMs = 148;
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// A training step is ~165 stream-ordered launches, many of them a few microseconds long at the deep levels.
+// Every hot-path kernel can be launched with programmatic stream serialization: its CTAs may be scheduled while the
+// previous kernel drains, run their prologue (barrier init, TMEM allocation, tensor-map prefetch) and then block
+// in pdl_wait() until the previous grid has completed and its memory is visible.  pdl_launch_dependents() at the
+// top of a kernel allows the NEXT kernel to start that early.  Both are no-ops for a normal launch.
+// Opt-in with RVIP_PDL=1 (measured neutral on the bench step, see rvip_abi.cu:pdl_enabled).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---------------------------------------------------------------- storage-type traits
 // Activations are NHWC in T = float ("fp32 mode") or __nv_bfloat16 ("bf16 mode").
 // All element-wise kernels move 8 channels per thread (16 B for bf16, 32 B for fp32).

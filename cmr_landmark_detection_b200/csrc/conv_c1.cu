@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(256, 2) conv3x3_c1_fwd_kernel(const float* __r
                                                              double* __restrict__ stats, int B, int H, int W, int Cout,
                                                              int want_stats) {
   extern __shared__ float red_s[];  // [2][Cout]
+  pdl_wait();
   const uint32_t G = Cout >> 3, lg = 31 - __clz(G);
   const uint32_t Wq = W / kQuad;
   const uint32_t n_items = ((uint32_t)B * H * Wq) << lg;
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(256, 2) conv3x3_c1_fwd_kernel(const float* __r
         Vec8<Tout>::store(dst + (size_t)p * Cout, acc);
       }
     }
+    pdl_launch_dependents();
     if (want_stats) {
       block_accumulate8(red_s, c, s, G);
       block_accumulate8(red_s + Cout, c, q, G);
@@ -94,6 +96,7 @@ template <typename Tdz>
 __global__ void __launch_bounds__(256, 2) wgrad3x3_c1_kernel(const float* __restrict__ x, const Tdz* __restrict__ dz,
                                                           float* __restrict__ dw, int B, int H, int W, int Cout) {
   extern __shared__ float red_s[];  // [9][Cout]
+  pdl_wait();
   const uint32_t G = Cout >> 3, lg = 31 - __clz(G);
   const uint32_t Wq = W / kQuad;
   const uint32_t n_items = ((uint32_t)B * H * Wq) << lg;
@@ -127,6 +130,7 @@ __global__ void __launch_bounds__(256, 2) wgrad3x3_c1_kernel(const float* __rest
         }
       }
     }
+    pdl_launch_dependents();
 #pragma unroll
     for (int t = 0; t < 9; ++t) block_accumulate8(red_s + t * Cout, c, acc[t], G);
   }
@@ -152,11 +156,11 @@ int conv_c1_fwd_launch(const float* x, const float* w, const float* bias, void* 
   if (c1_check(B, H, W, Cout)) return 1;
   const int grid = c1_grid((size_t)B * H * (W / kQuad) * (Cout / 8));
   if (out_is_bf16)
-    conv3x3_c1_fwd_kernel<__nv_bfloat16><<<grid, 256, 2 * Cout * sizeof(float), st>>>(
-        x, w, bias, static_cast<__nv_bfloat16*>(out), stats, B, H, W, Cout, want_stats);
+    launch_kernel(conv3x3_c1_fwd_kernel<__nv_bfloat16>, grid, 256, 2 * Cout * sizeof(float), st, x, w, bias,
+                  static_cast<__nv_bfloat16*>(out), stats, B, H, W, Cout, want_stats);
   else
-    conv3x3_c1_fwd_kernel<float><<<grid, 256, 2 * Cout * sizeof(float), st>>>(x, w, bias, static_cast<float*>(out),
-                                                                              stats, B, H, W, Cout, want_stats);
+    launch_kernel(conv3x3_c1_fwd_kernel<float>, grid, 256, 2 * Cout * sizeof(float), st, x, w, bias,
+                  static_cast<float*>(out), stats, B, H, W, Cout, want_stats);
   RVIP_LAUNCH_CHECK();
   return 0;
 }
@@ -166,11 +170,11 @@ int wgrad_c1_launch(const float* x, const void* dz, float* dw, int B, int H, int
   if (c1_check(B, H, W, Cout)) return 1;
   const int grid = c1_grid((size_t)B * H * (W / kQuad) * (Cout / 8));
   if (dz_is_bf16)
-    wgrad3x3_c1_kernel<__nv_bfloat16><<<grid, 256, 9 * Cout * sizeof(float), st>>>(
-        x, static_cast<const __nv_bfloat16*>(dz), dw, B, H, W, Cout);
+    launch_kernel(wgrad3x3_c1_kernel<__nv_bfloat16>, grid, 256, 9 * Cout * sizeof(float), st, x,
+                  static_cast<const __nv_bfloat16*>(dz), dw, B, H, W, Cout);
   else
-    wgrad3x3_c1_kernel<float><<<grid, 256, 9 * Cout * sizeof(float), st>>>(x, static_cast<const float*>(dz), dw, B, H,
-                                                                           W, Cout);
+    launch_kernel(wgrad3x3_c1_kernel<float>, grid, 256, 9 * Cout * sizeof(float), st, x, static_cast<const float*>(dz),
+                  dw, B, H, W, Cout);
   RVIP_LAUNCH_CHECK();
   return 0;
 }

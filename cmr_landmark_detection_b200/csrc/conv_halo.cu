@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
     tmem_alloc(&ctl->tmem_base, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
+  pdl_wait();   // everything above is independent of the previous kernel's output
   if (warp >= 4) {
     for (int c = threadIdx.x - 128; c < 4 * a.Cout; c += 256) s_part[c] = 0.f;
     // the bias lives in shared memory: per-element __ldg in the epilogue exposed one L2 latency per 8 channels
@@ -341,6 +342,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
         atomicAdd(&a.stats[c], (double)s_part[c] + (double)s_part[2 * a.Cout + c]);
     }
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -387,7 +389,7 @@ static int launch_halo(const ConvHaloArgs& a, int nbst, cudaStream_t st) {
     attr_set = true;
   }
   const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
-  conv3x3_halo_kernel<BN><<<grid, 384, smem, st>>>(a, nbst);
+  launch_kernel(conv3x3_halo_kernel<BN>, grid, 384, smem, st, a, nbst);
   RVIP_LAUNCH_CHECK();
   return 0;
 }

@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
     tmem_alloc(&ctl->tmem_base, TMEM_COLS);
     tmem_relinquish();
   }
+  pdl_wait();   // everything above is independent of the previous kernel's output
   if (warp >= 4) {
     for (int c = threadIdx.x - 128; c < 16 * a.Cout; c += 256) s_slot[c] = 0.f;
     for (int c = threadIdx.x - 128; c < a.Cout; c += 256) s_bias[c] = a.mode != EPI_LINEAR ? a.bias[c] : 0.f;
@@ -293,6 +294,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
       }
     }
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
@@ -341,7 +343,7 @@ static int launch_row(const ConvRowArgs& a, int nst, cudaStream_t st) {
     attr_set = true;
   }
   const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
-  conv3x3_row_kernel<BN, R><<<grid, 384, smem, st>>>(a, nst);
+  launch_kernel(conv3x3_row_kernel<BN, R>, grid, 384, smem, st, a, nst);
   RVIP_LAUNCH_CHECK();
   return 0;
 }

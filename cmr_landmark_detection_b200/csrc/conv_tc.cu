@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(256, 1) conv3x3_tc_kernel(const __grid_constan
     tmem_alloc(&ctl->tmem_base, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
+  pdl_wait();   // everything above is independent of the previous kernel's output
   if (warp >= 4) {
     for (int c = threadIdx.x - 128; c < 2 * a.Cout; c += 128) s_sum[c] = 0.f;
     // bias in shared memory: a per-element __ldg in the epilogue exposes an L2 latency per 8 channels
@@ -319,6 +320,7 @@ __global__ void __launch_bounds__(256, 1) conv3x3_tc_kernel(const __grid_constan
       }
     }
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -339,7 +341,7 @@ static int launch_fwd(const ConvTcArgs& a, cudaStream_t st) {
     attr_set = true;
   }
   int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
-  conv3x3_tc_kernel<KC, BN><<<grid, 256, smem, st>>>(a, nst);
+  launch_kernel(conv3x3_tc_kernel<KC, BN>, dim3(grid), dim3(256), smem, st, a, nst);
   RVIP_LAUNCH_CHECK();
   return 0;
 }
@@ -417,6 +419,7 @@ __global__ void __launch_bounds__(256, 1) wgrad3x3_tc_kernel(const __grid_consta
     tmem_alloc(&ctl->tmem_base, tmem_cols);
     tmem_relinquish();
   }
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -506,6 +509,7 @@ __global__ void __launch_bounds__(256, 1) wgrad3x3_tc_kernel(const __grid_consta
       }
     }
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
@@ -528,7 +532,7 @@ static int launch_wgrad(const WgradTcArgs& a, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid(a.n_mgroups * a.n_ntiles, a.n_split);
-  wgrad3x3_tc_kernel<CBA, CBB><<<grid, 256, fixed + (size_t)nst * stage_bytes, st>>>(a, nst, cols);
+  launch_kernel(wgrad3x3_tc_kernel<CBA, CBB>, grid, dim3(256), fixed + (size_t)nst * stage_bytes, st, a, nst, cols);
   RVIP_LAUNCH_CHECK();
   return 0;
 }

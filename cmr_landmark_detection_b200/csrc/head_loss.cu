@@ -13,6 +13,7 @@ constexpr int kMaxNC = 4;
 template <typename T, bool TRAIN, int NCT>
 __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
   extern __shared__ float sm[];            // w [Cin*NC], b [NC], then (TRAIN) dw acc [Cin*NC], db acc [NC]
+  pdl_wait();
   const int NC = a.NC, Cin = a.Cin, G = Cin >> 3;
   float* w_s = sm;
   float* b_s = w_s + Cin * NC;
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
       }
     }
   }
+  pdl_launch_dependents();
   if (TRAIN) {
     // lanes l, l+G, l+2G, ... hold the same channels: fold them with shuffles so that G lanes per warp (not 32)
     // touch the shared accumulators (float atomicAdd on smem is a CAS loop; 64-way contention cost ~100 us)
@@ -181,14 +183,14 @@ int head_launch(const HeadArgs& a, int training, int is_bf16, cudaStream_t st) {
   if (a.NC == NCV) {                                                          \
     if (training) {                                                           \
       if (is_bf16)                                                            \
-        head_kernel<__nv_bfloat16, true, NCV><<<grid, 256, smem, st>>>(a);    \
+        launch_kernel(head_kernel<__nv_bfloat16, true, NCV>, grid, 256, smem, st, a);    \
       else                                                                    \
-        head_kernel<float, true, NCV><<<grid, 256, smem, st>>>(a);            \
+        launch_kernel(head_kernel<float, true, NCV>, grid, 256, smem, st, a);            \
     } else {                                                                  \
       if (is_bf16)                                                            \
-        head_kernel<__nv_bfloat16, false, NCV><<<grid, 256, smem, st>>>(a);   \
+        launch_kernel(head_kernel<__nv_bfloat16, false, NCV>, grid, 256, smem, st, a);   \
       else                                                                    \
-        head_kernel<float, false, NCV><<<grid, 256, smem, st>>>(a);           \
+        launch_kernel(head_kernel<float, false, NCV>, grid, 256, smem, st, a);           \
     }                                                                         \
   }
   RVIP_HEAD(1) RVIP_HEAD(2) RVIP_HEAD(3) RVIP_HEAD(4)

@@ -8,6 +8,7 @@ namespace rvip {
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, size_t n, float lr_t,
                                                    float b1, float b2, float eps, float gs) {
+  pdl_wait();
   const size_t n4 = n / 4;
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
@@ -27,6 +28,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     reinterpret_cast<float4*>(m)[i] = mm;
     reinterpret_cast<float4*>(v)[i] = vv;
   }
+  pdl_launch_dependents();
   if (blockIdx.x == 0) {
     for (size_t i = n4 * 4 + threadIdx.x; i < n; i += 256) {
       const float gr = g[i] * gs;
@@ -41,7 +43,7 @@ int adam_launch(float* p, const float* g, float* m, float* v, size_t n, float lr
   size_t blocks = (n / 4 + 255) / 256;
   if (blocks > (size_t)kNumSMs * 8) blocks = (size_t)kNumSMs * 8;
   if (blocks < 1) blocks = 1;
-  adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, n, lr_t, b1, b2, eps, grad_scale);
+  launch_kernel(adam_kernel, (unsigned)blocks, 256, 0, st, p, g, m, v, n, lr_t, b1, b2, eps, grad_scale);
   RVIP_LAUNCH_CHECK();
   return 0;
 }
@@ -52,6 +54,7 @@ int adam_launch(float* p, const float* g, float* m, float* v, size_t n, float lr
 template <typename TO, bool BF16>
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ params, TO* __restrict__ packed,
                                                            const PackEntry* __restrict__ table) {
+  pdl_wait();
   const PackEntry e = table[blockIdx.y];
   const long long n = 9LL * e.Ctot * e.Cout;
   const float* W = params + e.src;
@@ -77,10 +80,10 @@ int pack_weights_launch(const float* params, void* packed, const PackEntry* tabl
   if (n_entries == 0) return 0;
   dim3 grid(148, n_entries);
   if (to_bf16)
-    pack_weights_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>(params, static_cast<__nv_bfloat16*>(packed),
-                                                                    table_dev);
+    launch_kernel(pack_weights_kernel<__nv_bfloat16, true>, grid, 256, 0, st, params, static_cast<__nv_bfloat16*>(packed),
+                  table_dev);
   else
-    pack_weights_kernel<float, false><<<grid, 256, 0, st>>>(params, static_cast<float*>(packed), table_dev);
+    launch_kernel(pack_weights_kernel<float, false>, grid, 256, 0, st, params, static_cast<float*>(packed), table_dev);
   RVIP_LAUNCH_CHECK();
   return 0;
 }

@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(256, 1) wgrad3x3_halo_kernel(const __grid_cons
     tmem_alloc(&ctl->tmem_base, tmem_cols);
     tmem_relinquish();
   }
+  pdl_wait();   // everything above is independent of the previous kernel's output
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -210,6 +211,7 @@ __global__ void __launch_bounds__(256, 1) wgrad3x3_halo_kernel(const __grid_cons
       }
     }
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
@@ -274,7 +276,8 @@ static int launch_wh(const WgradHaloArgs& a, cudaStream_t st) {
                                    kWhMaxSmem));
     attr_set = true;
   }
-  wgrad3x3_halo_kernel<CIC, BN, TW><<<dim3(a.n_cchunks * a.n_ntiles, a.k_split), 256, smem, st>>>(a, nst, cols);
+  launch_kernel(wgrad3x3_halo_kernel<CIC, BN, TW>, dim3(a.n_cchunks * a.n_ntiles, a.k_split), dim3(256), smem, st, a, nst,
+                cols);
   RVIP_LAUNCH_CHECK();
   return 0;
 }

@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(256, 1) wgrad3x3_row_kernel(const __grid_const
     tmem_alloc(&ctl->tmem_base, tmem_cols);
     tmem_relinquish();
   }
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -187,6 +188,7 @@ __global__ void __launch_bounds__(256, 1) wgrad3x3_row_kernel(const __grid_const
       }
     }
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
@@ -227,7 +229,7 @@ static int launch_wg_row(const WgradRowArgs& a, int nst, cudaStream_t st) {
   int gx = kNumSMs / a.n_ntiles;
   if (gx > a.pixel_tiles) gx = a.pixel_tiles;
   if (gx < 1) gx = 1;
-  wgrad3x3_row_kernel<BN, R><<<dim3(gx, a.n_ntiles), 256, smem, st>>>(a, nst, cols);
+  launch_kernel(wgrad3x3_row_kernel<BN, R>, dim3(gx, a.n_ntiles), dim3(256), smem, st, a, nst, cols);
   RVIP_LAUNCH_CHECK();
   return 0;
 }

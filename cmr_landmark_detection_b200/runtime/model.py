@@ -467,6 +467,63 @@ class RvipUNet:
             loss = self.train_step_device(xd, yd)
             return float(loss.item())
 
+    def _run_steps(self, batches) -> List[float]:
+        """Pipelined training steps over an iterable of host (x, y) batches -- the loop inside fit().
+
+        Two staging slots: while the GPU runs step i, the host copies batch i+1 into pinned memory and a side
+        stream moves it to the device; the loss of step i is read back (async D2H + event) only after step i+1
+        has been queued, so the device never waits for the host.  Every step still pays its own H2D copy of
+        (x, y) and its own D2H read of the loss."""
+        losses: List[float] = []
+        with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream(self.device)
+            if not hasattr(self, '_copy_stream'):
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+                self._slot_ev = [dict(ready=torch.cuda.Event(), used=torch.cuda.Event(), loss=torch.cuda.Event())
+                                 for _ in range(2)]
+                self._loss_pin = [torch.zeros(1, dtype=torch.float64, pin_memory=True) for _ in range(2)]
+            cs = self._copy_stream
+            dev_slots: Dict[Tuple[int, Tuple[int, ...], Tuple[int, ...]], Tuple[torch.Tensor, torch.Tensor]] = {}
+            pending = None       # slot whose loss has not been read yet
+            used_once = [False, False]
+            for i, (x, y) in enumerate(batches):
+                x = np.ascontiguousarray(x, dtype=np.float32)
+                y = np.ascontiguousarray(y, dtype=np.float32)
+                self._check_x(x)
+                s = i & 1
+                ev = self._slot_ev[s]
+                if used_once[s]:
+                    ev['ready'].synchronize()       # the pinned slot's previous H2D has completed (long ago)
+                hx = self._pin('fx%d' % s, x.shape)
+                hy = self._pin('fy%d' % s, y.shape)
+                hx.copy_(torch.from_numpy(x))
+                hy.copy_(torch.from_numpy(y))
+                key = (s, tuple(x.shape), tuple(y.shape))
+                if key not in dev_slots:
+                    dev_slots[key] = (torch.empty(x.shape, dtype=torch.float32, device=self.device),
+                                      torch.empty(y.shape, dtype=torch.float32, device=self.device))
+                xd, yd = dev_slots[key]
+                if used_once[s]:
+                    cs.wait_event(ev['used'])       # step i-2 has finished reading this device slot
+                with torch.cuda.stream(cs):
+                    xd.copy_(hx, non_blocking=True)
+                    yd.copy_(hy, non_blocking=True)
+                    ev['ready'].record(cs)
+                main.wait_event(ev['ready'])
+                loss_dev = self.train_step_device(xd, yd)
+                ev['used'].record(main)
+                self._loss_pin[s].copy_(loss_dev.reshape(1), non_blocking=True)
+                ev['loss'].record(main)
+                used_once[s] = True
+                if pending is not None:
+                    self._slot_ev[pending]['loss'].synchronize()
+                    losses.append(float(self._loss_pin[pending][0]))
+                pending = s
+            if pending is not None:
+                self._slot_ev[pending]['loss'].synchronize()
+                losses.append(float(self._loss_pin[pending][0]))
+        return losses
+
     def evaluate(self, x, y=None, batch_size=32, verbose=0) -> float:
         """Validation loss (inference mode) -- reduction on the device with torch ops (not the hot path)."""
         tot, n = 0.0, 0
@@ -511,15 +568,12 @@ class RvipUNet:
             losses = []
             if is_seq:
                 n_steps = len(x) if steps_per_epoch is None else steps_per_epoch
-                for i in range(n_steps):
-                    xb, yb = x[i][:2]
-                    losses.append(self.train_on_batch(xb, yb))
+                losses = self._run_steps(tuple(x[i][:2]) for i in range(n_steps))
             else:
                 order = rng.permutation(len(x)) if shuffle else np.arange(len(x))
                 n_steps = len(x) // bs if steps_per_epoch is None else steps_per_epoch
-                for i in range(max(n_steps, 1)):
-                    idx = order[i * bs:(i + 1) * bs]
-                    losses.append(self.train_on_batch(x[idx], y[idx]))
+                losses = self._run_steps((x[order[i * bs:(i + 1) * bs]], y[order[i * bs:(i + 1) * bs]])
+                                         for i in range(max(n_steps, 1)))
             logs = {'loss': float(np.mean(losses)) if losses else float('nan'), 'lr': self.optimizer.lr}
             if validation_data is not None:
                 if isinstance(validation_data, (tuple, list)):

@@ -258,3 +258,29 @@ def test_fit_reduces_loss_and_callbacks_run():
                   verbose=0)
     assert len(seen) == 6 and h.history['loss'][-1] < h.history['loss'][0]
     assert 'val_loss' in h.history
+
+
+def test_pipelined_fit_equals_sequential_steps():
+    """fit() overlaps batch i+1's staging / H2D with step i: the per-step losses and the final weights must equal
+    the same batches pushed one by one through train_on_batch (fp32 mode, dropout off)."""
+    from cmr_landmark_detection_b200 import synth
+    from cmr_landmark_detection_b200.models.Unets import create_unet
+    x, y = synth.make_batch(20, 32, 32, seed=6)
+    batches = [(x[4 * i:4 * i + 4], y[4 * i:4 * i + 4]) for i in range(5)]
+
+    def run(pipelined):
+        model = create_unet(dict(BASE, DIM=[32, 32], DEPTH=2, PRECISION='fp32', SEED=3))
+        if pipelined:
+            losses = model._run_steps(iter(batches))
+        else:
+            losses = [model.train_on_batch(*b) for b in batches]
+        return losses, model.get_weights()
+    la, wa = run(True)
+    lb, wb = run(False)
+    assert len(la) == 5
+    # atomics make the gradient sums order-dependent at the 1e-6 level: compare to that, not bitwise
+    assert np.allclose(la, lb, rtol=1e-4), (la, lb)
+    # Adam turns 1e-6 gradient noise on near-zero elements into lr-sized differences: bound mean and max
+    for a, b in zip(wa, wb):
+        d = np.abs(a.astype(np.float64) - b)
+        assert d.mean() <= 2e-5 and d.max() <= 5e-3, (d.mean(), d.max())
