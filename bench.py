@@ -353,7 +353,10 @@ def extra_measurements(model, dev):
 
 
 def main():
-    os.environ['NCCL_DEBUG'] = os.environ.get('RVIP_NCCL_DEBUG', 'WARN')   # keep stdout to the one JSON line
+    if 'RVIP_NCCL_DEBUG' in os.environ:     # default: leave NCCL silent so stdout carries only the one JSON line
+        os.environ['NCCL_DEBUG'] = os.environ['RVIP_NCCL_DEBUG']
+    else:
+        os.environ.pop('NCCL_DEBUG', None)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)

@@ -48,14 +48,21 @@ __device__ __forceinline__ void row_mma_loop(const ConvRowArgs& a, RowCtl* ctl, 
   constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
   const uint32_t tmem_base = ZERO_BASE ? 0u : tmem_base_rt;
   int stage = 0, phase = 0, acc = 0, acc_phase = 0;
+  // optional wait accounting of the issuing thread (a.dbg != nullptr)
+  long long w_t = 0, w_f = 0, t0 = 0;
+  const long long t_begin = a.dbg ? clock64() : 0;
   if (a.wres) mbar_wait(&ctl->wfull, 0);
   for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
     const int nt = tile % a.n_ntiles;
+    if (a.dbg) t0 = clock64();
     mbar_wait(&ctl->tempty[acc], acc_phase ^ 1);
+    if (a.dbg) w_t += clock64() - t0;
     tc_fence_after();
     const uint32_t d0 = tmem_base + acc * ACC_COLS;
     for (int c = 0; c < nchunks; ++c) {
+      if (a.dbg) t0 = clock64();
       mbar_wait(&ctl->full[stage], phase);
+      if (a.dbg) w_f += clock64() - t0;
       tc_fence_after();
       const uint32_t a_base = smem_u32(stages + (size_t)stage * stage_bytes);
       const uint32_t w_base = a.wres ? smem_u32(wres) + ((nt * nchunks + c) * 9) * W_TILE : a_base + A_ST;
@@ -79,6 +86,12 @@ __device__ __forceinline__ void row_mma_loop(const ConvRowArgs& a, RowCtl* ctl, 
     mma_commit(&ctl->tfull[acc]);
     acc ^= 1;
     if (acc == 0) acc_phase ^= 1;
+  }
+  if (a.dbg) {
+    a.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin;
+    a.dbg[blockIdx.x * 8 + 1] = w_t;
+    a.dbg[blockIdx.x * 8 + 2] = w_f;
+    a.dbg[blockIdx.x * 8 + 3] = 0;
   }
 }
 
@@ -107,6 +120,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
   RowCtl* ctl = reinterpret_cast<RowCtl*>((reinterpret_cast<uintptr_t>(s_slot + 16 * a.Cout) + 15) & ~uintptr_t(15));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t_kernel = a.dbg ? clock64() : 0;
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&a.in0);
     prefetch_tmap(&a.in1);
@@ -207,6 +221,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
       row_bar_sync(1, 256);
       mbar_wait(&ctl->tfull[acc], acc_phase);
       tc_fence_after();
+      const long long t_e0 = a.dbg ? clock64() : 0;
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
         float bias[32], s1[32], s2[32];
@@ -282,6 +297,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+      if (a.dbg && et == 0) a.dbg[blockIdx.x * 8 + 5] += clock64() - t_e0;
     }
     if (et == 0) tma_store_wait_all0();
     if (a.mode == EPI_RELU_STATS) {
@@ -298,6 +314,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (a.dbg && threadIdx.x == 0) a.dbg[blockIdx.x * 8 + 4] = clock64() - t_kernel;
 }
 
 // ------------------------------------------------------------------------------------- host

@@ -19,6 +19,7 @@ struct ConvRowArgs {
   int base_offset_mode;    // debug knob: 1 = encode (addr>>7)&3 in the descriptor base-offset field
   const float* bias;
   double* stats;
+  long long* dbg;          // optional [grid][8]: issue-loop cycles, waits on TMEM / input stage, -, kernel, epilogue cycles
 };
 // Chooses the tile (BN, R), weight residency and stage count; false if the layer does not fit this kernel.
 bool conv_row_plan(int H, int W, int C0, int C1, int Cout, int mode, int out_split, int* BN, int* R, int* wres,

@@ -115,6 +115,7 @@ static int setup_conv_row(ConvRowArgs* a, int BN, int R, int wres, const void* i
   a->wres = wres;
   a->base_offset_mode = 0;
   a->bias = bias; a->stats = stats;
+  a->dbg = nullptr;
   if (make_act_map_box(&a->in0, in0, B, H, W, C0, 32, 130, R + 2, 1)) return 1;
   if (C1 > 0) {
     if (make_act_map_box(&a->in1, in1, B, H, W, C1, 32, 130, R + 2, 1)) return 1;
@@ -1130,6 +1131,7 @@ int rvip_conv3x3_row(const void* in0, const void* in1, int C0, int C1, const voi
                      stats))
     return 1;
   a.base_offset_mode = base_offset_mode;
+  a.dbg = g_halo_dbg;
   return conv_row_launch(a, BN, R, nst, (cudaStream_t)stream);
 }
 

@@ -23,20 +23,30 @@ SHAPES = [  # name, B, H, W, C0, C1, Cout
     ('enc2.conv_b', 32, 64, 64, 128, 0, 128),
     ('dec2.upconv', 32, 128, 128, 128, 0, 64),
 ]
+ROW_SHAPES = [
+    ('enc0.conv_b', 32, 256, 256, 32, 0, 32),
+    ('dec3.upconv', 32, 256, 256, 64, 0, 32),
+    ('dec3.conv_a', 32, 256, 256, 32, 32, 32),
+    ('dec3.up.dgrad', 32, 256, 256, 32, 0, 64),
+    ('enc1.conv_a', 32, 128, 128, 32, 0, 64),
+    ('enc1.conv_b', 32, 128, 128, 64, 0, 64),
+    ('dec2.upconv', 32, 128, 128, 128, 0, 64),
+    ('dec2.up.dgrad', 32, 128, 128, 64, 0, 128),
+]
 
 
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else 'halo'
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-    fn = {'halo': 'rvip_conv3x3_halo', 'tc': 'rvip_conv3x3_tc'}[which]
+    fn = {'halo': 'rvip_conv3x3_halo', 'tc': 'rvip_conv3x3_tc', 'row': 'rvip_conv3x3_row'}[which]
     L = ffi.lib()
     g = torch.Generator(device='cuda').manual_seed(1)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
     dbg = torch.zeros((148, 8), dtype=torch.int64, device='cuda')
-    if which == 'halo':
+    if which in ('halo', 'row'):
         L.rvip_conv3x3_halo_debug(ffi.ptr(dbg))
     print('kernel,layer,us,TFLOP/s,loop_cycles,wait_tmem,wait_act,wait_weights,kernel_cycles,epilogue_cycles')
-    for name, B, H, W, C0, C1, N in SHAPES:
+    for name, B, H, W, C0, C1, N in (ROW_SHAPES if which == 'row' else SHAPES):
         x0 = torch.randn((B, H, W, C0), generator=g, device='cuda').to(torch.bfloat16)
         x1 = torch.randn((B, H, W, C1), generator=g, device='cuda').to(torch.bfloat16) if C1 else None
         w = torch.randn((3, 3, C0 + C1, N), generator=g, device='cuda') * 0.02
@@ -47,8 +57,12 @@ def main():
         st = U.stream()
 
         def run():
-            ffi.check(getattr(L, fn)(ffi.ptr(x0), ffi.ptr(x1), C0, C1, ffi.ptr(wp), ffi.ptr(bias), ffi.ptr(out), None, N,
-                                     ffi.ptr(stats), B, H, W, N, 0, st))
+            if which == 'row':
+                ffi.check(L.rvip_conv3x3_row(ffi.ptr(x0), ffi.ptr(x1), C0, C1, ffi.ptr(wp), ffi.ptr(bias), ffi.ptr(out), None,
+                                             N, ffi.ptr(stats), B, H, W, N, 0, 0, st))
+            else:
+                ffi.check(getattr(L, fn)(ffi.ptr(x0), ffi.ptr(x1), C0, C1, ffi.ptr(wp), ffi.ptr(bias), ffi.ptr(out), None,
+                                         N, ffi.ptr(stats), B, H, W, N, 0, st))
         run()
         torch.cuda.synchronize()
         tot = 0.0
@@ -61,6 +75,9 @@ def main():
             torch.cuda.synchronize()
             tot += e0.elapsed_time(e1)
         us = tot / reps * 1e3
+        dbg.zero_()
+        run()
+        torch.cuda.synchronize()
         fl = 2.0 * 9 * (C0 + C1) * N * B * H * W
         d = dbg[0].tolist()
         print('%s,%s,%.1f,%.0f,%d,%d,%d,%d,%d,%d' % (which, name, us, fl / us / 1e6, d[0], d[1], d[2], d[3], d[4], d[5]))
