@@ -291,8 +291,18 @@ def run_b200(args):
         ach = cls_flops[dom] / (per_step[dom] * 1e-3) / 1e12
         conv_t = sum(per_step.get(k, 0.0) for k in cls_flops)
         conv_tf = sum(cls_flops.values()) / (conv_t * 1e-3) / 1e12
+        # DRAM traffic per launch of the dominant kernel class from the committed ncu --set full capture
+        traffic, traffic_src, ncu_pipe = None, None, None
+        tpath = os.path.join(ROOT, 'profiles', 'r1i_traffic.json')
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath)).get(dom)
+            if tj:
+                traffic = int(tj['dram_mbytes_per_launch'] * 1e6)
+                traffic_src = '%s, mean of %d launches' % (tj['source'], tj['launches_captured'])
+                ncu_pipe = tj.get('tensor_pipe_active_pct')
         roof = {'bound': 'tensor', 'kernel': dom, 'achieved': round(ach, 1), 'peak': peak_tf, 'unit': 'TFLOP/s',
-                'frac': round(ach / peak_tf, 4), 'traffic': None, 'peak_source': peak_src,
+                'frac': round(ach / peak_tf, 4), 'traffic': traffic, 'traffic_source': traffic_src,
+                'ncu_tensor_pipe_active_pct': ncu_pipe, 'peak_source': peak_src,
                 'all_conv_tcgen05_tflops': round(conv_tf, 1), 'all_conv_frac': round(conv_tf / peak_tf, 4),
                 'step_tensor_frac': round(fl['train'] * B / (ms / K * 1e-3) / 1e12 / peak_tf, 4),
                 'kernels': kern}
@@ -309,7 +319,7 @@ def run_b200(args):
                 'roofline': roof,
                 'cpu_baseline': {'value': round(cpu_rate, 3), 'unit': 'slices/s', 'cores': cores, 'kind': 'port',
                                  'sample': '4-slice fwd+bwd+Adam step x 2 (oracle, torch CPU fp32), %.2f s/step' % spt}}
-        if args.extra:
+        if not args.no_extra:
             line['extra'] = extra_measurements(model, dev)
         print(json.dumps(line))
     if world > 1:
@@ -362,7 +372,8 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--extra', action='store_true', help='also measure volume inference + extraction')
+    ap.add_argument('--no-extra', action='store_true', help='skip the secondary BASELINE metrics (volume inference '
+                    'vols/s with fused extraction, extraction GB/s)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -11,6 +11,8 @@
 //   dz = [a>0] * ( sc*dy - k1*a + c0 ),  sc = gamma*rstd, k1 = sc*rstd*mean(dy*ahat), c0 = k1*mu - sc*mean(dy)
 #include "kernels.cuh"
 
+#include <stdlib.h>
+
 namespace rvip {
 
 __device__ __forceinline__ void scale_shift8(const BnArgs& a, int c, float (&sc)[8], float (&sh)[8]) {
@@ -378,8 +380,10 @@ static int bn_bwd_t(const BnArgs& a, cudaStream_t st) {
   const size_t P = (size_t)a.B * a.H * a.W;
   const int G = a.C / 8;
   const size_t n = (a.post == POST_POOL ? P / 4 : P) * G;
-  // persistent grids: every block ends with C global atomics, so few, long-lived blocks
-  const int grid = ew_grid(n, a.post == POST_POOL ? 2 : 4);
+  // persistent grids: every block ends with C global atomics, so few, long-lived blocks; 3 (not 4) per SM leave
+  // registers for a co-resident weight-gradient CTA of the side stream (rvip_abi.cu:backward_body)
+  static const int per_sm = getenv("RVIP_BN_BWD_BLOCKS") ? atoi(getenv("RVIP_BN_BWD_BLOCKS")) : 3;
+  const int grid = ew_grid(n, a.post == POST_POOL ? 2 : per_sm);
   const size_t sm = (WHICH == 0 ? 2 : 5) * a.C * sizeof(float);
 #define RVIP_BWD(POSTV)                                                 \
   if (WHICH == 0)                                                       \

