@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
   // Software pipeline: the loads of y and of the target for the item kDepth grid-strides ahead are in flight
   // while the current item is processed (ncu: with the loads issued at the point of use, 55 % of the stall
   // samples of this kernel were long-scoreboard waits on exactly those two loads).
-  constexpr int kDepth = 3;
+  constexpr int kDepth = 4;
   Raw8<T> ybuf[kDepth];
   float tbuf[kDepth][NCT];
   auto issue = [&](int d, uint32_t i) {
