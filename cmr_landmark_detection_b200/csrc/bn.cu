@@ -24,6 +24,23 @@ __device__ __forceinline__ void scale_shift8(const BnArgs& a, int c, float (&sc)
 }
 
 // ------------------------------------------------------------------------------------- inference statistics
+__global__ void bn_eval_coef_kernel(const float* __restrict__ params, const float* __restrict__ state,
+                                    const BnEvalEntry* __restrict__ table, float eps, float* __restrict__ scale,
+                                    float* __restrict__ shift) {
+  const BnEvalEntry e = table[blockIdx.y];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= e.C) return;
+  const float sc = params[e.off_g + c] * (1.f / sqrtf(state[e.off_mv + c] + eps));
+  scale[e.off_stat + c] = sc;
+  shift[e.off_stat + c] = fmaf(-state[e.off_mm + c], sc, params[e.off_be + c]);
+}
+int bn_eval_coef_launch(const float* params, const float* bn_state, const BnEvalEntry* table_dev, int n_layers, int max_c,
+                        float eps, float* scale, float* shift, cudaStream_t st) {
+  if (n_layers == 0) return 0;
+  bn_eval_coef_kernel<<<dim3((max_c + 127) / 128, n_layers), 128, 0, st>>>(params, bn_state, table_dev, eps, scale, shift);
+  RVIP_LAUNCH_CHECK();
+  return 0;
+}
 __global__ void bn_eval_prepare_kernel(const float* mm, const float* mv, float* mean, float* rstd, int n, float eps) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n) return;
@@ -93,6 +110,10 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(BnArgs a) {
         a.mov_mean[k] = a.momentum * a.mov_mean[k] + (1.f - a.momentum) * m;
         a.mov_var[k] = a.momentum * a.mov_var[k] + (1.f - a.momentum) * (float)unb;
       }
+    } else if (a.identity) {
+      coef_s[k] = 1.f;
+      coef_s[a.C + k] = 0.f;
+      continue;
     } else {
       m = a.mean[k];
       r = a.rstd[k];
@@ -144,7 +165,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(BnArgs a) {
           v[j] = fmaf(v[j], sc[j], sh[j]);
           mx[j] = (k == 0) ? v[j] : fmaxf(mx[j], v[j]);
         }
-        Vec8<T>::store(y + (size_t)p[k] * a.C, v);
+        if (a.y) Vec8<T>::store(y + (size_t)p[k] * a.C, v);   // nullptr: pooling-only pass over an already normalised tensor
       }
       Vec8<T>::store(y2 + (size_t)win * a.C, mx);
     } else {  // POST_UPSAMPLE

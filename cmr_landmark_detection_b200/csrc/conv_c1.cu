@@ -30,7 +30,8 @@ template <typename Tout>
 __global__ void __launch_bounds__(256, 2) conv3x3_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ bias, Tout* __restrict__ out,
                                                              double* __restrict__ stats, int B, int H, int W, int Cout,
-                                                             int want_stats) {
+                                                             int want_stats, const float* __restrict__ scale,
+                                                             const float* __restrict__ shift) {
   extern __shared__ float red_s[];  // [2][Cout]
   pdl_wait();
   const uint32_t G = Cout >> 3, lg = 31 - __clz(G);
@@ -75,6 +76,10 @@ __global__ void __launch_bounds__(256, 2) conv3x3_c1_fwd_kernel(const float* __r
           acc[j] = fmaxf(acc[j], 0.f);
           s[j] += acc[j];
           q[j] = fmaf(acc[j], acc[j], q[j]);
+        }
+        if (scale) {   // inference: BatchNorm (moving statistics) folded into the epilogue
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(acc[j], __ldg(scale + c + j), __ldg(shift + c + j));
         }
         Vec8<Tout>::store(dst + (size_t)p * Cout, acc);
       }
@@ -152,15 +157,16 @@ static int c1_check(int B, int H, int W, int Cout) {
 }
 
 int conv_c1_fwd_launch(const float* x, const float* w, const float* bias, void* out, double* stats, int B, int H, int W,
-                       int Cout, int want_stats, int out_is_bf16, cudaStream_t st) {
+                       int Cout, int want_stats, int out_is_bf16, const float* scale, const float* shift,
+                       cudaStream_t st) {
   if (c1_check(B, H, W, Cout)) return 1;
   const int grid = c1_grid((size_t)B * H * (W / kQuad) * (Cout / 8));
   if (out_is_bf16)
     launch_kernel(conv3x3_c1_fwd_kernel<__nv_bfloat16>, grid, 256, 2 * Cout * sizeof(float), st, x, w, bias,
-                  static_cast<__nv_bfloat16*>(out), stats, B, H, W, Cout, want_stats);
+                  static_cast<__nv_bfloat16*>(out), stats, B, H, W, Cout, want_stats, scale, shift);
   else
     launch_kernel(conv3x3_c1_fwd_kernel<float>, grid, 256, 2 * Cout * sizeof(float), st, x, w, bias,
-                  static_cast<float*>(out), stats, B, H, W, Cout, want_stats);
+                  static_cast<float*>(out), stats, B, H, W, Cout, want_stats, scale, shift);
   RVIP_LAUNCH_CHECK();
   return 0;
 }

@@ -64,8 +64,8 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
   uint8_t* staging = b_ring + (size_t)nbst * Cfg::B_BYTES;    // 2 groups x SB slices
   float* s_part = reinterpret_cast<float*>(staging + 2 * Cfg::SB * Cfg::STG);   // [2 groups][2][Cout] sum, sum^2
   float* s_scr = s_part + 4 * a.Cout;                                            // [2 groups][4 warps][8][16]
-  float* s_bias = s_scr + 2 * 4 * 8 * 16;                                        // [Cout]
-  HaloCtl* ctl = reinterpret_cast<HaloCtl*>((reinterpret_cast<uintptr_t>(s_bias + a.Cout) + 15) & ~uintptr_t(15));
+  float* s_bias = s_scr + 2 * 4 * 8 * 16;                                        // [3][Cout]: bias, scale, shift
+  HaloCtl* ctl = reinterpret_cast<HaloCtl*>((reinterpret_cast<uintptr_t>(s_bias + 3 * a.Cout) + 15) & ~uintptr_t(15));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long t_kernel = a.dbg ? clock64() : 0;
@@ -97,7 +97,11 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
   if (warp >= 4) {
     for (int c = threadIdx.x - 128; c < 4 * a.Cout; c += 256) s_part[c] = 0.f;
     // the bias lives in shared memory: per-element __ldg in the epilogue exposed one L2 latency per 8 channels
-    for (int c = threadIdx.x - 128; c < a.Cout; c += 256) s_bias[c] = a.mode != EPI_LINEAR ? a.bias[c] : 0.f;
+    for (int c = threadIdx.x - 128; c < a.Cout; c += 256) {
+      s_bias[c] = a.mode != EPI_LINEAR ? a.bias[c] : 0.f;
+      s_bias[a.Cout + c] = a.mode == EPI_RELU_AFFINE ? a.scale[c] : 1.f;
+      s_bias[2 * a.Cout + c] = a.mode == EPI_RELU_AFFINE ? a.shift[c] : 0.f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -254,6 +258,11 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
               f[4] = fmaxf(f[4] + b1.x, 0.f); f[5] = fmaxf(f[5] + b1.y, 0.f);
               f[6] = fmaxf(f[6] + b1.z, 0.f); f[7] = fmaxf(f[7] + b1.w, 0.f);
             }
+            if (a.mode == EPI_RELU_AFFINE) {
+              const float* sc = s_bias + a.Cout + n0 + sl * 64 + hc * 32 + q * 8;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sc[a.Cout + j]);
+            }
             uint4 pk;
             __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
@@ -352,7 +361,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
 // ------------------------------------------------------------------------------------- host
 static size_t halo_fixed_bytes(int BN, int Cout) {
   const int sb = BN <= 128 ? 2 : 1;
-  return 1024 + 2 * (size_t)kHaloASlot + 2 * (size_t)sb * 128 * 128 + (5 * (size_t)Cout + 2 * 4 * 8 * 16) * sizeof(float) + sizeof(HaloCtl) + 64;
+  return 1024 + 2 * (size_t)kHaloASlot + 2 * (size_t)sb * 128 * 128 + (7 * (size_t)Cout + 2 * 4 * 8 * 16) * sizeof(float) + sizeof(HaloCtl) + 64;
 }
 
 bool conv_halo_plan(int B, int H, int W, int C0, int C1, int Cout, int mode, int out_split, int* BN, int* nbst) {

@@ -18,6 +18,8 @@ struct ConvHaloArgs {
   int mode, out_split;     // ConvEpilogue; EPI_LINEAR: output channels >= out_split go to out1
   const float* bias;
   double* stats;
+  const float* scale;      // [Cout] (EPI_RELU_AFFINE)
+  const float* shift;
   long long* dbg;          // optional [grid][8]: issue-loop cycles, waits on TMEM / activation block / weight tile, kernel cycles, epilogue cycles
 };
 // false if the layer does not fit (H, W not multiples of 16; channels not multiples of 64)

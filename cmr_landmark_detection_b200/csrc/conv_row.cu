@@ -117,7 +117,8 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
   uint8_t* staging = stages + (size_t)nst * stage_bytes;
   float* s_bias = reinterpret_cast<float*>(staging + STAGING);     // [Cout]
   float* s_slot = s_bias + a.Cout;                                  // [8 warps][2][Cout] sum / sum^2 partials
-  RowCtl* ctl = reinterpret_cast<RowCtl*>((reinterpret_cast<uintptr_t>(s_slot + 16 * a.Cout) + 15) & ~uintptr_t(15));
+  float* s_aff = s_slot + 16 * a.Cout;                              // [2][Cout] scale, shift (EPI_RELU_AFFINE)
+  RowCtl* ctl = reinterpret_cast<RowCtl*>((reinterpret_cast<uintptr_t>(s_aff + 2 * a.Cout) + 15) & ~uintptr_t(15));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long t_kernel = a.dbg ? clock64() : 0;
@@ -147,7 +148,11 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
   pdl_wait();   // everything above is independent of the previous kernel's output
   if (warp >= 4) {
     for (int c = threadIdx.x - 128; c < 16 * a.Cout; c += 256) s_slot[c] = 0.f;
-    for (int c = threadIdx.x - 128; c < a.Cout; c += 256) s_bias[c] = a.mode != EPI_LINEAR ? a.bias[c] : 0.f;
+    for (int c = threadIdx.x - 128; c < a.Cout; c += 256) {
+      s_bias[c] = a.mode != EPI_LINEAR ? a.bias[c] : 0.f;
+      s_aff[c] = a.mode == EPI_RELU_AFFINE ? a.scale[c] : 1.f;
+      s_aff[a.Cout + c] = a.mode == EPI_RELU_AFFINE ? a.shift[c] : 0.f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -246,6 +251,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
           for (int j = 0; j < 32; ++j) {
             f[j] = __uint_as_float(v[j]);
             if (a.mode != EPI_LINEAR) f[j] = fmaxf(f[j] + bias[j], 0.f);
+            if (a.mode == EPI_RELU_AFFINE) f[j] = fmaf(f[j], s_aff[n0 + ch * 32 + j], s_aff[a.Cout + n0 + ch * 32 + j]);
             if (a.mode == EPI_RELU_STATS) {
               s1[j] += f[j];
               s2[j] = fmaf(f[j], f[j], s2[j]);
@@ -319,7 +325,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
 
 // ------------------------------------------------------------------------------------- host
 static size_t row_fixed_bytes(int BN, int R, int Cout, int wres_bytes) {
-  return 1024 + (size_t)round1k(wres_bytes) + (size_t)R * 128 * BN * 2 + 17 * (size_t)Cout * sizeof(float) +
+  return 1024 + (size_t)round1k(wres_bytes) + (size_t)R * 128 * BN * 2 + 19 * (size_t)Cout * sizeof(float) +
          sizeof(RowCtl) + 64;
 }
 static size_t row_stage_bytes(int BN, int R, int wres) { return round1k(row_a_bytes(R)) + (wres ? 0 : 9 * BN * kPixB); }

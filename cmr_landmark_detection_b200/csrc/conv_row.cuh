@@ -19,6 +19,8 @@ struct ConvRowArgs {
   int base_offset_mode;    // debug knob: 1 = encode (addr>>7)&3 in the descriptor base-offset field
   const float* bias;
   double* stats;
+  const float* scale;      // [Cout] (EPI_RELU_AFFINE)
+  const float* shift;
   long long* dbg;          // optional [grid][8]: issue-loop cycles, waits on TMEM / input stage, -, kernel, epilogue cycles
 };
 // Chooses the tile (BN, R), weight residency and stage count; false if the layer does not fit this kernel.

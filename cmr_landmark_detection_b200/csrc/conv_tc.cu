@@ -93,7 +93,7 @@ struct FwdCfg {
 
 size_t conv_tc_smem_bytes(int KC, int BN, int Cout) {
   // stages are added by the launcher; this is the fixed part
-  return 1024 + (size_t)128 * BN * 2 + (size_t)3 * Cout * sizeof(float) + sizeof(SmemCtl) + 64;
+  return 1024 + (size_t)128 * BN * 2 + (size_t)5 * Cout * sizeof(float) + sizeof(SmemCtl) + 64;
 }
 
 template <int KC, int BN>
@@ -104,8 +104,8 @@ __global__ void __launch_bounds__(256, 1) conv3x3_tc_kernel(const __grid_constan
   uint8_t* staging = smem + (size_t)nst * Cfg::STAGE;
   float* s_sum = reinterpret_cast<float*>(staging + Cfg::STAGING);
   float* s_sq = s_sum + a.Cout;
-  float* s_bias = s_sq + a.Cout;
-  SmemCtl* ctl = reinterpret_cast<SmemCtl*>((reinterpret_cast<uintptr_t>(s_bias + a.Cout) + 15) & ~uintptr_t(15));
+  float* s_bias = s_sq + a.Cout;     // [3][Cout]: bias, scale, shift
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>((reinterpret_cast<uintptr_t>(s_bias + 3 * a.Cout) + 15) & ~uintptr_t(15));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const TileGeom g = a.g;
@@ -136,7 +136,11 @@ __global__ void __launch_bounds__(256, 1) conv3x3_tc_kernel(const __grid_constan
   if (warp >= 4) {
     for (int c = threadIdx.x - 128; c < 2 * a.Cout; c += 128) s_sum[c] = 0.f;
     // bias in shared memory: a per-element __ldg in the epilogue exposes an L2 latency per 8 channels
-    for (int c = threadIdx.x - 128; c < a.Cout; c += 128) s_bias[c] = a.mode != EPI_LINEAR ? a.bias[c] : 0.f;
+    for (int c = threadIdx.x - 128; c < a.Cout; c += 128) {
+      s_bias[c] = a.mode != EPI_LINEAR ? a.bias[c] : 0.f;
+      s_bias[a.Cout + c] = a.mode == EPI_RELU_AFFINE ? a.scale[c] : 1.f;
+      s_bias[2 * a.Cout + c] = a.mode == EPI_RELU_AFFINE ? a.shift[c] : 0.f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -238,6 +242,8 @@ __global__ void __launch_bounds__(256, 1) conv3x3_tc_kernel(const __grid_constan
           for (int j = 0; j < 8; ++j) {
             f[j] = __uint_as_float(v[q * 8 + j]);
             if (a.mode != EPI_LINEAR) f[j] = fmaxf(f[j] + s_bias[n0 + ch * 32 + q * 8 + j], 0.f);
+            if (a.mode == EPI_RELU_AFFINE)
+              f[j] = fmaf(f[j], s_bias[a.Cout + n0 + ch * 32 + q * 8 + j], s_bias[2 * a.Cout + n0 + ch * 32 + q * 8 + j]);
           }
           uint4 pk;
           __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);

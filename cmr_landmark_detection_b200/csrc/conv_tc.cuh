@@ -18,6 +18,7 @@ enum ConvEpilogue {
   EPI_RELU_STATS = 0,  // a = relu(acc + bias), bf16 store, per-channel sum / sum-of-squares (training, BN follows)
   EPI_RELU = 1,        // a = relu(acc + bias), bf16 store (up-conv; inference)
   EPI_LINEAR = 2,      // acc, bf16 store (dgrad); output channels >= out_split go to out1
+  EPI_RELU_AFFINE = 3, // y = scale * relu(acc + bias) + shift: inference, BatchNorm (moving statistics) folded in
 };
 
 // ---- forward / dgrad: out[p, n] = epi( sum_{tap, c} in[p + off(tap), c] * Wp[n][tap][c] )
@@ -32,6 +33,8 @@ struct ConvTcArgs {
   int mode, out_split;
   const float* bias;  // [Cout] (EPI_RELU*)
   double* stats;      // [2][Cout] (EPI_RELU_STATS)
+  const float* scale; // [Cout] (EPI_RELU_AFFINE)
+  const float* shift;
 };
 int conv_tc_launch(const ConvTcArgs& a, int KC, int BN, cudaStream_t st);
 size_t conv_tc_smem_bytes(int KC, int BN, int Cout);

@@ -28,8 +28,10 @@ struct WgradSimtArgs {
 int wgrad_simt_launch(const WgradSimtArgs& a, int in_is_bf16, int dz_is_bf16, cudaStream_t st);
 
 // Cin == 1 first layer (x fp32 [B,H,W], w [9][Cout] fp32)
+// scale / shift != nullptr: y = scale * relu(conv + bias) + shift (inference with BatchNorm folded in)
 int conv_c1_fwd_launch(const float* x, const float* w, const float* bias, void* out, double* stats, int B, int H, int W,
-                       int Cout, int want_stats, int out_is_bf16, cudaStream_t st);
+                       int Cout, int want_stats, int out_is_bf16, const float* scale, const float* shift,
+                       cudaStream_t st);
 int wgrad_c1_launch(const float* x, const void* dz, float* dw, int B, int H, int W, int Cout, int dz_is_bf16,
                     cudaStream_t st);
 
@@ -68,9 +70,18 @@ struct BnArgs {
   float* dgamma;
   float* dbeta;
   float* dbias;            // conv bias gradient = sum dz
+  int identity;            // forward: scale 1 / shift 0 (the affine already happened in the conv epilogue)
 };
 int bn_eval_prepare_launch(const float* mov_mean, const float* mov_var, float* mean, float* rstd, int n, float eps,
                            cudaStream_t st);
+// inference: scale = gamma / sqrt(moving_var + eps), shift = beta - moving_mean * scale for EVERY BatchNorm layer in
+// one launch (table entry per layer: offsets into params / bn_state / the per-channel coefficient arrays)
+struct BnEvalEntry {
+  long long off_g, off_be, off_mm, off_mv, off_stat;
+  int C;
+};
+int bn_eval_coef_launch(const float* params, const float* bn_state, const BnEvalEntry* table_dev, int n_layers, int max_c,
+                        float eps, float* scale, float* shift, cudaStream_t st);
 int bn_apply_launch(const BnArgs& a, int is_bf16, cudaStream_t st);
 int bn_bwd_reduce_launch(const BnArgs& a, int is_bf16, cudaStream_t st);
 int bn_bwd_apply_launch(const BnArgs& a, int is_bf16, cudaStream_t st);

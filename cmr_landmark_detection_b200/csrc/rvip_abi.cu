@@ -357,6 +357,9 @@ struct rvip_handle {
   float *params = nullptr, *grads = nullptr, *bn_state = nullptr;
   uint8_t* ws = nullptr;
   float *mean = nullptr, *rstd = nullptr;
+  float *aff_scale = nullptr, *aff_shift = nullptr;   // inference: BatchNorm folded into the conv epilogues
+  rvip::BnEvalEntry* bn_table_dev = nullptr;
+  int n_bn = 0, max_bn_c = 0;
   double *stats = nullptr, *red = nullptr;
   void *packed = nullptr, *dz = nullptr, *head_dy = nullptr;
   void* dz2[2] = {nullptr, nullptr};        // alternating dz scratch buffers (layer i uses dz2[i & 1])
@@ -538,6 +541,10 @@ static size_t carve(rvip_handle* h, uint8_t* base, int B, int training, bool ass
     if (assign) h->mean = (float*)p;
     p = cv.take(sizeof(float) * h->n_stat_ch);
     if (assign) h->rstd = (float*)p;
+    p = cv.take(sizeof(float) * h->n_stat_ch);
+    if (assign) h->aff_scale = (float*)p;
+    p = cv.take(sizeof(float) * h->n_stat_ch);
+    if (assign) h->aff_shift = (float*)p;
     p = cv.take(sizeof(double) * 2 * h->n_stat_ch);
     if (assign) h->stats = (double*)p;
     p = cv.take(sizeof(double) * 2 * kRedStripes * h->n_stat_ch);
@@ -592,6 +599,13 @@ static const void* buffer_of(const rvip_handle* h, int layer, int which) {
   }
 }
 
+// Inference in bf16 mode folds BatchNorm (moving statistics) into the conv epilogue: the conv writes the block
+// output y directly (where the layer has one; up-sampling layers keep writing `a`, replicated by the pass after).
+static bool fused_inference(const rvip_handle* h, const Layer& l) { return !h->training && is_bf16(h) && l.bn; }
+static void* conv_output(const rvip_handle* h, const Layer& l) {
+  return (fused_inference(h, l) && l.y) ? l.y : l.a;
+}
+
 static int build_descriptors(rvip_handle* h) {
   const int B = h->batch;
   for (size_t i = 0; i < h->L.size(); ++i) h->L[i].dz = h->training ? h->dz2[i & 1] : nullptr;
@@ -602,20 +616,25 @@ static int build_descriptors(rvip_handle* h) {
     const void* in1 = l.in1_layer >= 0 ? buffer_of(h, l.in1_layer, 1) : nullptr;
     const __nv_bfloat16* pk = static_cast<const __nv_bfloat16*>(h->packed);
     const int mode = (l.bn && h->training) ? EPI_RELU_STATS : EPI_RELU;
-    if (setup_conv_tc(&l.fwd, &l.fKC, &l.fBN, in0, in1, l.C0, l.C1, pk + l.pk_f, l.a, nullptr, l.Cout, B, l.H, l.W,
+    void* conv_out = conv_output(h, l);
+    if (setup_conv_tc(&l.fwd, &l.fKC, &l.fBN, in0, in1, l.C0, l.C1, pk + l.pk_f, conv_out, nullptr, l.Cout, B, l.H, l.W,
                       l.Cout, mode, h->params + l.off_b, h->stats + 2 * l.off_stat))
       return 1;
     const bool allow_row = getenv("RVIP_NO_ROW") == nullptr;
     int wres = 0;
     l.use_rfwd = allow_row && conv_row_plan(l.H, l.W, l.C0, l.C1, l.Cout, mode, l.Cout, &l.rfBN, &l.rfR, &wres, &l.rfNst);
-    if (l.use_rfwd && setup_conv_row(&l.rfwd, l.rfBN, l.rfR, wres, in0, in1, l.C0, l.C1, pk + l.pk_f, l.a, nullptr,
+    if (l.use_rfwd && setup_conv_row(&l.rfwd, l.rfBN, l.rfR, wres, in0, in1, l.C0, l.C1, pk + l.pk_f, conv_out, nullptr,
                                      l.Cout, B, l.H, l.W, l.Cout, mode, h->params + l.off_b, h->stats + 2 * l.off_stat))
       return 1;
     const bool allow_halo = getenv("RVIP_NO_HALO_CONV") == nullptr;
     l.use_hfwd = !l.use_rfwd && allow_halo && conv_halo_plan(B, l.H, l.W, l.C0, l.C1, l.Cout, mode, l.Cout, &l.hfBN, &l.hfNb);
-    if (l.use_hfwd && setup_conv_halo(&l.hfwd, l.hfBN, in0, in1, l.C0, l.C1, pk + l.pk_f, l.a, nullptr, l.Cout, B, l.H,
+    if (l.use_hfwd && setup_conv_halo(&l.hfwd, l.hfBN, in0, in1, l.C0, l.C1, pk + l.pk_f, conv_out, nullptr, l.Cout, B, l.H,
                                       l.W, l.Cout, mode, h->params + l.off_b, h->stats + 2 * l.off_stat))
       return 1;
+    if (l.bn) {
+      l.fwd.scale = l.rfwd.scale = l.hfwd.scale = h->aff_scale + l.off_stat;
+      l.fwd.shift = l.rfwd.shift = l.hfwd.shift = h->aff_shift + l.off_stat;
+    }
     if (h->training) {
       const int dsplit = l.C1 ? l.C0 : l.C0 + l.C1;
       l.use_rdgrad = allow_row && conv_row_plan(l.H, l.W, l.Cout, 0, l.C0 + l.C1, EPI_LINEAR, dsplit, &l.rdBN, &l.rdR,
@@ -652,7 +671,7 @@ static int build_descriptors(rvip_handle* h) {
 
 // ------------------------------------------------------------------------------------- passes
 static int conv_forward(rvip_handle* h, Layer& l, const float* x, bool training, cudaStream_t st) {
-  const int mode = (l.bn && training) ? EPI_RELU_STATS : EPI_RELU;
+  const int mode = (l.bn && training) ? EPI_RELU_STATS : (fused_inference(h, l) ? EPI_RELU_AFFINE : EPI_RELU);
   if (is_bf16(h) && !l.first) {
     if (l.use_rfwd) {
       l.rfwd.mode = mode;
@@ -667,8 +686,10 @@ static int conv_forward(rvip_handle* h, Layer& l, const float* x, bool training,
   }
   if (l.first && l.C0 == 1 && l.Cout <= 256 && l.W % 4 == 0) {
     return timed(h, KC_CONV_SIMT, 1, st, [&] {
-      return conv_c1_fwd_launch(x, h->params + l.off_k, h->params + l.off_b, l.a, h->stats + 2 * l.off_stat, h->batch,
-                                l.H, l.W, l.Cout, mode == EPI_RELU_STATS, is_bf16(h), st);
+      const bool aff = mode == EPI_RELU_AFFINE;
+      return conv_c1_fwd_launch(x, h->params + l.off_k, h->params + l.off_b, conv_output(h, l), h->stats + 2 * l.off_stat,
+                                h->batch, l.H, l.W, l.Cout, mode == EPI_RELU_STATS, is_bf16(h),
+                                aff ? h->aff_scale + l.off_stat : nullptr, aff ? h->aff_shift + l.off_stat : nullptr, st);
     });
   }
   ConvSimtArgs a;
@@ -707,6 +728,13 @@ static int forward_body(rvip_handle* h, const float* x, bool training, uint64_t 
           return 0;
         }))
       return 1;
+  } else if (is_bf16(h)) {
+    // one launch: scale / shift of every BatchNorm layer from the moving statistics
+    if (timed(h, KC_BN_FWD, 1, st, [&] {
+          return bn_eval_coef_launch(h->params, h->bn_state, h->bn_table_dev, h->n_bn, h->max_bn_c, h->cfg.bn_eps,
+                                     h->aff_scale, h->aff_shift, st);
+        }))
+      return 1;
   } else {
     int n_bn = 0;
     for (Layer& l : h->L) n_bn += l.bn ? 1 : 0;
@@ -727,6 +755,13 @@ static int forward_body(rvip_handle* h, const float* x, bool training, uint64_t 
     h->cur_tag = l.name + ":bn_fwd";
     BnArgs a;
     fill_bn(h, l, &a, training, seed);
+    if (fused_inference(h, l)) {
+      // the conv epilogue already produced y = BN(relu(conv)); only pooling / up-sampling remain
+      if (a.post != POST_POOL && a.post != POST_UPSAMPLE) continue;
+      a.identity = 1;
+      a.a = conv_output(h, l);
+      if (a.post == POST_POOL) a.y = nullptr;
+    }
     if (training) {
       a.stats = h->stats + 2 * l.off_stat;
       a.count = (double)h->batch * l.H * l.W;
@@ -886,6 +921,7 @@ int rvip_create(const rvip_cfg* cfg, rvip_handle** out) {
 void rvip_destroy(rvip_handle* h) {
   if (!h) return;
   if (h->pack_table_dev) cudaFree(h->pack_table_dev);
+  if (h->bn_table_dev) cudaFree(h->bn_table_dev);
   for (cudaEvent_t e : h->ev_dz) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_wg) if (e) cudaEventDestroy(e);
   if (h->side) cudaStreamDestroy(h->side);
@@ -945,6 +981,25 @@ int rvip_bind(rvip_handle* h, float* params, float* grads, float* bn_state, void
   if (!tab.empty()) {
     RVIP_CUDA(cudaMalloc(&h->pack_table_dev, sizeof(PackEntry) * tab.size()));
     RVIP_CUDA(cudaMemcpy(h->pack_table_dev, tab.data(), sizeof(PackEntry) * tab.size(), cudaMemcpyHostToDevice));
+  }
+  if (h->bn_table_dev) cudaFree(h->bn_table_dev);
+  h->bn_table_dev = nullptr;
+  {
+    std::vector<BnEvalEntry> bt;
+    h->max_bn_c = 0;
+    for (const Layer& l : h->L) {
+      if (!l.bn) continue;
+      BnEvalEntry e;
+      e.off_g = l.off_g; e.off_be = l.off_be; e.off_mm = l.off_mm; e.off_mv = l.off_mv; e.off_stat = l.off_stat;
+      e.C = l.Cout;
+      bt.push_back(e);
+      h->max_bn_c = std::max(h->max_bn_c, l.Cout);
+    }
+    h->n_bn = (int)bt.size();
+    if (!bt.empty()) {
+      RVIP_CUDA(cudaMalloc(&h->bn_table_dev, sizeof(BnEvalEntry) * bt.size()));
+      RVIP_CUDA(cudaMemcpy(h->bn_table_dev, bt.data(), sizeof(BnEvalEntry) * bt.size(), cudaMemcpyHostToDevice));
+    }
   }
   if (build_descriptors(h)) return 1;
   if (training && !h->side) {

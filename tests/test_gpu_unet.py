@@ -280,7 +280,8 @@ def test_pipelined_fit_equals_sequential_steps():
     lb, wb = run(False)
     assert len(la) == 5
     # atomics make the gradient sums order-dependent at the 1e-6 level: compare to that, not bitwise
-    assert np.allclose(la, lb, rtol=1e-4), (la, lb)
+    # the first step sees identical weights; afterwards Adam amplifies the atomics-order noise step by step
+    assert abs(la[0] - lb[0]) <= 1e-6 * abs(lb[0]) and np.allclose(la, lb, rtol=2e-3), (la, lb)
     # Adam turns 1e-6 gradient noise on near-zero elements into lr-sized differences: bound mean and max
     for a, b in zip(wa, wb):
         d = np.abs(a.astype(np.float64) - b)
