@@ -181,6 +181,100 @@ int label_map_launch(const float* heat, size_t n_pix, int C, float thr, uint8_t*
   return 0;
 }
 
+// ------------------------------------------------------------------------------------- per-volume landmark metrics
+// The step after extraction (src/models/evaluate_cv.py): septum angle per slice (get_angle2x :508-536), distances to
+// the ground truth with spacing / threshold (get_distances :549-561) and with the missing-prediction upper bound
+// (get_distances_upper_bound :572-595), mean insertion points (calc_mean_ip :113-120) and the TP / FN / FP counters
+// behind calc_tpr_thresh :267-308 / calc_ppv_thresh :311-353.  One block per call, one thread per slice, float64.
+// Points are (y, x) pairs, NaN = missing (the reference's None).
+__device__ __forceinline__ bool pt_ok(const double* p) { return isfinite(p[0]) && isfinite(p[1]); }
+
+__global__ void __launch_bounds__(256) landmark_metrics_kernel(const double* __restrict__ gt, const double* __restrict__ pr,
+                                                               int Z, double spacing, double thr, double dim,
+                                                               double* __restrict__ angle, double* __restrict__ dist,
+                                                               double* __restrict__ dist_thr, double* __restrict__ dist_ub,
+                                                               double* __restrict__ summary) {
+  // shared accumulators: [which (0 gt, 1 pred)][landmark][y, x, n]  then counters [landmark][tp, fn, fp]
+  __shared__ double s_sum[2][2][3];
+  __shared__ unsigned int s_cnt[2][3];
+  if (threadIdx.x < 12) (&s_sum[0][0][0])[threadIdx.x] = 0.0;
+  if (threadIdx.x < 6) (&s_cnt[0][0])[threadIdx.x] = 0u;
+  __syncthreads();
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  for (int z = threadIdx.x; z < Z; z += blockDim.x) {
+    const double* g = gt + (size_t)z * 4;   // [landmark][y, x]
+    const double* p = pr + (size_t)z * 4;
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const double* a = w == 0 ? g : p;
+      double ang = nan;
+      if (pt_ok(a) && pt_ok(a + 2)) {
+        ang = atan2(a[2] - a[0], a[3] - a[1]) * (180.0 / 3.14159265358979323846);
+        if (ang < 0) ang = 360.0 + ang;
+      }
+      angle[(size_t)w * Z + z] = ang;
+    }
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+      const bool hg = pt_ok(g + 2 * l), hp = pt_ok(p + 2 * l);
+      double d = nan, dt = nan, du = nan;
+      if (hg && hp) {
+        const double dy = g[2 * l] - p[2 * l], dx = g[2 * l + 1] - p[2 * l + 1];
+        d = sqrt(dy * dy + dx * dx) * spacing;
+        dt = d <= thr ? d : nan;
+        du = d;
+        atomicAdd(&s_cnt[l][d <= thr ? 0 : 2], 1u);
+      } else if (hg) {
+        // farthest corner of the dim x dim image
+        const double y = g[2 * l], x = g[2 * l + 1];
+        const double my = fmax(fabs(y), fabs(y - dim)), mx = fmax(fabs(x), fabs(x - dim));
+        du = sqrt(my * my + mx * mx) * spacing;
+        atomicAdd(&s_cnt[l][1], 1u);
+      } else if (hp) {
+        atomicAdd(&s_cnt[l][2], 1u);
+      }
+      dist[(size_t)l * Z + z] = d;
+      dist_thr[(size_t)l * Z + z] = dt;
+      dist_ub[(size_t)l * Z + z] = du;
+      if (hg) {
+        atomicAdd(&s_sum[0][l][0], g[2 * l]);
+        atomicAdd(&s_sum[0][l][1], g[2 * l + 1]);
+        atomicAdd(&s_sum[0][l][2], 1.0);
+      }
+      if (hp) {
+        atomicAdd(&s_sum[1][l][0], p[2 * l]);
+        atomicAdd(&s_sum[1][l][1], p[2 * l + 1]);
+        atomicAdd(&s_sum[1][l][2], 1.0);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // summary: mean points [which][landmark][2] (8), tpr[2], ppv[2], counters [landmark][tp, fn, fp] (6)
+    for (int w = 0; w < 2; ++w) {
+      const bool both = s_sum[w][0][2] > 0 && s_sum[w][1][2] > 0;
+      for (int l = 0; l < 2; ++l)
+        for (int k = 0; k < 2; ++k) summary[(w * 2 + l) * 2 + k] = both ? s_sum[w][l][k] / s_sum[w][l][2] : nan;
+    }
+    for (int l = 0; l < 2; ++l) {
+      const double tp = s_cnt[l][0], fn = s_cnt[l][1], fp = s_cnt[l][2];
+      summary[8 + l] = tp > 0 ? tp / (tp + fn) : 0.0;
+      summary[10 + l] = tp > 0 ? tp / (tp + fp) : 0.0;
+      summary[12 + l * 3 + 0] = tp;
+      summary[12 + l * 3 + 1] = fn;
+      summary[12 + l * 3 + 2] = fp;
+    }
+  }
+}
+int landmark_metrics_launch(const double* gt, const double* pred, int Z, double spacing, double thr, double dim,
+                            double* angle, double* dist, double* dist_thr, double* dist_ub, double* summary,
+                            cudaStream_t st) {
+  RVIP_REQUIRE(Z >= 0, "landmark_metrics: bad slice count");
+  landmark_metrics_kernel<<<1, 256, 0, st>>>(gt, pred, Z, spacing, thr, dim, angle, dist, dist_thr, dist_ub, summary);
+  RVIP_LAUNCH_CHECK();
+  return 0;
+}
+
 int extract_launch(const float* heat, int Z, int H, int W, int C, float thr, double* yx, int* count, int* argmax,
                    float* maxv, unsigned long long* scratch, cudaStream_t st) {
   RVIP_REQUIRE(C >= 1 && C <= kMaxC, "extract: C=%d not in [1,%d]", C, kMaxC);

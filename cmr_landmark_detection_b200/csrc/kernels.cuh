@@ -115,6 +115,10 @@ int extract_launch(const float* heat, int Z, int H, int W, int C, float thr, dou
                    float* maxv, unsigned long long* scratch, cudaStream_t st);
 size_t extract_scratch_bytes(int Z, int C);
 int label_map_launch(const float* heat, size_t n_pix, int C, float thr, uint8_t* out, cudaStream_t st);
+// gt / pred [Z][2 landmarks][y, x] float64 (NaN = missing) -> angle [2][Z], dist / dist_thr / dist_ub [2][Z], summary [18]
+int landmark_metrics_launch(const double* gt, const double* pred, int Z, double spacing, double thr, double dim,
+                            double* angle, double* dist, double* dist_thr, double* dist_ub, double* summary,
+                            cudaStream_t st);
 
 // ------------------------------------------------------------------ optimizer / weight packing (optim.cu)
 int adam_launch(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float b1, float b2, float eps,

@@ -1098,6 +1098,13 @@ int rvip_label_map(const float* heat, long long n_pixels, int C, float thr, uint
   return label_map_launch(heat, (size_t)n_pixels, C, thr, labels, (cudaStream_t)stream);
 }
 
+int rvip_landmark_metrics(const double* gt_yx, const double* pred_yx, int Z, double spacing, double threshold, double dim,
+                          double* angle, double* dist, double* dist_thr, double* dist_ub, double* summary, void* stream) {
+  RVIP_REQUIRE(gt_yx && pred_yx && angle && dist && dist_thr && dist_ub && summary, "rvip_landmark_metrics: null argument");
+  return landmark_metrics_launch(gt_yx, pred_yx, Z, spacing, threshold, dim, angle, dist, dist_thr, dist_ub, summary,
+                                 (cudaStream_t)stream);
+}
+
 int rvip_debug_buffer(const rvip_handle* h, const char* name, int which, void** ptr, long long* count,
                       int* elem_bytes) {
   RVIP_REQUIRE(h && h->bound, "rvip_debug_buffer: handle not bound");

@@ -63,3 +63,35 @@ def get_ip_from_heatmaps(preds, thr: float = 0.5, keepdim: bool = False, both_on
         preds = torch.from_numpy(np.ascontiguousarray(preds, dtype=np.float32)).to(dev)
     r = extract_device(preds, thr)
     return points_from_stats(r['yx'].cpu().numpy(), r['count'].cpu().numpy(), keepdim=keepdim, both_only=both_only)
+
+
+def landmark_metrics_device(gt_yx: torch.Tensor, pred_yx: torch.Tensor, spacing: float = 1.0, threshold: float = 1000.0,
+                            dim: float = 224.0) -> Dict[str, torch.Tensor]:
+    """Per-volume landmark metrics on the device (evaluate_cv.py: get_angle2x, get_distances,
+    get_distances_upper_bound, calc_mean_ip, calc_tpr_thresh, calc_ppv_thresh).  gt_yx / pred_yx: CUDA float64
+    [Z, 2, 2] = [slice][anterior, inferior][y, x] with NaN for a missing point (extract_device's 'yx' layout)."""
+    if gt_yx.shape != pred_yx.shape or gt_yx.dim() != 3 or gt_yx.shape[1:] != (2, 2):
+        raise ValueError('landmark_metrics_device expects two [Z, 2, 2] tensors')
+    gt_yx = gt_yx.to(torch.float64).contiguous()
+    pred_yx = pred_yx.to(torch.float64).contiguous()
+    Z, dev = gt_yx.shape[0], gt_yx.device
+    angle = torch.empty((2, Z), dtype=torch.float64, device=dev)
+    dist = torch.empty((2, Z), dtype=torch.float64, device=dev)
+    dist_thr = torch.empty((2, Z), dtype=torch.float64, device=dev)
+    dist_ub = torch.empty((2, Z), dtype=torch.float64, device=dev)
+    summary = torch.empty(18, dtype=torch.float64, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    ffi.check(ffi.lib().rvip_landmark_metrics(ffi.ptr(gt_yx), ffi.ptr(pred_yx), Z, float(spacing), float(threshold),
+                                              float(dim), ffi.ptr(angle), ffi.ptr(dist), ffi.ptr(dist_thr),
+                                              ffi.ptr(dist_ub), ffi.ptr(summary), st))
+    return {'angle_gt': angle[0], 'angle_pred': angle[1], 'dist': dist, 'dist_thr': dist_thr, 'dist_ub': dist_ub,
+            'mean_ip': summary[:8].view(2, 2, 2), 'tpr': summary[8:10], 'ppv': summary[10:12],
+            'counters': summary[12:18].view(2, 3)}
+
+
+def _points_to_tensor(ips, device) -> torch.Tensor:
+    """(anterior list, inferior list) of [y, x] / None -> float64 [Z, 2, 2] with NaN rows."""
+    ants, infs = ips
+    a = np.array([[np.nan, np.nan] if p is None else [float(p[0]), float(p[1])] for p in ants], np.float64).reshape(-1, 2)
+    b = np.array([[np.nan, np.nan] if p is None else [float(p[0]), float(p[1])] for p in infs], np.float64).reshape(-1, 2)
+    return torch.from_numpy(np.stack([a, b], axis=1)).to(device)

@@ -99,6 +99,16 @@ int rvip_extract(const float* heat, int Z, int H, int W, int C, float thr, doubl
  * whose value is > thr); heat [n_pixels, C] fp32 -> labels [n_pixels] */
 int rvip_label_map(const float* heat, long long n_pixels, int C, float thr, uint8_t* labels, void* stream);
 
+/* ---- per-volume landmark metrics, the step after extraction (src/models/evaluate_cv.py): get_angle2x :508-536,
+ * get_distances :549-561, get_distances_upper_bound :572-595, calc_mean_ip :113-120, calc_tpr_thresh :267-308,
+ * calc_ppv_thresh :311-353.  gt_yx / pred_yx [Z][2 landmarks: anterior, inferior][y, x] float64, NaN = missing.
+ * Outputs (device, float64): angle [2: gt, pred][Z] degrees in [0,360) or NaN; dist / dist_thr / dist_ub
+ * [2 landmarks][Z] (spacing applied; dist_thr NaN above `threshold`; dist_ub = distance to the farthest corner of the
+ * dim x dim image when the prediction is missing); summary [18] = mean points [gt,pred][ant,inf][y,x] (8),
+ * tpr[2], ppv[2], counters [landmark][tp, fn, fp] (6). */
+int rvip_landmark_metrics(const double* gt_yx, const double* pred_yx, int Z, double spacing, double threshold, double dim,
+                          double* angle, double* dist, double* dist_thr, double* dist_ub, double* summary, void* stream);
+
 /* ---- introspection for parity tests and profiling */
 /* which: 0 = relu(conv) output `a`, 1 = block output `y`, 2 = pooled / up-sampled output, 3 = dL/d(in0),
  * 4 = dL/d(in1). Returns the device pointer, element count and element size of layer `name`. */

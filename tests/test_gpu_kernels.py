@@ -171,3 +171,30 @@ def test_reference_signature_wrappers():
     assert a == [[6.0, 11.0], None, [6.0, 11.0]] and b[1] is None
     a, b = get_ip_from_rvip_mask_3d(vol)
     assert len(a) == 2
+
+
+def test_landmark_metrics_match_oracle_and_reference_golden(golden_dir):
+    """Per-volume metrics kernel (rvip_landmark_metrics) against the oracle restatement and, through it, the golden
+    vectors of the reference's own get_angle2x / get_distances / ... (float64: 1e-12)."""
+    from cmr_landmark_detection_b200.extract import landmark_metrics_device
+    from oracle import metrics_ref as M
+    g = np.load(os.path.join(golden_dir, 'metrics_golden.npz'))
+    for c in [str(c) for c in g['cases']]:
+        gt = np.stack([g[c + '_gt_ant'], g[c + '_gt_inf']], axis=1)
+        pr = np.stack([g[c + '_pr_ant'], g[c + '_pr_inf']], axis=1)
+        spacing, thr, dim = [float(v) for v in g[c + '_params']]
+        r = landmark_metrics_device(torch.from_numpy(gt).cuda(), torch.from_numpy(pr).cuda(), spacing, thr, dim)
+        r = {k: v.cpu().numpy() for k, v in r.items()}
+
+        def eq(a, b):
+            return np.allclose(a, b, rtol=1e-12, atol=1e-11, equal_nan=True)
+        assert eq(r['angle_gt'], g[c + '_angle_gt']) and eq(r['angle_pred'], g[c + '_angle_pr']), c
+        for i, lm in enumerate(('ant', 'inf')):
+            assert eq(r['dist'][i], g['%s_dist_%s' % (c, lm)]), c
+            assert eq(r['dist_thr'][i], g['%s_dist_thr_%s' % (c, lm)]), c
+            assert eq(r['dist_ub'][i], g['%s_ub_%s' % (c, lm)]), c
+            tpr, ppv, tp, fn, fp = M.tpr_ppv(gt[:, i], pr[:, i], thr, spacing)
+            assert abs(r['tpr'][i] - g[c + '_tpr'][i]) < 1e-15 and abs(r['ppv'][i] - g[c + '_ppv'][i]) < 1e-15, c
+            assert list(r['counters'][i]) == [tp, fn, fp], c
+        assert eq(r['mean_ip'][0, 0], g[c + '_mean_gt_ant']) and eq(r['mean_ip'][0, 1], g[c + '_mean_gt_inf']), c
+        assert eq(r['mean_ip'][1, 0], g[c + '_mean_pr_ant']) and eq(r['mean_ip'][1, 1], g[c + '_mean_pr_inf']), c
