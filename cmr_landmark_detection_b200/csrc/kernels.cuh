@@ -120,6 +120,11 @@ int landmark_metrics_launch(const double* gt, const double* pred, int Z, double 
                             double* angle, double* dist, double* dist_thr, double* dist_ub, double* summary,
                             cudaStream_t st);
 
+// ------------------------------------------------------------------ largest-connected-component filter (cc.cu)
+size_t cc_scratch_bytes(int Z, int H, int W);
+int cc_filter_launch(const uint8_t* labels, int Z, int H, int W, int connectivity, uint8_t* out, void* scratch,
+                     cudaStream_t st);
+
 // ------------------------------------------------------------------ optimizer / weight packing (optim.cu)
 int adam_launch(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float b1, float b2, float eps,
                 float grad_scale, cudaStream_t st);

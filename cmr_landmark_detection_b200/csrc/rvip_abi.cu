@@ -1098,6 +1098,12 @@ int rvip_label_map(const float* heat, long long n_pixels, int C, float thr, uint
   return label_map_launch(heat, (size_t)n_pixels, C, thr, labels, (cudaStream_t)stream);
 }
 
+size_t rvip_cc_scratch_bytes(int Z, int H, int W) { return cc_scratch_bytes(Z, H, W); }
+int rvip_cc_filter(const uint8_t* labels, int Z, int H, int W, int connectivity, uint8_t* out, void* scratch, void* stream) {
+  RVIP_REQUIRE(labels && out && scratch, "rvip_cc_filter: null argument");
+  return cc_filter_launch(labels, Z, H, W, connectivity, out, scratch, (cudaStream_t)stream);
+}
+
 int rvip_landmark_metrics(const double* gt_yx, const double* pred_yx, int Z, double spacing, double threshold, double dim,
                           double* angle, double* dist, double* dist_thr, double* dist_ub, double* summary, void* stream) {
   RVIP_REQUIRE(gt_yx && pred_yx && angle && dist && dist_thr && dist_ub && summary, "rvip_landmark_metrics: null argument");

@@ -42,6 +42,22 @@ def label_map_device(heat: torch.Tensor, thr: float = 0.5) -> torch.Tensor:
     return out
 
 
+def cc_filter_device(labels: torch.Tensor, connectivity: int = 8) -> torch.Tensor:
+    """Largest-connected-component filter on the device: labels [Z,H,W] uint8 CUDA tensor -> same shape, only the
+    largest component of each label value per slice (Postprocess.py:108-120; 8-connected like the reference's
+    cv2 call actually runs, see oracle/cc_ref.py)."""
+    if not labels.is_cuda or labels.dtype != torch.uint8 or labels.dim() != 3:
+        raise ValueError('cc_filter_device expects a CUDA uint8 [Z,H,W] tensor')
+    labels = labels.contiguous()
+    Z, H, W = labels.shape
+    L = ffi.lib()
+    out = torch.empty_like(labels)
+    scratch = torch.empty(int(L.rvip_cc_scratch_bytes(Z, H, W)) // 8 + 1, dtype=torch.int64, device=labels.device)
+    st = C.c_void_p(torch.cuda.current_stream(labels.device).cuda_stream)
+    ffi.check(L.rvip_cc_filter(ffi.ptr(labels), Z, H, W, int(connectivity), ffi.ptr(out), ffi.ptr(scratch), st))
+    return out
+
+
 def points_from_stats(yx: np.ndarray, count: np.ndarray, keepdim: bool = False, both_only: bool = True):
     """(yx, count) -> the reference's (first_ips, second_ips) lists (evaluate_cv.py:389-442)."""
     first, second = [], []
@@ -55,12 +71,18 @@ def points_from_stats(yx: np.ndarray, count: np.ndarray, keepdim: bool = False, 
     return first, second
 
 
-def get_ip_from_heatmaps(preds, thr: float = 0.5, keepdim: bool = False, both_only: bool = True, device=None):
+def get_ip_from_heatmaps(preds, thr: float = 0.5, keepdim: bool = False, both_only: bool = True, device=None,
+                         cc_filter: bool = False):
     """model.predict output [Z,H,W,2] (ndarray or CUDA tensor) -> (anterior list, inferior list):
-    == get_ip_from_rvip_mask_3d(label_map(preds)) of the reference, fused on the device."""
+    == get_ip_from_rvip_mask_3d(label_map(preds)) of the reference, fused on the device.  cc_filter=True inserts the
+    largest-connected-component filter of predict_model.py:159-161 (CC_FILTER) between the two."""
     if isinstance(preds, np.ndarray):
         dev = device or torch.device('cuda', torch.cuda.current_device())
         preds = torch.from_numpy(np.ascontiguousarray(preds, dtype=np.float32)).to(dev)
+    if cc_filter:
+        lab = cc_filter_device(label_map_device(preds, thr))
+        preds = torch.stack([lab == c + 1 for c in range(preds.shape[-1])], dim=-1).to(torch.float32)
+        thr = 0.5
     r = extract_device(preds, thr)
     return points_from_stats(r['yx'].cpu().numpy(), r['count'].cpu().numpy(), keepdim=keepdim, both_only=both_only)
 

@@ -61,6 +61,8 @@ _SIGS = {
     'rvip_extract_scratch_bytes': (_SZ, [_I, _I]),
     'rvip_extract': (_I, [_VP, _I, _I, _I, _I, _F, _VP, _VP, _VP, _VP, _VP, _VP]),
     'rvip_label_map': (_I, [_VP, _LL, _I, _F, _VP, _VP]),
+    'rvip_cc_scratch_bytes': (_SZ, [_I, _I, _I]),
+    'rvip_cc_filter': (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _VP]),
     'rvip_landmark_metrics': (_I, [_VP, _VP, _I, C.c_double, C.c_double, C.c_double, _VP, _VP, _VP, _VP, _VP, _VP]),
     'rvip_debug_buffer': (_I, [_VP, C.c_char_p, _I, C.POINTER(_VP), C.POINTER(_LL), C.POINTER(_I)]),
     'rvip_dropout_mask': (_I, [C.c_uint64, C.c_uint32, _F, _LL, _VP, _VP]),

@@ -99,6 +99,14 @@ int rvip_extract(const float* heat, int Z, int H, int W, int C, float thr, doubl
  * whose value is > thr); heat [n_pixels, C] fp32 -> labels [n_pixels] */
 int rvip_label_map(const float* heat, long long n_pixels, int C, float thr, uint8_t* labels, void* stream);
 
+/* ---- largest-connected-component filter (src/data/Postprocess.py:108-120 clean_3d_prediction_2d_cc; CC_FILTER in
+ * predict_model.py:159-161): labels [Z,H,W] uint8 (0 = background, values 1..4) -> out, only the largest component of
+ * each value per slice. connectivity 8 is what the reference's cv2 call actually runs (its positional 4 lands in the
+ * `labels` slot); 4 is offered too. Equal maximal areas: the component whose first pixel comes first in raster order.
+ * scratch: rvip_cc_scratch_bytes(Z,H,W) bytes (8-byte aligned). */
+size_t rvip_cc_scratch_bytes(int Z, int H, int W);
+int rvip_cc_filter(const uint8_t* labels, int Z, int H, int W, int connectivity, uint8_t* out, void* scratch, void* stream);
+
 /* ---- per-volume landmark metrics, the step after extraction (src/models/evaluate_cv.py): get_angle2x :508-536,
  * get_distances :549-561, get_distances_upper_bound :572-595, calc_mean_ip :113-120, calc_tpr_thresh :267-308,
  * calc_ppv_thresh :311-353.  gt_yx / pred_yx [Z][2 landmarks: anterior, inferior][y, x] float64, NaN = missing.

@@ -198,3 +198,33 @@ def test_landmark_metrics_match_oracle_and_reference_golden(golden_dir):
             assert list(r['counters'][i]) == [tp, fn, fp], c
         assert eq(r['mean_ip'][0, 0], g[c + '_mean_gt_ant']) and eq(r['mean_ip'][0, 1], g[c + '_mean_gt_inf']), c
         assert eq(r['mean_ip'][1, 0], g[c + '_mean_pr_ant']) and eq(r['mean_ip'][1, 1], g[c + '_mean_pr_inf']), c
+
+
+def test_cc_filter_matches_oracle_and_reference_golden(golden_dir):
+    """Largest-connected-component filter (rvip_cc_filter) against the oracle (bit-exact, both connectivities) and the
+    golden outputs of the reference's own clean_3d_prediction_2d_cc (slices with a tied maximum: same area only)."""
+    from cmr_landmark_detection_b200.data.Postprocess import clean_3d_prediction_2d_cc
+    from cmr_landmark_detection_b200.extract import cc_filter_device
+    from oracle import cc_ref
+    g = np.load(os.path.join(golden_dir, 'cc_golden.npz'))
+    for c in [str(c) for c in g['cases']]:
+        vol, ref = g[c + '_in'], g[c + '_out']
+        got = clean_3d_prediction_2d_cc(vol)
+        assert got.shape == vol.shape and got.dtype == vol.dtype
+        mine, ties = cc_ref.clean_2d_cc(vol, return_ties=True)
+        assert np.array_equal(got, mine), c                                   # oracle: bit-exact incl. the tie rule
+        for z in range(len(vol)):
+            if ties[z]:     # tied maximum: OpenCV's internal numbering decides in the reference; same area required
+                for val in (1, 2):
+                    assert (got[z] == val).sum() == (ref[z] == val).sum(), (c, z)
+            else:
+                assert np.array_equal(got[z], ref[z]), (c, z)
+        four = cc_filter_device(torch.from_numpy(vol).cuda(), 4).cpu().numpy()
+        assert np.array_equal(four, cc_ref.clean_2d_cc(vol, connectivity=4)), c
+    # full-size property: idempotent, and never adds pixels
+    rng = np.random.default_rng(0)
+    big = (rng.random((16, 256, 256)) < 0.3).astype(np.uint8) * rng.integers(1, 3, size=(16, 256, 256)).astype(np.uint8)
+    d = torch.from_numpy(big).cuda()
+    once = cc_filter_device(d)
+    assert torch.equal(cc_filter_device(once), once)
+    assert bool(((once == d) | (once == 0)).all())
