@@ -45,7 +45,7 @@ def label_map_device(heat: torch.Tensor, thr: float = 0.5) -> torch.Tensor:
 def cc_filter_device(labels: torch.Tensor, connectivity: int = 8) -> torch.Tensor:
     """Largest-connected-component filter on the device: labels [Z,H,W] uint8 CUDA tensor -> same shape, only the
     largest component of each label value per slice (Postprocess.py:108-120; 8-connected like the reference's
-    cv2 call actually runs, see oracle/cc_ref.py)."""
+    cv2 call actually runs)."""
     if not labels.is_cuda or labels.dtype != torch.uint8 or labels.dim() != 3:
         raise ValueError('cc_filter_device expects a CUDA uint8 [Z,H,W] tensor')
     labels = labels.contiguous()
