@@ -48,21 +48,14 @@ __device__ __forceinline__ void row_mma_loop(const ConvRowArgs& a, RowCtl* ctl, 
   constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
   const uint32_t tmem_base = ZERO_BASE ? 0u : tmem_base_rt;
   int stage = 0, phase = 0, acc = 0, acc_phase = 0;
-  // optional wait accounting of the issuing thread (a.dbg != nullptr)
-  long long w_t = 0, w_f = 0, t0 = 0;
-  const long long t_begin = a.dbg ? clock64() : 0;
   if (a.wres) mbar_wait(&ctl->wfull, 0);
   for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
     const int nt = tile % a.n_ntiles;
-    if (a.dbg) t0 = clock64();
     mbar_wait(&ctl->tempty[acc], acc_phase ^ 1);
-    if (a.dbg) w_t += clock64() - t0;
     tc_fence_after();
     const uint32_t d0 = tmem_base + acc * ACC_COLS;
     for (int c = 0; c < nchunks; ++c) {
-      if (a.dbg) t0 = clock64();
       mbar_wait(&ctl->full[stage], phase);
-      if (a.dbg) w_f += clock64() - t0;
       tc_fence_after();
       const uint32_t a_base = smem_u32(stages + (size_t)stage * stage_bytes);
       const uint32_t w_base = a.wres ? smem_u32(wres) + ((nt * nchunks + c) * 9) * W_TILE : a_base + A_ST;
@@ -87,15 +80,9 @@ __device__ __forceinline__ void row_mma_loop(const ConvRowArgs& a, RowCtl* ctl, 
     acc ^= 1;
     if (acc == 0) acc_phase ^= 1;
   }
-  if (a.dbg) {
-    a.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin;
-    a.dbg[blockIdx.x * 8 + 1] = w_t;
-    a.dbg[blockIdx.x * 8 + 2] = w_f;
-    a.dbg[blockIdx.x * 8 + 3] = 0;
-  }
 }
 
-template <int BN, int R>
+template <int BN, int R, bool AFFINE>
 __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_constant__ ConvRowArgs a, int nst) {
   constexpr int A_TX = row_a_bytes(R);
   constexpr int A_ST = round1k(A_TX);
@@ -121,7 +108,6 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
   RowCtl* ctl = reinterpret_cast<RowCtl*>((reinterpret_cast<uintptr_t>(s_aff + 2 * a.Cout) + 15) & ~uintptr_t(15));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long t_kernel = a.dbg ? clock64() : 0;
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&a.in0);
     prefetch_tmap(&a.in1);
@@ -150,8 +136,10 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
     for (int c = threadIdx.x - 128; c < 16 * a.Cout; c += 256) s_slot[c] = 0.f;
     for (int c = threadIdx.x - 128; c < a.Cout; c += 256) {
       s_bias[c] = a.mode != EPI_LINEAR ? a.bias[c] : 0.f;
-      s_aff[c] = a.mode == EPI_RELU_AFFINE ? a.scale[c] : 1.f;
-      s_aff[a.Cout + c] = a.mode == EPI_RELU_AFFINE ? a.shift[c] : 0.f;
+      if (AFFINE) {
+        s_aff[c] = a.scale[c];
+        s_aff[a.Cout + c] = a.shift[c];
+      }
     }
   }
   tc_fence_before();
@@ -226,7 +214,6 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
       row_bar_sync(1, 256);
       mbar_wait(&ctl->tfull[acc], acc_phase);
       tc_fence_after();
-      const long long t_e0 = a.dbg ? clock64() : 0;
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
         float bias[32], s1[32], s2[32];
@@ -251,11 +238,15 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
           for (int j = 0; j < 32; ++j) {
             f[j] = __uint_as_float(v[j]);
             if (a.mode != EPI_LINEAR) f[j] = fmaxf(f[j] + bias[j], 0.f);
-            if (a.mode == EPI_RELU_AFFINE) f[j] = fmaf(f[j], s_aff[n0 + ch * 32 + j], s_aff[a.Cout + n0 + ch * 32 + j]);
             if (a.mode == EPI_RELU_STATS) {
               s1[j] += f[j];
               s2[j] = fmaf(f[j], f[j], s2[j]);
             }
+          }
+          if (AFFINE) {   // inference-only instantiation: the training kernels carry none of this
+            const float* sa = s_aff + n0 + ch * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaf(f[j], sa[j], sa[a.Cout + j]);
           }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -303,7 +294,6 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
-      if (a.dbg && et == 0) a.dbg[blockIdx.x * 8 + 5] += clock64() - t_e0;
     }
     if (et == 0) tma_store_wait_all0();
     if (a.mode == EPI_RELU_STATS) {
@@ -320,7 +310,6 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
-  if (a.dbg && threadIdx.x == 0) a.dbg[blockIdx.x * 8 + 4] = clock64() - t_kernel;
 }
 
 // ------------------------------------------------------------------------------------- host
@@ -353,7 +342,7 @@ bool conv_row_plan(int H, int W, int C0, int C1, int Cout, int mode, int out_spl
   return false;
 }
 
-template <int BN, int R>
+template <int BN, int R, bool AFFINE>
 static int launch_row(const ConvRowArgs& a, int nst, cudaStream_t st) {
   const int nchunks = a.Ctot / 32;
   const int wres_bytes = a.wres ? nchunks * 9 * a.Cout * kPixB : 0;
@@ -361,21 +350,25 @@ static int launch_row(const ConvRowArgs& a, int nst, cudaStream_t st) {
   RVIP_REQUIRE(smem <= (size_t)kMaxDynSmemRow, "conv_row: %zu bytes of shared memory needed", smem);
   static bool attr_set = false;
   if (!attr_set) {
-    RVIP_CUDA(cudaFuncSetAttribute(conv3x3_row_kernel<BN, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RVIP_CUDA(cudaFuncSetAttribute(conv3x3_row_kernel<BN, R, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    kMaxDynSmemRow));
     attr_set = true;
   }
   const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
-  launch_kernel(conv3x3_row_kernel<BN, R>, grid, 384, smem, st, a, nst);
+  launch_kernel(conv3x3_row_kernel<BN, R, AFFINE>, grid, 384, smem, st, a, nst);
   RVIP_LAUNCH_CHECK();
   return 0;
 }
 
 int conv_row_launch(const ConvRowArgs& a, int BN, int R, int nst, cudaStream_t st) {
-  if (BN == 32 && R == 4) return launch_row<32, 4>(a, nst, st);
-  if (BN == 32 && R == 2) return launch_row<32, 2>(a, nst, st);
-  if (BN == 64 && R == 4) return launch_row<64, 4>(a, nst, st);
-  if (BN == 64 && R == 2) return launch_row<64, 2>(a, nst, st);
+  const bool aff = a.mode == EPI_RELU_AFFINE;
+#define RVIP_ROW_CASE(bn, r) \
+  if (BN == bn && R == r) return aff ? launch_row<bn, r, true>(a, nst, st) : launch_row<bn, r, false>(a, nst, st);
+  RVIP_ROW_CASE(32, 4)
+  RVIP_ROW_CASE(32, 2)
+  RVIP_ROW_CASE(64, 4)
+  RVIP_ROW_CASE(64, 2)
+#undef RVIP_ROW_CASE
   set_error("conv_row: unsupported tile BN=%d R=%d", BN, R);
   return 1;
 }
