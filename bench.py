@@ -359,6 +359,43 @@ def extra_measurements(model, dev):
     gbs = heat.numel() * 4 * n / (e0.elapsed_time(e1) * 1e-3) / 1e9
     out['extract_gbs'] = round(gbs, 1)
     out['extract_frac_of_hbm_peak'] = round(gbs / peaks()[1], 4)
+    del heat
+    # throughput-oriented inference: 8 volumes per call
+    x8, _ = synth.make_batch(128, 256, 256, seed=4)
+    x8d = torch.from_numpy(x8).to(dev)
+    for _ in range(2):
+        extract_device(model.predict_device(x8d))
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        extract_device(model.predict_device(x8d))
+    e1.record()
+    torch.cuda.synchronize()
+    out['infer_vols_per_s_8_per_call'] = round(5 * 8 / (e0.elapsed_time(e1) * 1e-3), 1)
+    del x8d
+    # BASELINE config C5 (tensor-core stress): 5 levels, 64 base filters, 512 x 512, batch 8
+    try:
+        from cmr_landmark_detection_b200.models.Unets import create_unet
+        c5 = dict(CONFIG, DIM=[512, 512], DEPTH=5, FILTERS=64)
+        m5 = create_unet(c5)
+        x5, y5 = synth.make_batch(8, 512, 512, seed=5)
+        x5d, y5d = torch.from_numpy(x5).to(dev), torch.from_numpy(y5).to(dev)
+        for _ in range(3):
+            m5.train_step_device(x5d, y5d)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            m5.train_step_device(x5d, y5d)
+        e1.record()
+        torch.cuda.synchronize()
+        ms5 = e0.elapsed_time(e1) / 5
+        fl5 = conv_flops_per_slice(c5)['train'] * 8
+        out['c5_train'] = {'workload': 'C5: U-Net d5 f64 fwd+bwd+MSE+Adam, batch 8, 512x512', 'ms_per_step': round(ms5, 3),
+                           'slices_per_s': round(8 / ms5 * 1e3, 1), 'conv_tflops': round(fl5 / ms5 / 1e9, 1),
+                           'frac_of_sustained_bf16_peak': round(fl5 / ms5 / 1e9 / peaks()[0], 4)}
+        del m5
+    except Exception as e:          # secondary metric: never fail the bench line over it
+        out['c5_train'] = {'error': str(e)[:200]}
     return out
 
 

@@ -194,7 +194,8 @@ static int bn_apply_t(const BnArgs& a, cudaStream_t st) {
   const size_t P = (size_t)a.B * a.H * a.W;
   const int G = a.C / 8;
   const size_t n = (a.post == POST_POOL ? P / 4 : P) * G;
-  const int grid = ew_grid(n, 6);   // persistent blocks: the per-block coefficient prologue is amortised
+  static const int fwd_per_sm = getenv("RVIP_BN_FWD_BLOCKS") ? atoi(getenv("RVIP_BN_FWD_BLOCKS")) : 6;
+  const int grid = ew_grid(n, fwd_per_sm);   // persistent blocks: the per-block coefficient prologue is amortised
   const size_t sm = 2 * a.C * sizeof(float);
   switch (a.post) {
     case POST_NONE: launch_kernel(bn_apply_kernel<T, POST_NONE>, grid, 256, sm, st, a); break;

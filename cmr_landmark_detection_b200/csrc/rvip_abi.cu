@@ -1006,7 +1006,7 @@ int rvip_bind(rvip_handle* h, float* params, float* grads, float* bn_state, void
     h->overlap_wgrad = getenv("RVIP_NO_WGRAD_OVERLAP") == nullptr;
     int lo = 0, hi = 0;
     RVIP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = least priority
-    RVIP_CUDA(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, lo));
+    RVIP_CUDA(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, getenv("RVIP_SIDE_PRIO_HIGH") ? hi : lo));
     h->ev_dz.assign(h->L.size(), nullptr);
     h->ev_wg.assign(h->L.size(), nullptr);
     for (size_t i = 0; i < h->L.size(); ++i) {

@@ -286,3 +286,25 @@ def test_pipelined_fit_equals_sequential_steps():
     for a, b in zip(wa, wb):
         d = np.abs(a.astype(np.float64) - b)
         assert d.mean() <= 1e-3 and d.max() <= 6e-3, (d.mean(), d.max())   # 5 steps x lr 1e-3
+
+
+def test_c5_topology_matches_oracle():
+    """BASELINE config C5 topology (5 levels, 64 base filters: 1024 / 2048 channels at the bottom, 138 M parameters) at
+    a size the CPU oracle finishes in seconds: parameter count, inference heat maps and the training loss."""
+    from cmr_landmark_detection_b200 import synth
+    from cmr_landmark_detection_b200.models.Unets import create_unet
+    from oracle import unet_ref as R
+    config = dict(BASE, DIM=[64, 64], DEPTH=5, FILTERS=64, PRECISION='bf16')
+    model = create_unet(config)
+    assert model.count_params() == 138376578
+    cfg = R.cfg_from_config(config)
+    ws = R.init_weights(cfg, seed=5, randomize_bn=True)
+    model.set_weights(ws)
+    x, y = synth.make_batch(2, 64, 64, seed=8)
+    heat = model.predict(x, batch_size=2)
+    ref = R.predict(cfg, ws, x)
+    assert np.abs(heat - ref).max() <= TOL['bf16']['heat'], np.abs(heat - ref).max()
+    out = R.train_grads(cfg, ws, x, y)
+    loss = float(model.train_step_device(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(),
+                                         apply_optimizer=False).item())
+    assert abs(loss - out['loss']) <= TOL['bf16']['loss'] * abs(out['loss']), (loss, out['loss'])
