@@ -207,20 +207,14 @@ static int setup_conv_tc(ConvTcArgs* a, int* KC, int* BN, const void* in0, const
                C0, C1, Cout);
   *KC = pick_kc(C0, C1);
   a->g = make_tile_geom(B, H, W, 128);
-  // widest N tile that divides the channels -- unless a narrower one fills the 148 persistent CTAs clearly
-  // better (e.g. 256 M-tiles x 1 N-tile = 1.73 waves -> 58 %; x 2 N-tiles = 3.46 waves -> 86 %)
+  // widest N tile that divides the channels (measured: narrower tiles lose more to activation re-reads than they
+  // gain in wave efficiency on this per-tap kernel)
   int bn = 0;
-  double best_eff = 0.0;
   for (int cand : {256, 128, 64, 32}) {
     if (cand > Cout || Cout % cand != 0) continue;
     if (mode == EPI_LINEAR && out_split < Cout && (cand > out_split || out_split % cand != 0)) continue;
-    const long tiles = (long)(Cout / cand) * a->g.tiles_x * a->g.tiles_y * a->g.tiles_b;
-    const double eff = (double)tiles / (double)(((tiles + kNumSMs - 1) / kNumSMs) * kNumSMs);
-    (void)eff;
-    if (bn == 0) {   // measured: narrower tiles lose more to A re-reads than they gain in wave efficiency
-      bn = cand;
-      best_eff = eff;
-    }
+    bn = cand;
+    break;
   }
   RVIP_REQUIRE(bn >= 32, "conv_tc: no valid N tile for Cout=%d split=%d", Cout, out_split);
   *BN = bn;
