@@ -621,7 +621,13 @@ static int build_descriptors(rvip_handle* h) {
                                      l.Cout, B, l.H, l.W, l.Cout, mode, h->params + l.off_b, h->stats + 2 * l.off_stat))
       return 1;
     const bool allow_halo = getenv("RVIP_NO_HALO_CONV") == nullptr;
-    l.use_hfwd = !l.use_rfwd && allow_halo && conv_halo_plan(B, l.H, l.W, l.C0, l.C1, l.Cout, mode, l.Cout, &l.hfBN, &l.hfNb);
+    // both kernels stage the input once with its halo; where both apply (128-wide levels) the halo kernel wins when
+    // it can run N >= 128 (the row kernel is limited to N = 64 tiles: 54-cycle MMAs instead of 66 per 2x the work)
+    l.use_hfwd = allow_halo && conv_halo_plan(B, l.H, l.W, l.C0, l.C1, l.Cout, mode, l.Cout, &l.hfBN, &l.hfNb);
+    if (l.use_hfwd && l.use_rfwd) {
+      if (l.hfBN >= 128 && getenv("RVIP_PREFER_ROW") == nullptr) l.use_rfwd = 0;
+      else l.use_hfwd = 0;
+    }
     if (l.use_hfwd && setup_conv_halo(&l.hfwd, l.hfBN, in0, in1, l.C0, l.C1, pk + l.pk_f, conv_out, nullptr, l.Cout, B, l.H,
                                       l.W, l.Cout, mode, h->params + l.off_b, h->stats + 2 * l.off_stat))
       return 1;
@@ -636,8 +642,12 @@ static int build_descriptors(rvip_handle* h) {
       if (l.use_rdgrad && setup_conv_row(&l.rdgrad, l.rdBN, l.rdR, wres, l.dz, nullptr, l.Cout, 0, pk + l.pk_d, l.dx0,
                                          l.dx1, dsplit, B, l.H, l.W, l.C0 + l.C1, EPI_LINEAR, nullptr, nullptr))
         return 1;
-      l.use_hdgrad = !l.use_rdgrad && allow_halo &&
+      l.use_hdgrad = allow_halo &&
                      conv_halo_plan(B, l.H, l.W, l.Cout, 0, l.C0 + l.C1, EPI_LINEAR, dsplit, &l.hdBN, &l.hdNb);
+      if (l.use_hdgrad && l.use_rdgrad) {
+        if (l.hdBN >= 128 && getenv("RVIP_PREFER_ROW") == nullptr) l.use_rdgrad = 0;
+        else l.use_hdgrad = 0;
+      }
       if (l.use_hdgrad && setup_conv_halo(&l.hdgrad, l.hdBN, l.dz, nullptr, l.Cout, 0, pk + l.pk_d, l.dx0, l.dx1, dsplit,
                                           B, l.H, l.W, l.C0 + l.C1, EPI_LINEAR, nullptr, nullptr))
         return 1;
