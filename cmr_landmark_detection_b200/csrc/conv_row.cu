@@ -82,12 +82,11 @@ __device__ __forceinline__ void row_mma_loop(const ConvRowArgs& a, RowCtl* ctl, 
   }
 }
 
-template <int BN, int R, bool AFFINE>
+template <int BN, int R, bool AFFINE, int OCH>
 __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_constant__ ConvRowArgs a, int nst) {
   constexpr int A_TX = row_a_bytes(R);
   constexpr int A_ST = round1k(A_TX);
   constexpr int W_TILE = BN * kPixB;           // one (chunk, tap) weight tile: BN rows x 64 B
-  constexpr int OCH = BN >= 64 ? 64 : 32;
   constexpr int OROWB = OCH * 2;
   constexpr int OCHUNK = R * 128 * OROWB;
   constexpr int STAGING = R * 128 * BN * 2;
@@ -323,8 +322,9 @@ bool conv_row_plan(int H, int W, int C0, int C1, int Cout, int mode, int out_spl
                    int* nst) {
   if (W % 128 != 0 || C0 % 32 != 0 || C1 % 32 != 0 || Cout % 32 != 0) return false;
   int bn = (Cout % 64 == 0) ? 64 : 32;
-  if (mode == EPI_LINEAR && out_split < Cout && out_split % bn != 0) bn = 32;
-  if (mode == EPI_LINEAR && out_split < Cout && out_split % bn != 0) return false;
+  // a concat split on a 32-channel boundary keeps the N = 64 tile (54-cycle MMAs for twice the work of an N = 32
+  // one); only the TMA store boxes shrink to 32 channels (ConvRowArgs::och)
+  if (mode == EPI_LINEAR && out_split < Cout && out_split % 32 != 0) return false;
   const int nchunks = (C0 + C1) / 32;
   const int wbytes = nchunks * 9 * Cout * kPixB;
   const int wr = wbytes <= 40960 ? 1 : 0;
@@ -342,7 +342,7 @@ bool conv_row_plan(int H, int W, int C0, int C1, int Cout, int mode, int out_spl
   return false;
 }
 
-template <int BN, int R, bool AFFINE>
+template <int BN, int R, bool AFFINE, int OCH>
 static int launch_row(const ConvRowArgs& a, int nst, cudaStream_t st) {
   const int nchunks = a.Ctot / 32;
   const int wres_bytes = a.wres ? nchunks * 9 * a.Cout * kPixB : 0;
@@ -350,24 +350,28 @@ static int launch_row(const ConvRowArgs& a, int nst, cudaStream_t st) {
   RVIP_REQUIRE(smem <= (size_t)kMaxDynSmemRow, "conv_row: %zu bytes of shared memory needed", smem);
   static bool attr_set = false;
   if (!attr_set) {
-    RVIP_CUDA(cudaFuncSetAttribute(conv3x3_row_kernel<BN, R, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RVIP_CUDA(cudaFuncSetAttribute(conv3x3_row_kernel<BN, R, AFFINE, OCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    kMaxDynSmemRow));
     attr_set = true;
   }
   const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
-  launch_kernel(conv3x3_row_kernel<BN, R, AFFINE>, grid, 384, smem, st, a, nst);
+  launch_kernel(conv3x3_row_kernel<BN, R, AFFINE, OCH>, grid, 384, smem, st, a, nst);
   RVIP_LAUNCH_CHECK();
   return 0;
 }
 
 int conv_row_launch(const ConvRowArgs& a, int BN, int R, int nst, cudaStream_t st) {
   const bool aff = a.mode == EPI_RELU_AFFINE;
-#define RVIP_ROW_CASE(bn, r) \
-  if (BN == bn && R == r) return aff ? launch_row<bn, r, true>(a, nst, st) : launch_row<bn, r, false>(a, nst, st);
-  RVIP_ROW_CASE(32, 4)
-  RVIP_ROW_CASE(32, 2)
-  RVIP_ROW_CASE(64, 4)
-  RVIP_ROW_CASE(64, 2)
+  RVIP_REQUIRE(a.och == 32 || (a.och == 64 && BN == 64), "conv_row: bad store box width %d for BN=%d", a.och, BN);
+#define RVIP_ROW_CASE(bn, r, oc) \
+  if (BN == bn && R == r && a.och == oc)   \
+    return aff ? launch_row<bn, r, true, oc>(a, nst, st) : launch_row<bn, r, false, oc>(a, nst, st);
+  RVIP_ROW_CASE(32, 4, 32)
+  RVIP_ROW_CASE(32, 2, 32)
+  RVIP_ROW_CASE(64, 4, 64)
+  RVIP_ROW_CASE(64, 2, 64)
+  RVIP_ROW_CASE(64, 4, 32)
+  RVIP_ROW_CASE(64, 2, 32)
 #undef RVIP_ROW_CASE
   set_error("conv_row: unsupported tile BN=%d R=%d", BN, R);
   return 1;

@@ -123,7 +123,9 @@ static int setup_conv_row(ConvRowArgs* a, int BN, int R, int wres, const void* i
     a->in1 = a->in0;
   }
   if (make_w_map(&a->w, wpk, Cout, 9 * Ctot, 32, BN)) return 1;
-  const int och = BN >= 64 ? 64 : 32;
+  const bool split32 = mode == EPI_LINEAR && out_split < Cout && out_split % 64 != 0;
+  const int och = (BN >= 64 && !split32) ? 64 : 32;
+  a->och = och;
   const int c_out0 = (mode == EPI_LINEAR) ? a->out_split : Cout;
   if (make_act_map_box(&a->out0, out0, B, H, W, c_out0, och, 128, R, 1)) return 1;
   if (mode == EPI_LINEAR && out_split < Cout) {
