@@ -53,6 +53,13 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
   }
   float loss_acc = 0.f;
   const float inv_n = 1.f / ((float)P * (float)NC);
+  float dice_D = 1.f, dice_num = 0.f, dice_invD2 = 0.f;
+  if (TRAIN && a.loss_kind == LOSS_BCE_DICE) {
+    const double I = a.dice_sums[0], D = a.dice_sums[1] + a.dice_sums[2] + 1.0;
+    dice_D = (float)D;
+    dice_num = (float)(2.0 * I + 1.0);
+    dice_invD2 = (float)(1.0 / (D * D));
+  }
   // all lanes of a warp run the same trip count (n_items and the stride are multiples of 32)
   const uint32_t n_round = (n_items + 31) / 32 * 32;
   const uint32_t stride = gridDim.x * 256;
@@ -113,14 +120,32 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
         bool any = false;
 #pragma unroll
         for (int k = 0; k < NCT; ++k) any = any || (k < NC && tgt[k] > a.mask_thr);
-        if (a.loss_kind != LOSS_MSE) wpx = any ? 1.f : 0.f;
+        if (a.loss_kind == LOSS_MASKED || a.loss_kind == LOSS_WEIGHTED) wpx = any ? 1.f : 0.f;
         if (a.loss_kind == LOSS_WEIGHTED) wpx *= a.inplane[(uint32_t)p % HW];
         float dl[NCT], se = 0.f;
+        if (a.loss_kind == LOSS_BCE_DICE) {
+          // w_bce * mean_c BCE(t, clip(p)) - w_dice * dice;  d dice / d p_i = (2 t_i D - (2 I + 1)) / D^2
 #pragma unroll
-        for (int k = 0; k < NCT; ++k) {
-          const float d2 = k < NC ? prob[k] - tgt[k] : 0.f;
-          se = fmaf(d2, d2, se);
-          dl[k] = 2.f * d2 * wpx * inv_n * prob[k] * (1.f - prob[k]);
+          for (int k = 0; k < NCT; ++k) {
+            if (k < NC) {
+              const float pc = fminf(fmaxf(prob[k], a.eps), 1.f - a.eps);
+              const bool inside = prob[k] > a.eps && prob[k] < 1.f - a.eps;     // clip passes no gradient outside
+              se -= tgt[k] * logf(pc + a.eps) + (1.f - tgt[k]) * logf(1.f - pc + a.eps);
+              const float dbce = inside ? (-tgt[k] / (pc + a.eps) + (1.f - tgt[k]) / (1.f - pc + a.eps)) : 0.f;
+              const float ddice = (2.f * tgt[k] * dice_D - dice_num) * dice_invD2;
+              dl[k] = (a.w_bce * inv_n * dbce - a.w_dice * ddice) * prob[k] * (1.f - prob[k]);
+            } else {
+              dl[k] = 0.f;
+            }
+          }
+          se *= a.w_bce;                    // the common accumulation below divides by NC (mean over channels)
+        } else {
+#pragma unroll
+          for (int k = 0; k < NCT; ++k) {
+            const float d2 = k < NC ? prob[k] - tgt[k] : 0.f;
+            se = fmaf(d2, d2, se);
+            dl[k] = 2.f * d2 * wpx * inv_n * prob[k] * (1.f - prob[k]);
+          }
         }
         if (cg == 0) {
           loss_acc += se / (float)NC * wpx + (a.loss_kind == LOSS_WEIGHTED ? a.eps : 0.f);
@@ -165,8 +190,40 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
     __syncthreads();
     for (int k = threadIdx.x; k < Cin * NC; k += 256) atomicAdd(&a.dw[k], dw_s[k]);
     if (threadIdx.x < NC) atomicAdd(&a.db[threadIdx.x], db_s[threadIdx.x]);
-    if (threadIdx.x == 0) atomicAdd(a.loss_acc, loss_s / (double)P);  // mean over B*H*W
+    if (threadIdx.x == 0) {
+      double l = loss_s / (double)P;                                  // mean over B*H*W
+      if (a.loss_kind == LOSS_BCE_DICE && blockIdx.x == 0)
+        l -= (double)a.w_dice * (2.0 * a.dice_sums[0] + 1.0) / (a.dice_sums[1] + a.dice_sums[2] + 1.0);
+      atomicAdd(a.loss_acc, l);
+    }
   }
+}
+
+__global__ void __launch_bounds__(256) head_dice_sums_kernel(const float* __restrict__ heat, const float* __restrict__ tgt,
+                                                             size_t n, double* __restrict__ sums) {
+  float s_tp = 0.f, s_p = 0.f, s_t = 0.f;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    const float p = heat[i], t = tgt[i];
+    s_tp = fmaf(t, p, s_tp);
+    s_p += p;
+    s_t += t;
+  }
+  s_tp = warp_sum(s_tp); s_p = warp_sum(s_p); s_t = warp_sum(s_t);
+  __shared__ double acc[3];
+  if (threadIdx.x < 3) acc[threadIdx.x] = 0.0;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&acc[0], (double)s_tp);
+    atomicAdd(&acc[1], (double)s_p);
+    atomicAdd(&acc[2], (double)s_t);
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) atomicAdd(&sums[threadIdx.x], acc[threadIdx.x]);
+}
+int head_dice_sums_launch(const float* heat, const float* target, size_t n, double* sums, cudaStream_t st) {
+  head_dice_sums_kernel<<<kNumSMs * 2, 256, 0, st>>>(heat, target, n, sums);
+  RVIP_LAUNCH_CHECK();
+  return 0;
 }
 
 int head_launch(const HeadArgs& a, int training, int is_bf16, cudaStream_t st) {

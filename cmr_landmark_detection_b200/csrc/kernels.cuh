@@ -91,7 +91,7 @@ int relu_bwd_launch(const void* u, const void* du, void* dz, float* dbias, size_
 int dropout_mask_launch(uint64_t seed, uint32_t site, uint32_t thr16, size_t n_vec8, uint8_t* keep, cudaStream_t st);
 
 // ------------------------------------------------------------------ head + loss (head_loss.cu)
-enum LossKind { LOSS_MSE = 0, LOSS_MASKED = 1, LOSS_WEIGHTED = 2 };
+enum LossKind { LOSS_MSE = 0, LOSS_MASKED = 1, LOSS_WEIGHTED = 2, LOSS_BCE_DICE = 3 };
 struct HeadArgs {
   int B, H, W, Cin, NC;
   const void* y;           // [B,H,W,Cin]
@@ -107,8 +107,14 @@ struct HeadArgs {
   float* dw;
   float* db;
   double* loss_acc;        // scalar accumulator (sum of per-pixel losses)
+  // LOSS_BCE_DICE (Loss_and_metrics.py:208-245): w_bce * BCE - w_dice * Dice; the Dice term needs the batch-global
+  // sums {sum t*p, sum p, sum t} before any gradient can be formed (head_dice_sums_launch)
+  const double* dice_sums;
+  float w_bce, w_dice;
 };
 int head_launch(const HeadArgs& a, int training, int is_bf16, cudaStream_t st);
+// heat, target [n] fp32 -> sums[3] += {sum t*p, sum p, sum t} (double)
+int head_dice_sums_launch(const float* heat, const float* target, size_t n, double* sums, cudaStream_t st);
 
 // ------------------------------------------------------------------ landmark extraction (extract.cu)
 int extract_launch(const float* heat, int Z, int H, int W, int C, float thr, double* yx, int* count, int* argmax,

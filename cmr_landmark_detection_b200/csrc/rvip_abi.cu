@@ -362,6 +362,8 @@ struct rvip_handle {
   cudaStream_t side = nullptr;              // low-priority stream running the weight gradients beside the main chain
   std::vector<cudaEvent_t> ev_dz, ev_wg;    // per layer: dz ready (main) / wgrad done (side)
   int overlap_wgrad = 1;
+  double* dice_sums = nullptr;              // {sum t*p, sum p, sum t} of the BCE+Dice loss
+  float w_bce = 1.f, w_dice = 1.f;
   rvip::PackEntry* pack_table_dev = nullptr;
   int n_pack = 0;
   std::vector<std::pair<long long, long long>> buckets;   // (offset, count) in grads
@@ -537,6 +539,8 @@ static size_t carve(rvip_handle* h, uint8_t* base, int B, int training, bool ass
     if (assign) h->mean = (float*)p;
     p = cv.take(sizeof(float) * h->n_stat_ch);
     if (assign) h->rstd = (float*)p;
+    p = cv.take(sizeof(double) * 4);
+    if (assign) h->dice_sums = (double*)p;
     p = cv.take(sizeof(float) * h->n_stat_ch);
     if (assign) h->aff_scale = (float*)p;
     p = cv.take(sizeof(float) * h->n_stat_ch);
@@ -1058,9 +1062,28 @@ int rvip_train_step(rvip_handle* h, const float* x, const float* target, const f
   a.dy = h->head_dy;
   a.dw = h->grads + h->head_k; a.db = h->grads + h->head_b;
   a.loss_acc = loss_out;
+  a.dice_sums = h->dice_sums; a.w_bce = h->w_bce; a.w_dice = h->w_dice;
   h->cur_tag = "head:loss";
+  if (loss_kind == RVIP_LOSS_BCE_DICE) {
+    // the Dice term needs batch-global sums first: inference-mode head (writes the heat map), a small reduction,
+    // then the training head with the sums in hand
+    if (timed(h, KC_HEAD, 3, st, [&] {
+          RVIP_CUDA(cudaMemsetAsync(h->dice_sums, 0, sizeof(double) * 4, st));
+          if (head_launch(a, 0, is_bf16(h), st)) return 1;
+          const Layer& hl = h->L[h->head_in];
+          return head_dice_sums_launch(heat, target, (size_t)h->batch * hl.H * hl.W * h->cfg.classes, h->dice_sums, st);
+        }))
+      return 1;
+  }
   if (timed(h, KC_HEAD, 1, st, [&] { return head_launch(a, 1, is_bf16(h), st); })) return 1;
   return backward_body(h, x, seed, st);
+}
+
+int rvip_set_loss_weights(rvip_handle* h, float w_bce, float w_dice) {
+  RVIP_REQUIRE(h, "rvip_set_loss_weights: null handle");
+  h->w_bce = w_bce;
+  h->w_dice = w_dice;
+  return 0;
 }
 
 int rvip_adam_step(rvip_handle* h, float* m, float* v, float lr, float beta1, float beta2, float eps, long long step,

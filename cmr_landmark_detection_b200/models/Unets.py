@@ -26,9 +26,12 @@ def create_unet(config, metrics=None, networkname='unet', single_model=True, sup
         raise NotImplementedError('only the 2D U-Net of the RVIP path is implemented')
     model = RvipUNet(config, name=networkname)
     loss_f = config.get('LOSS_FUNCTION', mse)
+    if isinstance(loss_f, str) and 'BcdDiceLoss' in loss_f:          # train_model.py:178 (substring match, its spelling)
+        from .Loss_and_metrics import BceDiceLoss
+        loss_f = BceDiceLoss()
     if isinstance(loss_f, str) and 'mse' not in loss_f.lower():
         # train_model.py:178-184 picks BceDiceLoss by substring, otherwise MSE
-        raise NotImplementedError('LOSS_FUNCTION=%r: BCE+Dice is SURVEY row N2; use Loss_and_metrics.mse' % loss_f)
+        raise NotImplementedError('LOSS_FUNCTION=%r is not implemented (mse / BcdDiceLoss are)' % loss_f)
     if isinstance(loss_f, str):
         loss_f = mse
     model.compile(optimizer=mutils.get_optimizer(config, networkname), loss={'unet': loss_f}, metrics=metrics)

@@ -14,7 +14,7 @@ CSRC_DIR = os.path.join(PKG_DIR, 'csrc')
 
 RVIP_MAX_DEPTH = 8
 NUM_KERNEL_CLASSES = 10
-LOSS_KINDS = {'mse': 0, 'masked': 1, 'weighted': 2}
+LOSS_KINDS = {'mse': 0, 'masked': 1, 'weighted': 2, 'bce_dice': 3}
 
 
 class RvipError(RuntimeError):
@@ -54,6 +54,7 @@ _SIGS = {
     'rvip_pack_weights': (_I, [_VP, _VP]),
     'rvip_predict': (_I, [_VP, _VP, _VP, _VP]),
     'rvip_train_step': (_I, [_VP, _VP, _VP, _VP, _I, _F, C.c_uint64, _VP, _VP, _VP]),
+    'rvip_set_loss_weights': (_I, [_VP, _F, _F]),
     'rvip_adam_step': (_I, [_VP, _VP, _VP, _F, _F, _F, _F, _LL, _F, _VP]),
     'rvip_num_buckets': (_I, [_VP]),
     'rvip_bucket': (_I, [_VP, _I, C.POINTER(_LL), C.POINTER(_LL)]),

@@ -317,7 +317,7 @@ class RvipUNet:
                 kind = kind.lower().replace('mean_squared_error', 'mse')
             if kind not in ffi.LOSS_KINDS:
                 raise NotImplementedError('loss %r is not implemented on the device path (MSE / masked / weighted '
-                                          'MSE are; BCE+Dice is SURVEY row N2)' % (loss,))
+                                          'MSE and BCE+Dice are)' % (loss,))
             self.loss_kind = kind
             self.loss_args = dict(getattr(loss, 'rvip_args', {'mask_smaller_than': 0.01}))
         self.metrics = list(metrics or [])
@@ -412,6 +412,9 @@ class RvipUNet:
         self._step += 1
         seed = (self._seed * 1000003 + self._step) ^ (self.dp.rank << 40)
         thr = float(self.loss_args.get('mask_smaller_than', 0.01))
+        if self.loss_kind == 'bce_dice':
+            ffi.check(L.rvip_set_loss_weights(b.h, float(self.loss_args.get('w_bce', 1.0)),
+                                              float(self.loss_args.get('w_dice', 1.0))))
         ffi.check(L.rvip_train_step(b.h, ffi.ptr(x_dev), ffi.ptr(y_dev), ffi.ptr(self._inplane),
                                     ffi.LOSS_KINDS[self.loss_kind], thr, C.c_uint64(seed & (2 ** 64 - 1)),
                                     ffi.ptr(heat), ffi.ptr(self._loss_dev), self._stream()))
@@ -534,6 +537,15 @@ class RvipUNet:
         for xb, yb in items:
             p = torch.from_numpy(self.predict(np.asarray(xb, np.float32), batch_size=len(xb)))
             t = torch.from_numpy(np.asarray(yb, np.float32))
+            if self.loss_kind == 'bce_dice':
+                e = 1e-7
+                pc = p.clamp(e, 1 - e)
+                bce = -(t * torch.log(pc + e) + (1 - t) * torch.log(1 - pc + e)).mean(dim=-1)
+                dice = (2 * (t * p).sum() + 1) / (t.sum() + p.sum() + 1)
+                per = float(self.loss_args.get('w_bce', 1.0)) * bce - float(self.loss_args.get('w_dice', 1.0)) * dice
+                tot += float(per.mean()) * len(xb)
+                n += len(xb)
+                continue
             per = ((p - t) ** 2).mean(dim=-1)
             if self.loss_kind != 'mse':
                 per = per * (t > self.loss_args.get('mask_smaller_than', 0.01)).any(dim=-1).float()

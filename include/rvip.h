@@ -40,7 +40,9 @@ typedef struct rvip_cfg {
 
 typedef struct rvip_handle rvip_handle;
 
-enum { RVIP_LOSS_MSE = 0, RVIP_LOSS_MASKED = 1, RVIP_LOSS_WEIGHTED = 2 };
+/* RVIP_LOSS_BCE_DICE: w_bce * binary_crossentropy - w_dice * dice_coef (src/models/Loss_and_metrics.py:165-171,
+ * 208-245; the reference's default LOSS_FUNCTION 'BcdDiceLoss'), weights via rvip_set_loss_weights (default 1, 1). */
+enum { RVIP_LOSS_MSE = 0, RVIP_LOSS_MASKED = 1, RVIP_LOSS_WEIGHTED = 2, RVIP_LOSS_BCE_DICE = 3 };
 
 const char* rvip_last_error(void);
 int rvip_abi_version(void);
@@ -74,6 +76,8 @@ int rvip_predict(rvip_handle* h, const float* x, float* heat, void* stream);
  * loss_out is a device double.  inplane [H,W] is only read for RVIP_LOSS_WEIGHTED. */
 int rvip_train_step(rvip_handle* h, const float* x, const float* target, const float* inplane, int loss_kind,
                     float mask_thr, uint64_t seed, float* heat, double* loss_out, void* stream);
+
+int rvip_set_loss_weights(rvip_handle* h, float w_bce, float w_dice);
 
 /* ---- Adam apply (ModelUtils.py:107; Keras epsilon-hat form) + operand re-pack.
  * grad_scale folds the data-parallel 1/world into the update. step counts from 1. */

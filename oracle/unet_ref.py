@@ -370,11 +370,25 @@ def inplane_weights(H: int, W: int) -> np.ndarray:
     return temp.astype(np.float32)
 
 
-def loss_torch(heat_nchw, target_nchw, kind='mse', mask_smaller_than=0.01, weights_hw=None, eps=1e-7):
+def loss_torch(heat_nchw, target_nchw, kind='mse', mask_smaller_than=0.01, weights_hw=None, eps=1e-7, w_bce=1.0,
+               w_dice=1.0):
     """'mse': mean((t-p)^2, axis=-1) then Keras SUM_OVER_BATCH_SIZE = global mean (Appendix C.11/14).
     'masked' / 'weighted': loss_with_zero_mask (Loss_and_metrics.py:40-89). The reference squeezes
     the mask on axis -1 (C must be 1); for C>1 the per-pixel mask is any_c(t > thr) -- an
     EXTENSION that reduces to the reference for C=1."""
+    if kind == 'bce_dice':
+        # BceDiceLoss.__call__ (Loss_and_metrics.py:208-228; bce_dice_loss :231-245 is the same with w_bce = 0.5):
+        #   w_bce * keras.binary_crossentropy(t, p) - w_dice * dice_coef(t, p)          (per pixel, dice a batch scalar)
+        # keras binary_crossentropy on probabilities [TF-2.3 backend]: p clipped to [eps, 1-eps], then
+        #   -mean_c( t * log(p + eps) + (1 - t) * log(1 - p + eps) );  dice_coef (:165-171): smooth = 1, raw p.
+        # Reduction: mean over (B, H, W) -- the value Keras logs.  [TF-2.3 semantics, unpinned]: the class overrides
+        # __call__, so Keras differentiates the SUM of the unreduced tensor; that is this gradient times B*H*W, a
+        # constant factor Adam's normalisation removes (up to its epsilon).
+        p = heat_nchw.clamp(eps, 1 - eps)
+        bce = -(target_nchw * torch.log(p + eps) + (1 - target_nchw) * torch.log(1 - p + eps)).mean(dim=1)
+        inter = (target_nchw * heat_nchw).sum()
+        dice = (2.0 * inter + 1.0) / (target_nchw.sum() + heat_nchw.sum() + 1.0)
+        return (w_bce * bce - w_dice * dice).mean()
     per_px = ((target_nchw - heat_nchw) ** 2).mean(dim=1)          # [B,H,W]
     if kind == 'mse':
         return per_px.mean()
@@ -391,18 +405,20 @@ def loss_torch(heat_nchw, target_nchw, kind='mse', mask_smaller_than=0.01, weigh
 # training step (fwd, loss, bwd) and Adam
 # --------------------------------------------------------------------------------------
 def train_grads(cfg: NetCfg, weights: Sequence[np.ndarray], x_nhwc, t_nhwc, dtype=torch.float32,
-                loss_kind='mse', dropout_masks=None, return_acts=False, weights_hw=None, storage='fp32'):
+                loss_kind='mse', dropout_masks=None, return_acts=False, weights_hw=None, storage='fp32',
+                loss_params=None):
     """One replica's forward + loss + backward. Returns dict(loss, heat, grads (Keras order,
     None for non-trainable), new_stats, [acts, act_grads]). storage='bf16' restates the device path's
     bf16 storage points (see _block_bf16)."""
     _STORAGE['mode'] = storage
     try:
-        return _train_grads(cfg, weights, x_nhwc, t_nhwc, dtype, loss_kind, dropout_masks, return_acts, weights_hw)
+        return _train_grads(cfg, weights, x_nhwc, t_nhwc, dtype, loss_kind, dropout_masks, return_acts, weights_hw,
+                            loss_params or {})
     finally:
         _STORAGE['mode'] = 'fp32'
 
 
-def _train_grads(cfg, weights, x_nhwc, t_nhwc, dtype, loss_kind, dropout_masks, return_acts, weights_hw):
+def _train_grads(cfg, weights, x_nhwc, t_nhwc, dtype, loss_kind, dropout_masks, return_acts, weights_hw, loss_params):
     ps = _to_params(weights, dtype)
     tm = trainable_mask(cfg)
     for p_, t_ in zip(ps, tm):
@@ -414,7 +430,7 @@ def _train_grads(cfg, weights, x_nhwc, t_nhwc, dtype, loss_kind, dropout_masks, 
         for v in acts.values():
             if v.requires_grad:
                 v.retain_grad()
-    loss = loss_torch(heat, t, loss_kind, weights_hw=weights_hw)
+    loss = loss_torch(heat, t, loss_kind, weights_hw=weights_hw, **loss_params)
     loss.backward()
     grads = [p_.grad.numpy().copy() if t_ else None for p_, t_ in zip(ps, tm)]
     out = dict(loss=float(loss.detach()), heat=heat.detach().permute(0, 2, 3, 1).contiguous().numpy(),

@@ -145,3 +145,20 @@ def test_inplane_weights_match_reference_loop():
     w = R.inplane_weights(10, 10)
     assert w[0].max() == 0 and w[:, 0].max() == 0
     assert w[4, 4] == 100.0 and abs(w[1, 1] - 25.0) < 1e-6 and abs(w[2, 5] - 50.0) < 1e-6
+
+
+def test_bce_dice_oracle_formula():
+    """loss_torch('bce_dice') against a direct numpy evaluation of Loss_and_metrics.py:165-171, 208-228."""
+    import torch
+    from oracle import unet_ref as R
+    rng = np.random.default_rng(3)
+    p = rng.uniform(0.001, 0.999, size=(2, 2, 6, 5))
+    p[0, 0, 0, 0], p[0, 1, 1, 1] = 0.0, 1.0          # exercise the clipping
+    t = (rng.random((2, 2, 6, 5)) < 0.2).astype(np.float64) * rng.uniform(0.5, 1.0, size=(2, 2, 6, 5))
+    e = 1e-7
+    pc = np.clip(p, e, 1 - e)
+    bce = -(t * np.log(pc + e) + (1 - t) * np.log(1 - pc + e)).mean(axis=1)
+    dice = (2 * (t * p).sum() + 1) / (t.sum() + p.sum() + 1)
+    want = (0.5 * bce - 1.0 * dice).mean()
+    got = float(R.loss_torch(torch.tensor(p), torch.tensor(t), 'bce_dice', w_bce=0.5, w_dice=1.0))
+    assert abs(got - want) < 1e-12
