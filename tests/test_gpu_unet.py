@@ -1,4 +1,6 @@
 """End-to-end parity of the device U-Net path (through create_unet -> C ABI) against the CPU oracle."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -340,3 +342,22 @@ def test_bce_dice_loss_matches_oracle(precision):
     from cmr_landmark_detection_b200.models.Unets import create_unet
     m2 = create_unet(dict(BASE, DIM=[32, 32], DEPTH=2, PRECISION=precision, LOSS_FUNCTION='BcdDiceLoss'))
     assert m2.loss_kind == 'bce_dice'
+
+
+def test_fit_with_reference_style_callbacks(tmp_path):
+    """train_model.py:95-112 flow: get_callbacks(config) -> model.fit(..., callbacks=...): the best-only checkpoint is
+    written, reloads into a fresh model and reproduces the predictions; ReduceLROnPlateau / LR log see optimizer.lr."""
+    from cmr_landmark_detection_b200 import synth
+    from cmr_landmark_detection_b200.models.Unets import create_unet
+    from cmr_landmark_detection_b200.utils.KerasCallbacks import get_callbacks
+    config = dict(BASE, DIM=[32, 32], DEPTH=2, PRECISION='bf16', LEARNING_RATE=2e-3, MODEL_PATH=str(tmp_path / 'model'),
+                  TENSORBOARD_PATH=str(tmp_path / 'tb'), MONITOR_FUNCTION='loss', SAVE_MODEL_FUNCTION='loss')
+    model = create_unet(config)
+    x, y = synth.make_batch(8, 32, 32, seed=12)
+    h = model.fit(x, y, batch_size=4, epochs=3, callbacks=get_callbacks(config), verbose=0, shuffle=False)
+    assert len(h.history['loss']) == 3 and 'lr' in h.history
+    m2 = create_unet(dict(config, SEED=123))
+    m2.load_weights(os.path.join(config['MODEL_PATH'], 'model.h5'))
+    # the checkpoint holds the weights of the best epoch (loss fell every epoch here -> the last one)
+    if h.history['loss'][-1] == min(h.history['loss']):
+        assert np.array_equal(m2.predict(x, batch_size=4), model.predict(x, batch_size=4))
