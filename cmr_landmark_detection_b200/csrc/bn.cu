@@ -54,6 +54,85 @@ int bn_eval_prepare_launch(const float* mm, const float* mv, float* mean, float*
   return 0;
 }
 
+// ------------------------------------------------------------------------------------- first layer recompute
+// out[j] = relu(b[c+j] + sum_t x[p + off(t)] * w[t][c+j]), 8 channels of pixel p of the 1-channel image (zero padding).
+// ONE function for the statistics pass, the forward apply and both backward passes: identical arithmetic everywhere, so
+// the ReLU mask and the normalised values seen by backward are exactly those of forward.
+__device__ __forceinline__ void c1_recompute8(const float* __restrict__ x, int H, int W, uint32_t p, const float* w_s,
+                                              const float* b_s, int C, int c, float (&out)[8]) {
+  const int xx = (int)(p % (uint32_t)W), yy = (int)((p / (uint32_t)W) % (uint32_t)H);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) out[j] = b_s[c + j];
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy) {
+    const bool rowok = (unsigned)(yy + dy) < (unsigned)H;
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const bool ok = rowok && (unsigned)(xx + dx) < (unsigned)W;
+      const float xv = ok ? __ldg(x + (size_t)p + dy * W + dx) : 0.f;
+      const float4 w0 = *reinterpret_cast<const float4*>(w_s + ((dy + 1) * 3 + dx + 1) * C + c);
+      const float4 w1 = *reinterpret_cast<const float4*>(w_s + ((dy + 1) * 3 + dx + 1) * C + c + 4);
+      out[0] = fmaf(xv, w0.x, out[0]); out[1] = fmaf(xv, w0.y, out[1]);
+      out[2] = fmaf(xv, w0.z, out[2]); out[3] = fmaf(xv, w0.w, out[3]);
+      out[4] = fmaf(xv, w1.x, out[4]); out[5] = fmaf(xv, w1.y, out[5]);
+      out[6] = fmaf(xv, w1.z, out[6]); out[7] = fmaf(xv, w1.w, out[7]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) out[j] = fmaxf(out[j], 0.f);
+}
+// stages w [9][C] and b [C] of the first layer into shared memory at dst (10 * C floats)
+__device__ __forceinline__ void c1_stage_weights(const BnArgs& a, float* dst) {
+  for (int k = threadIdx.x; k < 9 * a.C; k += 256) dst[k] = a.w0[k];
+  for (int k = threadIdx.x; k < a.C; k += 256) dst[9 * a.C + k] = a.b0[k];
+}
+
+__global__ void __launch_bounds__(256) c1_stats_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, double* __restrict__ stats, int B,
+                                                       int H, int W, int C) {
+  extern __shared__ float sm_c1[];    // w [9][C], b [C], sum [C], sumsq [C]
+  pdl_wait();
+  float* w_s = sm_c1;
+  float* b_s = w_s + 9 * C;
+  float* red = b_s + C;
+  for (int k = threadIdx.x; k < 9 * C; k += 256) w_s[k] = w[k];
+  for (int k = threadIdx.x; k < C; k += 256) b_s[k] = bias[k];
+  for (int k = threadIdx.x; k < 2 * C; k += 256) red[k] = 0.f;
+  __syncthreads();
+  const uint32_t G = C >> 3, lg = 31 - __clz(G);
+  const uint32_t n_items = ((uint32_t)B * H * W) << lg;
+  const uint32_t i0 = blockIdx.x * 256 + threadIdx.x;
+  if ((i0 & ~31u) < n_items) {
+    const int c = (int)(i0 & (G - 1)) * 8;
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    for (uint32_t i = i0; i < n_items; i += gridDim.x * 256) {
+      float v[8];
+      c1_recompute8(x, H, W, i >> lg, w_s, b_s, C, c, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += v[j];
+        q[j] = fmaf(v[j], v[j], q[j]);
+      }
+    }
+    block_accumulate8(red, c, s, G);
+    block_accumulate8(red + C, c, q, G);
+  }
+  pdl_launch_dependents();
+  __syncthreads();
+  for (int k = threadIdx.x; k < 2 * C; k += 256) atomicAdd(&stats[k], (double)red[k]);
+}
+int c1_stats_launch(const float* x, const float* w, const float* bias, double* stats, int B, int H, int W, int C,
+                    cudaStream_t st) {
+  const int G = C / 8;
+  RVIP_REQUIRE(C % 8 == 0 && G <= 32 && (G & (G - 1)) == 0, "c1_stats: C=%d must be 8 * power of two <= 256", C);
+  RVIP_REQUIRE((size_t)B * H * W * G < 0x7fffffffULL, "c1_stats: tensor too large for 32-bit indexing");
+  launch_kernel(c1_stats_kernel, kNumSMs * 4, 256, (size_t)12 * C * sizeof(float), st, x, w, bias, stats, B, H, W, C);
+  RVIP_LAUNCH_CHECK();
+  return 0;
+}
+
 // item index -> pixel coordinates (32-bit; all tensors of this path have < 2^31 16-byte vectors)
 struct Geo {
   uint32_t lg;       // log2(C / 8)
@@ -89,9 +168,9 @@ __device__ __forceinline__ void upsampled_pixels(const BnArgs& a, uint32_t p, ui
 // (a.stats, double) into shared memory -- the former one-block bn_finalize launch, folded in; block 0 also
 // publishes mean / rstd for the backward pass and updates the moving statistics (momentum 0.99, unbiased
 // variance: TF fused batch norm).  Inference: mean / rstd were prepared from the moving statistics.
-template <typename T, int POST>
+template <typename T, int POST, bool FROMX>
 __global__ void __launch_bounds__(256) bn_apply_kernel(BnArgs a) {
-  extern __shared__ float coef_s[];   // [2][C]: scale, shift
+  extern __shared__ float coef_s[];   // [2][C]: scale, shift  (+ FROMX: first-layer w [9][C], b [C])
   pdl_wait();
   for (int k = threadIdx.x; k < a.C; k += 256) {
     float m, r;
@@ -122,6 +201,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(BnArgs a) {
     coef_s[k] = sck;
     coef_s[a.C + k] = fmaf(-m, sck, a.beta[k]);
   }
+  if (FROMX) c1_stage_weights(a, coef_s + 2 * a.C);
   __syncthreads();
   const Geo g = make_geo(a, POST == POST_POOL);
   const uint32_t i0 = blockIdx.x * 256 + threadIdx.x;
@@ -141,7 +221,10 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(BnArgs a) {
     if (POST == POST_NONE || POST == POST_DROPOUT) {
       const size_t off = (size_t)(i >> g.lg) * a.C;
       float v[8];
-      Vec8<T>::load(av + off, v);
+      if (FROMX)
+        c1_recompute8(a.x0, a.H, a.W, i >> g.lg, coef_s + 2 * a.C, coef_s + 11 * a.C, a.C, c, v);
+      else
+        Vec8<T>::load(av + off, v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
       if (POST == POST_DROPOUT) {
@@ -196,12 +279,19 @@ static int bn_apply_t(const BnArgs& a, cudaStream_t st) {
   const size_t n = (a.post == POST_POOL ? P / 4 : P) * G;
   static const int fwd_per_sm = getenv("RVIP_BN_FWD_BLOCKS") ? atoi(getenv("RVIP_BN_FWD_BLOCKS")) : 6;
   const int grid = ew_grid(n, fwd_per_sm);   // persistent blocks: the per-block coefficient prologue is amortised
-  const size_t sm = 2 * a.C * sizeof(float);
+  const size_t sm = (a.x0 ? 12 : 2) * a.C * sizeof(float);
+  if (a.x0) {
+    RVIP_REQUIRE(a.post == POST_NONE || a.post == POST_DROPOUT, "bn: first-layer recompute with post op %d", a.post);
+    if (a.post == POST_NONE) launch_kernel(bn_apply_kernel<T, POST_NONE, true>, grid, 256, sm, st, a);
+    else launch_kernel(bn_apply_kernel<T, POST_DROPOUT, true>, grid, 256, sm, st, a);
+    RVIP_LAUNCH_CHECK();
+    return 0;
+  }
   switch (a.post) {
-    case POST_NONE: launch_kernel(bn_apply_kernel<T, POST_NONE>, grid, 256, sm, st, a); break;
-    case POST_DROPOUT: launch_kernel(bn_apply_kernel<T, POST_DROPOUT>, grid, 256, sm, st, a); break;
-    case POST_POOL: launch_kernel(bn_apply_kernel<T, POST_POOL>, grid, 256, sm, st, a); break;
-    default: launch_kernel(bn_apply_kernel<T, POST_UPSAMPLE>, grid, 256, sm, st, a); break;
+    case POST_NONE: launch_kernel(bn_apply_kernel<T, POST_NONE, false>, grid, 256, sm, st, a); break;
+    case POST_DROPOUT: launch_kernel(bn_apply_kernel<T, POST_DROPOUT, false>, grid, 256, sm, st, a); break;
+    case POST_POOL: launch_kernel(bn_apply_kernel<T, POST_POOL, false>, grid, 256, sm, st, a); break;
+    default: launch_kernel(bn_apply_kernel<T, POST_UPSAMPLE, false>, grid, 256, sm, st, a); break;
   }
   RVIP_LAUNCH_CHECK();
   return 0;
@@ -222,18 +312,22 @@ int bn_apply_launch(const BnArgs& a, int is_bf16, cudaStream_t st) {
 // ------------------------------------------------------------------------------------- backward
 // Work item -> K pixels (4 for a pooling window, else 1) with dy = dL/d(BN output) gathered from the
 // consumers' gradient buffers and the stored relu(conv) values.
-template <typename T, int POST>
+template <typename T, int POST, bool FROMX = false>
 struct Gather {
   static constexpr int K = POST == POST_POOL ? 4 : 1;
+  // w1_s: first-layer weights / bias staged in shared memory (FROMX only)
   __device__ static __forceinline__ void run(const BnArgs& a, const Geo& g, const DropKey& key, uint32_t i, int c,
                                              const float (&sc)[8], const float (&sh)[8], uint32_t (&pix)[K],
-                                             float (&av)[K][8], float (&dy)[K][8]) {
+                                             float (&av)[K][8], float (&dy)[K][8], const float* w1_s = nullptr) {
     const T* A = static_cast<const T*>(a.a) + c;
     const T* g0 = static_cast<const T*>(a.g0) + c;
     if constexpr (POST == POST_NONE || POST == POST_DROPOUT) {
       const uint32_t p = i >> g.lg;
       pix[0] = p;
-      Vec8<T>::load(A + (size_t)p * a.C, av[0]);
+      if (FROMX)
+        c1_recompute8(a.x0, a.H, a.W, p, w1_s, w1_s + 9 * a.C, a.C, c, av[0]);
+      else
+        Vec8<T>::load(A + (size_t)p * a.C, av[0]);
       Vec8<T>::load(g0 + (size_t)p * a.C, dy[0]);
       if (POST == POST_DROPOUT) {
         bool keep[8];
@@ -286,13 +380,14 @@ struct Gather {
 // pass 1: red[stripe][c] += sum dy, red[stripe][C + c] += sum dy * a   (raw a; normalised by the finalize kernel).
 // Blocks spread their double atomics over kRedStripes copies: ~1200 blocks adding to ONE copy serialise in the L2
 // atomic unit for ~17 us (profiles/microbench/atomics.cu), 16 copies cost nothing measurable.
-template <typename T, int POST>
+template <typename T, int POST, bool FROMX>
 __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_reduce_kernel(BnArgs a) {
-  extern __shared__ float red_s[];  // [2][C]
+  extern __shared__ float red_s[];  // [2][C]  (+ FROMX: first-layer w [9][C], b [C])
   pdl_wait();
   constexpr int K = Gather<T, POST>::K;
   const Geo g = make_geo(a, POST == POST_POOL);
   for (int k = threadIdx.x; k < 2 * a.C; k += 256) red_s[k] = 0.f;
+  if (FROMX) c1_stage_weights(a, red_s + 2 * a.C);
   __syncthreads();
   const uint32_t i0 = blockIdx.x * 256 + threadIdx.x;
   if ((i0 & ~31u) < g.n_items) {   // warp-uniform: n_items is a multiple of 32 vectors or the warp is partial
@@ -305,7 +400,7 @@ __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_reduce_
     for (uint32_t i = i0; i < g.n_items; i += g.stride) {
       uint32_t pix[K];
       float av[K][8], dy[K][8];
-      Gather<T, POST>::run(a, g, key, i, c, sc, sh, pix, av, dy);
+      Gather<T, POST, FROMX>::run(a, g, key, i, c, sc, sh, pix, av, dy, red_s + 2 * a.C);
 #pragma unroll
       for (int k = 0; k < K; ++k)
 #pragma unroll
@@ -326,9 +421,9 @@ __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_reduce_
 // pass 2: dz and the conv-bias gradient.  Prologue (every block, one thread per channel): fold the stripes and
 // derive the coefficients of  dz = [a>0] * ( sc*dy - k1*a + c0 )  in double, once per channel; block 0 also
 // writes dgamma / dbeta.
-template <typename T, int POST>
+template <typename T, int POST, bool FROMX>
 __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_apply_kernel(BnArgs a) {
-  extern __shared__ float red_s[];  // [C] bias-gradient partials, then [4][C] sc, k1, c0, shift
+  extern __shared__ float red_s[];  // [C] bias-gradient partials, then [4][C] sc, k1, c0, shift (+ FROMX: w [9][C], b [C])
   pdl_wait();
   float* coef_s = red_s + a.C;
   constexpr int K = Gather<T, POST>::K;
@@ -354,6 +449,7 @@ __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_apply_k
       a.dgamma[k] = (float)sda;
     }
   }
+  if (FROMX) c1_stage_weights(a, red_s + 5 * a.C);
   __syncthreads();
   const uint32_t i0 = blockIdx.x * 256 + threadIdx.x;
   if ((i0 & ~31u) < g.n_items) {
@@ -377,7 +473,7 @@ __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_apply_k
     for (uint32_t i = i0; i < g.n_items; i += g.stride) {
       uint32_t pix[K];
       float av[K][8], dy[K][8];
-      Gather<T, POST>::run(a, g, key, i, c, sc, sh, pix, av, dy);
+      Gather<T, POST, FROMX>::run(a, g, key, i, c, sc, sh, pix, av, dy, red_s + 5 * a.C);
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         float dz[8];
@@ -406,12 +502,24 @@ static int bn_bwd_t(const BnArgs& a, cudaStream_t st) {
   // registers for a co-resident weight-gradient CTA of the side stream (rvip_abi.cu:backward_body)
   static const int per_sm = getenv("RVIP_BN_BWD_BLOCKS") ? atoi(getenv("RVIP_BN_BWD_BLOCKS")) : 3;
   const int grid = ew_grid(n, a.post == POST_POOL ? 2 : per_sm);
-  const size_t sm = (WHICH == 0 ? 2 : 5) * a.C * sizeof(float);
-#define RVIP_BWD(POSTV)                                                 \
-  if (WHICH == 0)                                                       \
-    launch_kernel(bn_bwd_reduce_kernel<T, POSTV>, grid, 256, sm, st, a); \
-  else                                                                  \
-    launch_kernel(bn_bwd_apply_kernel<T, POSTV>, grid, 256, sm, st, a);
+  const size_t sm = ((WHICH == 0 ? 2 : 5) + (a.x0 ? 10 : 0)) * a.C * sizeof(float);
+  if (a.x0) {
+    RVIP_REQUIRE(a.post == POST_NONE || a.post == POST_DROPOUT, "bn: first-layer recompute with post op %d", a.post);
+    if (a.post == POST_NONE) {
+      if (WHICH == 0) launch_kernel(bn_bwd_reduce_kernel<T, POST_NONE, true>, grid, 256, sm, st, a);
+      else launch_kernel(bn_bwd_apply_kernel<T, POST_NONE, true>, grid, 256, sm, st, a);
+    } else {
+      if (WHICH == 0) launch_kernel(bn_bwd_reduce_kernel<T, POST_DROPOUT, true>, grid, 256, sm, st, a);
+      else launch_kernel(bn_bwd_apply_kernel<T, POST_DROPOUT, true>, grid, 256, sm, st, a);
+    }
+    RVIP_LAUNCH_CHECK();
+    return 0;
+  }
+#define RVIP_BWD(POSTV)                                                        \
+  if (WHICH == 0)                                                              \
+    launch_kernel(bn_bwd_reduce_kernel<T, POSTV, false>, grid, 256, sm, st, a); \
+  else                                                                         \
+    launch_kernel(bn_bwd_apply_kernel<T, POSTV, false>, grid, 256, sm, st, a);
   switch (a.post) {
     case POST_NONE: RVIP_BWD(POST_NONE) break;
     case POST_DROPOUT: RVIP_BWD(POST_DROPOUT) break;

@@ -71,7 +71,15 @@ struct BnArgs {
   float* dbeta;
   float* dbias;            // conv bias gradient = sum dz
   int identity;            // forward: scale 1 / shift 0 (the affine already happened in the conv epilogue)
+  // first layer (Cin = 1, training): `a` = relu(conv(x) + b) is never stored -- K = 9, so every pass that needs it
+  // recomputes it from the 1-channel image (saves a 134 MB write and three 134 MB reads per step at C2)
+  const float* x0;         // [B,H,W] fp32 image, nullptr = read `a`
+  const float* w0;         // [9][C] fp32 (Keras HWIO with Cin = 1)
+  const float* b0;         // [C]
 };
+// first layer, training: per-channel sum / sum of squares of relu(conv(x) + b) without storing it
+int c1_stats_launch(const float* x, const float* w, const float* bias, double* stats, int B, int H, int W, int C,
+                    cudaStream_t st);
 int bn_eval_prepare_launch(const float* mov_mean, const float* mov_var, float* mean, float* rstd, int n, float eps,
                            cudaStream_t st);
 // inference: scale = gamma / sqrt(moving_var + eps), shift = beta - moving_mean * scale for EVERY BatchNorm layer in

@@ -680,6 +680,20 @@ static int build_descriptors(rvip_handle* h) {
 }
 
 // ------------------------------------------------------------------------------------- passes
+// First layer in training, opt-in (RVIP_C1_RECOMPUTE=1): `a` = relu(conv(x) + b) is recomputed from the 1-channel image
+// by every pass that needs it (bn.cu: c1_recompute8) instead of being written once and read three times.  Measured
+// SLOWER at C2 (forward 134 -> 199 us, BN backward 140 -> 274 us): 9 FMAs + 2.25 shared-memory weight loads per output
+// element make those HBM-bound passes issue-bound.  Kept as a tested variant (it saves the 134 MB buffer).
+static bool c1_recompute(const rvip_handle* h, const Layer& l) {
+  return l.first && l.bn && l.C0 == 1 && l.Cout <= 256 && l.W % 4 == 0 && getenv("RVIP_C1_RECOMPUTE") != nullptr &&
+         (l.post == POST_NONE || l.post == POST_DROPOUT);
+}
+static void set_c1_source(const rvip_handle* h, const Layer& l, BnArgs* a, const float* x) {
+  a->x0 = x;
+  a->w0 = h->params + l.off_k;
+  a->b0 = h->params + l.off_b;
+}
+
 static int conv_forward(rvip_handle* h, Layer& l, const float* x, bool training, cudaStream_t st) {
   const int mode = (l.bn && training) ? EPI_RELU_STATS : (fused_inference(h, l) ? EPI_RELU_AFFINE : EPI_RELU);
   if (is_bf16(h) && !l.first) {
@@ -693,6 +707,12 @@ static int conv_forward(rvip_handle* h, Layer& l, const float* x, bool training,
     }
     l.fwd.mode = mode;
     return timed(h, KC_CONV_FWD_TC, 1, st, [&] { return conv_tc_launch(l.fwd, l.fKC, l.fBN, st); });
+  }
+  if (training && c1_recompute(h, l)) {
+    return timed(h, KC_CONV_SIMT, 1, st, [&] {
+      return c1_stats_launch(x, h->params + l.off_k, h->params + l.off_b, h->stats + 2 * l.off_stat, h->batch, l.H, l.W,
+                             l.Cout, st);
+    });
   }
   if (l.first && l.C0 == 1 && l.Cout <= 256 && l.W % 4 == 0) {
     return timed(h, KC_CONV_SIMT, 1, st, [&] {
@@ -765,6 +785,7 @@ static int forward_body(rvip_handle* h, const float* x, bool training, uint64_t 
     h->cur_tag = l.name + ":bn_fwd";
     BnArgs a;
     fill_bn(h, l, &a, training, seed);
+    if (training && c1_recompute(h, l)) set_c1_source(h, l, &a, x);
     if (fused_inference(h, l)) {
       // the conv epilogue already produced y = BN(relu(conv)); only pooling / up-sampling remain
       if (a.post != POST_POOL && a.post != POST_UPSAMPLE) continue;
@@ -820,6 +841,7 @@ static int backward_body(rvip_handle* h, const float* x, uint64_t seed, cudaStre
     if (l.bn) {
       BnArgs a;
       fill_bn(h, l, &a, true, seed);
+      if (c1_recompute(h, l)) set_c1_source(h, l, &a, x);
       if (i == h->head_in) {
         a.g0 = h->head_dy;
       } else {

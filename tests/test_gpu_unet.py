@@ -361,3 +361,22 @@ def test_fit_with_reference_style_callbacks(tmp_path):
     # the checkpoint holds the weights of the best epoch (loss fell every epoch here -> the last one)
     if h.history['loss'][-1] == min(h.history['loss']):
         assert np.array_equal(m2.predict(x, batch_size=4), model.predict(x, batch_size=4))
+
+
+def test_first_layer_recompute_variant_matches_default(monkeypatch):
+    """RVIP_C1_RECOMPUTE=1 (first-layer activation recomputed from the image instead of stored; opt-in because it measured
+    slower) must give the same loss and gradients as the default path."""
+    from oracle import unet_ref as R
+    res = {}
+    for flag in ('0', '1'):
+        if flag == '1':
+            monkeypatch.setenv('RVIP_C1_RECOMPUTE', '1')
+        else:
+            monkeypatch.delenv('RVIP_C1_RECOMPUTE', raising=False)
+        model, cfg, ws, x, y = _setup('fp32', 32, 2, 3, randomize_bn=False, seed=4)
+        loss = float(model.train_step_device(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(),
+                                             apply_optimizer=False).item())
+        res[flag] = (loss, model.grads.cpu().numpy().copy())
+    assert abs(res['0'][0] - res['1'][0]) <= 1e-6 * abs(res['0'][0])
+    d = np.linalg.norm(res['0'][1] - res['1'][1]) / np.linalg.norm(res['0'][1])
+    assert d <= 1e-4, d
