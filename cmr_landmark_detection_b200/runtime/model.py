@@ -528,15 +528,19 @@ class RvipUNet:
         return losses
 
     def evaluate(self, x, y=None, batch_size=32, verbose=0) -> float:
-        """Validation loss (inference mode) -- reduction on the device with torch ops (not the hot path)."""
+        """Validation loss (inference mode): device forward (rvip_predict), heat maps stay on the GPU and the scalar
+        reduction runs there with torch CUDA ops (validation bookkeeping, not the training hot path)."""
         tot, n = 0.0, 0
         if isinstance(x, np.ndarray):
             items = ((x[i:i + batch_size], y[i:i + batch_size]) for i in range(0, len(x), batch_size))
         else:
             items = (x[i] for i in range(len(x)))
         for xb, yb in items:
-            p = torch.from_numpy(self.predict(np.asarray(xb, np.float32), batch_size=len(xb)))
-            t = torch.from_numpy(np.asarray(yb, np.float32))
+            xb = np.ascontiguousarray(xb, dtype=np.float32)
+            self._check_x(xb)
+            with torch.cuda.device(self.device):
+                p = self.predict_device(torch.from_numpy(xb).to(self.device)).clone()
+                t = torch.from_numpy(np.ascontiguousarray(yb, dtype=np.float32)).to(self.device)
             if self.loss_kind == 'bce_dice':
                 e = 1e-7
                 pc = p.clamp(e, 1 - e)
@@ -550,7 +554,7 @@ class RvipUNet:
             if self.loss_kind != 'mse':
                 per = per * (t > self.loss_args.get('mask_smaller_than', 0.01)).any(dim=-1).float()
                 if self.loss_kind == 'weighted':
-                    per = per * self._inplane.cpu()[None] + 1e-7
+                    per = per * self._inplane[None] + 1e-7
             tot += float(per.mean()) * len(xb)
             n += len(xb)
         return tot / max(n, 1)
