@@ -428,3 +428,33 @@ def test_full_size_c2_properties():
     mb.set_weights(m32.get_weights())
     hb, h32 = mb.predict(x[:4], batch_size=4), m32.predict(x[:4], batch_size=4)
     assert np.abs(hb - h32).max() <= 2e-2
+
+
+@pytest.mark.parametrize('dim,depth,batch', [((96, 160), 3, 5), ((48, 80), 2, 3), ((128, 384), 2, 2)])
+def test_non_square_odd_batch_matches_oracle(dim, depth, batch):
+    """Shapes off the bench's beaten path (non-square images, widths that are not multiples of 128, odd batch sizes):
+    every level picks a different kernel family (row / halo / generic per-tap) and partial tiles appear."""
+    from cmr_landmark_detection_b200 import synth
+    from cmr_landmark_detection_b200.models.Unets import create_unet
+    from oracle import unet_ref as R
+    config = dict(BASE, DIM=list(dim), DEPTH=depth, PRECISION='bf16')
+    model = create_unet(config)
+    cfg = R.cfg_from_config(config)
+    ws = R.init_weights(cfg, seed=31, randomize_bn=True)
+    model.set_weights(ws)
+    x, y = synth.make_batch(batch, dim[0], dim[1], seed=13)
+    heat = model.predict(x, batch_size=batch)
+    ref = R.predict(cfg, ws, x)
+    assert heat.shape == ref.shape
+    assert np.abs(heat - ref).max() <= TOL['bf16']['heat'], np.abs(heat - ref).max()
+    out = R.train_grads(cfg, ws, x, y)
+    loss = float(model.train_step_device(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(),
+                                         apply_optimizer=False).item())
+    assert abs(loss - out['loss']) <= TOL['bf16']['loss'] * abs(out['loss']), (loss, out['loss'])
+    g = model.grads.cpu().numpy()
+    last = 'dec%d.conv_b/' % (depth - 1)
+    for (name, is_state, off, shape), rg in zip(model.tensors, out['grads']):
+        if is_state or not (name.startswith('head/') or name.startswith(last)) or name.endswith('conv_b/bias'):
+            continue
+        mine = g[off:off + int(np.prod(shape))].reshape(shape).astype(np.float64)
+        assert np.linalg.norm(mine - rg) <= 7e-2 * np.linalg.norm(rg), name
