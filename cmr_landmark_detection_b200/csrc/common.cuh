@@ -34,7 +34,7 @@ constexpr int kNumSMs = 148;
 // previous kernel drains, run their prologue (barrier init, TMEM allocation, tensor-map prefetch) and then block
 // in pdl_wait() until the previous grid has completed and its memory is visible.  pdl_launch_dependents() at the
 // top of a kernel allows the NEXT kernel to start that early.  Both are no-ops for a normal launch.
-// Opt-in with RVIP_PDL=1 (measured neutral on the bench step, see rvip_abi.cu:pdl_enabled).
+// On by default; RVIP_NO_PDL=1 falls back to plain stream serialisation (see rvip_abi.cu:pdl_enabled).
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
           tphase ^= 1;
         }
       }
+      pdl_launch_dependents();   // all MMAs issued: the next kernel may start launching behind this CTA's epilogue
       if (a.dbg) {
         a.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin;
         a.dbg[blockIdx.x * 8 + 1] = w_t;
@@ -351,7 +352,6 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
         atomicAdd(&a.stats[c], (double)s_part[c] + (double)s_part[2 * a.Cout + c]);
     }
   }
-  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);

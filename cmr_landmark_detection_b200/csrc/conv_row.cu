@@ -80,6 +80,7 @@ __device__ __forceinline__ void row_mma_loop(const ConvRowArgs& a, RowCtl* ctl, 
     acc ^= 1;
     if (acc == 0) acc_phase ^= 1;
   }
+  pdl_launch_dependents();   // all MMAs issued: the next kernel may start launching behind the last epilogue
 }
 
 template <int BN, int R, bool AFFINE, int OCH>
@@ -305,7 +306,6 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
       }
     }
   }
-  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);

@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(256, 1) wgrad3x3_halo_kernel(const __grid_cons
         }
       }
       mma_commit(&ctl->done);
+      pdl_launch_dependents();   // all MMAs issued: the next kernel may start launching behind the flush
     }
   } else if (warp >= 4 && has_work) {
     // ------------------------------------------------------------------ epilogue: TMEM -> fp32 reductions into HWIO
@@ -211,7 +212,6 @@ __global__ void __launch_bounds__(256, 1) wgrad3x3_halo_kernel(const __grid_cons
       }
     }
   }
-  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);

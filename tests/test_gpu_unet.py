@@ -272,7 +272,9 @@ def test_pipelined_fit_equals_sequential_steps():
     batches = [(x[4 * i:4 * i + 4], y[4 * i:4 * i + 4]) for i in range(5)]
 
     def run(pipelined):
-        model = create_unet(dict(BASE, DIM=[32, 32], DEPTH=2, PRECISION='fp32', SEED=3))
+        # small learning rate: Adam turns atomics-order noise into sign flips of near-zero gradient elements, which a
+        # large step would amplify from step to step (a routing bug, by contrast, changes the losses by > 5 %)
+        model = create_unet(dict(BASE, DIM=[32, 32], DEPTH=2, PRECISION='fp32', SEED=3, LEARNING_RATE=1e-4))
         if pipelined:
             losses = model._run_steps(iter(batches))
         else:
@@ -283,11 +285,11 @@ def test_pipelined_fit_equals_sequential_steps():
     assert len(la) == 5
     # atomics make the gradient sums order-dependent at the 1e-6 level: compare to that, not bitwise
     # the first step sees identical weights; afterwards Adam amplifies the atomics-order noise step by step
-    assert abs(la[0] - lb[0]) <= 1e-6 * abs(lb[0]) and np.allclose(la, lb, rtol=2e-3), (la, lb)
+    assert abs(la[0] - lb[0]) <= 1e-6 * abs(lb[0]) and np.allclose(la, lb, rtol=5e-3), (la, lb)
     # Adam turns 1e-6 gradient noise on near-zero elements into lr-sized differences: bound mean and max
     for a, b in zip(wa, wb):
         d = np.abs(a.astype(np.float64) - b)
-        assert d.mean() <= 1e-3 and d.max() <= 6e-3, (d.mean(), d.max())   # 5 steps x lr 1e-3
+        assert d.mean() <= 2e-4 and d.max() <= 6e-4, (d.mean(), d.max())   # 5 steps x lr 1e-4
 
 
 def test_c5_topology_matches_oracle():
