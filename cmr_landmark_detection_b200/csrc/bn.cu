@@ -259,8 +259,11 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(BnArgs a) {
       Vec8<T>::load(av + (size_t)p * a.C, v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+      if (a.y2) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) Vec8<T>::store(y2 + (size_t)q[k] * a.C, v);
+        for (int k = 0; k < 4; ++k) Vec8<T>::store(y2 + (size_t)q[k] * a.C, v);
+      }
+      if (a.y) Vec8<T>::store(y + (size_t)p * a.C, v);   // low-resolution copy for the phase-decomposed up-conv
     }
   }
   pdl_launch_dependents();

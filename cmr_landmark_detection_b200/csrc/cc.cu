@@ -67,7 +67,10 @@ __global__ void __launch_bounds__(256) cc_union_kernel(const uint8_t* __restrict
 __global__ void __launch_bounds__(256) cc_count_kernel(int* parent, unsigned int* __restrict__ size, int n) {
   const int p = blockIdx.x * 256 + threadIdx.x;
   if (p >= n || parent[p] < 0) return;
-  const int r = cc_find(parent, p);
+  // read-only walk: a path-halving store of another thread's walk could land AFTER this thread's final
+  // parent[p] = root and leave p pointing at an inner node (cc_write_kernel compares parent[p] with the root)
+  int r = p;
+  for (int q = __ldcg(parent + r); q != r; q = __ldcg(parent + r)) r = q;
   parent[p] = r;
   atomicAdd(size + r, 1u);
 }

@@ -54,18 +54,29 @@ struct HaloCfg {
   static_assert(TMEM_COLS <= 512, "TMEM budget");
 };
 
-template <int BN>
+// NS = 0: plain 3x3 convolution (9 taps).  NS = 2 / 3: phase-decomposed up-convolution (conv_halo.cuh): 2 x NS taps
+// per phase; the taps of a phase are the halo offsets (ty0 + rr, tx0 + ss), rr < 2, ss < NS, so every operand offset
+// is still an immediate on top of one per-phase shift of the activation descriptor.
+template <int BN, int NS>
 __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_constant__ ConvHaloArgs a, int nbst) {
   using Cfg = HaloCfg<BN>;
+  constexpr int NSX = NS ? NS : 3;             // taps per halo row
+  constexpr int NT = NS ? 2 * NS : 9;          // taps per K group
+  const bool up_k = NS && a.up_dir == 1;       // phases enumerate K groups (dgrad of the up-convolution)
+  const int n_eff = a.n_ntiles * ((NS && a.up_dir == 0) ? a.up_nph : 1);   // (phase, N tile) pairs per pixel block
+  const int cpp = up_k ? a.up_cz / 64 : 1;     // 64-channel chunks per phase view
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_ring = smem;                                     // 2 activation blocks
   uint8_t* b_ring = a_ring + 2 * kHaloASlot;                  // nbst weight tiles
   uint8_t* staging = b_ring + (size_t)nbst * Cfg::B_BYTES;    // 2 groups x SB slices
+  // the per-channel arrays exist only where the epilogue needs them (EPI_LINEAR = dgrad: none), so wide dgrads
+  // (Cout = 2048 input channels at the bottom of the 5-level net) keep their weight ring
+  const int auxc = a.mode == EPI_LINEAR ? 0 : a.Cout;
   float* s_part = reinterpret_cast<float*>(staging + 2 * Cfg::SB * Cfg::STG);   // [2 groups][2][Cout] sum, sum^2
-  float* s_scr = s_part + 4 * a.Cout;                                            // [2 groups][4 warps][8][16]
+  float* s_scr = s_part + 4 * auxc;                                              // [2 groups][4 warps][8][16]
   float* s_bias = s_scr + 2 * 4 * 8 * 16;                                        // [3][Cout]: bias, scale, shift
-  HaloCtl* ctl = reinterpret_cast<HaloCtl*>((reinterpret_cast<uintptr_t>(s_bias + 3 * a.Cout) + 15) & ~uintptr_t(15));
+  HaloCtl* ctl = reinterpret_cast<HaloCtl*>((reinterpret_cast<uintptr_t>(s_bias + 3 * auxc) + 15) & ~uintptr_t(15));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long t_kernel = a.dbg ? clock64() : 0;
@@ -95,10 +106,10 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
   }
   pdl_wait();   // everything above is independent of the previous kernel's output
   if (warp >= 4) {
-    for (int c = threadIdx.x - 128; c < 4 * a.Cout; c += 256) s_part[c] = 0.f;
+    for (int c = threadIdx.x - 128; c < 4 * auxc; c += 256) s_part[c] = 0.f;
     // the bias lives in shared memory: per-element __ldg in the epilogue exposed one L2 latency per 8 channels
-    for (int c = threadIdx.x - 128; c < a.Cout; c += 256) {
-      s_bias[c] = a.mode != EPI_LINEAR ? a.bias[c] : 0.f;
+    for (int c = threadIdx.x - 128; c < auxc; c += 256) {
+      s_bias[c] = a.mode != EPI_LINEAR ? a.bias[NS ? c % a.bias_mod : c] : 0.f;
       s_bias[a.Cout + c] = a.mode == EPI_RELU_AFFINE ? a.scale[c] : 1.f;
       s_bias[2 * a.Cout + c] = a.mode == EPI_RELU_AFFINE ? a.shift[c] : 0.f;
     }
@@ -107,7 +118,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
-  const int nchunks = a.Ctot / 64;
+  const int nchunks = up_k ? a.up_nph * cpp : a.Ctot / 64;   // K groups per tile
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -117,14 +128,16 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
       // tiles -- late enough that its ring slot has been released (no stall of the weight stream), early enough
       // that the ~3000-cycle load lands before the chunk starts
       auto load_act = [&](int tile, int c) {
-        const int pt = tile / a.n_ntiles;
+        const int pt = tile / n_eff;
         const int x0 = (pt % a.tiles_x) * 16;
         const int y0 = ((pt / a.tiles_x) % a.tiles_y) * 16;
         const int b = pt / (a.tiles_x * a.tiles_y);
-        const int cc = c * 64;
+        const int cc = up_k ? (c % cpp) * 64 : c * 64;
         mbar_wait(&ctl->aempty[as], aphase ^ 1);
         mbar_expect_tx(&ctl->afull[as], kHaloATx);
-        if (cc < a.C0)
+        if (up_k)
+          tma_load_4d(a_ring + as * kHaloASlot, &a.upin[c / cpp], &ctl->afull[as], cc, x0 - 1, y0 - 1, b);
+        else if (cc < a.C0)
           tma_load_4d(a_ring + as * kHaloASlot, &a.in0, &ctl->afull[as], cc, x0 - 1, y0 - 1, b);
         else
           tma_load_4d(a_ring + as * kHaloASlot, &a.in1, &ctl->afull[as], cc - a.C0, x0 - 1, y0 - 1, b);
@@ -133,17 +146,20 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
       };
       if ((int)blockIdx.x < a.total_tiles) load_act(blockIdx.x, 0);
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-        const int n0 = (tile % a.n_ntiles) * BN;
+        const int n0 = (tile % n_eff) * BN;     // weight rows: (phase, N tile) pairs are consecutive row blocks
         for (int c = 0; c < nchunks; ++c) {
-          const int cc = c * 64;
-          for (int tap = 0; tap < 9; ++tap) {
-            if (tap == (nbst < 6 ? nbst : 6)) {   // the MMA pipe is then inside this chunk: the slot of chunk c-1 is free
+          // K coordinate of tap t of this group = kb + t * ks
+          const int kb = up_k ? (c / cpp) * NT * a.up_cz + (c % cpp) * 64 : c * 64;
+          const int ks = up_k ? a.up_cz : a.Ctot;
+          const int pre = nbst < 6 ? nbst : 6;
+          for (int tap = 0; tap < NT; ++tap) {
+            if (tap == (pre < NT - 1 ? pre : NT - 1)) {   // the MMA pipe is then inside this chunk: the slot of chunk c-1 is free
               if (c + 1 < nchunks) load_act(tile, c + 1);
               else if (tile + (int)gridDim.x < a.total_tiles) load_act(tile + gridDim.x, 0);
             }
             mbar_wait(&ctl->bempty[bs], bphase ^ 1);
             mbar_expect_tx(&ctl->bfull[bs], Cfg::B_BYTES);
-            tma_load_2d(b_ring + (size_t)bs * Cfg::B_BYTES, &a.w, &ctl->bfull[bs], tap * a.Ctot + cc, n0);
+            tma_load_2d(b_ring + (size_t)bs * Cfg::B_BYTES, &a.w, &ctl->bfull[bs], tap * ks + kb, n0);
             if (++bs == nbst) {
               bs = 0;
               bphase ^= 1;
@@ -165,15 +181,25 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
         if (a.dbg) w_t += clock64() - t0;
         tc_fence_after();
         const uint32_t d0 = tmem_base + buf * 2 * BN;
+        const int ph_t = (tile % n_eff) / a.n_ntiles;   // output phase of this tile (forward up-convolution)
         for (int c = 0; c < nchunks; ++c) {
           t0 = a.dbg ? clock64() : 0;
           mbar_wait(&ctl->afull[as], aphase);
           if (a.dbg) w_a += clock64() - t0;
           tc_fence_after();
           // rows = 8-pixel groups (one image row of the half tile each), kHaloPitch pixels apart
-          const uint64_t adesc0 = make_smem_desc(smem_u32(a_ring + as * kHaloASlot), 16, kHaloPitch * 128, kLayoutSW128);
+          uint64_t adesc0 = make_smem_desc(smem_u32(a_ring + as * kHaloASlot), 16, kHaloPitch * 128, kLayoutSW128);
+          if (NS) {
+            // first halo offset (ty0, tx0) of the phase: forward (a, b) -> rows {a, a+1}, columns {b, b+1};
+            // dgrad -> rows {1-a, 2-a}, columns {1-b, 2-b}; NS == 3 (column phase merged into channels): all 3 columns
+            const int ph = up_k ? c / cpp : ph_t;
+            const int pa = NS == 2 ? ph >> 1 : ph, pb = NS == 2 ? ph & 1 : 0;
+            const int ty0 = up_k ? 1 - pa : pa;
+            const int tx0 = NS == 2 ? (up_k ? 1 - pb : pb) : 0;
+            adesc0 += (uint64_t)(((ty0 * kHaloPitch + tx0) * 128) >> 4);
+          }
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int tap = 0; tap < NT; ++tap) {
             t0 = a.dbg ? clock64() : 0;
             mbar_wait(&ctl->bfull[bs], bphase);
             if (a.dbg) w_b += clock64() - t0;
@@ -183,7 +209,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
             for (int half = 0; half < 2; ++half) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const uint32_t a_off = (uint32_t)((((tap / 3) * kHaloPitch + (tap % 3) + 8 * half) * 128 + k * 32) >> 4);
+                const uint32_t a_off = (uint32_t)((((tap / NSX) * kHaloPitch + (tap % NSX) + 8 * half) * 128 + k * 32) >> 4);
                 mma_bf16_ss(d0 + half * BN, adesc0 + a_off, bdesc0 + 2 * k, idesc, (tap | k) != 0 ? 1u : (uint32_t)(c != 0));
               }
             }
@@ -223,7 +249,8 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
     int buf = 0, tphase = 0, sb = 0;
     long long t_epi = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-      const int nt = tile % a.n_ntiles, pt = tile / a.n_ntiles;
+      const int nt = tile % a.n_ntiles, pt = tile / n_eff;
+      const int ph_t = (tile % n_eff) / a.n_ntiles;
       const int x0 = (pt % a.tiles_x) * 16 + 8 * grp;
       const int y0 = ((pt / a.tiles_x) % a.tiles_y) * 16;
       const int b = pt / (a.tiles_x * a.tiles_y);
@@ -280,7 +307,9 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
         halo_bar_sync(1 + grp, 128);
         if (gt == 0) {
           const int n = n0 + sl * 64;
-          if (a.mode == EPI_LINEAR && n >= a.out_split)
+          if (NS && a.up_dir == 0)
+            tma_store_4d(&a.upout[ph_t], sbuf, n, x0, y0, b);
+          else if (a.mode == EPI_LINEAR && n >= a.out_split)
             tma_store_4d(&a.out1, sbuf, n - a.out_split, x0, y0, b);
           else
             tma_store_4d(&a.out0, sbuf, n, x0, y0, b);
@@ -359,9 +388,10 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
 }
 
 // ------------------------------------------------------------------------------------- host
-static size_t halo_fixed_bytes(int BN, int Cout) {
+static size_t halo_fixed_bytes(int BN, int Cout, int mode) {
   const int sb = BN <= 128 ? 2 : 1;
-  return 1024 + 2 * (size_t)kHaloASlot + 2 * (size_t)sb * 128 * 128 + (7 * (size_t)Cout + 2 * 4 * 8 * 16) * sizeof(float) + sizeof(HaloCtl) + 64;
+  const size_t auxc = mode == EPI_LINEAR ? 0 : Cout;
+  return 1024 + 2 * (size_t)kHaloASlot + 2 * (size_t)sb * 128 * 128 + (7 * auxc + 2 * 4 * 8 * 16) * sizeof(float) + sizeof(HaloCtl) + 64;
 }
 
 bool conv_halo_plan(int B, int H, int W, int C0, int C1, int Cout, int mode, int out_split, int* BN, int* nbst) {
@@ -378,37 +408,82 @@ bool conv_halo_plan(int B, int H, int W, int C0, int C1, int Cout, int mode, int
   if (bn == 256 && waves_eff(256) < 0.67 && waves_eff(128) > waves_eff(256)) bn = 128;
   // BN = 256 fills TMEM with one tile (no double buffering): with several tiles per CTA every epilogue is exposed
   if (bn == 256 && mtiles * (Cout / 256) > kNumSMs && getenv("RVIP_HALO_BN256") == nullptr) bn = 128;
-  const size_t fixed = halo_fixed_bytes(bn, Cout);
+  const size_t fixed = halo_fixed_bytes(bn, Cout, mode);
   if (fixed >= (size_t)kHaloMaxSmem) return false;
   int n = (int)((kHaloMaxSmem - fixed) / ((size_t)bn * 128));
   if (n > kHaloMaxB) n = kHaloMaxB;
   if (n < 3) return false;
   *BN = bn; *nbst = n;
-  (void)mode;
   return true;
 }
 
-template <int BN>
+template <int BN, int NS>
 static int launch_halo(const ConvHaloArgs& a, int nbst, cudaStream_t st) {
-  const size_t smem = halo_fixed_bytes(BN, a.Cout) + (size_t)nbst * BN * 128;
+  const size_t smem = halo_fixed_bytes(BN, a.Cout, a.mode) + (size_t)nbst * BN * 128;
   RVIP_REQUIRE(smem <= (size_t)kHaloMaxSmem, "conv_halo: %zu bytes of shared memory needed", smem);
   static bool attr_set = false;
   if (!attr_set) {
-    RVIP_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloMaxSmem));
+    RVIP_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<BN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloMaxSmem));
     attr_set = true;
   }
   const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
-  launch_kernel(conv3x3_halo_kernel<BN>, grid, 384, smem, st, a, nbst);
+  launch_kernel(conv3x3_halo_kernel<BN, NS>, grid, 384, smem, st, a, nbst);
   RVIP_LAUNCH_CHECK();
   return 0;
 }
 
+int conv_halo_up_variant(int h, int w, int Cin, int Cout) {
+  if (h % 16 != 0 || w % 16 != 0 || Cin % 64 != 0) return 0;
+  if (Cout % 64 == 0) return 2;
+  if (Cout == 32) return 3;
+  return 0;
+}
+long long conv_halo_up_pack_elems(int Cin, int Cout) {
+  return Cout % 64 == 0 ? 16LL * Cin * Cout : 2LL * 6 * 64 * Cin;
+}
+bool conv_halo_up_plan(int B, int h, int w, int Cin, int Cout, int dir, int* BN, int* nbst) {
+  const int ns = conv_halo_up_variant(h, w, Cin, Cout);
+  if (!ns) return false;
+  const int nph = ns == 2 ? 4 : 2;
+  const int n_phase = ns == 2 ? Cout : 64;              // channels of one phase view
+  const int N = dir == 0 ? n_phase : Cin;               // accumulator columns needed per pixel block (and phase)
+  int bn = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64);
+  const long tiles_at = (long)B * (h / 16) * (w / 16) * (dir == 0 ? nph : 1);
+  auto waves_eff = [&](int n) {
+    const long t = tiles_at * (N / n);
+    return (double)t / (double)(((t + kNumSMs - 1) / kNumSMs) * kNumSMs);
+  };
+  if (bn == 256 && waves_eff(256) < 0.67 && waves_eff(128) > waves_eff(256)) bn = 128;
+  if (bn == 256 && tiles_at * (N / 256) > kNumSMs) bn = 128;
+  // narrower N tiles need less shared memory (8 KB per weight-ring slot at BN = 64): fall back until one fits
+  for (; bn >= 64; bn >>= 1) {
+    if (N % bn != 0) continue;
+    const size_t fixed = halo_fixed_bytes(bn, N, dir == 0 ? EPI_RELU : EPI_LINEAR);
+    if (fixed >= (size_t)kHaloMaxSmem) continue;
+    int n = (int)((kHaloMaxSmem - fixed) / ((size_t)bn * 128));
+    if (n > kHaloMaxB) n = kHaloMaxB;
+    if (n < 3) continue;
+    *BN = bn; *nbst = n;
+    return true;
+  }
+  return false;
+}
+
 int conv_halo_launch(const ConvHaloArgs& a, int BN, int nbst, cudaStream_t st) {
+  RVIP_REQUIRE(a.up_ns == 0 || a.up_ns == 2 || a.up_ns == 3, "conv_halo: bad up-convolution variant %d", a.up_ns);
   RVIP_REQUIRE(a.C0 % 64 == 0 && a.Ctot % 64 == 0 && a.Cout % BN == 0 && a.H % 16 == 0 && a.W % 16 == 0,
                "conv_halo: bad shape %dx%d C0=%d Ctot=%d Cout=%d BN=%d", a.H, a.W, a.C0, a.Ctot, a.Cout, BN);
-  if (BN == 256) return launch_halo<256>(a, nbst, st);
-  if (BN == 128) return launch_halo<128>(a, nbst, st);
-  if (BN == 64) return launch_halo<64>(a, nbst, st);
+  if (a.up_ns == 2) {
+    if (BN == 256) return launch_halo<256, 2>(a, nbst, st);
+    if (BN == 128) return launch_halo<128, 2>(a, nbst, st);
+    if (BN == 64) return launch_halo<64, 2>(a, nbst, st);
+  } else if (a.up_ns == 3) {
+    if (BN == 64) return launch_halo<64, 3>(a, nbst, st);
+  } else {
+    if (BN == 256) return launch_halo<256, 0>(a, nbst, st);
+    if (BN == 128) return launch_halo<128, 0>(a, nbst, st);
+    if (BN == 64) return launch_halo<64, 0>(a, nbst, st);
+  }
   set_error("conv_halo: unsupported N tile %d", BN);
   return 1;
 }

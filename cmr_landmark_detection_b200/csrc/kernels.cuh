@@ -153,4 +153,13 @@ struct PackEntry {
 int pack_weights_launch(const float* params, void* packed, const PackEntry* table_dev, int n_entries, int to_bf16,
                         cudaStream_t st);
 
+// phase-decomposed up-convolution operands (conv_halo.cuh): C == 32 -> ns = 3, C % 64 == 0 -> ns = 2
+struct UpPackEntry {
+  long long src;      // float offset of the HWIO kernel [3][3][Cin][C]
+  long long dst_f;    // element offset of the forward copy
+  long long dst_d;    // element offset of the dgrad copy, -1 = none
+  int Cin, C, ns;
+};
+int pack_up_launch(const float* params, void* packed, const UpPackEntry* table_dev, int n_entries, cudaStream_t st);
+
 }  // namespace rvip

@@ -167,6 +167,7 @@ static int setup_conv_halo(ConvHaloArgs* a, int BN, const void* in0, const void*
   a->out_split = (mode == EPI_LINEAR) ? out_split : Cout;
   a->bias = bias; a->stats = stats;
   a->dbg = nullptr;
+  a->up_ns = 0; a->up_dir = 0; a->up_nph = 1; a->up_cz = 64; a->bias_mod = Cout;
   if (make_act_map_box(&a->in0, in0, B, H, W, C0, 64, 18, 18, 1)) return 1;
   if (C1 > 0) {
     if (make_act_map_box(&a->in1, in1, B, H, W, C1, 64, 18, 18, 1)) return 1;
@@ -184,12 +185,79 @@ static int setup_conv_halo(ConvHaloArgs* a, int BN, const void* in0, const void*
   return 0;
 }
 
+// Phase view of a high-resolution NHWC bf16 tensor [B, 2h, 2w, C] as a low-resolution tensor (conv_halo.cuh):
+//   ns = 2: view (a, b) = pixels (2i + a, 2j + b), C channels, pixel stride 2C, row stride 2 * (2w) * C
+//   ns = 3: view (a)    = rows 2i + a with the column phase merged into 2C channels, pixel stride 2C
+static int make_phase_map(CUtensorMap* m, const void* ptr, int B, int h, int w, int C, int ns, int pa, int pb, int bw,
+                          int bh, int boxC = 64) {
+  EncodeTiledFn enc = get_encode();
+  RVIP_REQUIRE(enc, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  CUtensorMapSwizzle sw;
+  if (swizzle_for(boxC * 2, &sw)) return 1;
+  const int Cv = ns == 2 ? C : 2 * C;
+  const size_t Wh = 2 * (size_t)w, Hh = 2 * (size_t)h;
+  const uint8_t* base = static_cast<const uint8_t*>(ptr) + ((size_t)pa * Wh + (ns == 2 ? pb : 0)) * C * 2;
+  cuuint64_t dims[4] = {(cuuint64_t)Cv, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)2 * C * 2, (cuuint64_t)2 * Wh * C * 2, (cuuint64_t)Hh * Wh * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)boxC, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<uint8_t*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RVIP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(phase view %dx%dx%dx%d ns %d) failed: %d", B, h, w, C, ns,
+               (int)r);
+  return 0;
+}
+
+// dir 0: u[B,2h,2w,C] = relu(conv3x3(upsample2x(x[B,h,w,Cin])) + bias) from the packed forward copy;
+// dir 1: dx[B,h,w,Cin] = the matching input gradient from dz[B,2h,2w,C] and the packed dgrad copy.
+static int setup_conv_halo_up(ConvHaloArgs* a, int dir, int BN, const void* low, const void* high, const void* wpk,
+                              const float* bias, int B, int h, int w, int Cin, int C) {
+  const int ns = conv_halo_up_variant(h, w, Cin, C);
+  RVIP_REQUIRE(ns != 0, "up-convolution %dx%d %d->%d is not eligible for the phase-decomposed kernel", h, w, Cin, C);
+  const int nph = ns == 2 ? 4 : 2, NT = 2 * ns, Cv = ns == 2 ? C : 2 * C;
+  memset(a, 0, sizeof(*a));
+  a->B = B; a->H = h; a->W = w;
+  a->up_ns = ns; a->up_dir = dir; a->up_nph = nph; a->up_cz = Cv; a->bias_mod = C;
+  a->tiles_x = w / 16; a->tiles_y = h / 16;
+  a->bias = bias; a->stats = nullptr; a->scale = a->shift = nullptr; a->dbg = nullptr;
+  if (dir == 0) {
+    a->C0 = a->Ctot = Cin; a->Cout = Cv;
+    a->n_ntiles = Cv / BN;
+    a->total_tiles = a->n_ntiles * nph * a->tiles_x * a->tiles_y * B;
+    a->mode = EPI_RELU; a->out_split = Cv;
+    if (make_act_map_box(&a->in0, low, B, h, w, Cin, 64, 18, 18, 1)) return 1;
+    a->in1 = a->in0;
+    if (make_w_map(&a->w, wpk, nph * Cv, NT * Cin, 64, BN)) return 1;
+    for (int ph = 0; ph < nph; ++ph)
+      if (make_phase_map(&a->upout[ph], high, B, h, w, C, ns, ns == 2 ? ph >> 1 : ph, ph & 1, 8, 16)) return 1;
+    for (int ph = nph; ph < 4; ++ph) a->upout[ph] = a->upout[0];
+    a->out0 = a->out1 = a->upout[0];
+    for (int ph = 0; ph < 4; ++ph) a->upin[ph] = a->in0;
+  } else {
+    a->C0 = a->Ctot = nph * Cv; a->Cout = Cin;
+    a->n_ntiles = Cin / BN;
+    a->total_tiles = a->n_ntiles * a->tiles_x * a->tiles_y * B;
+    a->mode = EPI_LINEAR; a->out_split = Cin;
+    for (int ph = 0; ph < nph; ++ph)
+      if (make_phase_map(&a->upin[ph], high, B, h, w, C, ns, ns == 2 ? ph >> 1 : ph, ph & 1, 18, 18)) return 1;
+    for (int ph = nph; ph < 4; ++ph) a->upin[ph] = a->upin[0];
+    a->in0 = a->in1 = a->upin[0];
+    if (make_w_map(&a->w, wpk, Cin, nph * NT * Cv, 64, BN)) return 1;
+    if (make_act_map_box(&a->out0, const_cast<void*>(low), B, h, w, Cin, 64, 8, 16, 1)) return 1;
+    a->out1 = a->out0;
+    for (int ph = 0; ph < 4; ++ph) a->upout[ph] = a->out0;
+  }
+  return 0;
+}
+
 static int setup_wgrad_halo(WgradHaloArgs* a, const WgradHaloPlan& p, const void* x0, const void* x1, int C0, int C1,
                             const void* dz, float* dw, int B, int H, int W, int Cout) {
   a->B = B; a->H = H; a->W = W; a->C0 = C0; a->Ctot = C0 + C1; a->Cout = Cout;
   a->TW = p.TW; a->TH = p.TH; a->tiles_x = p.tiles_x; a->tiles_y = p.tiles_y; a->pixel_tiles = p.pixel_tiles;
   a->n_cchunks = p.n_cchunks; a->n_ntiles = p.n_ntiles; a->k_split = p.k_split;
   a->dw = dw;
+  a->up = 0;
   if (make_act_map_box(&a->x0, x0, B, H, W, C0, p.CIC, p.TW + 2, p.TH + 2, 1)) return 1;
   if (C1 > 0) {
     if (make_act_map_box(&a->x1, x1, B, H, W, C1, p.CIC, p.TW + 2, p.TH + 2, 1)) return 1;
@@ -197,6 +265,23 @@ static int setup_wgrad_halo(WgradHaloArgs* a, const WgradHaloPlan& p, const void
     a->x1 = a->x0;
   }
   if (make_act_map_box(&a->dz, dz, B, H, W, Cout, p.BN >= 64 ? 64 : 32, p.TW, p.TH, 1)) return 1;
+  return 0;
+}
+
+// weight gradient of the phase-decomposed up-convolution: x_low [B,h,w,Cin], dz [B,2h,2w,C] -> dw [3][3][Cin][C]
+static int setup_wgrad_halo_up(WgradHaloArgs* a, const WgradHaloPlan& p, const void* x_low, const void* dz, float* dw,
+                               int B, int h, int w, int Cin, int C) {
+  memset(a, 0, sizeof(*a));
+  a->B = B; a->H = h; a->W = w; a->C0 = Cin; a->Ctot = Cin; a->Cout = C;
+  a->TW = p.TW; a->TH = p.TH; a->tiles_x = p.tiles_x; a->tiles_y = p.tiles_y; a->pixel_tiles = p.pixel_tiles;
+  a->n_cchunks = p.n_cchunks; a->n_ntiles = p.n_ntiles; a->k_split = p.k_split;
+  a->dw = dw;
+  a->up = 1;
+  if (make_act_map_box(&a->x0, x_low, B, h, w, Cin, 64, p.TW + 2, p.TH + 2, 1)) return 1;
+  a->x1 = a->x0;
+  for (int ph = 0; ph < 4; ++ph)
+    if (make_phase_map(&a->dzp[ph], dz, B, h, w, C, 2, ph >> 1, ph & 1, p.TW, p.TH, p.BN >= 64 ? 64 : 32)) return 1;
+  a->dz = a->dzp[0];
   return 0;
 }
 
@@ -322,6 +407,16 @@ struct Layer {
   WgradHaloArgs hwg;
   WgradHaloPlan hwp;
   ConvHaloArgs hfwd, hdgrad;
+  // phase-decomposed up-convolution (decoder up-conv layers, bf16): forward reads the producer's low-resolution y,
+  // dgrad writes the low-resolution gradient directly (conv_halo.cuh)
+  int up_ns = 0, up_dgrad = 0;         // variant (0 = off); dgrad also phase-decomposed
+  int up_wgrad = 0;                    // weight gradient from the low-resolution input (no up-sampled copy needed)
+  int needs_y2 = 1;                    // POST_UPSAMPLE layers: some consumer still reads the up-sampled copy
+  int feeds_up = 0;                    // this (POST_UPSAMPLE) layer's y feeds a phase-decomposed up-convolution
+  int g0_lowres = 0;                   // ... and its gradient arrives at its own (low) resolution
+  long long pk_uf = -1, pk_ud = -1;    // packed up-convolution operands
+  ConvHaloArgs ufwd, udgrad;
+  int ufBN = 0, ufNb = 0, udBN = 0, udNb = 0;
   int use_hfwd = 0, use_hdgrad = 0, hfBN = 0, hfNb = 0, hdBN = 0, hdNb = 0;
   int use_rfwd = 0, use_rdgrad = 0, use_rwg = 0, use_hwg = 0;
   int rfBN = 0, rfR = 0, rfNst = 0, rdBN = 0, rdR = 0, rdNst = 0, rwBN = 0, rwR = 0, rwNst = 0;
@@ -368,6 +463,8 @@ struct rvip_handle {
   float w_bce = 1.f, w_dice = 1.f;
   rvip::PackEntry* pack_table_dev = nullptr;
   int n_pack = 0;
+  rvip::UpPackEntry* up_pack_table_dev = nullptr;
+  int n_up_pack = 0;
   std::vector<std::pair<long long, long long>> buckets;   // (offset, count) in grads
   std::vector<int> bucket_after_layer;                    // bucket i completes after backward of this layer index
   std::vector<cudaEvent_t> bucket_events;
@@ -459,6 +556,23 @@ static int build_plan(rvip_handle* h) {
     low = ib; clow = f;
   }
   h->head_in = low;
+  if (is_bf16(h) && getenv("RVIP_NO_PHASED") == nullptr) {
+    for (Layer& l : h->L) {
+      if (l.bn || l.in0_layer < 0 || h->L[l.in0_layer].post != POST_UPSAMPLE) continue;   // decoder up-conv layers
+      l.up_ns = conv_halo_up_variant(l.H / 2, l.W / 2, l.C0, l.Cout);
+      int bn_ = 0, nb_ = 0;   // shared-memory feasibility does not depend on the batch size
+      if (l.up_ns && !conv_halo_up_plan(1, l.H / 2, l.W / 2, l.C0, l.Cout, 0, &bn_, &nb_)) l.up_ns = 0;
+      if (!l.up_ns) continue;
+      l.up_dgrad = getenv("RVIP_NO_PHASED_DGRAD") == nullptr &&
+                   conv_halo_up_plan(1, l.H / 2, l.W / 2, l.C0, l.Cout, 1, &bn_, &nb_);
+      WgradHaloPlan wp;
+      l.up_wgrad = l.up_dgrad && getenv("RVIP_NO_PHASED_WGRAD") == nullptr &&
+                   wgrad_halo_up_plan(1, l.H / 2, l.W / 2, l.C0, l.Cout, &wp);
+      h->L[l.in0_layer].feeds_up = 1;
+      h->L[l.in0_layer].g0_lowres = l.up_dgrad;
+      h->L[l.in0_layer].needs_y2 = !l.up_wgrad;
+    }
+  }
   // flat offsets + tensor table in model.get_weights() order
   long long po = 0, so = 0, ch = 0;
   auto push = [&](const std::string& n, int is_state, long long off, std::initializer_list<int> dims) {
@@ -491,6 +605,14 @@ static int build_plan(rvip_handle* h) {
     const long long n = 9LL * (l.C0 + l.C1) * l.Cout;
     if (is_bf16(h)) {
       if (l.first) continue;
+      if (l.up_ns) {
+        const long long nu = conv_halo_up_pack_elems(l.C0, l.Cout);
+        l.pk_uf = pk; pk += nu;
+        if (l.up_dgrad) {
+          l.pk_ud = pk; pk += nu;
+          continue;                       // the plain 3x3 operand copies are not needed
+        }
+      }
       l.pk_f = pk; pk += n;
       l.pk_d = pk; pk += n;
     } else {
@@ -561,8 +683,11 @@ static size_t carve(rvip_handle* h, uint8_t* base, int B, int training, bool ass
     T(assign ? &l.a : sink, P * l.Cout);
     if (l.bn) {
       if (l.post == POST_UPSAMPLE) {
-        T(assign ? &l.y2 : sink, 4 * P * l.Cout);
-        if (assign) l.y = nullptr;
+        // the up-sampled copy feeds the plain 3x3 up-conv kernels and (training) the up-conv's weight gradient; the
+        // phase-decomposed up-conv reads the low-resolution y instead
+        if (assign) l.y = l.y2 = nullptr;
+        if (l.feeds_up) T(assign ? &l.y : sink, P * l.Cout);
+        if ((training && l.needs_y2) || !l.feeds_up) T(assign ? &l.y2 : sink, 4 * P * l.Cout);
       } else {
         T(assign ? &l.y : sink, P * l.Cout);
         if (l.post == POST_POOL) T(assign ? &l.y2 : sink, P / 4 * l.Cout);
@@ -573,7 +698,7 @@ static size_t carve(rvip_handle* h, uint8_t* base, int B, int training, bool ass
     if (training) {
       max_dz = std::max(max_dz, P * l.Cout);
       if (!l.first) {
-        T(assign ? &l.dx0 : sink, P * l.C0);
+        T(assign ? &l.dx0 : sink, (l.up_dgrad ? P / 4 : P) * l.C0);
         if (l.C1) T(assign ? &l.dx1 : sink, P * l.C1);
       }
     }
@@ -614,6 +739,32 @@ static int build_descriptors(rvip_handle* h) {
   for (size_t i = 0; i < h->L.size(); ++i) {
     Layer& l = h->L[i];
     if (l.first || !is_bf16(h)) continue;
+    if (l.up_ns) {
+      const __nv_bfloat16* pk = static_cast<const __nv_bfloat16*>(h->packed);
+      const Layer& lo = h->L[l.in0_layer];
+      RVIP_REQUIRE(conv_halo_up_plan(B, lo.H, lo.W, l.C0, l.Cout, 0, &l.ufBN, &l.ufNb), "%s: no up-conv plan", l.name.c_str());
+      if (setup_conv_halo_up(&l.ufwd, 0, l.ufBN, lo.y, l.a, pk + l.pk_uf, h->params + l.off_b, B, lo.H, lo.W, l.C0, l.Cout))
+        return 1;
+      if (h->training) {
+        if (l.up_dgrad) {
+          RVIP_REQUIRE(conv_halo_up_plan(B, lo.H, lo.W, l.C0, l.Cout, 1, &l.udBN, &l.udNb), "%s: no up-conv dgrad plan",
+                       l.name.c_str());
+          if (setup_conv_halo_up(&l.udgrad, 1, l.udBN, l.dx0, l.dz, pk + l.pk_ud, nullptr, B, lo.H, lo.W, l.C0, l.Cout))
+            return 1;
+        }
+        if (l.up_wgrad) {
+          l.use_hwg = wgrad_halo_up_plan(B, lo.H, lo.W, l.C0, l.Cout, &l.hwp);
+          RVIP_REQUIRE(l.use_hwg, "%s: no up-conv weight-gradient plan", l.name.c_str());
+          if (setup_wgrad_halo_up(&l.hwg, l.hwp, lo.y, l.dz, h->grads + l.off_k, B, lo.H, lo.W, l.C0, l.Cout)) return 1;
+        } else {
+          l.use_hwg = wgrad_halo_plan(B, l.H, l.W, l.C0, 0, l.Cout, &l.hwp);
+          RVIP_REQUIRE(l.use_hwg, "%s: the halo weight-gradient kernel does not fit", l.name.c_str());
+          if (setup_wgrad_halo(&l.hwg, l.hwp, lo.y2, nullptr, l.C0, 0, l.dz, h->grads + l.off_k, B, l.H, l.W, l.Cout))
+            return 1;
+        }
+      }
+      if (l.up_dgrad || !h->training) continue;
+    }
     const void* in0 = buffer_of(h, l.in0_layer, l.in0_which);
     const void* in1 = l.in1_layer >= 0 ? buffer_of(h, l.in1_layer, 1) : nullptr;
     const __nv_bfloat16* pk = static_cast<const __nv_bfloat16*>(h->packed);
@@ -699,6 +850,7 @@ static void set_c1_source(const rvip_handle* h, const Layer& l, BnArgs* a, const
 static int conv_forward(rvip_handle* h, Layer& l, const float* x, bool training, cudaStream_t st) {
   const int mode = (l.bn && training) ? EPI_RELU_STATS : (fused_inference(h, l) ? EPI_RELU_AFFINE : EPI_RELU);
   if (is_bf16(h) && !l.first) {
+    if (l.up_ns) return timed(h, KC_CONV_FWD_TC, 1, st, [&] { return conv_halo_launch(l.ufwd, l.ufBN, l.ufNb, st); });
     if (l.use_rfwd) {
       l.rfwd.mode = mode;
       return timed(h, KC_CONV_FWD_TC, 1, st, [&] { return conv_row_launch(l.rfwd, l.rfBN, l.rfR, l.rfNst, st); });
@@ -791,6 +943,7 @@ static int forward_body(rvip_handle* h, const float* x, bool training, uint64_t 
     if (fused_inference(h, l)) {
       // the conv epilogue already produced y = BN(relu(conv)); only pooling / up-sampling remain
       if (a.post != POST_POOL && a.post != POST_UPSAMPLE) continue;
+      if (a.post == POST_UPSAMPLE && !l.y2) continue;   // consumed at low resolution by the phase-decomposed up-conv
       a.identity = 1;
       a.a = conv_output(h, l);
       if (a.post == POST_POOL) a.y = nullptr;
@@ -849,6 +1002,7 @@ static int backward_body(rvip_handle* h, const float* x, uint64_t seed, cudaStre
       } else {
         a.g0 = buffer_of(h, l.g0_layer, l.g0_which);
         if (l.post == POST_POOL) a.g1 = buffer_of(h, l.g1_layer, 3);
+        if (l.g0_lowres) a.post = POST_NONE;   // the phase-decomposed up-conv dgrad already summed the 2x2 replicas
       }
       a.red = h->red + 2 * kRedStripes * l.off_stat;
       a.dz = l.dz;
@@ -879,6 +1033,7 @@ static int backward_body(rvip_handle* h, const float* x, uint64_t seed, cudaStre
           }))
         return 1;
       if (timed(h, KC_CONV_DGRAD_TC, 1, st, [&] {
+            if (l.up_dgrad) return conv_halo_launch(l.udgrad, l.udBN, l.udNb, st);
             if (l.use_rdgrad) return conv_row_launch(l.rdgrad, l.rdBN, l.rdR, l.rdNst, st);
             if (l.use_hdgrad) return conv_halo_launch(l.hdgrad, l.hdBN, l.hdNb, st);
             return conv_tc_launch(l.dgrad, l.dKC, l.dBN, st);
@@ -923,8 +1078,9 @@ static int backward_body(rvip_handle* h, const float* x, uint64_t seed, cudaStre
 }
 
 static int pack_weights(rvip_handle* h, cudaStream_t st) {
-  return timed(h, KC_OPTIM, 1, st, [&] {
-    return pack_weights_launch(h->params, h->packed, h->pack_table_dev, h->n_pack, is_bf16(h), st);
+  return timed(h, KC_OPTIM, h->n_up_pack ? 2 : 1, st, [&] {
+    if (pack_weights_launch(h->params, h->packed, h->pack_table_dev, h->n_pack, is_bf16(h), st)) return 1;
+    return pack_up_launch(h->params, h->packed, h->up_pack_table_dev, h->n_up_pack, st);
   });
 }
 
@@ -955,6 +1111,7 @@ int rvip_create(const rvip_cfg* cfg, rvip_handle** out) {
 void rvip_destroy(rvip_handle* h) {
   if (!h) return;
   if (h->pack_table_dev) cudaFree(h->pack_table_dev);
+  if (h->up_pack_table_dev) cudaFree(h->up_pack_table_dev);
   if (h->bn_table_dev) cudaFree(h->bn_table_dev);
   for (cudaEvent_t e : h->ev_dz) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_wg) if (e) cudaEventDestroy(e);
@@ -1003,8 +1160,15 @@ int rvip_bind(rvip_handle* h, float* params, float* grads, float* bn_state, void
   carve(h, h->ws, batch, training, true);
   // pack table
   std::vector<PackEntry> tab;
+  std::vector<UpPackEntry> utab;
   for (const Layer& l : h->L) {
     if (l.first) continue;
+    if (l.up_ns) {
+      UpPackEntry u;
+      u.src = l.off_k; u.dst_f = l.pk_uf; u.dst_d = l.pk_ud; u.Cin = l.C0; u.C = l.Cout; u.ns = l.up_ns;
+      utab.push_back(u);
+    }
+    if (l.pk_d < 0) continue;
     PackEntry e;
     e.src = l.off_k; e.dst_f = l.pk_f; e.dst_d = l.pk_d; e.Ctot = l.C0 + l.C1; e.Cout = l.Cout;
     tab.push_back(e);
@@ -1015,6 +1179,13 @@ int rvip_bind(rvip_handle* h, float* params, float* grads, float* bn_state, void
   if (!tab.empty()) {
     RVIP_CUDA(cudaMalloc(&h->pack_table_dev, sizeof(PackEntry) * tab.size()));
     RVIP_CUDA(cudaMemcpy(h->pack_table_dev, tab.data(), sizeof(PackEntry) * tab.size(), cudaMemcpyHostToDevice));
+  }
+  h->n_up_pack = (int)utab.size();
+  if (h->up_pack_table_dev) cudaFree(h->up_pack_table_dev);
+  h->up_pack_table_dev = nullptr;
+  if (!utab.empty()) {
+    RVIP_CUDA(cudaMalloc(&h->up_pack_table_dev, sizeof(UpPackEntry) * utab.size()));
+    RVIP_CUDA(cudaMemcpy(h->up_pack_table_dev, utab.data(), sizeof(UpPackEntry) * utab.size(), cudaMemcpyHostToDevice));
   }
   if (h->bn_table_dev) cudaFree(h->bn_table_dev);
   h->bn_table_dev = nullptr;
@@ -1034,6 +1205,11 @@ int rvip_bind(rvip_handle* h, float* params, float* grads, float* bn_state, void
       RVIP_CUDA(cudaMalloc(&h->bn_table_dev, sizeof(BnEvalEntry) * bt.size()));
       RVIP_CUDA(cudaMemcpy(h->bn_table_dev, bt.data(), sizeof(BnEvalEntry) * bt.size(), cudaMemcpyHostToDevice));
     }
+  }
+  // the phase-merged up-convolution operands have structural zeros that the packer never writes
+  if (h->n_up_pack) {
+    RVIP_CUDA(cudaMemset(h->packed, 0, 2 * (size_t)std::max<long long>(h->n_packed, 1)));
+    RVIP_CUDA(cudaStreamSynchronize(0));   // the packer runs on the caller's (possibly non-blocking) stream
   }
   if (build_descriptors(h)) return 1;
   if (training && !h->side) {
@@ -1176,7 +1352,7 @@ int rvip_debug_buffer(const rvip_handle* h, const char* name, int which, void** 
       case 0: n = P * l.Cout; break;
       case 1: n = l.y ? P * l.Cout : 0; break;
       case 2: n = l.post == POST_POOL ? P / 4 * l.Cout : (l.post == POST_UPSAMPLE ? 4 * P * l.Cout : 0); break;
-      case 3: n = l.dx0 ? P * l.C0 : 0; break;
+      case 3: n = l.dx0 ? (l.up_dgrad ? P / 4 : P) * l.C0 : 0; break;
       case 4: n = l.dx1 ? P * l.C1 : 0; break;
       default: set_error("rvip_debug_buffer: bad selector %d", which); return 1;
     }
@@ -1272,6 +1448,44 @@ int rvip_conv3x3_halo(const void* in0, const void* in1, int C0, int C1, const vo
     return 1;
   a.dbg = g_halo_dbg;
   return conv_halo_launch(a, BN, nb, (cudaStream_t)stream);
+}
+
+int rvip_upconv3x3_halo(int dir, const void* low, const void* high, const float* w_hwio, const float* bias,
+                        void* packed_scratch, int B, int h, int w, int Cin, int C, void* stream) {
+  const int ns = conv_halo_up_variant(h, w, Cin, C);
+  RVIP_REQUIRE(ns != 0, "rvip_upconv3x3_halo: shape not eligible for the phase-decomposed kernel");
+  cudaStream_t st = (cudaStream_t)stream;
+  UpPackEntry e;
+  e.src = 0; e.dst_f = 0; e.dst_d = conv_halo_up_pack_elems(Cin, C); e.Cin = Cin; e.C = C; e.ns = ns;
+  UpPackEntry* e_dev = nullptr;
+  RVIP_CUDA(cudaMalloc(&e_dev, sizeof(e)));
+  RVIP_CUDA(cudaMemcpy(e_dev, &e, sizeof(e), cudaMemcpyHostToDevice));
+  RVIP_CUDA(cudaMemsetAsync(packed_scratch, 0, 2 * sizeof(__nv_bfloat16) * (size_t)e.dst_d, st));
+  int rc = pack_up_launch(w_hwio, packed_scratch, e_dev, 1, st);
+  ConvHaloArgs a;
+  int BN = 0, nb = 0;
+  if (!rc && !conv_halo_up_plan(B, h, w, Cin, C, dir, &BN, &nb)) {
+    set_error("rvip_upconv3x3_halo: no plan");
+    rc = 1;
+  }
+  const __nv_bfloat16* pk = static_cast<const __nv_bfloat16*>(packed_scratch) + (dir ? e.dst_d : 0);
+  if (!rc) rc = setup_conv_halo_up(&a, dir, BN, low, high, pk, bias, B, h, w, Cin, C);
+  if (!rc) {
+    a.dbg = g_halo_dbg;
+    rc = conv_halo_launch(a, BN, nb, st);
+  }
+  cudaStreamSynchronize(st);
+  cudaFree(e_dev);
+  return rc;
+}
+
+int rvip_upconv_wgrad_halo(const void* x_low, const void* dz, float* dw, int B, int h, int w, int Cin, int C,
+                           void* stream) {
+  WgradHaloArgs a;
+  WgradHaloPlan p;
+  RVIP_REQUIRE(wgrad_halo_up_plan(B, h, w, Cin, C, &p), "rvip_upconv_wgrad_halo: shape not eligible");
+  if (setup_wgrad_halo_up(&a, p, x_low, dz, dw, B, h, w, Cin, C)) return 1;
+  return wgrad_halo_launch(a, p.CIC, p.BN, (cudaStream_t)stream);
 }
 
 int rvip_wgrad3x3_halo(const void* x0, const void* x1, int C0, int C1, const void* dz, float* dw, int B, int H, int W,

@@ -43,13 +43,14 @@ __device__ __forceinline__ void wh_red_add_v4(float* addr, float a, float b, flo
                : "memory");
 }
 
-template <int CIC, int BN>
+template <int CIC, int BN, bool UP = false>
 struct WhCfg {
   static constexpr int XPIXB = CIC * 2;                       // bytes per pixel of the x chunk
   static constexpr int CB = BN >= 64 ? 64 : 32;               // channels per dz TMA box
   static constexpr int DPIXB = CB * 2;
-  static constexpr int NDZ = BN / CB;                         // dz boxes per stage
-  static constexpr int MT = CIC == 32 ? 3 : 5;                // M tiles (accumulators) per CTA
+  static constexpr int NDZ = (UP ? 4 : 1) * (BN / CB);        // dz boxes per stage (UP: four phase views)
+  static constexpr int MT = UP ? 8 : (CIC == 32 ? 3 : 5);     // M tiles (accumulators) per CTA
+  static_assert(!UP || CIC == 64, "the phase-decomposed weight gradient packs column-neighbour pairs of 64 channels");
   static constexpr uint64_t LAYA = CIC == 64 ? kLayoutSW128 : kLayoutSW64;
   static constexpr uint64_t LAYB = CB == 64 ? kLayoutSW128 : kLayoutSW64;
   static_assert(MT * BN <= 512, "accumulators exceed TMEM");
@@ -61,10 +62,21 @@ __host__ __device__ constexpr int wh_tap_off(int t, int pitch) { return (t / 3) 
 // TW (16 | 32) is a template parameter so that every operand offset of the MT * 8 MMAs of a stage is an immediate:
 // with run-time tile geometry the single issuing thread spent ~120 dependent cycles per MMA on address
 // arithmetic -- twice the MMA itself (ncu: tensor pipe 27..55 % active, L2 at 10 %).
-template <int CIC, int BN, int TW>
+// does 3x3 tap index k (0..2) fall on low-resolution neighbour r (0 / 1) of an output row / column of parity p?
+__host__ __device__ constexpr bool wh_in_phase(int p, int r, int k) {
+  return p == 0 ? (r == 0 ? k == 0 : k >= 1) : (r == 0 ? k <= 1 : k == 2);
+}
+
+// UP: weight gradient of the phase-decomposed up-convolution (conv_halo.cuh).  x0 = LOW-resolution input; for output
+// phase (a, b) the pre-summed weight Wp[a][b][r][s] pairs low-resolution neighbour (a - 1 + r, b - 1 + s) with the
+// phase view dz_ab:  M tile (a, b, r) = column neighbours s = 0, 1 as two 64-channel chunks one pixel apart, N = the
+// phase's BN output channels -> 8 accumulators, 8 MMAs per 16 low-resolution pixels instead of 5 per 16 high-resolution
+// ones (2.5x fewer), and the up-sampled copy of x is never read.  dWp is folded onto the 3x3 taps in the flush:
+// dW[ky][kx] = sum over (a, r) with ky in S(a, r) and (b, s) with kx in S(b, s).
+template <int CIC, int BN, int TW, bool UP>
 __global__ void __launch_bounds__(256, 1) wgrad3x3_halo_kernel(const __grid_constant__ WgradHaloArgs a, int nst,
                                                                int tmem_cols) {
-  using Cfg = WhCfg<CIC, BN>;
+  using Cfg = WhCfg<CIC, BN, UP>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int TH = 128 / TW, pitch = TW + 2;
@@ -120,9 +132,16 @@ __global__ void __launch_bounds__(256, 1) wgrad3x3_halo_kernel(const __grid_cons
           tma_load_4d(X, &a.x0, &ctl->full[stage], c0, x0 - 1, y0 - 1, b);
         else
           tma_load_4d(X, &a.x1, &ctl->full[stage], c0 - a.C0, x0 - 1, y0 - 1, b);
+        if (UP) {
 #pragma unroll
-        for (int j = 0; j < Cfg::NDZ; ++j)
-          tma_load_4d(X + x_st + j * dz_box, &a.dz, &ctl->full[stage], n0 + j * Cfg::CB, x0, y0, b);
+          for (int j = 0; j < Cfg::NDZ; ++j)
+            tma_load_4d(X + x_st + j * dz_box, &a.dzp[j / (BN / Cfg::CB)], &ctl->full[stage],
+                        n0 + (j % (BN / Cfg::CB)) * Cfg::CB, x0, y0, b);
+        } else {
+#pragma unroll
+          for (int j = 0; j < Cfg::NDZ; ++j)
+            tma_load_4d(X + x_st + j * dz_box, &a.dz, &ctl->full[stage], n0 + j * Cfg::CB, x0, y0, b);
+        }
         if (++stage == nst) {
           stage = 0;
           phase ^= 1;
@@ -147,7 +166,11 @@ __global__ void __launch_bounds__(256, 1) wgrad3x3_halo_kernel(const __grid_cons
         for (int mt = 0; mt < Cfg::MT; ++mt) {
           // A: x halo block, MN-major: channel chunks LBO apart (= pixel shift between packed taps)
           int start_px, lbo_px;
-          if (CIC == 32) {
+          if (UP) {
+            const int ph = mt >> 1, r = mt & 1;   // phase (a, b) = (ph >> 1, ph & 1): halo rows a + r, columns b, b + 1
+            start_px = ((ph >> 1) + r) * pitch + (ph & 1);
+            lbo_px = 1;
+          } else if (CIC == 32) {
             start_px = mt * pitch;                // tap (dy = mt, dx = 0); chunks dx = 0, 1, 2, (3 = pad)
             lbo_px = 1;
           } else {
@@ -165,7 +188,8 @@ __global__ void __launch_bounds__(256, 1) wgrad3x3_halo_kernel(const __grid_cons
             for (int xb = 0; xb < runs_x; ++xb) {
               const uint32_t a_off = (uint32_t)((y * pitch + xb * 16) * Cfg::XPIXB) >> 4;
               const uint32_t b_off = (uint32_t)((y * TW + xb * 16) * Cfg::DPIXB) >> 4;
-              mma_bf16_ss(d, adesc0 + a_off, bdesc0 + b_off, idesc, (y | xb) != 0 ? 1u : accumulate);
+              const uint32_t b_ph = UP ? (uint32_t)((mt >> 1) * (BN / Cfg::CB) * dz_box) >> 4 : 0u;   // phase view of dz
+              mma_bf16_ss(d, adesc0 + a_off, bdesc0 + b_ph + b_off, idesc, (y | xb) != 0 ? 1u : accumulate);
             }
           }
         }
@@ -185,8 +209,41 @@ __global__ void __launch_bounds__(256, 1) wgrad3x3_halo_kernel(const __grid_cons
     const int m = ew * 32 + lane;               // accumulator row
     mbar_wait(&ctl->done, 0);
     tc_fence_after();
+    if (UP) {
+      const int s = m >> 6, ci = m & 63;        // column neighbour of this row's chunk (warp-uniform), input channel
 #pragma unroll 1
-    for (int mt = 0; mt < Cfg::MT; ++mt) {
+      for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll 1
+        for (int kk = 0; kk < 2; ++kk) {
+          const int kx = s + kk;                 // neighbour s = 0 carries kx in {0, 1}, s = 1 carries kx in {1, 2}
+          float* dst = a.dw + ((size_t)((ky * 3 + kx) * a.Ctot + c0 + ci) * a.Cout + n0);
+#pragma unroll 1
+          for (int ch = 0; ch < BN / 32; ++ch) {
+            float acc[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+#pragma unroll
+            for (int ar = 0; ar < 4; ++ar) {
+              if (!wh_in_phase(ar >> 1, ar & 1, ky)) continue;
+#pragma unroll
+              for (int pb = 0; pb < 2; ++pb) {
+                if (!wh_in_phase(pb, s, kx)) continue;
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (((ar >> 1) * 2 + pb) * 2 + (ar & 1)) * BN + ch * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(v[j]);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              wh_red_add_v4(dst + ch * 32 + j * 4, acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+          }
+        }
+      }
+    }
+#pragma unroll 1
+    for (int mt = 0; mt < (UP ? 0 : Cfg::MT); ++mt) {
       int tap, ci;
       if (CIC == 32) {
         tap = mt * 3 + (m >> 5);                // dy = mt, dx = chunk; chunk 3 is padding
@@ -218,17 +275,38 @@ __global__ void __launch_bounds__(256, 1) wgrad3x3_halo_kernel(const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------- host
-static size_t wh_stage_bytes(int CIC, int BN, int TW, int TH) {
+static size_t wh_stage_bytes(int CIC, int BN, int TW, int TH, bool up = false) {
   const int xpixb = CIC * 2, cb = BN >= 64 ? 64 : 32;
   const int x_st = wh_round1k((TH + 2) * (TW + 2) * xpixb + 4 * xpixb);
-  return (size_t)x_st + (size_t)TH * TW * cb * 2 * (BN / cb);
+  return (size_t)x_st + (size_t)TH * TW * cb * 2 * (BN / cb) * (up ? 4 : 1);
 }
 static size_t wh_fixed_bytes() { return 1024 + sizeof(WhCtl) + 64; }
 // Stages are small (128 pixels) and many: the ring has to cover the TMA latency (~2000 cycles) with loads in
 // flight while a stage's MMAs (1500..2000 cycles) run; two 256-pixel stages measured load-latency bound.
-static int wh_stages(int CIC, int BN, int TW, int TH) {
-  int n = (int)((kWhMaxSmem - wh_fixed_bytes()) / wh_stage_bytes(CIC, BN, TW, TH));
+static int wh_stages(int CIC, int BN, int TW, int TH, bool up = false) {
+  int n = (int)((kWhMaxSmem - wh_fixed_bytes()) / wh_stage_bytes(CIC, BN, TW, TH, up));
   return n > kWhMaxStages ? kWhMaxStages : n;
+}
+
+bool wgrad_halo_up_plan(int B, int h, int w, int Cin, int Cout, WgradHaloPlan* p) {
+  if (w < 16 || w % 16 != 0 || Cin % 64 != 0 || Cout % 32 != 0) return false;
+  p->CIC = 64;
+  p->BN = Cout % 64 == 0 ? 64 : 32;          // 8 accumulators x BN columns <= 512 TMEM columns
+  p->TW = w % 32 == 0 ? 32 : 16;
+  p->TH = 128 / p->TW;
+  if (wh_stages(64, p->BN, p->TW, p->TH, true) < 2) return false;
+  p->tiles_x = w / p->TW;
+  p->tiles_y = (h + p->TH - 1) / p->TH;
+  p->pixel_tiles = p->tiles_x * p->tiles_y * B;
+  p->n_cchunks = Cin / 64;
+  p->n_ntiles = Cout / p->BN;
+  const int units = p->n_cchunks * p->n_ntiles;
+  int split = kNumSMs / units;
+  if (split < 1) split = 1;
+  if (split > (p->pixel_tiles + 3) / 4) split = (p->pixel_tiles + 3) / 4;
+  if (split < 1) split = 1;
+  p->k_split = split;
+  return true;
 }
 
 bool wgrad_halo_plan(int B, int H, int W, int C0, int C1, int Cout, WgradHaloPlan* p) {
@@ -263,20 +341,20 @@ bool wgrad_halo_plan(int B, int H, int W, int C0, int C1, int Cout, WgradHaloPla
   return true;
 }
 
-template <int CIC, int BN, int TW>
+template <int CIC, int BN, int TW, bool UP = false>
 static int launch_wh(const WgradHaloArgs& a, cudaStream_t st) {
-  const int nst = wh_stages(CIC, BN, a.TW, a.TH);
+  const int nst = wh_stages(CIC, BN, a.TW, a.TH, UP);
   RVIP_REQUIRE(nst >= 2, "wgrad_halo: tile %dx%d does not fit shared memory", a.TW, a.TH);
-  const size_t smem = wh_fixed_bytes() + (size_t)nst * wh_stage_bytes(CIC, BN, a.TW, a.TH);
+  const size_t smem = wh_fixed_bytes() + (size_t)nst * wh_stage_bytes(CIC, BN, a.TW, a.TH, UP);
   int cols = 32;
-  while (cols < WhCfg<CIC, BN>::MT * BN) cols *= 2;
+  while (cols < WhCfg<CIC, BN, UP>::MT * BN) cols *= 2;
   static bool attr_set = false;
   if (!attr_set) {
-    RVIP_CUDA(cudaFuncSetAttribute(wgrad3x3_halo_kernel<CIC, BN, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RVIP_CUDA(cudaFuncSetAttribute(wgrad3x3_halo_kernel<CIC, BN, TW, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    kWhMaxSmem));
     attr_set = true;
   }
-  launch_kernel(wgrad3x3_halo_kernel<CIC, BN, TW>, dim3(a.n_cchunks * a.n_ntiles, a.k_split), dim3(256), smem, st, a, nst,
+  launch_kernel(wgrad3x3_halo_kernel<CIC, BN, TW, UP>, dim3(a.n_cchunks * a.n_ntiles, a.k_split), dim3(256), smem, st, a, nst,
                 cols);
   RVIP_LAUNCH_CHECK();
   return 0;
@@ -286,6 +364,11 @@ int wgrad_halo_launch(const WgradHaloArgs& a, int CIC, int BN, cudaStream_t st) 
   RVIP_REQUIRE(a.C0 % CIC == 0 && a.Ctot % CIC == 0 && a.Cout % BN == 0, "wgrad_halo: bad channel tiling C0=%d Ctot=%d "
                "Cout=%d CIC=%d BN=%d", a.C0, a.Ctot, a.Cout, CIC, BN);
   RVIP_REQUIRE((a.TW == 16 || a.TW == 32) && a.TH == 128 / a.TW, "wgrad_halo: unsupported pixel tile %dx%d", a.TW, a.TH);
+  if (a.up) {
+    RVIP_REQUIRE(CIC == 64 && (BN == 64 || BN == 32), "wgrad_halo: up-convolution tile CIC=%d BN=%d", CIC, BN);
+    if (BN == 64) return a.TW == 32 ? launch_wh<64, 64, 32, true>(a, st) : launch_wh<64, 64, 16, true>(a, st);
+    return a.TW == 32 ? launch_wh<64, 32, 32, true>(a, st) : launch_wh<64, 32, 16, true>(a, st);
+  }
 #define RVIP_WH_CASE(cic, bn)                                                        \
   if (CIC == cic && BN == bn)                                                        \
     return a.TW == 32 ? launch_wh<cic, bn, 32>(a, st) : launch_wh<cic, bn, 16>(a, st);

@@ -21,7 +21,14 @@ struct WgradHaloArgs {
   int C0, Ctot, Cout;
   int TW, TH, tiles_x, tiles_y, pixel_tiles;
   int n_cchunks, n_ntiles, k_split;
+  // phase-decomposed up-convolution (conv_halo.cuh): x0 is the LOW-resolution input (H, W = its size), dzp[2a + b] the
+  // phase view (pixels (2i + a, 2j + b)) of the high-resolution dz, box {min(BN,64), TW, TH, 1}
+  int up;
+  CUtensorMap dzp[4];
 };
+// weight gradient of the phase-decomposed up-convolution: eight accumulators (phase (a, b) x low-resolution row
+// neighbour r, each a pair of column neighbours s = 0, 1 packed in M), folded onto the nine 3x3 taps in the flush
+bool wgrad_halo_up_plan(int B, int h, int w, int Cin, int Cout, WgradHaloPlan* p);
 // false if the layer does not fit this kernel (W not a multiple of 16, channels not multiples of 32)
 bool wgrad_halo_plan(int B, int H, int W, int C0, int C1, int Cout, WgradHaloPlan* p);
 int wgrad_halo_launch(const WgradHaloArgs& a, int CIC, int BN, cudaStream_t st);

@@ -168,6 +168,21 @@ int rvip_conv3x3_halo_debug(long long* dbg);
  * with its halo, all nine taps accumulated in TMEM. Same contract as rvip_wgrad3x3_tc. */
 int rvip_wgrad3x3_halo(const void* x0, const void* x1, int C0, int C1, const void* dz, float* dw, int B, int H, int W,
                        int Cout, void* stream);
+/* Phase-decomposed decoder up-convolution (UpSampling2D(2) -> Conv2D 3x3 -> ReLU, src/models/KerasLayers.py:756-759)
+ * computed from the LOW-resolution tensor: output pixel (2i + a, 2j + b) sees only a 2 x 2 low-resolution neighbourhood,
+ * so the 3x3 taps that coincide are pre-summed in fp32 and each of the four phases is a 4-tap convolution (2.25x fewer
+ * MMAs; the up-sampled tensor is never materialised for this op).  h, w = low-resolution size (multiples of 16),
+ * Cin % 64 == 0, C % 64 == 0 or C == 32.  w_hwio: fp32 [3][3][Cin][C] (device); packed_scratch: device bf16 buffer of
+ * at least 2 * max(16*Cin*C, 768*Cin) elements (receives the packed forward and dgrad operands).
+ *   dir 0: high[B,2h,2w,C] = relu(conv3x3(upsample2x(low[B,h,w,Cin])) + bias)
+ *   dir 1: low[B,h,w,Cin]  = gradient of that convolution w.r.t. its low-resolution input, from high = dz[B,2h,2w,C]
+ * Synchronises the stream before returning (test / profiling entry point). */
+int rvip_upconv3x3_halo(int dir, const void* low, const void* high, const float* w_hwio, const float* bias,
+                        void* packed_scratch, int B, int h, int w, int Cin, int C, void* stream);
+/* Weight gradient of the same up-convolution from the LOW-resolution input: dw[3][3][Cin][C] (fp32, accumulated) from
+ * x_low[B,h,w,Cin] and dz[B,2h,2w,C] (bf16).  Cin % 64 == 0, C % 32 == 0, w % 16 == 0. */
+int rvip_upconv_wgrad_halo(const void* x_low, const void* dz, float* dw, int B, int h, int w, int Cin, int C,
+                           void* stream);
 
 #ifdef __cplusplus
 }

@@ -281,6 +281,41 @@ def _block_bf16(x, p: _Params, spec: ConvSpec, cfg: NetCfg, training, new_stats,
     return y
 
 
+def _phase_taps(parity, r):
+    """3x3 tap indices that fall on low-resolution neighbour r (0 / 1) of an output row / column of this parity."""
+    return ((0,), (1, 2))[r] if parity == 0 else ((0, 1), (2,))[r]
+
+
+def phased_upconv_eligible(h, w, cin, cout):
+    """Shapes the device path computes with the phase-decomposed up-convolution (conv_halo.cuh); h, w = low resolution."""
+    return h % 16 == 0 and w % 16 == 0 and cin % 64 == 0 and (cout % 64 == 0 or cout == 32)
+
+
+def _upconv_phased_bf16(x_low, p: _Params, spec: ConvSpec, acts):
+    """Calibration restatement of the device's phase-decomposed up-convolution: UpSampling2D(2) -> Conv3x3 is the same
+    linear map as four 2x2-tap convolutions on the low-resolution tensor (one per output parity (a, b)) whose weights are
+    sums of the 3x3 taps that coincide after nearest-neighbour up-sampling (KerasLayers.py:756-759). The device sums in
+    fp32 and rounds the SUM to bf16 once; everything else is as in _block_bf16."""
+    k, b = p.take(2)
+    x = _RoundBwd.apply(x_low)
+    h, w = x.shape[2], x.shape[3]
+    xp = F.pad(x, (1, 1, 1, 1))
+    rows = []
+    for a in range(2):
+        cols = []
+        for bb in range(2):
+            kp = torch.stack([torch.stack([sum(k[ky, kx] for ky in _phase_taps(a, r) for kx in _phase_taps(bb, s_))
+                                           for s_ in range(2)]) for r in range(2)])          # [2, 2, Cin, C]
+            kp = _RoundFwd.apply(kp)
+            cols.append(F.conv2d(xp, kp.permute(3, 2, 0, 1), b)[:, :, a:a + h, bb:bb + w])
+        rows.append(torch.stack(cols, dim=-1))                  # [B, C, h, w, 2]
+    z = torch.stack(rows, dim=3).reshape(x.shape[0], k.shape[3], 2 * h, 2 * w)   # [B, C, h, 2, w, 2] -> [B, C, 2h, 2w]
+    a_ = _RoundFwd.apply(torch.relu(_RoundBwd.apply(z)))
+    acts[spec.name + '/a'] = a_
+    acts[spec.name + '/y'] = a_
+    return a_
+
+
 def _dropout(x, rate, training, masks, name):
     if not training or rate == 0.0:
         return x
@@ -314,8 +349,13 @@ def forward_torch(cfg: NetCfg, params: Sequence[torch.Tensor], x_nchw: torch.Ten
         skip = skips.pop()
         if not cfg.use_upsample:
             raise NotImplementedError('Conv2DTranspose decoder variant (SURVEY row N5)')
-        up = F.interpolate(h, scale_factor=2, mode='nearest')       # UpSampling2D (Appendix C.6)
-        u = _block(up, p, specs[f'dec{l}.upconv'], cfg, training, new_stats, acts)
+        su = specs[f'dec{l}.upconv']
+        if (_STORAGE['mode'] == 'bf16' and _STORAGE.get('phased_up')
+                and phased_upconv_eligible(h.shape[2], h.shape[3], su.cin, su.cout)):
+            u = _upconv_phased_bf16(h, p, su, acts)
+        else:
+            up = F.interpolate(h, scale_factor=2, mode='nearest')       # UpSampling2D (Appendix C.6)
+            u = _block(up, p, su, cfg, training, new_stats, acts)
         h = torch.cat([u, skip], dim=1)               # Concatenate([deconv, skip]) KerasLayers.py:767
         h = _block(h, p, specs[f'dec{l}.conv_a'], cfg, training, new_stats, acts)
         h = _dropout(h, drops.pop(), training, dropout_masks, f'dec{l}')
@@ -406,16 +446,18 @@ def loss_torch(heat_nchw, target_nchw, kind='mse', mask_smaller_than=0.01, weigh
 # --------------------------------------------------------------------------------------
 def train_grads(cfg: NetCfg, weights: Sequence[np.ndarray], x_nhwc, t_nhwc, dtype=torch.float32,
                 loss_kind='mse', dropout_masks=None, return_acts=False, weights_hw=None, storage='fp32',
-                loss_params=None):
+                loss_params=None, phased_up=False):
     """One replica's forward + loss + backward. Returns dict(loss, heat, grads (Keras order,
     None for non-trainable), new_stats, [acts, act_grads]). storage='bf16' restates the device path's
-    bf16 storage points (see _block_bf16)."""
+    bf16 storage points (see _block_bf16); phased_up additionally restates its pre-summed up-convolution weights."""
     _STORAGE['mode'] = storage
+    _STORAGE['phased_up'] = bool(phased_up)
     try:
         return _train_grads(cfg, weights, x_nhwc, t_nhwc, dtype, loss_kind, dropout_masks, return_acts, weights_hw,
                             loss_params or {})
     finally:
         _STORAGE['mode'] = 'fp32'
+        _STORAGE['phased_up'] = False
 
 
 def _train_grads(cfg, weights, x_nhwc, t_nhwc, dtype, loss_kind, dropout_masks, return_acts, weights_hw, loss_params):

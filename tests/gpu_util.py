@@ -131,3 +131,52 @@ def conv_halo(in0, in1, w_packed, bias, cout, mode, out_split=None, want_stats=F
                                           stream()))
     torch.cuda.synchronize()
     return out0, out1, stats
+
+
+def upconv_halo(direction, x_or_dz, w_hwio, bias=None):
+    """Phase-decomposed up-convolution through the C ABI.  direction 0: x [B,h,w,Cin] -> u [B,2h,2w,C];
+    direction 1: dz [B,2h,2w,C] -> dx [B,h,w,Cin]."""
+    cin, c = w_hwio.shape[2], w_hwio.shape[3]
+    dev = x_or_dz.device
+    if direction == 0:
+        B, h, w, _ = x_or_dz.shape
+        low = x_or_dz
+        high = torch.full((B, 2 * h, 2 * w, c), float('nan'), dtype=torch.bfloat16, device=dev)
+        out = high
+    else:
+        B, H, W, _ = x_or_dz.shape
+        h, w = H // 2, W // 2
+        high = x_or_dz
+        low = torch.full((B, h, w, cin), float('nan'), dtype=torch.bfloat16, device=dev)
+        out = low
+    scratch = torch.zeros(2 * max(16 * cin * c, 768 * cin), dtype=torch.bfloat16, device=dev)
+    wf = w_hwio.float().contiguous()
+    ffi.check(ffi.lib().rvip_upconv3x3_halo(direction, ffi.ptr(low), ffi.ptr(high), ffi.ptr(wf), ffi.ptr(bias),
+                                            ffi.ptr(scratch), B, h, w, cin, c, stream()))
+    torch.cuda.synchronize()
+    return out
+
+
+def ref_upconv(x_low_nhwc, w_hwio, bias=None, relu=True, dz=None):
+    """fp32 reference: nearest x2 up-sampling followed by the 3x3 convolution (weights NOT pre-summed), and
+    optionally the gradient w.r.t. the low-resolution input for an output gradient dz."""
+    x = x_low_nhwc.float().permute(0, 3, 1, 2).clone().requires_grad_(dz is not None)
+    w = w_hwio.float().permute(3, 2, 0, 1)
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        y = F.conv2d(F.interpolate(x, scale_factor=2, mode='nearest'), w, bias, padding=1)
+    if dz is not None:
+        y.backward(dz.float().permute(0, 3, 1, 2))
+        return x.grad.permute(0, 2, 3, 1).contiguous()
+    if relu:
+        y = torch.relu(y)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def upconv_wgrad_halo(x_low, dz):
+    """Weight gradient of the phase-decomposed up-convolution: x [B,h,w,Cin], dz [B,2h,2w,C] -> dw [3,3,Cin,C] fp32."""
+    B, h, w, cin = x_low.shape
+    c = dz.shape[3]
+    dw = torch.zeros((3, 3, cin, c), dtype=torch.float32, device=x_low.device)
+    ffi.check(ffi.lib().rvip_upconv_wgrad_halo(ffi.ptr(x_low), ffi.ptr(dz), ffi.ptr(dw), B, h, w, cin, c, stream()))
+    torch.cuda.synchronize()
+    return dw

@@ -96,6 +96,88 @@ def test_conv_tc_dgrad(variant, shape):
     assert U.rel_err(got, ref) < 4e-3
 
 
+UPCONV_SHAPES = [  # B, h, w (LOW resolution), Cin, C
+    (2, 16, 16, 64, 32),          # two row phases, column phase merged into N = 64 (2 x 3 taps)
+    (1, 32, 48, 64, 32),          # non-square, several blocks
+    (2, 16, 16, 128, 64),         # four phases of 2 x 2 taps, BN = 64
+    (1, 32, 32, 256, 128),        # BN = 128, four K chunks
+    (3, 16, 16, 512, 256),        # deepest decoder level of the bench network
+    (40, 16, 16, 128, 64),        # more tiles than SMs
+]
+
+
+def _phase_sets(p, r):
+    """3x3 tap indices (0..2) that land on low-resolution neighbour r of output parity p."""
+    return ([0], [1, 2])[r] if p == 0 else ([0, 1], [2])[r]
+
+
+def _ref_upconv_phased(x_low, w_hwio, bias):
+    """Same arithmetic as the device path: taps pre-summed in fp32, ONE rounding to bf16, fp32 accumulation."""
+    B, h, w, cin = x_low.shape
+    c = w_hwio.shape[3]
+    xp = torch.nn.functional.pad(x_low.float().permute(0, 3, 1, 2), (1, 1, 1, 1))
+    out = torch.empty((B, c, 2 * h, 2 * w), device=x_low.device)
+    for a in range(2):
+        for b in range(2):
+            k = torch.zeros((2, 2, cin, c), device=x_low.device)
+            for r in range(2):
+                for s_ in range(2):
+                    for ky in _phase_sets(a, r):
+                        for kx in _phase_sets(b, s_):
+                            k[r, s_] += w_hwio[ky, kx].float()
+            k = k.to(torch.bfloat16).float().permute(3, 2, 0, 1)
+            o = torch.nn.functional.conv2d(xp, k, bias)
+            out[:, :, a::2, b::2] = o[:, :, a:a + h, b:b + w]
+    return torch.relu(out).permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize('shape', UPCONV_SHAPES)
+def test_upconv_phased_forward(shape):
+    """UpSampling2D(2) -> Conv3x3 -> ReLU from the low-resolution tensor (KerasLayers.py:756-759)."""
+    from tests import gpu_util as U
+    B, h, w, cin, c = shape
+    g = torch.Generator(device='cuda').manual_seed(11 + sum(shape))
+    x = _rand_bf16((B, h, w, cin), g)
+    wt = torch.randn((3, 3, cin, c), generator=g, device='cuda') * (2.0 / (9 * cin)) ** 0.5
+    bias = torch.randn(c, generator=g, device='cuda') * 0.1
+    out = U.upconv_halo(0, x, wt, bias)
+    assert torch.isfinite(out.float()).all()
+    tight = _ref_upconv_phased(x, wt, bias)
+    assert U.rel_err(out, tight) < 4e-3                       # bf16 output rounding only
+    true = U.ref_upconv(x, wt, bias, relu=True)               # un-summed fp32 weights on the up-sampled tensor
+    assert U.rel_err(out, true) < 8e-3                        # + one bf16 rounding of the pre-summed weights
+
+
+@pytest.mark.parametrize('shape', UPCONV_SHAPES)
+def test_upconv_phased_dgrad(shape):
+    from tests import gpu_util as U
+    B, h, w, cin, c = shape
+    g = torch.Generator(device='cuda').manual_seed(12 + sum(shape))
+    dz = _rand_bf16((B, 2 * h, 2 * w, c), g)
+    wt = torch.randn((3, 3, cin, c), generator=g, device='cuda') * (2.0 / (9 * c)) ** 0.5
+    dx = U.upconv_halo(1, dz, wt)
+    assert torch.isfinite(dx.float()).all()
+    ref = U.ref_upconv(torch.zeros((B, h, w, cin), device='cuda'), wt, None, relu=False, dz=dz)
+    assert U.rel_err(dx, ref) < 8e-3
+
+
+@pytest.mark.parametrize('shape', UPCONV_SHAPES + [(2, 24, 48, 64, 96), (1, 128, 128, 64, 32)])
+def test_upconv_phased_wgrad(shape):
+    """dW of UpSampling2D(2) -> Conv3x3 from the low-resolution input: eight phase accumulators folded onto the 3x3 taps."""
+    from tests import gpu_util as U
+    B, h, w, cin, c = shape
+    g = torch.Generator(device='cuda').manual_seed(13 + sum(shape))
+    x = _rand_bf16((B, h, w, cin), g)
+    dz = _rand_bf16((B, 2 * h, 2 * w, c), g)
+    dw = U.upconv_wgrad_halo(x, dz)
+    wv = torch.zeros((c, cin, 3, 3), device='cuda', requires_grad=True)
+    up = torch.nn.functional.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode='nearest')
+    y = torch.nn.functional.conv2d(up, wv, padding=1)
+    y.backward(dz.float().permute(0, 3, 1, 2))
+    ref = wv.grad.permute(2, 3, 1, 0)
+    assert U.rel_err(dw, ref) < 2e-3
+
+
 @pytest.mark.parametrize('variant,shape', WGRAD_CASES)
 def test_wgrad_tc(variant, shape):
     from tests import gpu_util as U

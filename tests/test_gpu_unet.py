@@ -59,7 +59,7 @@ def test_train_step_matches_oracle(precision, dim, depth, batch):
     # (DESIGN.md "bf16 gradient conditioning"). So bf16 mode is held to (a) the fp32 oracle on loss, heat maps
     # and the last block's gradients, and (b) the oracle restated with the same bf16 storage points on every
     # gradient tensor. fp32 mode is held to the fp32 oracle everywhere.
-    cal = R.train_grads(cfg, ws, x, y, storage='bf16') if precision == 'bf16' else ref
+    cal = R.train_grads(cfg, ws, x, y, storage='bf16', phased_up=True) if precision == 'bf16' else ref
     # float64 run of the oracle: the yardstick for how much fp32 rounding alone moves each gradient tensor
     ref64 = R.train_grads(cfg, ws, x, y, dtype=torch.float64) if precision == 'fp32' and depth > 2 else None
     last = ('head/', 'dec%d.conv_b/' % (depth - 1))
@@ -105,7 +105,10 @@ def test_train_step_matches_oracle(precision, dim, depth, batch):
                 assert e_dev <= 2.5 * e_cal and 0.3 <= ratio <= 3.0, ('bf16 path vs calibration', name, e_dev, e_cal, ratio)
             if name.startswith(last):
                 cos, rl2 = cmp(rg)
-                assert cos >= 0.998 and rl2 <= 7e-2, ('vs fp32 oracle', name, cos, rl2)
+                # conv biases under BatchNorm: the gradient is a sum of dz that nearly cancels, so every rounding
+                # upstream (here also the single bf16 rounding of the pre-summed up-convolution taps) shows first there
+                lim = 0.995 if name.endswith('/bias') else 0.998
+                assert cos >= lim and rl2 <= (0.1 if name.endswith('/bias') else 7e-2), ('vs fp32 oracle', name, cos, rl2)
     # BN moving statistics after one step
     new = R.apply_new_stats(cfg, ws, ref['new_stats'])
     mine = model.get_weights()

@@ -162,3 +162,35 @@ def test_bce_dice_oracle_formula():
     want = (0.5 * bce - 1.0 * dice).mean()
     got = float(R.loss_torch(torch.tensor(p), torch.tensor(t), 'bce_dice', w_bce=0.5, w_dice=1.0))
     assert abs(got - want) < 1e-12
+
+
+def test_phased_upconv_restatement_is_the_same_linear_map():
+    """UpSampling2D(2) -> Conv3x3 == four 2x2-tap convolutions on the low-resolution tensor with pre-summed taps: the
+    calibration restatement of the device's phase-decomposed up-convolution must equal the plain path when nothing is
+    rounded (float64, rounding hooks disabled), forward and gradients."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import unet_ref as R
+
+    class Spec:
+        name, cin, cout = 'dec0.upconv', 64, 32
+
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 64, 16, 32, dtype=torch.float64, generator=g, requires_grad=True)
+    k = torch.randn(3, 3, 64, 32, dtype=torch.float64, generator=g, requires_grad=True)
+    b = torch.randn(32, dtype=torch.float64, generator=g, requires_grad=True)
+    assert R.phased_upconv_eligible(16, 32, 64, 32) and not R.phased_upconv_eligible(8, 8, 64, 32)
+    fwd, bwd = R._RoundFwd.apply, R._RoundBwd.apply
+    try:
+        R._RoundFwd.apply = staticmethod(lambda v: v)
+        R._RoundBwd.apply = staticmethod(lambda v: v)
+        u = R._upconv_phased_bf16(x, R._Params([k, b]), Spec, {})
+    finally:
+        R._RoundFwd.apply, R._RoundBwd.apply = fwd, bwd
+    ref = torch.relu(R._conv(F.interpolate(x, scale_factor=2, mode='nearest'), k, b))
+    assert float((u - ref).abs().max()) < 1e-11
+    w = torch.randn(ref.shape, dtype=torch.float64, generator=g)
+    g1 = torch.autograd.grad((u * w).sum(), [x, k, b])
+    g2 = torch.autograd.grad((ref * w).sum(), [x, k, b])
+    for a_, b_ in zip(g1, g2):
+        assert float((a_ - b_).abs().max()) < 1e-9
