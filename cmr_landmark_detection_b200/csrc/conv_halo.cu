@@ -13,8 +13,8 @@
 //     18-pixel stride, which is exactly a stride-dimension byte offset of 18 * 128 B.  The swizzle is a function
 //     of the absolute shared-memory address, so shifted views stay consistent with what TMA wrote.
 // Per 64-channel chunk: 41.5 KB of activations + 9 weight tiles for 72 MMAs (36 B/cycle at BN = 256).
-// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (elected thread, all operand offsets immediates), warp 2
-// TMEM allocator, warps 4-7 / 8-11 epilogue of the left / right half (tcgen05.ld -> bias + ReLU -> bf16 ->
+// Warp roles: warp 0 TMA producer of the weight tiles, warp 3 TMA producer of the activation blocks, warp 1 MMA issuer
+// (elected thread, all operand offsets immediates), warp 2 TMEM allocator, warps 4-7 / 8-11 epilogue of the left / right half (tcgen05.ld -> bias + ReLU -> bf16 ->
 // swizzled staging -> TMA store per 64-channel slice, plus the BatchNorm sum / sum of squares).
 // Replaces tf.keras Conv2D forward and Conv2DBackpropInput (src/models/KerasLayers.py:683,689,758).
 #include "conv_halo.cuh"
@@ -120,13 +120,12 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
   const uint32_t tmem_base = ctl->tmem_base;
   const int nchunks = up_k ? a.up_nph * cpp : a.Ctot / 64;   // K groups per tile
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+  if (warp == 3) {
+    // ------------------------------------------------------------------ TMA producer: activation blocks
+    // Its own warp, so that a block is requested the moment its ring slot is released (= when the MMAs of the chunk
+    // before the previous one complete), a whole chunk ahead of its use, without ever stalling the weight stream.
     if (elect_one()) {
-      int as = 0, aphase = 0, bs = 0, bphase = 0;
-      // activation block of (tile, chunk c): issued one chunk AHEAD, in the middle of the previous chunk's weight
-      // tiles -- late enough that its ring slot has been released (no stall of the weight stream), early enough
-      // that the ~3000-cycle load lands before the chunk starts
+      int as = 0, aphase = 0;
       auto load_act = [&](int tile, int c) {
         const int pt = tile / n_eff;
         const int x0 = (pt % a.tiles_x) * 16;
@@ -144,19 +143,20 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
         as ^= 1;
         if (as == 0) aphase ^= 1;
       };
-      if ((int)blockIdx.x < a.total_tiles) load_act(blockIdx.x, 0);
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x)
+        for (int c = 0; c < nchunks; ++c) load_act(tile, c);
+    }
+  } else if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer: weight tiles
+    if (elect_one()) {
+      int bs = 0, bphase = 0;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
         const int n0 = (tile % n_eff) * BN;     // weight rows: (phase, N tile) pairs are consecutive row blocks
         for (int c = 0; c < nchunks; ++c) {
           // K coordinate of tap t of this group = kb + t * ks
           const int kb = up_k ? (c / cpp) * NT * a.up_cz + (c % cpp) * 64 : c * 64;
           const int ks = up_k ? a.up_cz : a.Ctot;
-          const int pre = nbst < 6 ? nbst : 6;
           for (int tap = 0; tap < NT; ++tap) {
-            if (tap == (pre < NT - 1 ? pre : NT - 1)) {   // the MMA pipe is then inside this chunk: the slot of chunk c-1 is free
-              if (c + 1 < nchunks) load_act(tile, c + 1);
-              else if (tile + (int)gridDim.x < a.total_tiles) load_act(tile + gridDim.x, 0);
-            }
             mbar_wait(&ctl->bempty[bs], bphase ^ 1);
             mbar_expect_tx(&ctl->bfull[bs], Cfg::B_BYTES);
             tma_load_2d(b_ring + (size_t)bs * Cfg::B_BYTES, &a.w, &ctl->bfull[bs], tap * ks + kb, n0);
