@@ -120,54 +120,65 @@ __global__ void __launch_bounds__(256) pack_weights_tile_kernel(const float* __r
 //                                         ns = 3: phase = a, row = b*C+co, tap = 3r+tx with s = tx - b (zero if outside)
 //   dgrad copy    [ci][phase][tap][cz]:   halo taps run in increasing offset: rr = 1-r, ss = 1-s (ns = 2);
 //                                         ns = 3: cz = b*C+co, tap = 3rr+tx with s = 2 - b - tx (zero if outside)
-// One block pass = one 32 (ci) x 32 (co) tile of one pre-summed phase weight Wp[a][b][r][s]: coalesced reads of the (up to
-// four) 3x3 taps it sums, then both operand copies are written from the shared-memory tile -- the dgrad copy (co fastest)
-// straight from it, the forward copy (ci fastest) from its transpose.  The structural zeros of the ns = 3 copies are
-// never written: the packed buffer is cleared once when the handle is bound.
+// One block pass = one 32 (ci) x 32 (co) tile position: the nine 3x3 taps of it are read ONCE (coalesced) into registers,
+// the 16 pre-summed phase weights Wp[a][b][r][s] are formed from them, and each goes through a shared-memory tile so that
+// both operand copies are written coalesced -- the dgrad copy (co fastest) straight from it, the forward copy (ci
+// fastest) from its transpose.  The structural zeros of the ns = 3 copies are never written: the packed buffer is
+// cleared once when the handle is bound.
 __global__ void __launch_bounds__(256) pack_up_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ packed,
                                                       const UpPackEntry* __restrict__ table) {
   pdl_wait();
-  __shared__ float tile[32][33];
+  __shared__ float tile[2][32][33];
   const UpPackEntry e = table[blockIdx.y];
   const float* W = params + e.src;
   const int Cin = e.Cin, C = e.C;
   const int ct_n = Cin >> 5, cot_n = C >> 5;
-  const int n_tiles = 16 * ct_n * cot_n;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const int cot = t % cot_n, ct = (t / cot_n) % ct_n, combo = t / (cot_n * ct_n);
-    const int a = combo >> 3, b = (combo >> 2) & 1, r = (combo >> 1) & 1, s = combo & 1;
-    const int ky0 = (a == 0) ? (r == 0 ? 0 : 1) : (r == 0 ? 0 : 2), ky1 = (a == 0) ? (r == 0 ? 0 : 2) : (r == 0 ? 1 : 2);
-    const int kx0 = (b == 0) ? (s == 0 ? 0 : 1) : (s == 0 ? 0 : 2), kx1 = (b == 0) ? (s == 0 ? 0 : 2) : (s == 0 ? 1 : 2);
+  for (int t = blockIdx.x; t < ct_n * cot_n; t += gridDim.x) {
+    const int cot = t % cot_n, ct = t / cot_n;
     const int c0 = ct << 5, co0 = cot << 5;
+    float w[9][4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int c = ty + 8 * q;
-      float acc = 0.f;
-      for (int ky = ky0; ky <= ky1; ++ky)
-        for (int kx = kx0; kx <= kx1; ++kx) acc += W[((long long)(ky * 3 + kx) * Cin + c0 + c) * C + co0 + tx];
-      tile[c][tx] = acc;
-    }
-    __syncthreads();
-    long long f_base, d_base;      // element offsets of (row = co0, ci = c0) / (ci = c0, cz = co0) in the two copies
-    long long f_row, d_row;        // strides between consecutive rows
-    if (e.ns == 2) {
-      const int ph = 2 * a + b;
-      f_row = 4LL * Cin;           // [ph][co][t][ci]
-      f_base = ((long long)(ph * C + co0) * 4 + (2 * r + s)) * Cin + c0;
-      d_row = 16LL * C;            // [ci][ph][t'][co]
-      d_base = ((long long)c0 * 4 + ph) * 4 * C + (long long)(2 * (1 - r) + (1 - s)) * C + co0;
-    } else {
-      f_row = 6LL * Cin;           // [a][b*C+co][t = 3r + s + b][ci]
-      f_base = ((long long)(a * 2 * C + b * C + co0) * 6 + (3 * r + s + b)) * Cin + c0;
-      d_row = 12LL * 2 * C;        // [ci][a][t' = 3(1-r) + 2-b-s][b*C+co]
-      d_base = ((long long)c0 * 2 + a) * 6 * 2 * C + (long long)(3 * (1 - r) + (2 - b - s)) * 2 * C + b * C + co0;
-    }
+    for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int row = ty + 8 * q;
-      packed[e.dst_f + f_base + row * f_row + tx] = __float2bfloat16_rn(tile[tx][row]);          // row = co, tx = ci
-      if (e.dst_d >= 0) packed[e.dst_d + d_base + row * d_row + tx] = __float2bfloat16_rn(tile[row][tx]);   // row = ci, tx = co
+      for (int q = 0; q < 4; ++q) w[tap][q] = W[((long long)tap * Cin + c0 + ty + 8 * q) * C + co0 + tx];
+#pragma unroll
+    for (int combo = 0; combo < 16; ++combo) {
+      const int a = combo >> 3, b = (combo >> 2) & 1, r = (combo >> 1) & 1, s = combo & 1;
+      const int ky0 = (a == 0) ? (r == 0 ? 0 : 1) : (r == 0 ? 0 : 2), ky1 = (a == 0) ? (r == 0 ? 0 : 2) : (r == 0 ? 1 : 2);
+      const int kx0 = (b == 0) ? (s == 0 ? 0 : 1) : (s == 0 ? 0 : 2), kx1 = (b == 0) ? (s == 0 ? 0 : 2) : (s == 0 ? 1 : 2);
+      float (*tl)[33] = tile[combo & 1];     // double-buffered: one barrier per combination
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float acc = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+            if (ky >= ky0 && ky <= ky1 && kx >= kx0 && kx <= kx1) acc += w[ky * 3 + kx][q];
+        tl[ty + 8 * q][tx] = acc;
+      }
+      __syncthreads();
+      long long f_base, d_base;      // element offsets of (row = co0, ci = c0) / (ci = c0, cz = co0) in the two copies
+      long long f_row, d_row;        // strides between consecutive rows
+      if (e.ns == 2) {
+        const int ph = 2 * a + b;
+        f_row = 4LL * Cin;           // [ph][co][t][ci]
+        f_base = ((long long)(ph * C + co0) * 4 + (2 * r + s)) * Cin + c0;
+        d_row = 16LL * C;            // [ci][ph][t'][co]
+        d_base = ((long long)c0 * 4 + ph) * 4 * C + (long long)(2 * (1 - r) + (1 - s)) * C + co0;
+      } else {
+        f_row = 6LL * Cin;           // [a][b*C+co][t = 3r + s + b][ci]
+        f_base = ((long long)(a * 2 * C + b * C + co0) * 6 + (3 * r + s + b)) * Cin + c0;
+        d_row = 12LL * 2 * C;        // [ci][a][t' = 3(1-r) + 2-b-s][b*C+co]
+        d_base = ((long long)c0 * 2 + a) * 6 * 2 * C + (long long)(3 * (1 - r) + (2 - b - s)) * 2 * C + b * C + co0;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int row = ty + 8 * q;
+        packed[e.dst_f + f_base + row * f_row + tx] = __float2bfloat16_rn(tl[tx][row]);          // row = co, tx = ci
+        if (e.dst_d >= 0) packed[e.dst_d + d_base + row * d_row + tx] = __float2bfloat16_rn(tl[row][tx]);   // row = ci, tx = co
+      }
     }
     __syncthreads();
   }
@@ -175,7 +186,7 @@ __global__ void __launch_bounds__(256) pack_up_kernel(const float* __restrict__ 
 }
 int pack_up_launch(const float* params, void* packed, const UpPackEntry* table_dev, int n_entries, cudaStream_t st) {
   if (n_entries == 0) return 0;
-  launch_kernel(pack_up_kernel, dim3(96, n_entries), 256, 0, st, params, static_cast<__nv_bfloat16*>(packed), table_dev);
+  launch_kernel(pack_up_kernel, dim3(128, n_entries), 256, 0, st, params, static_cast<__nv_bfloat16*>(packed), table_dev);
   RVIP_LAUNCH_CHECK();
   return 0;
 }
