@@ -3,18 +3,24 @@
 //   masked / weighted ........ loss_with_zero_mask (src/models/Loss_and_metrics.py:40-89)
 // One pass reads y (and the target), writes the fp32 heat map, dL/dy for the last decoder block, and
 // reduces the loss, dW_head and db_head with warp shuffles -> shared atomics -> one global atomic per
-// block and output.  G = Cin/8 adjacent lanes share a pixel, so all global traffic is coalesced.
+// block and output.  G = Cin/CPT adjacent lanes share a pixel (CPT = 8 or 16 channels per thread), so all global traffic
+// is coalesced.  The kernel is ISSUE bound (ncu: 62 % issue slots busy at 25 % occupancy, DRAM at 24 %): every lane of a
+// pixel repeats the sigmoid / loss / dlogit arithmetic, so CPT = 16 (two lanes per pixel at 32 channels) halves that
+// redundancy and the logit shuffles.
 #include "kernels.cuh"
+
+#include <stdlib.h>
 
 namespace rvip {
 
 constexpr int kMaxNC = 4;
 
-template <typename T, bool TRAIN, int NCT>
-__global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
+template <typename T, bool TRAIN, int NCT, int CPT>
+__global__ void __launch_bounds__(256, CPT == 16 ? 2 : 1) head_kernel(HeadArgs a) {
+  constexpr int NV = CPT / 8;              // 8-channel vectors per thread
   extern __shared__ float sm[];            // w [Cin*NC], b [NC], then (TRAIN) dw acc [Cin*NC], db acc [NC]
   pdl_wait();
-  const int NC = a.NC, Cin = a.Cin, G = Cin >> 3;
+  const int NC = a.NC, Cin = a.Cin, G = Cin / CPT;
   float* w_s = sm;
   float* b_s = w_s + Cin * NC;
   float* dw_s = b_s + NC;
@@ -35,21 +41,21 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
   const uint32_t lg = 31 - __clz(G);
   const uint32_t n_items = P << lg;
   const uint32_t i0 = blockIdx.x * 256 + threadIdx.x;
-  const int cg = (int)(i0 & (G - 1)), c = cg * 8;
+  const int cg = (int)(i0 & (G - 1)), c = cg * CPT;
   const uint32_t HW = (uint32_t)a.H * a.W;
   const T* y = static_cast<const T*>(a.y);
   T* dy = static_cast<T*>(a.dy);
-  float wreg[8][NCT];
+  float wreg[CPT][NCT];
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
+  for (int j = 0; j < CPT; ++j)
 #pragma unroll
     for (int k = 0; k < NCT; ++k) wreg[j][k] = k < NC ? w_s[(c + j) * NC + k] : 0.f;
-  float dw_acc[8][NCT], db_acc[NCT];
+  float dw_acc[CPT][NCT], db_acc[NCT];
 #pragma unroll
   for (int k = 0; k < NCT; ++k) {
     db_acc[k] = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dw_acc[j][k] = 0.f;
+    for (int j = 0; j < CPT; ++j) dw_acc[j][k] = 0.f;
   }
   float loss_acc = 0.f;
   const float inv_n = 1.f / ((float)P * (float)NC);
@@ -66,19 +72,21 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
   // Software pipeline: the loads of y and of the target for the item kDepth grid-strides ahead are in flight
   // while the current item is processed (ncu: with the loads issued at the point of use, 55 % of the stall
   // samples of this kernel were long-scoreboard waits on exactly those two loads).
-  constexpr int kDepth = 4;
-  Raw8<T> ybuf[kDepth];
+  constexpr int kDepth = CPT == 8 ? 4 : 2;
+  Raw8<T> ybuf[kDepth][NV];
   float tbuf[kDepth][NCT];
   auto issue = [&](int d, uint32_t i) {
     if (i < n_items) {
       const size_t p = i >> lg;
-      load_raw8(y + p * Cin + c, ybuf[d]);
+#pragma unroll
+      for (int u = 0; u < NV; ++u) load_raw8(y + p * Cin + c + 8 * u, ybuf[d][u]);
       if (TRAIN) {
 #pragma unroll
         for (int k = 0; k < NCT; ++k) tbuf[d][k] = k < NC ? a.target[p * NC + k] : 0.f;
       }
     } else {
-      zero_raw8(ybuf[d]);
+#pragma unroll
+      for (int u = 0; u < NV; ++u) zero_raw8(ybuf[d][u]);
 #pragma unroll
       for (int k = 0; k < NCT; ++k) tbuf[d][k] = 0.f;
     }
@@ -92,8 +100,14 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
       if (i >= n_round) break;           // warp-uniform
       const bool live = i < n_items;
       const size_t p = live ? (i >> lg) : 0;
-      float v[8], tgt[NCT];
-      unpack_raw8(ybuf[d], v);
+      float v[CPT], tgt[NCT];
+#pragma unroll
+      for (int u = 0; u < NV; ++u) {
+        float t8[8];
+        unpack_raw8(ybuf[d][u], t8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[8 * u + j] = t8[j];
+      }
 #pragma unroll
       for (int k = 0; k < NCT; ++k) tgt[k] = tbuf[d][k];
       issue(d, i + kDepth * stride);
@@ -102,7 +116,7 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
       for (int k = 0; k < NCT; ++k) {
         float s = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s = fmaf(v[j], wreg[j][k], s);
+        for (int j = 0; j < CPT; ++j) s = fmaf(v[j], wreg[j][k], s);
         for (int o = 1; o < G; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         logit[k] = s + (k < NC ? b_s[k] : 0.f);
       }
@@ -152,18 +166,21 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
 #pragma unroll
           for (int k = 0; k < NCT; ++k) db_acc[k] += dl[k];
         }
-        float g[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float s = 0.f;
+        for (int u = 0; u < NV; ++u) {
+          float g[8];
 #pragma unroll
-          for (int k = 0; k < NCT; ++k) {
-            s = fmaf(wreg[j][k], dl[k], s);
-            dw_acc[j][k] = fmaf(v[j], dl[k], dw_acc[j][k]);
+          for (int j = 0; j < 8; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < NCT; ++k) {
+              s = fmaf(wreg[8 * u + j][k], dl[k], s);
+              dw_acc[8 * u + j][k] = fmaf(v[8 * u + j], dl[k], dw_acc[8 * u + j][k]);
+            }
+            g[j] = s;
           }
-          g[j] = s;
+          Vec8<T>::store(dy + p * Cin + c + 8 * u, g);
         }
-        Vec8<T>::store(dy + p * Cin + c, g);
       }
     }
   }
@@ -173,7 +190,7 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
     // touch the shared accumulators (float atomicAdd on smem is a CAS loop; 64-way contention cost ~100 us)
     const int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < CPT; ++j)
 #pragma unroll
       for (int k = 0; k < NCT; ++k) {
         float v = dw_acc[j][k];
@@ -227,8 +244,11 @@ int head_dice_sums_launch(const float* heat, const float* target, size_t n, doub
 }
 
 int head_launch(const HeadArgs& a, int training, int is_bf16, cudaStream_t st) {
-  const int G = a.Cin / 8;
-  RVIP_REQUIRE(a.Cin % 8 == 0 && G <= 32 && (G & (G - 1)) == 0, "head: Cin=%d must be 8 * power of two <= 256", a.Cin);
+  RVIP_REQUIRE(a.Cin % 8 == 0 && a.Cin / 8 <= 32 && ((a.Cin / 8) & (a.Cin / 8 - 1)) == 0,
+               "head: Cin=%d must be 8 * power of two <= 256", a.Cin);
+  // 16 channels per thread where the class count keeps the per-thread weight / dW registers within budget
+  const int cpt = (a.Cin % 16 == 0 && a.NC <= 2 && getenv("RVIP_HEAD_CPT8") == nullptr) ? 16 : 8;
+  const int G = a.Cin / cpt;
   RVIP_REQUIRE((size_t)a.B * a.H * a.W * G < 0x7fffffffULL, "head: tensor too large for 32-bit indexing");
   RVIP_REQUIRE(a.NC >= 1 && a.NC <= kMaxNC, "head: MASK_CLASSES=%d not in [1,%d]", a.NC, kMaxNC);
   const size_t n = (size_t)a.B * a.H * a.W * G;
@@ -236,21 +256,21 @@ int head_launch(const HeadArgs& a, int training, int is_bf16, cudaStream_t st) {
   const size_t cap = (size_t)kNumSMs * 2;   // 2 blocks/SM resident (122 registers); every block ends with Cin*NC + NC + 1 global atomics: keep them few
   const int grid = (int)(g < cap ? (g ? g : 1) : cap);
   const size_t smem = (size_t)(2 * (a.Cin * a.NC + a.NC)) * sizeof(float);
-#define RVIP_HEAD(NCV)                                                        \
-  if (a.NC == NCV) {                                                          \
+#define RVIP_HEAD(NCV, CPTV)                                                  \
+  if (a.NC == NCV && cpt == CPTV) {                                           \
     if (training) {                                                           \
       if (is_bf16)                                                            \
-        launch_kernel(head_kernel<__nv_bfloat16, true, NCV>, grid, 256, smem, st, a);    \
+        launch_kernel(head_kernel<__nv_bfloat16, true, NCV, CPTV>, grid, 256, smem, st, a);    \
       else                                                                    \
-        launch_kernel(head_kernel<float, true, NCV>, grid, 256, smem, st, a);            \
+        launch_kernel(head_kernel<float, true, NCV, CPTV>, grid, 256, smem, st, a);            \
     } else {                                                                  \
       if (is_bf16)                                                            \
-        launch_kernel(head_kernel<__nv_bfloat16, false, NCV>, grid, 256, smem, st, a);   \
+        launch_kernel(head_kernel<__nv_bfloat16, false, NCV, CPTV>, grid, 256, smem, st, a);   \
       else                                                                    \
-        launch_kernel(head_kernel<float, false, NCV>, grid, 256, smem, st, a);           \
+        launch_kernel(head_kernel<float, false, NCV, CPTV>, grid, 256, smem, st, a);           \
     }                                                                         \
   }
-  RVIP_HEAD(1) RVIP_HEAD(2) RVIP_HEAD(3) RVIP_HEAD(4)
+  RVIP_HEAD(1, 8) RVIP_HEAD(2, 8) RVIP_HEAD(3, 8) RVIP_HEAD(4, 8) RVIP_HEAD(1, 16) RVIP_HEAD(2, 16)
 #undef RVIP_HEAD
   RVIP_LAUNCH_CHECK();
   return 0;

@@ -43,6 +43,32 @@ def test_predict_matches_oracle(precision, dim, depth, batch):
         assert np.abs(heat - ref).mean() <= 2e-3
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_first_layer_mappings_agree(precision, monkeypatch):
+    """The Cin = 1 first layer has two thread mappings (4 channels x 8 pixels, and 8 channels x 4 pixels for widths that
+    are not multiples of 8): same forward output and the same weight gradient up to summation order."""
+    from oracle import unet_ref as R
+    out = {}
+    for quad in (False, True):
+        if quad:
+            monkeypatch.setenv('RVIP_C1_QUAD', '1')
+        else:
+            monkeypatch.delenv('RVIP_C1_QUAD', raising=False)
+        model, cfg, ws, x, y = _setup(precision, 32, 2, 3, randomize_bn=False)
+        ref = R.train_grads(cfg, ws, x, y)
+        loss = float(model.train_step_device(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(),
+                                             apply_optimizer=False).item())
+        assert abs(loss - ref['loss']) <= TOL[precision]['loss'] * abs(ref['loss'])
+        name, _, off, shape = model.tensors[0]
+        assert name == 'enc0.conv_a/kernel'
+        n = int(np.prod(shape))
+        out[quad] = (model.debug_buffer('enc0.conv_a', 0, 3, True).float().cpu().numpy(),
+                     model.grads.cpu().numpy()[off:off + n].copy())
+    assert np.array_equal(out[False][0], out[True][0])              # same FMA order per output element
+    g0, g1 = out[False][1], out[True][1]
+    assert np.linalg.norm(g0 - g1) <= 1e-4 * np.linalg.norm(g0) + 1e-12
+
+
 @pytest.mark.parametrize('precision,dim,depth,batch', [('fp32', 32, 2, 3), ('bf16', 32, 2, 4), ('fp32', 64, 4, 2),
                                                        ('bf16', 64, 4, 4), ('bf16', 128, 4, 2)])
 def test_train_step_matches_oracle(precision, dim, depth, batch):
