@@ -159,6 +159,7 @@ struct UpPackEntry {
   long long dst_f;    // element offset of the forward copy
   long long dst_d;    // element offset of the dgrad copy, -1 = none
   int Cin, C, ns;
+  int transposed;     // source is a Conv2DTranspose kernel (kh, kw, C, Cin): every phase weight is ONE tap (or zero)
 };
 int pack_up_launch(const float* params, void* packed, const UpPackEntry* table_dev, int n_entries, cudaStream_t st);
 

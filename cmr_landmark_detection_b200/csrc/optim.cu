@@ -137,25 +137,40 @@ __global__ void __launch_bounds__(256) pack_up_kernel(const float* __restrict__ 
   for (int t = blockIdx.x; t < ct_n * cot_n; t += gridDim.x) {
     const int cot = t % cot_n, ct = t / cot_n;
     const int c0 = ct << 5, co0 = cot << 5;
+    // tile rows (ty + 8q) / columns (tx): (ci, co) for a Conv2D kernel (kh, kw, Cin, C), (co, ci) for a Conv2DTranspose
+    // kernel (kh, kw, C, Cin) -- the contiguous axis of the source is always the column
+    const bool tr = e.transposed != 0;
     float w[9][4];
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) w[tap][q] = W[((long long)tap * Cin + c0 + ty + 8 * q) * C + co0 + tx];
+      for (int q = 0; q < 4; ++q)
+        w[tap][q] = tr ? W[((long long)tap * C + co0 + ty + 8 * q) * Cin + c0 + tx]
+                       : W[((long long)tap * Cin + c0 + ty + 8 * q) * C + co0 + tx];
+    int nbuf = 0;
 #pragma unroll
     for (int combo = 0; combo < 16; ++combo) {
       const int a = combo >> 3, b = (combo >> 2) & 1, r = (combo >> 1) & 1, s = combo & 1;
       const int ky0 = (a == 0) ? (r == 0 ? 0 : 1) : (r == 0 ? 0 : 2), ky1 = (a == 0) ? (r == 0 ? 0 : 2) : (r == 0 ? 1 : 2);
       const int kx0 = (b == 0) ? (s == 0 ? 0 : 1) : (s == 0 ? 0 : 2), kx1 = (b == 0) ? (s == 0 ? 0 : 2) : (s == 0 ? 1 : 2);
-      float (*tl)[33] = tile[combo & 1];     // double-buffered: one barrier per combination
+      // Conv2DTranspose(3, strides 2, 'same'): out[2i + a] = sum_{2i' + k = 2i + a} x[i'] w[k] -> parity 0 sees tap 2 on
+      // neighbour i - 1 (r = 0) and tap 0 on i (r = 1), parity 1 sees tap 1 on i (r = 0) and nothing on i + 1
+      const int kyt = a == 0 ? (r == 0 ? 2 : 0) : (r == 0 ? 1 : -1), kxt = b == 0 ? (s == 0 ? 2 : 0) : (s == 0 ? 1 : -1);
+      if (tr && (kyt < 0 || kxt < 0)) continue;   // structurally zero (cleared at bind time); uniform over the block
+      float (*tl)[33] = tile[nbuf & 1];      // double-buffered over the combinations actually written: one barrier each
+      ++nbuf;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float acc = 0.f;
+        if (tr) {
+          acc = w[(kyt < 0 ? 0 : kyt) * 3 + (kxt < 0 ? 0 : kxt)][q];
+        } else {
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+          for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx)
-            if (ky >= ky0 && ky <= ky1 && kx >= kx0 && kx <= kx1) acc += w[ky * 3 + kx][q];
+            for (int kx = 0; kx < 3; ++kx)
+              if (ky >= ky0 && ky <= ky1 && kx >= kx0 && kx <= kx1) acc += w[ky * 3 + kx][q];
+        }
         tl[ty + 8 * q][tx] = acc;
       }
       __syncthreads();
@@ -176,8 +191,9 @@ __global__ void __launch_bounds__(256) pack_up_kernel(const float* __restrict__ 
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int row = ty + 8 * q;
-        packed[e.dst_f + f_base + row * f_row + tx] = __float2bfloat16_rn(tl[tx][row]);          // row = co, tx = ci
-        if (e.dst_d >= 0) packed[e.dst_d + d_base + row * d_row + tx] = __float2bfloat16_rn(tl[row][tx]);   // row = ci, tx = co
+        // forward copy: row = co, tx = ci; dgrad copy: row = ci, tx = co
+        packed[e.dst_f + f_base + row * f_row + tx] = __float2bfloat16_rn(tr ? tl[row][tx] : tl[tx][row]);
+        if (e.dst_d >= 0) packed[e.dst_d + d_base + row * d_row + tx] = __float2bfloat16_rn(tr ? tl[tx][row] : tl[row][tx]);
       }
     }
     __syncthreads();

@@ -258,6 +258,7 @@ static int setup_wgrad_halo(WgradHaloArgs* a, const WgradHaloPlan& p, const void
   a->n_cchunks = p.n_cchunks; a->n_ntiles = p.n_ntiles; a->k_split = p.k_split;
   a->dw = dw;
   a->up = 0;
+  a->transposed = 0;
   if (make_act_map_box(&a->x0, x0, B, H, W, C0, p.CIC, p.TW + 2, p.TH + 2, 1)) return 1;
   if (C1 > 0) {
     if (make_act_map_box(&a->x1, x1, B, H, W, C1, p.CIC, p.TW + 2, p.TH + 2, 1)) return 1;
@@ -270,13 +271,14 @@ static int setup_wgrad_halo(WgradHaloArgs* a, const WgradHaloPlan& p, const void
 
 // weight gradient of the phase-decomposed up-convolution: x_low [B,h,w,Cin], dz [B,2h,2w,C] -> dw [3][3][Cin][C]
 static int setup_wgrad_halo_up(WgradHaloArgs* a, const WgradHaloPlan& p, const void* x_low, const void* dz, float* dw,
-                               int B, int h, int w, int Cin, int C) {
+                               int B, int h, int w, int Cin, int C, int transposed) {
   memset(a, 0, sizeof(*a));
   a->B = B; a->H = h; a->W = w; a->C0 = Cin; a->Ctot = Cin; a->Cout = C;
   a->TW = p.TW; a->TH = p.TH; a->tiles_x = p.tiles_x; a->tiles_y = p.tiles_y; a->pixel_tiles = p.pixel_tiles;
   a->n_cchunks = p.n_cchunks; a->n_ntiles = p.n_ntiles; a->k_split = p.k_split;
   a->dw = dw;
   a->up = 1;
+  a->transposed = transposed;
   if (make_act_map_box(&a->x0, x_low, B, h, w, Cin, 64, p.TW + 2, p.TH + 2, 1)) return 1;
   a->x1 = a->x0;
   for (int ph = 0; ph < 4; ++ph)
@@ -412,6 +414,8 @@ struct Layer {
   int up_ns = 0, up_dgrad = 0;         // variant (0 = off); dgrad also phase-decomposed
   int up_wgrad = 0;                    // weight gradient from the low-resolution input (no up-sampled copy needed)
   int needs_y2 = 1;                    // POST_UPSAMPLE layers: some consumer still reads the up-sampled copy
+  int transposed = 0;                  // decoder up-conv is a Conv2DTranspose(3, strides 2, 'same') (USE_UPSAMPLE falsy):
+                                       // kernel layout (kh, kw, out, in); runs on the same phase kernels, other packing
   int feeds_up = 0;                    // this (POST_UPSAMPLE) layer's y feeds a phase-decomposed up-convolution
   int g0_lowres = 0;                   // ... and its gradient arrives at its own (low) resolution
   long long pk_uf = -1, pk_ud = -1;    // packed up-convolution operands
@@ -502,7 +506,8 @@ static int build_plan(rvip_handle* h) {
   RVIP_REQUIRE(c.depth >= 1 && c.depth <= RVIP_MAX_DEPTH, "DEPTH=%d not in [1,%d]", c.depth, RVIP_MAX_DEPTH);
   RVIP_REQUIRE(c.batch_norm == 1, "BATCH_NORMALISATION=false is not implemented (every shipped config enables it)");
   RVIP_REQUIRE(c.bn_first == 0, "BN_FIRST=true (Conv->BN->ReLU) is not implemented (SURVEY row N5)");
-  RVIP_REQUIRE(c.use_upsample == 1, "USE_UPSAMPLE=false (Conv2DTranspose decoder) is not implemented (SURVEY row N5)");
+  RVIP_REQUIRE(c.use_upsample == 1 || is_bf16(h), "USE_UPSAMPLE=false (Conv2DTranspose decoder, SURVEY row N5) is implemented "
+               "for PRECISION='bf16' only");
   RVIP_REQUIRE(c.H % (1 << c.depth) == 0 && c.W % (1 << c.depth) == 0, "DIM %dx%d must be divisible by 2^DEPTH=%d",
                c.H, c.W, 1 << c.depth);
   RVIP_REQUIRE(c.filters % 32 == 0 && c.filters >= 32, "FILTERS=%d must be a multiple of 32", c.filters);
@@ -573,6 +578,16 @@ static int build_plan(rvip_handle* h) {
       h->L[l.in0_layer].needs_y2 = !l.up_wgrad;
     }
   }
+  if (!c.use_upsample) {
+    for (Layer& l : h->L) {
+      if (l.bn || l.in0_layer < 0 || h->L[l.in0_layer].post != POST_UPSAMPLE) continue;
+      l.transposed = 1;
+      RVIP_REQUIRE(l.up_ns && l.up_dgrad && l.up_wgrad,
+                   "USE_UPSAMPLE=false: %s (%dx%d, %d -> %d channels) does not fit the phase-decomposed kernels (low-resolution "
+                   "size a multiple of 16, input channels %% 64 == 0, FILTERS 32 or a multiple of 64)",
+                   l.name.c_str(), l.H, l.W, l.C0, l.Cout);
+    }
+  }
   // flat offsets + tensor table in model.get_weights() order
   long long po = 0, so = 0, ch = 0;
   auto push = [&](const std::string& n, int is_state, long long off, std::initializer_list<int> dims) {
@@ -585,7 +600,10 @@ static int build_plan(rvip_handle* h) {
   };
   for (Layer& l : h->L) {
     const int Ct = l.C0 + l.C1;
-    l.off_k = po; push(l.name + "/kernel", 0, po, {3, 3, Ct, l.Cout}); po += 9LL * Ct * l.Cout;
+    l.off_k = po;
+    if (l.transposed) push(l.name + "/kernel", 0, po, {3, 3, l.Cout, Ct});   // Conv2DTranspose: (kh, kw, out, in)
+    else push(l.name + "/kernel", 0, po, {3, 3, Ct, l.Cout});
+    po += 9LL * Ct * l.Cout;
     l.off_b = po; push(l.name + "/bias", 0, po, {l.Cout}); po += l.Cout;
     if (l.bn) {
       l.off_g = po; push(l.name + "/bn/gamma", 0, po, {l.Cout}); po += l.Cout;
@@ -755,7 +773,8 @@ static int build_descriptors(rvip_handle* h) {
         if (l.up_wgrad) {
           l.use_hwg = wgrad_halo_up_plan(B, lo.H, lo.W, l.C0, l.Cout, &l.hwp);
           RVIP_REQUIRE(l.use_hwg, "%s: no up-conv weight-gradient plan", l.name.c_str());
-          if (setup_wgrad_halo_up(&l.hwg, l.hwp, lo.y, l.dz, h->grads + l.off_k, B, lo.H, lo.W, l.C0, l.Cout)) return 1;
+          if (setup_wgrad_halo_up(&l.hwg, l.hwp, lo.y, l.dz, h->grads + l.off_k, B, lo.H, lo.W, l.C0, l.Cout, l.transposed))
+            return 1;
         } else {
           l.use_hwg = wgrad_halo_plan(B, l.H, l.W, l.C0, 0, l.Cout, &l.hwp);
           RVIP_REQUIRE(l.use_hwg, "%s: the halo weight-gradient kernel does not fit", l.name.c_str());
@@ -1166,6 +1185,7 @@ int rvip_bind(rvip_handle* h, float* params, float* grads, float* bn_state, void
     if (l.up_ns) {
       UpPackEntry u;
       u.src = l.off_k; u.dst_f = l.pk_uf; u.dst_d = l.pk_ud; u.Cin = l.C0; u.C = l.Cout; u.ns = l.up_ns;
+      u.transposed = l.transposed;
       utab.push_back(u);
     }
     if (l.pk_d < 0) continue;
@@ -1451,12 +1471,13 @@ int rvip_conv3x3_halo(const void* in0, const void* in1, int C0, int C1, const vo
 }
 
 int rvip_upconv3x3_halo(int dir, const void* low, const void* high, const float* w_hwio, const float* bias,
-                        void* packed_scratch, int B, int h, int w, int Cin, int C, void* stream) {
+                        void* packed_scratch, int B, int h, int w, int Cin, int C, int transposed, void* stream) {
   const int ns = conv_halo_up_variant(h, w, Cin, C);
   RVIP_REQUIRE(ns != 0, "rvip_upconv3x3_halo: shape not eligible for the phase-decomposed kernel");
   cudaStream_t st = (cudaStream_t)stream;
   UpPackEntry e;
   e.src = 0; e.dst_f = 0; e.dst_d = conv_halo_up_pack_elems(Cin, C); e.Cin = Cin; e.C = C; e.ns = ns;
+  e.transposed = transposed;
   UpPackEntry* e_dev = nullptr;
   RVIP_CUDA(cudaMalloc(&e_dev, sizeof(e)));
   RVIP_CUDA(cudaMemcpy(e_dev, &e, sizeof(e), cudaMemcpyHostToDevice));
@@ -1480,11 +1501,11 @@ int rvip_upconv3x3_halo(int dir, const void* low, const void* high, const float*
 }
 
 int rvip_upconv_wgrad_halo(const void* x_low, const void* dz, float* dw, int B, int h, int w, int Cin, int C,
-                           void* stream) {
+                           int transposed, void* stream) {
   WgradHaloArgs a;
   WgradHaloPlan p;
   RVIP_REQUIRE(wgrad_halo_up_plan(B, h, w, Cin, C, &p), "rvip_upconv_wgrad_halo: shape not eligible");
-  if (setup_wgrad_halo_up(&a, p, x_low, dz, dw, B, h, w, Cin, C)) return 1;
+  if (setup_wgrad_halo_up(&a, p, x_low, dz, dw, B, h, w, Cin, C, transposed)) return 1;
   return wgrad_halo_launch(a, p.CIC, p.BN, (cudaStream_t)stream);
 }
 

@@ -43,6 +43,10 @@ __device__ __forceinline__ void wh_red_add_v4(float* addr, float a, float b, flo
                : "memory");
 }
 
+__device__ __forceinline__ void wh_red_add(float* addr, float a) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
+}
+
 template <int CIC, int BN, bool UP = false>
 struct WhCfg {
   static constexpr int XPIXB = CIC * 2;                       // bytes per pixel of the x chunk
@@ -209,7 +213,29 @@ __global__ void __launch_bounds__(256, 1) wgrad3x3_halo_kernel(const __grid_cons
     const int m = ew * 32 + lane;               // accumulator row
     mbar_wait(&ctl->done, 0);
     tc_fence_after();
-    if (UP) {
+    if (UP && a.transposed) {
+      // Conv2DTranspose(3, strides 2, 'same'): tap k of an axis pairs output parity / neighbour (p, r) = (0, 1) for k = 0,
+      // (1, 0) for k = 1, (0, 0) for k = 2 -- one accumulator per tap, nothing to fold.  dW is (kh, kw, Cout, Cin):
+      // rows of the accumulator (ci) are the contiguous axis, so a column is one coalesced scalar reduction per warp.
+      const int s = m >> 6, ci = m & 63;
+#pragma unroll 1
+      for (int ky = 0; ky < 3; ++ky) {
+        const int pa = ky == 1 ? 1 : 0, r = ky == 0 ? 1 : 0;
+#pragma unroll 1
+        for (int opt = 0; opt < (s == 0 ? 2 : 1); ++opt) {
+          const int kx = s == 0 ? (opt == 0 ? 2 : 1) : 0, pb = (s == 0 && opt == 1) ? 1 : 0;
+          float* dst = a.dw + ((size_t)((ky * 3 + kx) * a.Cout + n0) * a.Ctot + c0 + ci);
+#pragma unroll 1
+          for (int ch = 0; ch < BN / 32; ++ch) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + ((pa * 2 + pb) * 2 + r) * BN + ch * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) wh_red_add(dst + (size_t)(ch * 32 + j) * a.Ctot, __uint_as_float(v[j]));
+          }
+        }
+      }
+    } else if (UP) {
       const int s = m >> 6, ci = m & 63;        // column neighbour of this row's chunk (warp-uniform), input channel
 #pragma unroll 1
       for (int ky = 0; ky < 3; ++ky) {

@@ -24,6 +24,7 @@ struct WgradHaloArgs {
   // phase-decomposed up-convolution (conv_halo.cuh): x0 is the LOW-resolution input (H, W = its size), dzp[2a + b] the
   // phase view (pixels (2i + a, 2j + b)) of the high-resolution dz, box {min(BN,64), TW, TH, 1}
   int up;
+  int transposed;            // up: dw is a Conv2DTranspose kernel gradient (kh, kw, Cout, Cin); each tap has ONE accumulator
   CUtensorMap dzp[4];
 };
 // weight gradient of the phase-decomposed up-convolution: eight accumulators (phase (a, b) x low-resolution row

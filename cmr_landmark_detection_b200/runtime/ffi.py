@@ -80,8 +80,8 @@ _SIGS = {
     'rvip_wgrad3x3_row': (_I, [_VP, _VP, _I, _I, _VP, _VP, _I, _I, _I, _I, _VP]),
     'rvip_wgrad3x3_tc': (_I, [_VP, _VP, _I, _I, _VP, _VP, _I, _I, _I, _I, _VP]),
     'rvip_wgrad3x3_halo': (_I, [_VP, _VP, _I, _I, _VP, _VP, _I, _I, _I, _I, _VP]),
-    'rvip_upconv_wgrad_halo': (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),
-    'rvip_upconv3x3_halo': (_I, [_I, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),
+    'rvip_upconv_wgrad_halo': (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
+    'rvip_upconv3x3_halo': (_I, [_I, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
 

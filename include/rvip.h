@@ -30,7 +30,8 @@ typedef struct rvip_cfg {
   int filters;           /* FILTERS */
   int batch_norm;        /* BATCH_NORMALISATION (only 1 is implemented) */
   int bn_first;          /* BN_FIRST (only 0 is implemented: Conv -> ReLU -> BN, KerasLayers.py:687-691) */
-  int use_upsample;      /* USE_UPSAMPLE truthiness (only 1: UpSampling2D + Conv, KerasLayers.py:753-759) */
+  int use_upsample;      /* USE_UPSAMPLE truthiness: 1 = UpSampling2D + Conv (KerasLayers.py:753-759), 0 = Conv2DTranspose
+                            (:762-765; bf16 mode, shapes that fit the phase-decomposed kernels) */
   int precision;         /* 0 = fp32 storage, CUDA-core convs; 1 = bf16 storage, tcgen05 convs */
   float dropout[RVIP_MAX_DEPTH]; /* encoder level l; decoder pops from the back (Unets.py:105-106, :832) */
   float dropout_mid;     /* DROPOUT_MAX at the bottleneck (Unets.py:813) */
@@ -176,13 +177,16 @@ int rvip_wgrad3x3_halo(const void* x0, const void* x1, int C0, int C1, const voi
  * at least 2 * max(16*Cin*C, 768*Cin) elements (receives the packed forward and dgrad operands).
  *   dir 0: high[B,2h,2w,C] = relu(conv3x3(upsample2x(low[B,h,w,Cin])) + bias)
  *   dir 1: low[B,h,w,Cin]  = gradient of that convolution w.r.t. its low-resolution input, from high = dz[B,2h,2w,C]
+ * transposed = 1: the same kernels compute Conv2DTranspose(3x3, strides 2, padding 'same') -> ReLU (USE_UPSAMPLE falsy,
+ * KerasLayers.py:762-765): w is then the Keras kernel (kh, kw, C, Cin) and every phase weight is a single tap
+ * (output parity 0 sees tap 2 on neighbour i - 1 and tap 0 on i, parity 1 sees tap 1 on i).
  * Synchronises the stream before returning (test / profiling entry point). */
 int rvip_upconv3x3_halo(int dir, const void* low, const void* high, const float* w_hwio, const float* bias,
-                        void* packed_scratch, int B, int h, int w, int Cin, int C, void* stream);
+                        void* packed_scratch, int B, int h, int w, int Cin, int C, int transposed, void* stream);
 /* Weight gradient of the same up-convolution from the LOW-resolution input: dw[3][3][Cin][C] (fp32, accumulated) from
  * x_low[B,h,w,Cin] and dz[B,2h,2w,C] (bf16).  Cin % 64 == 0, C % 32 == 0, w % 16 == 0. */
 int rvip_upconv_wgrad_halo(const void* x_low, const void* dz, float* dw, int B, int h, int w, int Cin, int C,
-                           void* stream);
+                           int transposed, void* stream);
 
 #ifdef __cplusplus
 }

@@ -86,6 +86,7 @@ class ConvSpec:
     k: int          # 3 or 1
     bn: bool        # followed by BatchNormalization
     act: str        # 'relu' | 'sigmoid'
+    transposed: bool = False   # Conv2DTranspose(k, strides=2, 'same') instead of UpSampling2D + Conv2D (KerasLayers.py:762-765)
 
 
 def layer_specs(cfg: NetCfg) -> List[ConvSpec]:
@@ -101,7 +102,7 @@ def layer_specs(cfg: NetCfg) -> List[ConvSpec]:
     c_low = f
     for l in range(cfg.depth):
         f //= 2
-        specs.append(ConvSpec(f'dec{l}.upconv', c_low, f, 3, False, 'relu'))
+        specs.append(ConvSpec(f'dec{l}.upconv', c_low, f, 3, False, 'relu', transposed=not cfg.use_upsample))
         specs.append(ConvSpec(f'dec{l}.conv_a', 2 * f, f, 3, cfg.batch_norm, 'relu'))
         specs.append(ConvSpec(f'dec{l}.conv_b', f, f, 3, cfg.batch_norm, 'relu'))
         c_low = f
@@ -114,7 +115,8 @@ def weight_shapes(cfg: NetCfg) -> List[Tuple[str, Tuple[int, ...]]]:
     moving_mean, moving_variance."""
     out = []
     for s in layer_specs(cfg):
-        out.append((s.name + '/kernel', (s.k, s.k, s.cin, s.cout)))
+        # Conv2D kernels are HWIO; Conv2DTranspose kernels are (kh, kw, OUT, IN) [TF-2.3]
+        out.append((s.name + '/kernel', (s.k, s.k, s.cout, s.cin) if s.transposed else (s.k, s.k, s.cin, s.cout)))
         out.append((s.name + '/bias', (s.cout,)))
         if s.bn:
             for n in ('gamma', 'beta', 'moving_mean', 'moving_variance'):
@@ -139,14 +141,17 @@ def init_weights(cfg: NetCfg, seed: int = 1234, randomize_bn: bool = False) -> L
     rng = np.random.default_rng(seed)
     ws: List[np.ndarray] = []
     for s in layer_specs(cfg):
-        fan_in = s.k * s.k * s.cin
-        fan_out = s.k * s.k * s.cout
+        # Keras computes fans from the kernel SHAPE (fan_in = shape[-2] * receptive field): for the (kh, kw, out, in)
+        # kernel of Conv2DTranspose that is the OUTPUT channel count [TF-2.3 init_ops._compute_fans]
+        shape = (s.k, s.k, s.cout, s.cin) if s.transposed else (s.k, s.k, s.cin, s.cout)
+        fan_in = s.k * s.k * shape[2]
+        fan_out = s.k * s.k * shape[3]
         if s.name == 'head':
             lim = math.sqrt(6.0 / (fan_in + fan_out))
-            k = rng.uniform(-lim, lim, size=(s.k, s.k, s.cin, s.cout))
+            k = rng.uniform(-lim, lim, size=shape)
         else:
             std = math.sqrt(2.0 / fan_in) / 0.87962566103423978
-            k = rng.standard_normal(size=(s.k, s.k, s.cin, s.cout))
+            k = rng.standard_normal(size=shape)
             bad = np.abs(k) > 2.0
             while bad.any():
                 k[bad] = rng.standard_normal(size=int(bad.sum()))
@@ -192,6 +197,16 @@ def _conv(x, kernel_hwio, bias):
     w = kernel_hwio.permute(3, 2, 0, 1)
     pad = kernel_hwio.shape[0] // 2
     return F.conv2d(x, w, bias, stride=1, padding=pad)
+
+
+def _tconv(x, kernel_hwoi, bias):
+    """Conv2DTranspose(kernel 3, strides 2, padding 'same') [TF-2.3]: the gradient w.r.t. the input of the forward
+    convolution (2h -> h, stride 2, SAME: total padding max((h-1)*2 + 3 - 2h, 0) = 1, all of it at the END since
+    pad_before = total // 2 = 0), i.e. out[o] = sum_{2i + k = o} x[i] * w[k] cropped to the first 2h rows / columns.
+    torch's conv_transpose2d is the same scatter (weight [in, out, kh, kw]) on a (2h + 1)-long output."""
+    h, w = x.shape[2], x.shape[3]
+    y = F.conv_transpose2d(x, kernel_hwoi.permute(3, 2, 0, 1), bias, stride=2)
+    return y[:, :, :2 * h, :2 * w]
 
 
 def _bn(x, gamma, beta, mm, mv, training, new_stats, name):
@@ -240,7 +255,7 @@ def _block(x, p: _Params, spec: ConvSpec, cfg: NetCfg, training, new_stats, acts
     if _STORAGE['mode'] == 'bf16':
         return _block_bf16(x, p, spec, cfg, training, new_stats, acts)
     k, b = p.take(2)
-    z = _conv(x, k, b)
+    z = _tconv(x, k, b) if spec.transposed else _conv(x, k, b)
     if spec.bn:
         g, be, mm, mv = p.take(4)
         if cfg.bn_first:
@@ -269,7 +284,7 @@ def _block_bf16(x, p: _Params, spec: ConvSpec, cfg: NetCfg, training, new_stats,
     if not first:
         k = _RoundFwd.apply(k)
         x = _RoundBwd.apply(x)
-    z = _RoundBwd.apply(_conv(x, k, b))
+    z = _RoundBwd.apply(_tconv(x, k, b) if spec.transposed else _conv(x, k, b))
     a = _RoundFwd.apply(torch.relu(z))
     acts[spec.name + '/a'] = a
     if spec.bn:
@@ -347,10 +362,10 @@ def forward_torch(cfg: NetCfg, params: Sequence[torch.Tensor], x_nchw: torch.Ten
     drops = list(cfg.dropouts)
     for l in range(cfg.depth):
         skip = skips.pop()
-        if not cfg.use_upsample:
-            raise NotImplementedError('Conv2DTranspose decoder variant (SURVEY row N5)')
         su = specs[f'dec{l}.upconv']
-        if (_STORAGE['mode'] == 'bf16' and _STORAGE.get('phased_up')
+        if not cfg.use_upsample:
+            u = _block(h, p, su, cfg, training, new_stats, acts)      # Conv2DTranspose straight on the low-resolution tensor
+        elif (_STORAGE['mode'] == 'bf16' and _STORAGE.get('phased_up')
                 and phased_upconv_eligible(h.shape[2], h.shape[3], su.cin, su.cout)):
             u = _upconv_phased_bf16(h, p, su, acts)
         else:

@@ -133,10 +133,10 @@ def conv_halo(in0, in1, w_packed, bias, cout, mode, out_split=None, want_stats=F
     return out0, out1, stats
 
 
-def upconv_halo(direction, x_or_dz, w_hwio, bias=None):
+def upconv_halo(direction, x_or_dz, w_hwio, bias=None, transposed=False):
     """Phase-decomposed up-convolution through the C ABI.  direction 0: x [B,h,w,Cin] -> u [B,2h,2w,C];
-    direction 1: dz [B,2h,2w,C] -> dx [B,h,w,Cin]."""
-    cin, c = w_hwio.shape[2], w_hwio.shape[3]
+    direction 1: dz [B,2h,2w,C] -> dx [B,h,w,Cin].  transposed: w is a Conv2DTranspose kernel (kh, kw, C, Cin)."""
+    cin, c = (w_hwio.shape[3], w_hwio.shape[2]) if transposed else (w_hwio.shape[2], w_hwio.shape[3])
     dev = x_or_dz.device
     if direction == 0:
         B, h, w, _ = x_or_dz.shape
@@ -152,7 +152,7 @@ def upconv_halo(direction, x_or_dz, w_hwio, bias=None):
     scratch = torch.zeros(2 * max(16 * cin * c, 768 * cin), dtype=torch.bfloat16, device=dev)
     wf = w_hwio.float().contiguous()
     ffi.check(ffi.lib().rvip_upconv3x3_halo(direction, ffi.ptr(low), ffi.ptr(high), ffi.ptr(wf), ffi.ptr(bias),
-                                            ffi.ptr(scratch), B, h, w, cin, c, stream()))
+                                            ffi.ptr(scratch), B, h, w, cin, c, int(transposed), stream()))
     torch.cuda.synchronize()
     return out
 
@@ -172,11 +172,25 @@ def ref_upconv(x_low_nhwc, w_hwio, bias=None, relu=True, dz=None):
     return y.permute(0, 2, 3, 1).contiguous()
 
 
-def upconv_wgrad_halo(x_low, dz):
-    """Weight gradient of the phase-decomposed up-convolution: x [B,h,w,Cin], dz [B,2h,2w,C] -> dw [3,3,Cin,C] fp32."""
+def upconv_wgrad_halo(x_low, dz, transposed=False):
+    """Weight gradient of the phase-decomposed up-convolution: x [B,h,w,Cin], dz [B,2h,2w,C] -> dw [3,3,Cin,C] fp32
+    (transposed: the Conv2DTranspose kernel gradient [3,3,C,Cin])."""
     B, h, w, cin = x_low.shape
     c = dz.shape[3]
-    dw = torch.zeros((3, 3, cin, c), dtype=torch.float32, device=x_low.device)
-    ffi.check(ffi.lib().rvip_upconv_wgrad_halo(ffi.ptr(x_low), ffi.ptr(dz), ffi.ptr(dw), B, h, w, cin, c, stream()))
+    dw = torch.zeros((3, 3, c, cin) if transposed else (3, 3, cin, c), dtype=torch.float32, device=x_low.device)
+    ffi.check(ffi.lib().rvip_upconv_wgrad_halo(ffi.ptr(x_low), ffi.ptr(dz), ffi.ptr(dw), B, h, w, cin, c, int(transposed),
+                                               stream()))
     torch.cuda.synchronize()
     return dw
+
+
+def ref_tconv(x_low_nhwc, w_hwoi, bias=None, relu=True):
+    """fp32 reference of Conv2DTranspose(3, strides 2, 'same') [-> ReLU] on bf16-rounded weights; returns (y NHWC, the
+    autograd leaves (x, w)) so that callers can pull gradients."""
+    x = x_low_nhwc.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    w = w_hwoi.to(torch.bfloat16).float().clone().requires_grad_(True)
+    h, wd = x.shape[2], x.shape[3]
+    y = F.conv_transpose2d(x, w.permute(3, 2, 0, 1), bias, stride=2)[:, :, :2 * h, :2 * wd]
+    if relu:
+        y = torch.relu(y)
+    return y, x, w

@@ -60,6 +60,30 @@ def test_unsupported_configs_fail_loudly():
         assert len(L.rvip_last_error()) > 0
 
 
+def test_conv2d_transpose_plan():
+    """USE_UPSAMPLE falsy (Conv2DTranspose decoder): planned in bf16 mode when every up-conv fits the phase-decomposed
+    kernels, with Keras' (kh, kw, out, in) kernel shape in the tensor table; fp32 mode refuses."""
+    L = ffi.lib()
+    base = dict(H=256, W=256, in_ch=1, classes=2, depth=4, filters=32, batch_norm=1, bn_first=0, use_upsample=0,
+                precision=1, dropout_mid=0.5, bn_momentum=0.99, bn_eps=1e-3)
+    h = C.c_void_p()
+    ffi.check(L.rvip_create(C.byref(ffi.rvip_cfg(**base)), C.byref(h)))
+    assert L.rvip_param_count(h) == 8635842
+    found = {}
+    for i in range(L.rvip_num_tensors(h)):
+        name = C.create_string_buffer(128)
+        st, off, nd = C.c_int(), C.c_longlong(), C.c_int()
+        dims = (C.c_int * 4)()
+        ffi.check(L.rvip_tensor_info(h, i, name, 128, C.byref(st), C.byref(off), C.byref(nd), dims))
+        found[name.value.decode()] = tuple(dims[:nd.value])
+    assert found['dec0.upconv/kernel'] == (3, 3, 256, 512) and found['dec3.upconv/kernel'] == (3, 3, 32, 64)
+    assert found['dec0.conv_a/kernel'] == (3, 3, 512, 256)
+    L.rvip_destroy(h)
+    h = C.c_void_p()
+    assert L.rvip_create(C.byref(ffi.rvip_cfg(**dict(base, precision=0))), C.byref(h)) != 0
+    assert b'bf16' in L.rvip_last_error()
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():

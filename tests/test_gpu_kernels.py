@@ -178,6 +178,29 @@ def test_upconv_phased_wgrad(shape):
     assert U.rel_err(dw, ref) < 2e-3
 
 
+@pytest.mark.parametrize('shape', UPCONV_SHAPES[:5])
+def test_conv2d_transpose_on_the_phase_kernels(shape):
+    """USE_UPSAMPLE falsy: Conv2DTranspose(3, strides 2, 'same') -> ReLU (KerasLayers.py:762-765) forward, input gradient
+    and kernel gradient on the phase-decomposed kernels (single-tap phase weights), against torch conv_transpose2d."""
+    from tests import gpu_util as U
+    B, h, w, cin, c = shape
+    g = torch.Generator(device='cuda').manual_seed(21 + sum(shape))
+    x = _rand_bf16((B, h, w, cin), g)
+    wt = torch.randn((3, 3, c, cin), generator=g, device='cuda') * (2.0 / (9 * c)) ** 0.5       # (kh, kw, out, in)
+    bias = torch.randn(c, generator=g, device='cuda') * 0.1
+    dz = _rand_bf16((B, 2 * h, 2 * w, c), g)
+    out = U.upconv_halo(0, x, wt, bias, transposed=True)
+    ref, xl, wl = U.ref_tconv(x, wt, bias, relu=True)
+    assert torch.isfinite(out.float()).all()
+    assert U.rel_err(out, ref.detach().permute(0, 2, 3, 1)) < 4e-3
+    lin, xl, wl = U.ref_tconv(x, wt, None, relu=False)
+    lin.backward(dz.float().permute(0, 3, 1, 2))
+    dx = U.upconv_halo(1, dz, wt, transposed=True)
+    assert U.rel_err(dx, xl.grad.permute(0, 2, 3, 1)) < 4e-3
+    dw = U.upconv_wgrad_halo(x, dz, transposed=True)
+    assert dw.shape == wl.grad.shape and U.rel_err(dw, wl.grad) < 2e-3
+
+
 @pytest.mark.parametrize('variant,shape', WGRAD_CASES)
 def test_wgrad_tc(variant, shape):
     from tests import gpu_util as U

@@ -16,11 +16,11 @@ TOL = {'fp32': dict(heat=1e-4, loss=1e-5, cos=0.99999, rl2=3e-3, upd=1e-3),
        'bf16': dict(heat=2e-2, loss=1e-2, cos=0.999, rl2=3e-2, upd=5e-2)}
 
 
-def _setup(precision, dim, depth, batch, randomize_bn=True, seed=0):
+def _setup(precision, dim, depth, batch, randomize_bn=True, seed=0, extra=None):
     from cmr_landmark_detection_b200 import synth
     from cmr_landmark_detection_b200.models.Unets import create_unet
     from oracle import unet_ref as R
-    config = dict(BASE, DIM=[dim, dim], DEPTH=depth, PRECISION=precision)
+    config = dict(BASE, DIM=[dim, dim], DEPTH=depth, PRECISION=precision, **(extra or {}))
     model = create_unet(config)
     cfg = R.cfg_from_config(config)
     ws = R.init_weights(cfg, seed=11 + seed, randomize_bn=randomize_bn)
@@ -41,6 +41,47 @@ def test_predict_matches_oracle(precision, dim, depth, batch):
     assert np.abs(heat - ref).max() <= t['heat'], np.abs(heat - ref).max()
     if precision == 'bf16':
         assert np.abs(heat - ref).mean() <= 2e-3
+
+
+@pytest.mark.parametrize('dim,depth,batch', [(64, 2, 3), (128, 3, 2)])
+def test_conv2d_transpose_decoder_matches_oracle(dim, depth, batch):
+    """USE_UPSAMPLE=False (KerasLayers.py:762-765): the decoder's Conv2DTranspose(3, strides 2, 'same') layers run on the
+    phase-decomposed kernels; kernels are (kh, kw, out, in) in get_weights() order like Keras."""
+    from oracle import unet_ref as R
+    model, cfg, ws, x, y = _setup('bf16', dim, depth, batch, extra={'USE_UPSAMPLE': False})
+    assert cfg.use_upsample is False
+    shapes = {n: tuple(s) for n, _, _, s in model.tensors}
+    f = BASE['FILTERS']
+    assert shapes['dec%d.upconv/kernel' % (depth - 1)] == (3, 3, f, 2 * f)
+    assert [tuple(w.shape) for w in model.get_weights()] == [tuple(w.shape) for w in ws]
+    heat = model.predict(x, batch_size=batch)
+    ref = R.predict(cfg, ws, x)
+    assert np.abs(heat - ref).max() <= TOL['bf16']['heat'] and np.abs(heat - ref).mean() <= 2e-3
+    # training step: loss vs the fp32 oracle, every gradient tensor vs the oracle restated with bf16 storage points
+    model, cfg, ws, x, y = _setup('bf16', dim, depth, batch, randomize_bn=False, extra={'USE_UPSAMPLE': False})
+    fp = R.train_grads(cfg, ws, x, y)
+    cal = R.train_grads(cfg, ws, x, y, storage='bf16')
+    loss = float(model.train_step_device(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(),
+                                         apply_optimizer=False).item())
+    assert abs(loss - fp['loss']) <= TOL['bf16']['loss'] * abs(fp['loss']), (loss, fp['loss'])
+    g = model.grads.cpu().numpy()
+    for (name, is_state, off, shape), rg, cg in zip(model.tensors, fp['grads'], cal['grads']):
+        if is_state or np.linalg.norm(rg) < 1e-12:
+            continue
+        mine = g[off:off + int(np.prod(shape))].reshape(shape).astype(np.float64)
+        e_dev = float(np.linalg.norm(mine - rg) / np.linalg.norm(rg))
+        e_cal = float(np.linalg.norm(cg.astype(np.float64) - rg) / np.linalg.norm(rg))
+        if e_cal <= 0.3:
+            assert e_dev <= 1.5 * e_cal + 0.03, (name, e_dev, e_cal)
+        else:
+            assert e_dev <= 2.5 * e_cal, (name, e_dev, e_cal)
+
+
+def test_conv2d_transpose_decoder_needs_bf16():
+    from cmr_landmark_detection_b200.models.Unets import create_unet
+    with pytest.raises(Exception, match='bf16'):
+        m = create_unet(dict(BASE, DIM=[64, 64], DEPTH=2, PRECISION='fp32', USE_UPSAMPLE=False))
+        m.predict(np.zeros((1, 64, 64, 1), np.float32), batch_size=1)
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
@@ -66,7 +107,10 @@ def test_first_layer_mappings_agree(precision, monkeypatch):
                      model.grads.cpu().numpy()[off:off + n].copy())
     assert np.array_equal(out[False][0], out[True][0])              # same FMA order per output element
     g0, g1 = out[False][1], out[True][1]
-    assert np.linalg.norm(g0 - g1) <= 1e-4 * np.linalg.norm(g0) + 1e-12
+    # two separate steps: in bf16 mode the atomics-order noise of the BatchNorm reductions upstream flips bf16 roundings of
+    # dz (run-to-run ~0.5 % on this ill-conditioned first-layer gradient, same mapping or not); fp32 mode is tight
+    lim = 1e-4 if precision == 'fp32' else 3e-2
+    assert np.linalg.norm(g0 - g1) <= lim * np.linalg.norm(g0) + 1e-12
 
 
 @pytest.mark.parametrize('precision,dim,depth,batch', [('fp32', 32, 2, 3), ('bf16', 32, 2, 4), ('fp32', 64, 4, 2),

@@ -194,3 +194,62 @@ def test_phased_upconv_restatement_is_the_same_linear_map():
     g2 = torch.autograd.grad((ref * w).sum(), [x, k, b])
     for a_, b_ in zip(g1, g2):
         assert float((a_ - b_).abs().max()) < 1e-9
+
+
+def test_conv2d_transpose_restatement():
+    """USE_UPSAMPLE falsy (KerasLayers.py:762-765): Conv2DTranspose(3, strides 2, 'same') [TF-2.3 padding: the whole unit of
+    SAME padding sits at the end] is the scatter out[2i + k] += x[i] w[k] cropped to 2h; per output parity it is a
+    single-tap filter on the low-resolution tensor -- parity 0: tap 2 on neighbour i - 1 and tap 0 on i, parity 1: tap 1
+    on i.  That identity is what the device's phase kernels implement; kernels are (kh, kw, out, in) and the parameter
+    count equals the UpSampling2D + Conv2D variant's."""
+    import torch
+    from oracle import unet_ref as R
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 3, 5, 6, dtype=torch.float64, generator=g)
+    k = torch.randn(3, 3, 4, 3, dtype=torch.float64, generator=g)          # (kh, kw, out, in)
+    full = R._tconv(x, k, None)
+    assert full.shape == (2, 4, 10, 12)
+    # direct scatter definition
+    ref = torch.zeros(2, 4, 11, 13, dtype=torch.float64)
+    for i in range(5):
+        for j in range(6):
+            for ky in range(3):
+                for kx in range(3):
+                    ref[:, :, 2 * i + ky, 2 * j + kx] += torch.einsum('oi,ni->no', k[ky, kx], x[:, :, i, j])
+    assert torch.allclose(full, ref[:, :, :10, :12], atol=1e-12)
+    tap = {(0, 0): 2, (0, 1): 0, (1, 0): 1}          # (parity, neighbour) -> tap index; (1, 1) sees nothing
+    xp = torch.nn.functional.pad(x, (1, 1, 1, 1))
+    for a in range(2):
+        for b in range(2):
+            acc = torch.zeros(2, 4, 5, 6, dtype=torch.float64)
+            for r in range(2):
+                for s in range(2):
+                    if (a, r) in tap and (b, s) in tap:
+                        acc += torch.einsum('oi,nihw->nohw', k[tap[(a, r)], tap[(b, s)]], xp[:, :, a + r:a + r + 5, b + s:b + s + 6])
+            assert torch.allclose(acc, full[:, :, a::2, b::2], atol=1e-12)
+    up = R.cfg_from_config(dict(CFG, USE_UPSAMPLE=True))
+    tr = R.cfg_from_config(dict(CFG, USE_UPSAMPLE=False))
+    assert R.count_params(up) == R.count_params(tr)
+    shapes = dict(R.weight_shapes(tr))
+    spec = [s for s in R.layer_specs(tr) if s.name == 'dec0.upconv'][0]
+    assert spec.transposed and shapes['dec0.upconv/kernel'] == (3, 3, spec.cout, spec.cin)
+    # float64 finite differences through a small transposed-decoder net
+    cfg = R.cfg_from_config({'DIM': [16, 16], 'DEPTH': 2, 'FILTERS': 4, 'IMG_CHANNELS': 1, 'MASK_CLASSES': 2,
+                             'BATCH_NORMALISATION': True, 'USE_UPSAMPLE': False, 'DROPOUT_MIN': 0.0, 'DROPOUT_MAX': 0.0})
+    ws = R.init_weights(cfg, seed=2, randomize_bn=True)
+    rng = np.random.default_rng(4)
+    xs, ts = rng.random((2, 16, 16, 1)), rng.random((2, 16, 16, 2))
+    out = R.train_grads(cfg, ws, xs, ts, dtype=torch.float64)
+    names = [n for n, _ in R.weight_shapes(cfg)]
+    i = names.index('dec1.upconv/kernel')
+    errs = []
+    for _ in range(6):
+        idx = tuple(rng.integers(0, s) for s in ws[i].shape)
+        wp = [v.astype(np.float64) for v in ws]
+        wm = [v.astype(np.float64) for v in ws]
+        wp[i][idx] += 1e-5
+        wm[i][idx] -= 1e-5
+        fd = (R.train_grads(cfg, wp, xs, ts, dtype=torch.float64)['loss'] -
+              R.train_grads(cfg, wm, xs, ts, dtype=torch.float64)['loss']) / 2e-5
+        errs.append(abs(fd - out['grads'][i][idx]) / max(abs(out['grads'][i][idx]), 1e-4))
+    assert np.median(errs) < 1e-5
