@@ -293,7 +293,7 @@ def run_b200(args):
         conv_tf = sum(cls_flops.values()) / (conv_t * 1e-3) / 1e12
         # DRAM traffic per launch of the dominant kernel class from the committed ncu --set full capture
         traffic, traffic_src, ncu_pipe = None, None, None
-        tpath = os.path.join(ROOT, 'profiles', 'r1i_traffic.json')
+        tpath = os.path.join(ROOT, 'profiles', 'r1k_traffic.json')
         if os.path.exists(tpath):
             tj = json.load(open(tpath)).get(dom)
             if tj:
@@ -396,6 +396,28 @@ def extra_measurements(model, dev):
         del m5
     except Exception as e:          # secondary metric: never fail the bench line over it
         out['c5_train'] = {'error': str(e)[:200]}
+    # the reference's own training resolution (DIM [224, 224], Train_tests.ipynb): 224 is off the 128-pixel row tiles and
+    # only its 112-pixel level fits the 16-pixel halo blocks of the phase-decomposed up-conv
+    try:
+        c224 = dict(CONFIG, DIM=[224, 224])
+        m2 = create_unet(c224)
+        x2, y2 = synth.make_batch(32, 224, 224, seed=6)
+        x2d, y2d = torch.from_numpy(x2).to(dev), torch.from_numpy(y2).to(dev)
+        for _ in range(3):
+            m2.train_step_device(x2d, y2d)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            m2.train_step_device(x2d, y2d)
+        e1.record()
+        torch.cuda.synchronize()
+        ms2 = e0.elapsed_time(e1) / 10
+        out['train_224'] = {'workload': 'same net and batch at the reference\'s DIM 224x224', 'ms_per_step': round(ms2, 3),
+                            'slices_per_s': round(32 / ms2 * 1e3, 1),
+                            'conv_tflops': round(conv_flops_per_slice(c224)['train'] * 32 / ms2 / 1e9, 1)}
+        del m2
+    except Exception as e:
+        out['train_224'] = {'error': str(e)[:200]}
     return out
 
 
