@@ -142,6 +142,8 @@ int cc_filter_launch(const uint8_t* labels, int Z, int H, int W, int connectivit
 // ------------------------------------------------------------------ optimizer / weight packing (optim.cu)
 int adam_launch(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float b1, float b2, float eps,
                 float grad_scale, cudaStream_t st);
+int sgd_launch(float* p, const float* g, float* velocity, size_t n, float lr, float momentum, int nesterov,
+               float grad_scale, cudaStream_t st);
 struct PackEntry {
   long long src;      // float offset of the HWIO kernel in the parameter buffer
   long long dst_f;    // element offset in the packed buffer: forward  [Cout][9][Ctot]

@@ -48,6 +48,34 @@ int adam_launch(float* p, const float* g, float* m, float* v, size_t n, float lr
   return 0;
 }
 
+// tf.keras.optimizers.SGD (the optimizer the reference switches to in finetune_with_SGD, utils/KerasCallbacks.py:280-306,
+// and OPTIMIZER='sgd', ModelUtils.py:109-111):  v = momentum * v - lr * g;  w += nesterov ? momentum * v - lr * g : v;
+// with momentum == 0 (both call sites) no velocity buffer is needed: w -= lr * g.
+__global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ vel,
+                                                  size_t n, float lr, float momentum, int nesterov, float gs) {
+  pdl_wait();
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    const float gr = g[i] * gs;
+    if (vel != nullptr) {
+      const float v = momentum * vel[i] - lr * gr;
+      vel[i] = v;
+      p[i] += nesterov ? momentum * v - lr * gr : v;
+    } else {
+      p[i] -= lr * gr;
+    }
+  }
+  pdl_launch_dependents();
+}
+int sgd_launch(float* p, const float* g, float* vel, size_t n, float lr, float momentum, int nesterov, float grad_scale,
+               cudaStream_t st) {
+  size_t blocks = (n + 255) / 256;
+  if (blocks > (size_t)kNumSMs * 8) blocks = (size_t)kNumSMs * 8;
+  if (blocks < 1) blocks = 1;
+  launch_kernel(sgd_kernel, (unsigned)blocks, 256, 0, st, p, g, vel, n, lr, momentum, nesterov, grad_scale);
+  RVIP_LAUNCH_CHECK();
+  return 0;
+}
+
 // packed forward  operand: Wf[n][tap][c]  = W[tap][c][n]           (rows = output channels, K-major)
 // packed dgrad    operand: Wd[c][tap'][n] = W[8 - tap'][c][n]      (rows = input channels, taps rotated)
 // fp32 dgrad copy (CUDA-core path): Wr[tap'][n][c] = W[8 - tap'][c][n]

@@ -1321,6 +1321,19 @@ int rvip_adam_step(rvip_handle* h, float* m, float* v, float lr, float beta1, fl
   return pack_weights(h, st);
 }
 
+int rvip_sgd_step(rvip_handle* h, float* velocity, float lr, float momentum, int nesterov, float grad_scale, void* stream) {
+  RVIP_REQUIRE(h && h->bound && h->training, "rvip_sgd_step: handle not bound for training");
+  RVIP_REQUIRE(momentum == 0.f || velocity, "rvip_sgd_step: momentum needs a velocity buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  h->cur_tag = "step:sgd";
+  if (timed(h, KC_OPTIM, 1, st, [&] {
+        return sgd_launch(h->params, h->grads, momentum == 0.f ? nullptr : velocity, (size_t)h->n_params, lr, momentum,
+                          nesterov, grad_scale, st);
+      }))
+    return 1;
+  return pack_weights(h, st);
+}
+
 int rvip_num_buckets(const rvip_handle* h) { return (int)h->buckets.size(); }
 int rvip_bucket(const rvip_handle* h, int index, long long* offset, long long* count) {
   RVIP_REQUIRE(index >= 0 && index < (int)h->buckets.size(), "rvip_bucket: index out of range");

@@ -56,6 +56,7 @@ _SIGS = {
     'rvip_train_step': (_I, [_VP, _VP, _VP, _VP, _I, _F, C.c_uint64, _VP, _VP, _VP]),
     'rvip_set_loss_weights': (_I, [_VP, _F, _F]),
     'rvip_adam_step': (_I, [_VP, _VP, _VP, _F, _F, _F, _F, _LL, _F, _VP]),
+    'rvip_sgd_step': (_I, [_VP, _VP, _F, _F, _I, _F, _VP]),
     'rvip_num_buckets': (_I, [_VP]),
     'rvip_bucket': (_I, [_VP, _I, C.POINTER(_LL), C.POINTER(_LL)]),
     'rvip_set_bucket_event': (_I, [_VP, _I, _VP]),

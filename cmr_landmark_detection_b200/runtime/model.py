@@ -62,6 +62,31 @@ class Adam:
                 'epsilon': self.epsilon}
 
 
+class SGD:
+    """tf.keras.optimizers.SGD as the reference builds it: `SGD(lr, nesterov=True)` for OPTIMIZER='sgd'
+    (ModelUtils.py:109-111) and `SGD(name='SGD')` (learning rate 0.01) when OptimizerChanger switches a converged Adam
+    run over (utils/KerasCallbacks.py:280-306). Keras update: v = momentum v - lr g; w += nesterov ? momentum v - lr g : v."""
+
+    def __init__(self, lr: float = 0.01, momentum: float = 0.0, nesterov: bool = False, name: str = 'SGD',
+                 learning_rate: Optional[float] = None):
+        self.lr = float(lr if learning_rate is None else learning_rate)
+        self.momentum, self.nesterov = float(momentum), bool(nesterov)
+        self.iterations = 0
+        self.name = name
+        self.velocity = None
+
+    @property
+    def learning_rate(self):
+        return self.lr
+
+    @learning_rate.setter
+    def learning_rate(self, v):
+        self.lr = float(v)
+
+    def get_config(self):
+        return {'name': self.name, 'learning_rate': self.lr, 'momentum': self.momentum, 'nesterov': self.nesterov}
+
+
 class History:
     def __init__(self):
         self.history: Dict[str, List[float]] = {}
@@ -162,7 +187,7 @@ class RvipUNet:
         self._version = 0
         self._bindings: Dict[Tuple[int, bool], _Binding] = {}
         self._pinned: Dict[Tuple[str, Tuple[int, ...]], torch.Tensor] = {}
-        self.optimizer: Optional[Adam] = None
+        self.optimizer = None          # Adam | SGD
         self.loss_kind = 'mse'
         self.loss_args = {'mask_smaller_than': 0.01}
         self._inplane = None
@@ -306,8 +331,8 @@ class RvipUNet:
     # ------------------------------------------------------------------ compile
     def compile(self, optimizer=None, loss=None, metrics=None, **kw):
         if optimizer is not None:
-            if not isinstance(optimizer, Adam):
-                raise NotImplementedError('only the Adam optimizer of the shipped configs is implemented')
+            if not isinstance(optimizer, (Adam, SGD)):
+                raise NotImplementedError('only the Adam and SGD optimizers are implemented on the device path')
             self.optimizer = optimizer
         if isinstance(loss, dict):
             loss = loss.get('unet', next(iter(loss.values())))
@@ -426,14 +451,20 @@ class RvipUNet:
 
     def apply_gradients(self, b: Optional[_Binding] = None):
         opt = self.optimizer
-        if opt.m is None:
-            opt.m = torch.zeros_like(self.params)
-            opt.v = torch.zeros_like(self.params)
         if b is None:
             b = next(v for k, v in self._bindings.items() if k[1])
         opt.iterations += 1
-        ffi.check(ffi.lib().rvip_adam_step(b.h, ffi.ptr(opt.m), ffi.ptr(opt.v), opt.lr, opt.beta_1, opt.beta_2,
-                                           opt.epsilon, opt.iterations, 1.0 / self.dp.world, self._stream()))
+        if isinstance(opt, SGD):
+            if opt.momentum != 0.0 and opt.velocity is None:
+                opt.velocity = torch.zeros_like(self.params)
+            ffi.check(ffi.lib().rvip_sgd_step(b.h, ffi.ptr(opt.velocity), opt.lr, opt.momentum, int(opt.nesterov),
+                                              1.0 / self.dp.world, self._stream()))
+        else:
+            if opt.m is None:
+                opt.m = torch.zeros_like(self.params)
+                opt.v = torch.zeros_like(self.params)
+            ffi.check(ffi.lib().rvip_adam_step(b.h, ffi.ptr(opt.m), ffi.ptr(opt.v), opt.lr, opt.beta_1, opt.beta_2,
+                                               opt.epsilon, opt.iterations, 1.0 / self.dp.world, self._stream()))
         self._version += 1
         b.packed_version = self._version      # rvip_adam_step re-packs this binding's operand copies
 

@@ -2,8 +2,7 @@
 (src/utils/KerasCallbacks.py:20-114 get_callbacks): best-only weight checkpoints, ReduceLROnPlateau, EarlyStopping,
 learning-rate logging and the optional polynomial decay.  Pure host logic -- the reference's classes need TensorFlow;
 these only touch the model attributes RvipUNet provides (optimizer.lr, stop_training, save_weights).  The image writers
-(ImageSaver / CustomImageWritertf2) and the Adam->SGD OptimizerChanger belong to plotting / a different optimizer
-and are not provided."""
+(ImageSaver / CustomImageWritertf2) belong to plotting and are not provided."""
 from __future__ import annotations
 
 import logging
@@ -158,6 +157,38 @@ class EarlyStopping(Callback):
             print('Epoch %05d: early stopping' % (self.stopped_epoch + 1))
 
 
+class OptimizerChanger(EarlyStopping):
+    """Switches the optimizer instead of ending the run (KerasCallbacks.py:245-278): an EarlyStopping that, when training
+    ends, calls `on_train_end(config, train_generator, val_generator, model, metrics, last_epoch)`."""
+
+    def __init__(self, on_train_end, train_generator, val_generator, config, metrics, **kwargs):
+        self.do_on_train_end = on_train_end
+        self.train_generator, self.val_generator = train_generator, val_generator
+        self.config, self.metrics = config, metrics
+        self.current_epoch = 0
+        super().__init__(**kwargs)
+
+    def on_epoch_end(self, epoch, logs=None):
+        super().on_epoch_end(epoch, logs)
+        self.current_epoch = epoch
+
+    def on_train_end(self, logs=None):
+        super().on_train_end(logs)
+        self.do_on_train_end(self.config, self.train_generator, self.val_generator, self.model, self.metrics,
+                             self.current_epoch)
+
+
+def finetune_with_SGD(config, train_g, val_g, model, metrics, epoch_init):
+    """Fine-tunes a converged model with plain SGD (KerasCallbacks.py:280-306): recompiles with
+    tf.keras.optimizers.SGD(name='SGD') (learning rate 0.01, no momentum) and fits again from `epoch_init` with the
+    callbacks of get_callbacks WITHOUT metrics, i.e. with a plain EarlyStopping (no recursion)."""
+    from ..runtime.model import SGD
+    model.compile(optimizer=SGD(name='SGD'), loss=config.get('LOSS_FUNCTION', None), metrics=metrics)
+    return model.fit(x=train_g, epochs=config['EPOCHS'], callbacks=get_callbacks(config, train_g, val_g),
+                     steps_per_epoch=len(train_g), validation_data=val_g, max_queue_size=20, initial_epoch=epoch_init,
+                     workers=0, verbose=1)
+
+
 class LRLogger(Callback):
     """Stand-in for LRTensorBoard (KerasCallbacks.py:166-176): records the learning rate of every epoch in the logs and
     appends 'epoch,lr,<logs...>' lines to <log_dir>/lr_log.csv instead of TensorBoard event files."""
@@ -222,9 +253,13 @@ def get_callbacks(config=None, batch_generator=None, validation_generator=None, 
     if config.get('POLY_LR_DECAY', False):
         cbs.append(LearningRateScheduler(PolynomialDecay(maxEpochs=config.get('EPOCHS', 100),
                                                          initAlpha=config.get('LEARNING_RATE', 1e-4), power=2), verbose=1))
-    if metrics:
-        raise NotImplementedError('OptimizerChanger (Adam -> SGD fine-tuning, KerasCallbacks.py:91-105) is not implemented: '
-                                  'only Adam is on the device path; call get_callbacks without metrics')
+    if metrics:   # optimizer is changed to SGD once Adam stops improving (KerasCallbacks.py:89-105)
+        logging.info('optimizer will be changed to SGD after adam does not improve any more')
+        cbs.append(OptimizerChanger(on_train_end=finetune_with_SGD, train_generator=batch_generator,
+                                    val_generator=validation_generator, config=config, metrics=metrics, patience=15,
+                                    verbose=1, monitor=config.get('MONITOR_FUNCTION', 'loss'),
+                                    mode=config.get('MONITOR_MODE', 'min')))
+        return cbs
     cbs.append(EarlyStopping(patience=config.get('EARLY_STOPPING_PATIENCE', 25), verbose=1,
                              monitor=config.get('MONITOR_FUNCTION', 'loss'), mode=config.get('MONITOR_MODE', 'min')))
     return cbs

@@ -84,6 +84,11 @@ int rvip_set_loss_weights(rvip_handle* h, float w_bce, float w_dice);
  * grad_scale folds the data-parallel 1/world into the update. step counts from 1. */
 int rvip_adam_step(rvip_handle* h, float* m, float* v, float lr, float beta1, float beta2, float eps, long long step,
                    float grad_scale, void* stream);
+/* tf.keras.optimizers.SGD apply (OPTIMIZER='sgd', ModelUtils.py:109-111, and the Adam -> SGD switch of
+ * utils/KerasCallbacks.py:280-306) + operand re-pack: v = momentum v - lr g; w += nesterov ? momentum v - lr g : v.
+ * velocity [n_params] may be NULL when momentum == 0. */
+int rvip_sgd_step(rvip_handle* h, float* velocity, float lr, float momentum, int nesterov, float grad_scale, void* stream);
+
 
 /* ---- data-parallel plumbing (MirroredStrategy, Unets.py:70-75): gradient buckets are contiguous
  * ranges of `grads` in backward-completion order; each records a cudaEvent_t when complete so the

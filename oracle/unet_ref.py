@@ -539,6 +539,29 @@ class Adam:
         return out
 
 
+class SGD:
+    """tf.keras.optimizers.SGD [TF-2.3] (ModelUtils.py:109-111: SGD(lr, nesterov=True); KerasCallbacks.py:295: SGD()):
+    v = momentum * v - lr * g;  w += momentum * v - lr * g if nesterov else v.  float64 state, float32 weights."""
+
+    def __init__(self, lr=0.01, momentum=0.0, nesterov=False):
+        self.lr, self.momentum, self.nesterov = lr, momentum, nesterov
+        self.v: Optional[List[Optional[np.ndarray]]] = None
+
+    def step(self, weights: List[np.ndarray], grads: List[Optional[np.ndarray]]) -> List[np.ndarray]:
+        if self.v is None:
+            self.v = [None if g is None else np.zeros(g.shape, np.float64) for g in grads]
+        out = []
+        for i, (w, g) in enumerate(zip(weights, grads)):
+            if g is None:
+                out.append(w)
+                continue
+            g = g.astype(np.float64)
+            self.v[i] = self.momentum * self.v[i] - self.lr * g
+            upd = self.momentum * self.v[i] - self.lr * g if self.nesterov else self.v[i]
+            out.append((w.astype(np.float64) + upd).astype(np.float32))
+        return out
+
+
 def data_parallel_grads(cfg, weights, x_nhwc, t_nhwc, world: int, dtype=torch.float32, loss_kind='mse'):
     """MirroredStrategy semantics (Unets.py:70-75; Appendix C.11): each replica runs its shard with
     per-replica BN statistics; per-replica loss is divided by the GLOBAL batch and gradients are

@@ -68,3 +68,45 @@ def test_get_callbacks_matches_reference_configuration(tmp_path):
     m, lrs, _ = _run(cbs, [1.0, 0.9, 0.8])
     assert np.allclose(lrs, [1e-3, 1e-3 * 0.81, 1e-3 * 0.64])           # polynomial decay, power 2
     assert os.path.exists(os.path.join(cfg['TENSORBOARD_PATH'], 'lr_log.csv'))
+
+
+def test_optimizer_changer_switches_to_sgd(tmp_path):
+    """get_callbacks(metrics=...) ends with the OptimizerChanger (KerasCallbacks.py:89-105): an EarlyStopping that hands the
+    model to finetune_with_SGD when training ends; get_optimizer('sgd') builds SGD(lr, nesterov=True) (ModelUtils.py:109)."""
+    from cmr_landmark_detection_b200.models.ModelUtils import get_optimizer
+    from cmr_landmark_detection_b200.runtime.model import SGD
+    from cmr_landmark_detection_b200.utils import KerasCallbacks as K
+    opt = get_optimizer({'OPTIMIZER': 'SGD', 'LEARNING_RATE': 0.02})
+    assert isinstance(opt, SGD) and opt.lr == 0.02 and opt.nesterov and opt.momentum == 0.0
+    cfg = {'MODEL_PATH': str(tmp_path), 'EPOCHS': 7, 'MONITOR_FUNCTION': 'loss', 'MONITOR_MODE': 'min'}
+    cbs = K.get_callbacks(cfg, batch_generator=[1, 2, 3], validation_generator=[4], metrics=['m'])
+    ch = cbs[-1]
+    assert isinstance(ch, K.OptimizerChanger) and ch.patience == 15 and ch.do_on_train_end is K.finetune_with_SGD
+    assert not any(type(c) is K.EarlyStopping for c in cbs)
+    assert type(K.get_callbacks(cfg)[-1]) is K.EarlyStopping
+
+    calls = []
+
+    class FakeModel:
+        stop_training = False
+
+        def compile(self, optimizer=None, loss=None, metrics=None):
+            calls.append(('compile', optimizer, metrics))
+
+        def fit(self, **kw):
+            calls.append(('fit', kw))
+            return 'history'
+
+    m = FakeModel()
+    ch = K.OptimizerChanger(on_train_end=K.finetune_with_SGD, train_generator=[1, 2, 3], val_generator=[4], config=cfg,
+                            metrics=['m'], patience=2, monitor='loss', mode='min')
+    ch.set_model(m)
+    ch.on_train_begin()
+    for epoch, loss in enumerate([1.0, 0.9, 0.95, 0.97]):
+        ch.on_epoch_end(epoch, {'loss': loss})
+    assert m.stop_training and ch.stopped_epoch == 3
+    ch.on_train_end()
+    (c0, opt, metrics), (c1, kw) = calls
+    assert c0 == 'compile' and isinstance(opt, SGD) and opt.lr == 0.01 and opt.momentum == 0.0 and metrics == ['m']
+    assert c1 == 'fit' and kw['initial_epoch'] == 3 and kw['epochs'] == 7 and kw['steps_per_epoch'] == 3
+    assert type(kw['callbacks'][-1]) is K.EarlyStopping            # no recursion: the second fit stops for good

@@ -84,6 +84,32 @@ def test_conv2d_transpose_decoder_needs_bf16():
         m.predict(np.zeros((1, 64, 64, 1), np.float32), batch_size=1)
 
 
+@pytest.mark.parametrize('momentum,nesterov', [(0.0, False), (0.0, True), (0.9, True), (0.9, False)])
+def test_sgd_steps_match_oracle(momentum, nesterov):
+    """tf.keras.optimizers.SGD on the device (OPTIMIZER='sgd' and the Adam -> SGD switch of the reference's
+    OptimizerChanger): two steps from the device's own gradients against the Keras update formula."""
+    from cmr_landmark_detection_b200.runtime.model import SGD
+    from oracle import unet_ref as R
+    model, cfg, ws, x, y = _setup('fp32', 32, 2, 3, randomize_bn=False)
+    model.compile(optimizer=SGD(lr=0.05, momentum=momentum, nesterov=nesterov))
+    ref_opt = R.SGD(lr=0.05, momentum=momentum, nesterov=nesterov)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    cur = [w.copy() for w in ws]
+    for _ in range(2):
+        model.train_step_device(xd, yd, apply_optimizer=False)
+        g = model.grads.cpu().numpy()
+        grads = [None if st else g[off:off + int(np.prod(shape))].reshape(shape).copy()
+                 for (name, st, off, shape) in model.tensors]
+        model.apply_gradients()
+        new = model.get_weights()
+        cur = ref_opt.step(cur, grads)
+        for (name, st, off, shape), a, b in zip(model.tensors, new, cur):
+            if not st:
+                assert np.allclose(a, b, rtol=1e-6, atol=1e-7), name
+        # BatchNorm moving statistics moved on the device; carry them over so that both sides keep the same state
+        cur = [a if st else b for (name, st, off, shape), a, b in zip(model.tensors, new, cur)]
+
+
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
 def test_first_layer_mappings_agree(precision, monkeypatch):
     """The Cin = 1 first layer has two thread mappings (4 channels x 8 pixels, and 8 channels x 4 pixels for widths that
