@@ -259,6 +259,9 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
       tc_fence_after();
       const long long t_e0 = a.dbg ? clock64() : 0;
       const uint32_t acc = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * 2 * BN + grp * BN;
+      // rows of the accumulator that lie outside the image (image sizes that are not multiples of 16): their stores are
+      // clipped by TMA, but they must not enter the BatchNorm sums
+      const bool oob = a.mode == EPI_RELU_STATS && (x0 + (r & 7) >= a.W || y0 + (r >> 3) >= a.H);
 #pragma unroll 1
       for (int sl = 0; sl < BN / 64; ++sl) {
         uint8_t* sbuf = stg + (size_t)sb * Cfg::STG;
@@ -285,6 +288,10 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
               f[2] = fmaxf(f[2] + b0.z, 0.f); f[3] = fmaxf(f[3] + b0.w, 0.f);
               f[4] = fmaxf(f[4] + b1.x, 0.f); f[5] = fmaxf(f[5] + b1.y, 0.f);
               f[6] = fmaxf(f[6] + b1.z, 0.f); f[7] = fmaxf(f[7] + b1.w, 0.f);
+            }
+            if (oob) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = 0.f;
             }
             if (a.mode == EPI_RELU_AFFINE) {
               const float* sc = s_bias + a.Cout + n0 + sl * 64 + hc * 32 + q * 8;
@@ -395,12 +402,15 @@ static size_t halo_fixed_bytes(int BN, int Cout, int mode) {
 }
 
 bool conv_halo_plan(int B, int H, int W, int C0, int C1, int Cout, int mode, int out_split, int* BN, int* nbst) {
-  if (H % 16 != 0 || W % 16 != 0 || C0 % 64 != 0 || C1 % 64 != 0 || Cout % 64 != 0) return false;
+  // any image size: blocks that stick out of the image load zero-filled pixels and their stores are clipped by TMA;
+  // the BatchNorm statistics skip the out-of-image rows of the accumulator (the reference trains at 224 x 224, whose
+  // deeper levels are 56, 28 and 14 pixels wide)
+  if (H < 1 || W < 1 || C0 % 64 != 0 || C1 % 64 != 0 || Cout % 64 != 0) return false;
   if (mode == EPI_LINEAR && out_split < Cout && out_split % 64 != 0) return false;
   int bn = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
   // a wider N tile halves the activation re-reads, a narrower one fills the 148 SMs: take the narrower tile when
   // the wide one would leave more than a third of the SMs idle in the last wave
-  const long mtiles = (long)B * (H / 16) * (W / 16);
+  const long mtiles = (long)B * ((H + 15) / 16) * ((W + 15) / 16);
   auto waves_eff = [&](int n) {
     const long t = mtiles * (Cout / n);
     return (double)t / (double)(((t + kNumSMs - 1) / kNumSMs) * kNumSMs);
@@ -433,7 +443,7 @@ static int launch_halo(const ConvHaloArgs& a, int nbst, cudaStream_t st) {
 }
 
 int conv_halo_up_variant(int h, int w, int Cin, int Cout) {
-  if (h % 16 != 0 || w % 16 != 0 || Cin % 64 != 0) return 0;
+  if (h < 1 || w < 1 || Cin % 64 != 0) return 0;
   if (Cout % 64 == 0) return 2;
   if (Cout == 32) return 3;
   return 0;
@@ -448,7 +458,7 @@ bool conv_halo_up_plan(int B, int h, int w, int Cin, int Cout, int dir, int* BN,
   const int n_phase = ns == 2 ? Cout : 64;              // channels of one phase view
   const int N = dir == 0 ? n_phase : Cin;               // accumulator columns needed per pixel block (and phase)
   int bn = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64);
-  const long tiles_at = (long)B * (h / 16) * (w / 16) * (dir == 0 ? nph : 1);
+  const long tiles_at = (long)B * ((h + 15) / 16) * ((w + 15) / 16) * (dir == 0 ? nph : 1);
   auto waves_eff = [&](int n) {
     const long t = tiles_at * (N / n);
     return (double)t / (double)(((t + kNumSMs - 1) / kNumSMs) * kNumSMs);
@@ -471,7 +481,8 @@ bool conv_halo_up_plan(int B, int h, int w, int Cin, int Cout, int dir, int* BN,
 
 int conv_halo_launch(const ConvHaloArgs& a, int BN, int nbst, cudaStream_t st) {
   RVIP_REQUIRE(a.up_ns == 0 || a.up_ns == 2 || a.up_ns == 3, "conv_halo: bad up-convolution variant %d", a.up_ns);
-  RVIP_REQUIRE(a.C0 % 64 == 0 && a.Ctot % 64 == 0 && a.Cout % BN == 0 && a.H % 16 == 0 && a.W % 16 == 0,
+  RVIP_REQUIRE(a.C0 % 64 == 0 && a.Ctot % 64 == 0 && a.Cout % BN == 0 && a.tiles_x == (a.W + 15) / 16 &&
+                   a.tiles_y == (a.H + 15) / 16,
                "conv_halo: bad shape %dx%d C0=%d Ctot=%d Cout=%d BN=%d", a.H, a.W, a.C0, a.Ctot, a.Cout, BN);
   if (a.up_ns == 2) {
     if (BN == 256) return launch_halo<256, 2>(a, nbst, st);

@@ -161,7 +161,7 @@ static int setup_conv_halo(ConvHaloArgs* a, int BN, const void* in0, const void*
   const int Ctot = C0 + C1;
   a->B = B; a->H = H; a->W = W; a->C0 = C0; a->Ctot = Ctot; a->Cout = Cout;
   a->n_ntiles = Cout / BN;
-  a->tiles_x = W / 16; a->tiles_y = H / 16;
+  a->tiles_x = (W + 15) / 16; a->tiles_y = (H + 15) / 16;
   a->total_tiles = a->n_ntiles * a->tiles_x * a->tiles_y * B;
   a->mode = mode;
   a->out_split = (mode == EPI_LINEAR) ? out_split : Cout;
@@ -219,7 +219,7 @@ static int setup_conv_halo_up(ConvHaloArgs* a, int dir, int BN, const void* low,
   memset(a, 0, sizeof(*a));
   a->B = B; a->H = h; a->W = w;
   a->up_ns = ns; a->up_dir = dir; a->up_nph = nph; a->up_cz = Cv; a->bias_mod = C;
-  a->tiles_x = w / 16; a->tiles_y = h / 16;
+  a->tiles_x = (w + 15) / 16; a->tiles_y = (h + 15) / 16;
   a->bias = bias; a->stats = nullptr; a->scale = a->shift = nullptr; a->dbg = nullptr;
   if (dir == 0) {
     a->C0 = a->Ctot = Cin; a->Cout = Cv;

@@ -306,6 +306,12 @@ static size_t wh_stage_bytes(int CIC, int BN, int TW, int TH, bool up = false) {
   const int x_st = wh_round1k((TH + 2) * (TW + 2) * xpixb + 4 * xpixb);
   return (size_t)x_st + (size_t)TH * TW * cb * 2 * (BN / cb) * (up ? 4 : 1);
 }
+// pixel-tile width for an image row of W pixels: the wider tile unless it wastes more zero-filled columns
+static int wh_tile_w(int W) {
+  if (W < 32) return 16;
+  const int waste32 = (W + 31) / 32 * 32 - W, waste16 = (W + 15) / 16 * 16 - W;
+  return waste32 <= waste16 ? 32 : 16;
+}
 static size_t wh_fixed_bytes() { return 1024 + sizeof(WhCtl) + 64; }
 // Stages are small (128 pixels) and many: the ring has to cover the TMA latency (~2000 cycles) with loads in
 // flight while a stage's MMAs (1500..2000 cycles) run; two 256-pixel stages measured load-latency bound.
@@ -315,13 +321,13 @@ static int wh_stages(int CIC, int BN, int TW, int TH, bool up = false) {
 }
 
 bool wgrad_halo_up_plan(int B, int h, int w, int Cin, int Cout, WgradHaloPlan* p) {
-  if (w < 16 || w % 16 != 0 || Cin % 64 != 0 || Cout % 32 != 0) return false;
+  if (w < 1 || Cin % 64 != 0 || Cout % 32 != 0) return false;   // columns past the image are zero-filled by TMA
   p->CIC = 64;
   p->BN = Cout % 64 == 0 ? 64 : 32;          // 8 accumulators x BN columns <= 512 TMEM columns
-  p->TW = w % 32 == 0 ? 32 : 16;
+  p->TW = wh_tile_w(w);
   p->TH = 128 / p->TW;
   if (wh_stages(64, p->BN, p->TW, p->TH, true) < 2) return false;
-  p->tiles_x = w / p->TW;
+  p->tiles_x = (w + p->TW - 1) / p->TW;
   p->tiles_y = (h + p->TH - 1) / p->TH;
   p->pixel_tiles = p->tiles_x * p->tiles_y * B;
   p->n_cchunks = Cin / 64;
@@ -336,7 +342,7 @@ bool wgrad_halo_up_plan(int B, int h, int w, int Cin, int Cout, WgradHaloPlan* p
 }
 
 bool wgrad_halo_plan(int B, int H, int W, int C0, int C1, int Cout, WgradHaloPlan* p) {
-  if (W < 16 || W % 16 != 0 || C0 % 32 != 0 || C1 % 32 != 0 || Cout % 32 != 0) return false;
+  if (W < 1 || C0 % 32 != 0 || C1 % 32 != 0 || Cout % 32 != 0) return false;   // columns past the image are zero-filled by TMA
   const int Ctot = C0 + C1;
   int cic, bn;
   if (Cout % 128 == 0) {
@@ -349,10 +355,10 @@ bool wgrad_halo_plan(int B, int H, int W, int C0, int C1, int Cout, WgradHaloPla
     else { cic = 32; bn = 32; }
   }
   p->CIC = cic; p->BN = bn;
-  p->TW = W % 32 == 0 ? 32 : 16;
-  p->TH = 128 / p->TW;                     // rows past the image are zero-filled by TMA and contribute nothing
+  p->TW = wh_tile_w(W);
+  p->TH = 128 / p->TW;                     // rows / columns past the image are zero-filled by TMA and contribute nothing
   if (wh_stages(cic, bn, p->TW, p->TH) < 2) return false;
-  p->tiles_x = W / p->TW;
+  p->tiles_x = (W + p->TW - 1) / p->TW;
   p->tiles_y = (H + p->TH - 1) / p->TH;
   p->pixel_tiles = p->tiles_x * p->tiles_y * B;
   p->n_cchunks = Ctot / cic;

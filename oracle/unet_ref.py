@@ -303,7 +303,7 @@ def _phase_taps(parity, r):
 
 def phased_upconv_eligible(h, w, cin, cout):
     """Shapes the device path computes with the phase-decomposed up-convolution (conv_halo.cuh); h, w = low resolution."""
-    return h % 16 == 0 and w % 16 == 0 and cin % 64 == 0 and (cout % 64 == 0 or cout == 32)
+    return h >= 1 and w >= 1 and cin % 64 == 0 and (cout % 64 == 0 or cout == 32)
 
 
 def _upconv_phased_bf16(x_low, p: _Params, spec: ConvSpec, acts):

@@ -39,6 +39,9 @@ HALO_SHAPES = [  # W % 16 == 0: eligible for the halo-staged wgrad kernel
     (3, 16, 16, 32, 0, 32),       # CIC=32, BN=32
     (1, 8, 16, 256, 0, 128),      # image lower than the nominal tile
     (2, 128, 128, 128, 0, 64),    # level-1 shape of the bench network
+    (2, 28, 28, 64, 0, 64),       # image sizes off the 16-pixel grid (the reference trains at 224: levels 56 / 28 / 14):
+    (1, 14, 14, 128, 0, 128),     #   columns / rows past the image are zero-filled by TMA
+    (1, 56, 40, 32, 32, 64),
 ]
 WGRAD_CASES = ALL_CASES + [('halo', s) for s in HALO_SHAPES]
 CONV_HALO_SHAPES = [  # H, W % 16 == 0, channels % 64 == 0: eligible for the halo-staged conv kernel
@@ -48,6 +51,9 @@ CONV_HALO_SHAPES = [  # H, W % 16 == 0, channels % 64 == 0: eligible for the hal
     (3, 16, 16, 256, 0, 512),     # two N tiles, persistent loop over several tiles per CTA
     (40, 16, 16, 64, 0, 128),     # more tiles than SMs: double-buffered accumulators wrap around
     (2, 16, 16, 128, 0, 192),     # Cout = 3 x 64
+    (2, 24, 40, 64, 0, 64),       # image sizes off the 16-pixel grid: partial blocks, statistics skip the outside rows
+    (1, 14, 14, 128, 0, 128),     # image smaller than one block (mid level of a 224 x 224 input)
+    (3, 28, 28, 64, 64, 64),      # concat + partial blocks
 ]
 CONV_CASES = ALL_CASES + [('halo', s) for s in CONV_HALO_SHAPES]
 
@@ -103,6 +109,9 @@ UPCONV_SHAPES = [  # B, h, w (LOW resolution), Cin, C
     (1, 32, 32, 256, 128),        # BN = 128, four K chunks
     (3, 16, 16, 512, 256),        # deepest decoder level of the bench network
     (40, 16, 16, 128, 64),        # more tiles than SMs
+    (2, 14, 14, 128, 64),         # low-resolution sizes off the 16-pixel grid (224 x 224 input: 14 / 28 / 56 / 112)
+    (1, 28, 28, 64, 32),
+    (1, 56, 40, 64, 32),
 ]
 
 

@@ -179,7 +179,8 @@ def test_phased_upconv_restatement_is_the_same_linear_map():
     x = torch.randn(2, 64, 16, 32, dtype=torch.float64, generator=g, requires_grad=True)
     k = torch.randn(3, 3, 64, 32, dtype=torch.float64, generator=g, requires_grad=True)
     b = torch.randn(32, dtype=torch.float64, generator=g, requires_grad=True)
-    assert R.phased_upconv_eligible(16, 32, 64, 32) and not R.phased_upconv_eligible(8, 8, 64, 32)
+    assert R.phased_upconv_eligible(16, 32, 64, 32) and R.phased_upconv_eligible(14, 14, 128, 64)
+    assert not R.phased_upconv_eligible(16, 16, 32, 32) and not R.phased_upconv_eligible(16, 16, 64, 48)
     fwd, bwd = R._RoundFwd.apply, R._RoundBwd.apply
     try:
         R._RoundFwd.apply = staticmethod(lambda v: v)
