@@ -583,8 +583,8 @@ static int build_plan(rvip_handle* h) {
       if (l.bn || l.in0_layer < 0 || h->L[l.in0_layer].post != POST_UPSAMPLE) continue;
       l.transposed = 1;
       RVIP_REQUIRE(l.up_ns && l.up_dgrad && l.up_wgrad,
-                   "USE_UPSAMPLE=false: %s (%dx%d, %d -> %d channels) does not fit the phase-decomposed kernels (low-resolution "
-                   "size a multiple of 16, input channels %% 64 == 0, FILTERS 32 or a multiple of 64)",
+                   "USE_UPSAMPLE=false: %s (%dx%d, %d -> %d channels) does not fit the phase-decomposed kernels (input "
+                   "channels %% 64 == 0, FILTERS 32 or a multiple of 64)",
                    l.name.c_str(), l.H, l.W, l.C0, l.Cout);
     }
   }

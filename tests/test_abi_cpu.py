@@ -51,7 +51,8 @@ def test_plan_and_tensor_table_without_gpu():
 
 def test_unsupported_configs_fail_loudly():
     L = ffi.lib()
-    for kw in (dict(batch_norm=0), dict(bn_first=1), dict(use_upsample=0), dict(H=100)):
+    for kw in (dict(batch_norm=0), dict(bn_first=1), dict(use_upsample=0, precision=0), dict(use_upsample=0, filters=96),
+               dict(H=100)):
         base = dict(H=128, W=128, in_ch=1, classes=2, depth=4, filters=32, batch_norm=1, bn_first=0, use_upsample=1,
                     precision=1, dropout_mid=0.5, bn_momentum=0.99, bn_eps=1e-3)
         base.update(kw)
