@@ -81,6 +81,7 @@ template <int CIC, int BN, int TW, bool UP>
 __global__ void __launch_bounds__(256, 1) wgrad3x3_halo_kernel(const __grid_constant__ WgradHaloArgs a, int nst,
                                                                int tmem_cols) {
   using Cfg = WhCfg<CIC, BN, UP>;
+  constexpr bool MERGE = !UP && CIC == 32 && BN <= 64;   // row-merged MMAs (see the issue loop)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int TH = 128 / TW, pitch = TW + 2;
@@ -164,10 +165,43 @@ __global__ void __launch_bounds__(256, 1) wgrad3x3_halo_kernel(const __grid_cons
         tc_fence_after();
         const uint32_t x_base = smem_u32(smem + (size_t)stage * stage_bytes);
         const uint32_t dz_base = x_base + x_st;
+        if constexpr (MERGE) {
+          // Row-merged form for N = BN <= 64 (an N = 32 MMA costs 48 cycles for 16 cycles of work): input row hr of the halo
+          // block pairs with the output rows i = hr - ty of the dz tile for the taps ty = 0, 1, 2 -- ONE M tile (the dx taps
+          // packed in M as before) times N = up to 3 * BN, the dz rows i_lo .. i_hi being consecutive N chunks TW pixels
+          // apart (LBO) that land in accumulator column blocks 2 - ty (ascending with i).  (TH + 2) MMAs of N <= 3 BN per
+          // 16-pixel column run instead of 3 TH of N = BN: ~1.8x (TH = 4) / 2x (TH = 8) fewer tensor cycles.
+          constexpr uint32_t idesc2 = make_idesc_bf16(128, 2 * BN, 1, 1), idesc3 = make_idesc_bf16(128, 3 * BN, 1, 1);
+          const uint64_t bdescM = make_smem_desc(dz_base, TW * Cfg::DPIXB, 8 * Cfg::DPIXB, Cfg::LAYB);
+#pragma unroll
+          for (int hr = 0; hr < TH + 2; ++hr) {
+            const int i_lo = hr - 2 < 0 ? 0 : hr - 2, i_hi = hr > TH - 1 ? TH - 1 : hr;
+            const int nblk = i_hi - i_lo + 1;
+            const uint64_t adesc0 =
+                make_smem_desc(x_base + hr * pitch * Cfg::XPIXB, Cfg::XPIXB, 8 * Cfg::XPIXB, Cfg::LAYA);
+#pragma unroll
+            for (int xb = 0; xb < runs_x; ++xb) {
+              const uint32_t a_off = (uint32_t)((xb * 16) * Cfg::XPIXB) >> 4;
+              if (accumulate == 0) {
+                // first stage of this CTA: column block 2 - ty is first touched by (hr = ty, i = 0, xb = 0)
+#pragma unroll
+                for (int i = i_lo; i <= i_hi; ++i) {
+                  const uint32_t b_off = (uint32_t)((i * TW + xb * 16) * Cfg::DPIXB) >> 4;
+                  mma_bf16_ss(tmem_base + (2 - hr + i) * BN, adesc0 + a_off, bdescM + b_off, idesc,
+                              (i == 0 && xb == 0) ? 0u : 1u);
+                }
+              } else {
+                const uint32_t b_off = (uint32_t)((i_lo * TW + xb * 16) * Cfg::DPIXB) >> 4;
+                mma_bf16_ss(tmem_base + (2 - hr + i_lo) * BN, adesc0 + a_off, bdescM + b_off,
+                            nblk == 3 ? idesc3 : (nblk == 2 ? idesc2 : idesc), 1u);
+              }
+            }
+          }
+        }
         // B: dz, MN-major: 64-channel chunks one box apart, 8-pixel groups 8 * DPIXB apart
         const uint64_t bdesc0 = make_smem_desc(dz_base, dz_box, 8 * Cfg::DPIXB, Cfg::LAYB);
 #pragma unroll
-        for (int mt = 0; mt < Cfg::MT; ++mt) {
+        for (int mt = 0; mt < (MERGE ? 0 : Cfg::MT); ++mt) {
           // A: x halo block, MN-major: channel chunks LBO apart (= pixel shift between packed taps)
           int start_px, lbo_px;
           if (UP) {
@@ -268,8 +302,29 @@ __global__ void __launch_bounds__(256, 1) wgrad3x3_halo_kernel(const __grid_cons
         }
       }
     }
+    if (MERGE) {
+      // one M tile: rows = (dx chunk, ci); column block cb holds tap ty = 2 - cb
+      const int dxc = m >> 5, ci = m & 31;
 #pragma unroll 1
-    for (int mt = 0; mt < (UP ? 0 : Cfg::MT); ++mt) {
+      for (int cb = 0; cb < 3; ++cb) {
+        const int tap = (2 - cb) * 3 + (dxc < 3 ? dxc : 0);
+        float* dst = a.dw + ((size_t)(tap * a.Ctot + c0 + ci) * a.Cout + n0);
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + cb * BN + ch * 32, v);
+          tmem_ld_wait();
+          if (dxc < 3) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              wh_red_add_v4(dst + ch * 32 + j * 4, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                            __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          }
+        }
+      }
+    }
+#pragma unroll 1
+    for (int mt = 0; mt < ((UP || MERGE) ? 0 : Cfg::MT); ++mt) {
       int tap, ci;
       if (CIC == 32) {
         tap = mt * 3 + (m >> 5);                // dy = mt, dx = chunk; chunk 3 is padding
