@@ -1,4 +1,4 @@
-// Row-tiled tcgen05 3x3 convolution for the wide, few-channel layers (W % 128 == 0: the full- and
+// Row-tiled tcgen05 3x3 convolution for the wide, few-channel layers (rows of 128-pixel tiles: the full- and
 // half-resolution levels of the U-Net), forward and dgrad.
 //
 // The generic kernel (conv_tc.cu) fetches one shifted input box per tap, i.e. reads the activation nine
@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
       const int y0 = ((pt / a.tiles_x) % a.tiles_y) * R;
       const int b = pt / (a.tiles_x * a.tiles_y);
       const int n0 = nt * BN;
+      const bool oobx = a.mode == EPI_RELU_STATS && x0 + r >= a.W;
       if (et == 0) tma_store_wait_read0();   // previous tile's TMA store has drained the staging buffer
       row_bar_sync(1, 256);
       mbar_wait(&ctl->tfull[acc], acc_phase);
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
           for (int j = 0; j < 32; ++j) {
             f[j] = __uint_as_float(v[j]);
             if (a.mode != EPI_LINEAR) f[j] = fmaxf(f[j] + bias[j], 0.f);
+            if (oobx) f[j] = 0.f;            // pixel past the end of the image row: clipped by the store, not counted
             if (a.mode == EPI_RELU_STATS) {
               s1[j] += f[j];
               s2[j] = fmaf(f[j], f[j], s2[j]);
@@ -348,7 +350,9 @@ static size_t row_stage_bytes(int BN, int R, int wres) { return round1k(row_a_by
 
 bool conv_row_plan(int H, int W, int C0, int C1, int Cout, int mode, int out_split, int* BN, int* R, int* wres,
                    int* nst) {
-  if (W % 128 != 0 || C0 % 32 != 0 || C1 % 32 != 0 || Cout % 32 != 0) return false;
+  // rows are cut into 128-pixel tiles; a last partial tile loads zero-filled pixels, has its stores clipped by TMA and is
+  // kept out of the BatchNorm sums.  Accepted when at least 3/4 of the tile columns are real pixels (224 = 128 + 96).
+  if (W < 96 || 4 * W < 3 * ((W + 127) / 128) * 128 || C0 % 32 != 0 || C1 % 32 != 0 || Cout % 32 != 0) return false;
   int bn = (Cout % 64 == 0) ? 64 : 32;
   // a concat split on a 32-channel boundary keeps the N = 64 tile (54-cycle MMAs for twice the work of an N = 32
   // one); only the TMA store boxes shrink to 32 channels (ConvRowArgs::och)

@@ -110,7 +110,7 @@ static int setup_conv_row(ConvRowArgs* a, int BN, int R, int wres, const void* i
   const int Ctot = C0 + C1;
   a->B = B; a->H = H; a->W = W; a->C0 = C0; a->Ctot = Ctot; a->Cout = Cout;
   a->n_ntiles = Cout / BN;
-  a->tiles_x = W / 128; a->tiles_y = H / R;
+  a->tiles_x = (W + 127) / 128; a->tiles_y = H / R;
   a->total_tiles = a->n_ntiles * a->tiles_x * a->tiles_y * B;
   a->mode = mode;
   a->out_split = (mode == EPI_LINEAR) ? out_split : Cout;

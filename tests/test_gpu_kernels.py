@@ -55,7 +55,13 @@ CONV_HALO_SHAPES = [  # H, W % 16 == 0, channels % 64 == 0: eligible for the hal
     (1, 14, 14, 128, 0, 128),     # image smaller than one block (mid level of a 224 x 224 input)
     (3, 28, 28, 64, 64, 64),      # concat + partial blocks
 ]
-CONV_CASES = ALL_CASES + [('halo', s) for s in CONV_HALO_SHAPES]
+ROW_EDGE_SHAPES = [  # rows that are not a whole number of 128-pixel tiles (the reference's 224 x 224 input and its 112 level)
+    (1, 8, 224, 32, 0, 32),
+    (2, 4, 96, 64, 0, 64),
+    (1, 8, 224, 32, 32, 32),
+    (1, 4, 112, 64, 0, 64),
+]
+CONV_CASES = ALL_CASES + [('halo', s) for s in CONV_HALO_SHAPES] + [('row', s) for s in ROW_EDGE_SHAPES]
 
 
 def _rand_bf16(shape, gen, scale=1.0):
