@@ -141,40 +141,6 @@ __device__ __forceinline__ void mma_bf16_ss_k8(uint32_t tmem_d, uint64_t adesc, 
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first), "n"(A_STEP), "n"(B_STEP)
       : "memory");
 }
-// One filter tap applied to NROWS accumulators (row i: D += D_STEP columns, A += A_ROW_STEP), two K halves
-// (+2 descriptor units) each; the B (weight) descriptor is shared by all rows.
-template <int NROWS, int D_STEP, int A_ROW_STEP>
-__device__ __forceinline__ void mma_bf16_ss_tap(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                                uint32_t accumulate_first) {
-  static_assert(NROWS == 2 || NROWS == 4, "NROWS");
-  if (NROWS == 4) {
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\t.reg .b64 a, a2, b2;\n\t.reg .b32 d;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 q, 0, 0;\n\t"
-        "add.u64 b2, %2, 2;\n\t"
-        "mov.b64 a, %1;\n\tadd.u64 a2, a, 2;\n\tmov.b32 d, %0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], a, %2, %3, p;\n\ttcgen05.mma.cta_group::1.kind::f16 [d], a2, b2, %3, q;\n\t"
-        "add.u64 a, a, %6;\n\tadd.u64 a2, a2, %6;\n\tadd.u32 d, d, %5;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], a, %2, %3, p;\n\ttcgen05.mma.cta_group::1.kind::f16 [d], a2, b2, %3, q;\n\t"
-        "add.u64 a, a, %6;\n\tadd.u64 a2, a2, %6;\n\tadd.u32 d, d, %5;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], a, %2, %3, p;\n\ttcgen05.mma.cta_group::1.kind::f16 [d], a2, b2, %3, q;\n\t"
-        "add.u64 a, a, %6;\n\tadd.u64 a2, a2, %6;\n\tadd.u32 d, d, %5;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], a, %2, %3, p;\n\ttcgen05.mma.cta_group::1.kind::f16 [d], a2, b2, %3, q;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first), "n"(D_STEP), "n"(A_ROW_STEP)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\t.reg .b64 a, a2, b2;\n\t.reg .b32 d;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 q, 0, 0;\n\t"
-        "add.u64 b2, %2, 2;\n\t"
-        "mov.b64 a, %1;\n\tadd.u64 a2, a, 2;\n\tmov.b32 d, %0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], a, %2, %3, p;\n\ttcgen05.mma.cta_group::1.kind::f16 [d], a2, b2, %3, q;\n\t"
-        "add.u64 a, a, %6;\n\tadd.u64 a2, a2, %6;\n\tadd.u32 d, d, %5;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [d], a, %2, %3, p;\n\ttcgen05.mma.cta_group::1.kind::f16 [d], a2, b2, %3, q;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first), "n"(D_STEP), "n"(A_ROW_STEP)
-        : "memory");
-  }
-}
 // Arrive on an mbarrier once all previously issued MMAs of this thread have completed
 // (implicitly performs tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
