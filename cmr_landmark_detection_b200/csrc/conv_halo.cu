@@ -1,5 +1,6 @@
 // Halo-staged tcgen05 3x3 convolution (forward and dgrad) for the deep levels of the U-Net
-// (H, W multiples of 16; input channels in chunks of 64; Cout a multiple of 64).
+// (any image size -- blocks sticking out of the image are zero-filled / clipped by TMA; input channels in chunks of
+// 64; Cout a multiple of 64).
 //
 // The generic kernel (conv_tc.cu) moves one shifted activation box AND one weight tile per (tap, 64-channel
 // chunk) for a 128-pixel tile: (128 + BN) * 128 B per 4 MMAs, i.e. 96 B/cycle at BN = 256 -- more than twice

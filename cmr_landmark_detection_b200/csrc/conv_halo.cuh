@@ -32,7 +32,7 @@ struct ConvHaloArgs {
   CUtensorMap upin[4];     // dgrad: strided phase views of the high-resolution dz, box {64, 18, 18, 1}
   CUtensorMap upout[4];    // forward: strided phase views of the high-resolution output, box {64, 8, 16, 1}
 };
-// false if the layer does not fit (H, W not multiples of 16; channels not multiples of 64)
+// false if the layer does not fit (channels not multiples of 64, or no shared memory for a weight ring)
 bool conv_halo_plan(int B, int H, int W, int C0, int C1, int Cout, int mode, int out_split, int* BN, int* nbst);
 int conv_halo_launch(const ConvHaloArgs& a, int BN, int nbst, cudaStream_t st);
 

@@ -1,4 +1,5 @@
-// Row-tiled tcgen05 convolution kernels for W % 128 == 0 layers (conv_row.cu, wgrad_row.cu).
+// Row-tiled tcgen05 convolution kernels for the wide levels (conv_row.cu: rows of 128-pixel tiles, the last one may be
+// partial; wgrad_row.cu: W % 128 == 0).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>

@@ -403,7 +403,7 @@ struct Layer {
   ConvTcArgs fwd, dgrad;
   WgradTcArgs wg;
   int fKC = 0, fBN = 0, dKC = 0, dBN = 0, wCBA = 0, wCBB = 0;
-  // row-tiled variants for W % 128 == 0 layers
+  // row-tiled variants for the wide levels (rows of 128-pixel tiles)
   ConvRowArgs rfwd, rdgrad;
   WgradRowArgs rwg;
   WgradHaloArgs hwg;

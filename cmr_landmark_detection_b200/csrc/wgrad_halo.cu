@@ -1,4 +1,4 @@
-// Halo-staged tcgen05 weight gradient for the deep levels of the U-Net (W a multiple of 16, any channel count
+// Halo-staged tcgen05 weight gradient for every level of the U-Net (any image size, any channel count
 // that is a multiple of 32):
 //
 //   dW[tap][ci][co] = sum_p x[p + off(tap), ci] * dz[p, co]

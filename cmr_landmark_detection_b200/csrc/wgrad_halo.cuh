@@ -30,7 +30,7 @@ struct WgradHaloArgs {
 // weight gradient of the phase-decomposed up-convolution: eight accumulators (phase (a, b) x low-resolution row
 // neighbour r, each a pair of column neighbours s = 0, 1 packed in M), folded onto the nine 3x3 taps in the flush
 bool wgrad_halo_up_plan(int B, int h, int w, int Cin, int Cout, WgradHaloPlan* p);
-// false if the layer does not fit this kernel (W not a multiple of 16, channels not multiples of 32)
+// false if the layer does not fit this kernel (channels not multiples of 32)
 bool wgrad_halo_plan(int B, int H, int W, int C0, int C1, int Cout, WgradHaloPlan* p);
 int wgrad_halo_launch(const WgradHaloArgs& a, int CIC, int BN, cudaStream_t st);
 

@@ -154,7 +154,8 @@ int rvip_conv3x3_tc(const void* in0, const void* in1, int C0, int C1, const void
 int rvip_wgrad3x3_tc(const void* x0, const void* x1, int C0, int C1, const void* dz, float* dw, int B, int H, int W,
                      int Cout, void* stream);
 
-/* Row-tiled variants (W % 128 == 0): the input tile is staged once with its halo and all nine taps are
+/* Row-tiled variants (rows of 128-pixel tiles; the conv accepts a partial last tile when >= 3/4 of it is image, the
+ * weight gradient needs W % 128 == 0): the input tile is staged once with its halo and all nine taps are
  * issued from shifted shared-memory descriptors. Same contracts as the two entry points above. */
 int rvip_conv3x3_row(const void* in0, const void* in1, int C0, int C1, const void* w_packed, const float* bias,
                      void* out0, void* out1, int out_split, double* stats, int B, int H, int W, int Cout, int mode,
@@ -162,7 +163,7 @@ int rvip_conv3x3_row(const void* in0, const void* in1, int C0, int C1, const voi
 int rvip_wgrad3x3_row(const void* x0, const void* x1, int C0, int C1, const void* dz, float* dw, int B, int H, int W,
                       int Cout, void* stream);
 
-/* Halo-staged conv for the deep levels (H, W % 16 == 0, channels % 64 == 0): 16 x 16 pixel blocks staged once with
+/* Halo-staged conv for the deep levels (any H, W; channels % 64 == 0): 16 x 16 pixel blocks staged once with
  * their halo, two 128-row accumulators per CTA share every weight tile. Same contract as rvip_conv3x3_tc. */
 int rvip_conv3x3_halo(const void* in0, const void* in1, int C0, int C1, const void* w_packed, const float* bias,
                       void* out0, void* out1, int out_split, double* stats, int B, int H, int W, int Cout, int mode,
@@ -170,14 +171,14 @@ int rvip_conv3x3_halo(const void* in0, const void* in1, int C0, int C1, const vo
 /* profiling aid: dbg (device, [148][8] int64) receives per CTA {issue-loop cycles, cycles waiting for a free
  * accumulator, for the activation block, for a weight tile, whole-kernel cycles, epilogue cycles} of subsequent rvip_conv3x3_halo calls; NULL = off */
 int rvip_conv3x3_halo_debug(long long* dbg);
-/* Halo-staged wgrad for the deep levels (W % 16 == 0): one input-channel chunk per CTA, the x tile staged once
+/* Halo-staged wgrad (any H, W; channels % 32 == 0): one input-channel chunk per CTA, the x tile staged once
  * with its halo, all nine taps accumulated in TMEM. Same contract as rvip_wgrad3x3_tc. */
 int rvip_wgrad3x3_halo(const void* x0, const void* x1, int C0, int C1, const void* dz, float* dw, int B, int H, int W,
                        int Cout, void* stream);
 /* Phase-decomposed decoder up-convolution (UpSampling2D(2) -> Conv2D 3x3 -> ReLU, src/models/KerasLayers.py:756-759)
  * computed from the LOW-resolution tensor: output pixel (2i + a, 2j + b) sees only a 2 x 2 low-resolution neighbourhood,
  * so the 3x3 taps that coincide are pre-summed in fp32 and each of the four phases is a 4-tap convolution (2.25x fewer
- * MMAs; the up-sampled tensor is never materialised for this op).  h, w = low-resolution size (multiples of 16),
+ * MMAs; the up-sampled tensor is never materialised for this op).  h, w = low-resolution size (any),
  * Cin % 64 == 0, C % 64 == 0 or C == 32.  w_hwio: fp32 [3][3][Cin][C] (device); packed_scratch: device bf16 buffer of
  * at least 2 * max(16*Cin*C, 768*Cin) elements (receives the packed forward and dgrad operands).
  *   dir 0: high[B,2h,2w,C] = relu(conv3x3(upsample2x(low[B,h,w,Cin])) + bias)
@@ -189,7 +190,7 @@ int rvip_wgrad3x3_halo(const void* x0, const void* x1, int C0, int C1, const voi
 int rvip_upconv3x3_halo(int dir, const void* low, const void* high, const float* w_hwio, const float* bias,
                         void* packed_scratch, int B, int h, int w, int Cin, int C, int transposed, void* stream);
 /* Weight gradient of the same up-convolution from the LOW-resolution input: dw[3][3][Cin][C] (fp32, accumulated) from
- * x_low[B,h,w,Cin] and dz[B,2h,2w,C] (bf16).  Cin % 64 == 0, C % 32 == 0, w % 16 == 0. */
+ * x_low[B,h,w,Cin] and dz[B,2h,2w,C] (bf16).  Cin % 64 == 0, C % 32 == 0. */
 int rvip_upconv_wgrad_halo(const void* x_low, const void* dz, float* dw, int B, int h, int w, int Cin, int C,
                            int transposed, void* stream);
 
