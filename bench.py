@@ -306,7 +306,12 @@ def run_b200(args):
                 'all_conv_tcgen05_tflops': round(conv_tf, 1), 'all_conv_frac': round(conv_tf / peak_tf, 4),
                 'step_tensor_frac': round(fl['train'] * B / (ms / K * 1e-3) / 1e12 / peak_tf, 4),
                 'kernels': kern}
-        cpu_rate, cores, spt = oracle_train_rate(n_slices=4, steps=2, warmup=1)
+        # CPU baseline: rank 0 at N = 1 only (under torchrun OMP_NUM_THREADS=1 and N ranks share the host cores)
+        cpu = None
+        if world == 1:
+            cpu_rate, cores, spt = oracle_train_rate(n_slices=4, steps=2, warmup=1)
+            cpu = {'value': round(cpu_rate, 3), 'unit': 'slices/s', 'cores': cores, 'kind': 'port',
+                   'sample': '4-slice fwd+bwd+Adam step x 2 (oracle, torch CPU fp32), %.2f s/step' % spt}
         line = {'metric': 'unet_train_slices_per_s_256', 'value': round(value, 1), 'unit': 'slices/s', 'n_gpus': world,
                 'steps': K, 'warmup': Wm, 'ms_per_step': round(ms / K, 4), 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
@@ -317,9 +322,10 @@ def run_b200(args):
                 'e2e': {'value': round(e2e, 1), 'unit': 'slices/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 8,
                         'ms_per_step': round(ms_e2e / K, 4), 'api': 'model.fit(Sequence of host batches)'},
                 'roofline': roof,
-                'cpu_baseline': {'value': round(cpu_rate, 3), 'unit': 'slices/s', 'cores': cores, 'kind': 'port',
-                                 'sample': '4-slice fwd+bwd+Adam step x 2 (oracle, torch CPU fp32), %.2f s/step' % spt}}
-        if not args.no_extra:
+                'cpu_baseline': cpu}
+        # secondary metrics build further models on this rank only: single-process runs only (a data-parallel model
+        # issues collectives the other ranks would never match)
+        if not args.no_extra and world == 1:
             line['extra'] = extra_measurements(model, dev)
         print(json.dumps(line))
     if world > 1:
@@ -422,10 +428,6 @@ def extra_measurements(model, dev):
 
 
 def main():
-    if 'RVIP_NCCL_DEBUG' in os.environ:     # default: leave NCCL silent so stdout carries only the one JSON line
-        os.environ['NCCL_DEBUG'] = os.environ['RVIP_NCCL_DEBUG']
-    else:
-        os.environ.pop('NCCL_DEBUG', None)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)

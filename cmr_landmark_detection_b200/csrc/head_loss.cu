@@ -243,6 +243,86 @@ int head_dice_sums_launch(const float* heat, const float* target, size_t n, doub
   return 0;
 }
 
+// ------------------------------------------------------------------------------------- validation loss / Dice metrics
+// One pass over a heat map and its target (both [P][NC] fp32): the sum of the per-pixel loss terms of the compiled loss
+// (model.evaluate / validation_data of fit, inference-mode heat maps) and, per channel, {sum t*p, sum p, sum t} -- the
+// three sums every dice_coef* metric of src/models/Loss_and_metrics.py:124-171 is made of.  out[0] += sum loss terms,
+// out[1 + 3c ..] += channel c's sums (double).  The host divides (mean over pixels, Dice ratio): no torch arithmetic.
+template <int NC>
+__global__ void __launch_bounds__(256) heat_stats_kernel(const float* __restrict__ heat, const float* __restrict__ tgt,
+                                                         const float* __restrict__ inplane, size_t P, uint32_t HW,
+                                                         int loss_kind, float mask_thr, float eps,
+                                                         double* __restrict__ out) {
+  float l = 0.f, s_tp[NC], s_p[NC], s_t[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) s_tp[k] = s_p[k] = s_t[k] = 0.f;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < P; i += (size_t)gridDim.x * 256) {
+    float p[NC], t[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      p[k] = heat[i * NC + k];
+      t[k] = tgt[i * NC + k];
+      s_tp[k] = fmaf(t[k], p[k], s_tp[k]);
+      s_p[k] += p[k];
+      s_t[k] += t[k];
+    }
+    float se = 0.f;
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      any = any || t[k] > mask_thr;
+      if (loss_kind == LOSS_BCE_DICE) {
+        const float pc = fminf(fmaxf(p[k], eps), 1.f - eps);
+        se -= t[k] * logf(pc + eps) + (1.f - t[k]) * logf(1.f - pc + eps);
+      } else {
+        const float d = p[k] - t[k];
+        se = fmaf(d, d, se);
+      }
+    }
+    se *= 1.f / (float)NC;
+    if (loss_kind == LOSS_MASKED || loss_kind == LOSS_WEIGHTED) se = any ? se : 0.f;
+    if (loss_kind == LOSS_WEIGHTED) se = fmaf(se, inplane[i % HW], eps);
+    l += se;
+  }
+  __shared__ double acc[1 + 3 * NC];
+  if (threadIdx.x < 1 + 3 * NC) acc[threadIdx.x] = 0.0;
+  __syncthreads();
+  l = warp_sum(l);
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    s_tp[k] = warp_sum(s_tp[k]);
+    s_p[k] = warp_sum(s_p[k]);
+    s_t[k] = warp_sum(s_t[k]);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&acc[0], (double)l);
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      atomicAdd(&acc[1 + 3 * k], (double)s_tp[k]);
+      atomicAdd(&acc[2 + 3 * k], (double)s_p[k]);
+      atomicAdd(&acc[3 + 3 * k], (double)s_t[k]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 1 + 3 * NC) atomicAdd(&out[threadIdx.x], acc[threadIdx.x]);
+}
+int heat_stats_launch(const float* heat, const float* target, const float* inplane, size_t n_pixels, int HW, int NC,
+                      int loss_kind, float mask_thr, double* out, cudaStream_t st) {
+  RVIP_REQUIRE(NC >= 1 && NC <= kMaxNC, "heat_stats: %d channels not in [1,%d]", NC, kMaxNC);
+  RVIP_REQUIRE(loss_kind != LOSS_WEIGHTED || inplane, "heat_stats: weighted loss needs in-plane weights");
+  RVIP_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * (1 + 3 * NC), st));
+  size_t g = (n_pixels + 255) / 256;
+  const int grid = (int)(g < (size_t)kNumSMs * 4 ? (g ? g : 1) : (size_t)kNumSMs * 4);
+  switch (NC) {
+    case 1: heat_stats_kernel<1><<<grid, 256, 0, st>>>(heat, target, inplane, n_pixels, HW, loss_kind, mask_thr, 1e-7f, out); break;
+    case 2: heat_stats_kernel<2><<<grid, 256, 0, st>>>(heat, target, inplane, n_pixels, HW, loss_kind, mask_thr, 1e-7f, out); break;
+    case 3: heat_stats_kernel<3><<<grid, 256, 0, st>>>(heat, target, inplane, n_pixels, HW, loss_kind, mask_thr, 1e-7f, out); break;
+    default: heat_stats_kernel<4><<<grid, 256, 0, st>>>(heat, target, inplane, n_pixels, HW, loss_kind, mask_thr, 1e-7f, out); break;
+  }
+  RVIP_LAUNCH_CHECK();
+  return 0;
+}
+
 int head_launch(const HeadArgs& a, int training, int is_bf16, cudaStream_t st) {
   RVIP_REQUIRE(a.Cin % 8 == 0 && a.Cin / 8 <= 32 && ((a.Cin / 8) & (a.Cin / 8 - 1)) == 0,
                "head: Cin=%d must be 8 * power of two <= 256", a.Cin);

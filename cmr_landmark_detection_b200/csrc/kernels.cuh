@@ -124,6 +124,11 @@ int head_launch(const HeadArgs& a, int training, int is_bf16, cudaStream_t st);
 // heat, target [n] fp32 -> sums[3] += {sum t*p, sum p, sum t} (double)
 int head_dice_sums_launch(const float* heat, const float* target, size_t n, double* sums, cudaStream_t st);
 
+// heat, target [n_pixels][NC] fp32 -> out[0] = sum of the per-pixel loss terms, out[1 + 3c ..] = {sum t*p, sum p, sum t}
+// of channel c (double; zeroed by the launch)
+int heat_stats_launch(const float* heat, const float* target, const float* inplane, size_t n_pixels, int HW, int NC,
+                      int loss_kind, float mask_thr, double* out, cudaStream_t st);
+
 // ------------------------------------------------------------------ landmark extraction (extract.cu)
 int extract_launch(const float* heat, int Z, int H, int W, int C, float thr, double* yx, int* count, int* argmax,
                    float* maxv, unsigned long long* scratch, cudaStream_t st);

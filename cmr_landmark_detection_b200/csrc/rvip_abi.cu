@@ -1347,6 +1347,13 @@ int rvip_set_bucket_event(rvip_handle* h, int index, void* ev) {
   return 0;
 }
 
+int rvip_heat_stats(const float* heat, const float* target, const float* inplane, long long n_pixels, int hw, int classes,
+                    int loss_kind, float mask_thr, double* out, void* stream) {
+  RVIP_REQUIRE(heat && target && out && n_pixels >= 0 && hw > 0, "rvip_heat_stats: bad argument");
+  return heat_stats_launch(heat, target, inplane, (size_t)n_pixels, hw, classes, loss_kind, mask_thr, out,
+                           (cudaStream_t)stream);
+}
+
 size_t rvip_extract_scratch_bytes(int Z, int C) { return extract_scratch_bytes(Z, C); }
 int rvip_extract(const float* heat, int Z, int H, int W, int C, float thr, double* yx, int* count, int* argmax,
                  float* maxv, void* scratch, void* stream) {

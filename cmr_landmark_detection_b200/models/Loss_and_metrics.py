@@ -43,3 +43,58 @@ def loss_with_zero_mask(loss=mse, mask_smaller_than=0.01, weight_inplane=False, 
         raise NotImplementedError('loss_with_zero_mask is implemented for loss=mse')
     return _DeviceLoss('weighted' if weight_inplane else 'masked', mask_smaller_than=float(mask_smaller_than),
                        xy_shape=int(xy_shape))
+
+
+def resolve_loss(loss):
+    """One place that turns whatever a caller hands over as a loss into a device-loss descriptor: a descriptor itself, a
+    Keras-style {'unet': loss} dict (Unets.py:130), or a config string -- train_model.py:178-184 selects BceDiceLoss by
+    the substring 'BcdDiceLoss' (its spelling) and falls back to MSE otherwise; 'mse' / 'mean_squared_error' are the
+    Keras string forms.  Returns None for None (keep the compiled loss)."""
+    if isinstance(loss, dict):
+        loss = loss.get('unet', next(iter(loss.values())))
+    if loss is None or hasattr(loss, 'rvip_kind'):
+        return loss
+    if isinstance(loss, str):
+        low = loss.lower()
+        if 'bcddiceloss' in low or 'bcedice' in low.replace('_', '') or low == 'bce_dice':
+            return BceDiceLoss()
+        if low in ('mse', 'mean_squared_error') or 'mse' in low:
+            return mse
+        if low in ('masked', 'weighted'):
+            return loss_with_zero_mask(weight_inplane=low == 'weighted')
+    raise NotImplementedError('loss %r is not implemented on the device path (MSE / masked / weighted MSE and '
+                              'BCE+Dice are)' % (loss,))
+
+
+class _DiceMetric:
+    """dice_coef restricted to a channel selection (Loss_and_metrics.py:124-171): smooth = 1,
+    (2 sum(t p) + 1) / (sum t + sum p + 1) over the WHOLE batch of the selected channels.  Evaluated from the three
+    per-channel sums rvip_heat_stats reduces on the device; Keras logs the mean of the per-batch values under the
+    function's name (and val_<name>), which is what MONITOR_FUNCTION / SAVE_MODEL_FUNCTION select."""
+
+    def __init__(self, name, select):
+        self.__name__ = name
+        self.name = name
+        self._select = select
+
+    def rvip_channels(self, n_classes):
+        idx = self._select(n_classes)
+        if isinstance(idx, int):
+            if not -n_classes <= idx < n_classes:
+                # tf: "slice index -3 of dimension 3 out of bounds" when the heat map has fewer channels
+                raise ValueError('%s selects channel %d of a %d-channel output' % (self.__name__, idx, n_classes))
+            idx = [idx % n_classes]
+        return list(idx)
+
+    def __call__(self, y_true, y_pred):
+        raise RuntimeError('device metrics are evaluated by rvip_heat_stats, not called from Python')
+
+
+dice_coef = _DiceMetric('dice_coef', lambda c: range(c))                               # :165-171
+dice_coef_labels = _DiceMetric('dice_coef_labels', lambda c: range(max(c - 3, 0), c))    # :154-161 y[..., -3:]
+dice_coef_background = _DiceMetric('dice_coef_background', lambda c: 0)                  # :124-127
+dice_coef_rv = _DiceMetric('dice_coef_rv', lambda c: -3)                                 # :129-132
+dice_coef_lower = _DiceMetric('dice_coef_lower', lambda c: -2)                           # :134-137
+dice_coef_upper = _DiceMetric('dice_coef_upper', lambda c: -1)                           # :139-142
+dice_coef_myo = _DiceMetric('dice_coef_myo', lambda c: -2)                               # :144-147
+dice_coef_lv = _DiceMetric('dice_coef_lv', lambda c: -1)                                 # :149-152

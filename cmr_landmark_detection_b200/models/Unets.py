@@ -4,14 +4,15 @@ import logging
 
 from ..runtime.model import RvipUNet
 from . import ModelUtils as mutils
-from .Loss_and_metrics import mse
+from .Loss_and_metrics import mse, resolve_loss
 
 
 def create_unet(config, metrics=None, networkname='unet', single_model=True, supervision=False):
     """Factory for the 2D RVIP heat-map U-Net.
     :param config: key/value pairs, UPPERCASE keys (exp/template_cfgs/example_config.json). Extra key
                    PRECISION ('bf16' default -> tcgen05 tensor cores, 'fp32' -> CUDA-core parity mode).
-    :param metrics: accepted for signature parity; Keras metric callables are not evaluated on device
+    :param metrics: dice_coef* descriptors of models/Loss_and_metrics.py (train_model.py:54-59); evaluated on the device
+                    per batch and logged under the Keras names (dice_coef_labels, val_dice_coef_labels, ...)
     :param networkname: model name (the head layer is called 'unet' like the reference's, Unets.py:128)
     :param single_model: True -> sigmoid head + compile, as every caller uses it (train_model.py:83)
     :param supervision: deep-supervision branch (Unets.py:840-863) -- off in all callers, not implemented
@@ -25,15 +26,7 @@ def create_unet(config, metrics=None, networkname='unet', single_model=True, sup
     if len(config.get('DIM', [224, 224])) != 2:
         raise NotImplementedError('only the 2D U-Net of the RVIP path is implemented')
     model = RvipUNet(config, name=networkname)
-    loss_f = config.get('LOSS_FUNCTION', mse)
-    if isinstance(loss_f, str) and 'BcdDiceLoss' in loss_f:          # train_model.py:178 (substring match, its spelling)
-        from .Loss_and_metrics import BceDiceLoss
-        loss_f = BceDiceLoss()
-    if isinstance(loss_f, str) and 'mse' not in loss_f.lower():
-        # train_model.py:178-184 picks BceDiceLoss by substring, otherwise MSE
-        raise NotImplementedError('LOSS_FUNCTION=%r is not implemented (mse / BcdDiceLoss are)' % loss_f)
-    if isinstance(loss_f, str):
-        loss_f = mse
+    loss_f = resolve_loss(config.get('LOSS_FUNCTION', mse))          # config strings: train_model.py:178-184
     model.compile(optimizer=mutils.get_optimizer(config, networkname), loss={'unet': loss_f}, metrics=metrics)
     logging.info('created %s: %d parameters', networkname, model.count_params())
     return model

@@ -23,6 +23,14 @@ def get_ip_from_rvip_mask_3d(msk_3d, debug=False, keepdim=False, both_only=True)
     return points_from_stats(r['yx'].cpu().numpy(), r['count'].cpu().numpy(), keepdim=keepdim, both_only=both_only)
 
 
+def get_ip_from_rvip_file(f_name, keepdim=False, both_only=True):
+    """evaluate_cv.py:385-387: label volume file -> insertion points.  The reference reads through SimpleITK; the .nrrd
+    volumes pred_fold writes here are read by utils/nrrd_io.py."""
+    from ..utils.nrrd_io import read_nrrd
+    vol, _ = read_nrrd(f_name)
+    return get_ip_from_rvip_mask_3d(vol, keepdim=keepdim, both_only=both_only)
+
+
 def get_mean_rvip_2d(nda_2d, both_only=False):
     """evaluate_cv.py:418-442."""
     nda_2d = np.asarray(nda_2d)

@@ -52,9 +52,9 @@ def bucket_ranges(layer_offsets: Sequence[int], total: int, n_buckets: int = 4) 
 
 
 class DataParallel:
-    def __init__(self, device):
+    def __init__(self, device, enabled: bool = True):
         self.device = device
-        self.enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.enabled = bool(enabled) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.world = dist.get_world_size() if self.enabled else 1
         self.rank = dist.get_rank() if self.enabled else 0
         self._comm_stream = None
@@ -89,6 +89,16 @@ class DataParallel:
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             t /= self.world
         return t
+
+    def mean_floats(self, vals: Sequence[float]) -> List[float]:
+        """Mean over replicas of a few host scalars (epoch logs: every rank must make the SAME callback decisions,
+        or a checkpoint's collective on some ranks pairs with a gradient bucket on others)."""
+        if not self.enabled:
+            return [float(v) for v in vals]
+        dev = self.device if dist.get_backend() == 'nccl' else 'cpu'
+        t = torch.tensor([float(v) for v in vals], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) / self.world for v in t.cpu().tolist()]
 
     def max_float(self, v: float) -> float:
         if not self.enabled:

@@ -55,6 +55,7 @@ _SIGS = {
     'rvip_predict': (_I, [_VP, _VP, _VP, _VP]),
     'rvip_train_step': (_I, [_VP, _VP, _VP, _VP, _I, _F, C.c_uint64, _VP, _VP, _VP]),
     'rvip_set_loss_weights': (_I, [_VP, _F, _F]),
+    'rvip_heat_stats': (_I, [_VP, _VP, _VP, _LL, _I, _I, _I, _F, _VP, _VP]),
     'rvip_adam_step': (_I, [_VP, _VP, _VP, _F, _F, _F, _F, _LL, _F, _VP]),
     'rvip_sgd_step': (_I, [_VP, _VP, _F, _F, _I, _F, _VP]),
     'rvip_num_buckets': (_I, [_VP]),

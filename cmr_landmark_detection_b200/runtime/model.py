@@ -194,9 +194,14 @@ class RvipUNet:
         self.metrics = []
         self.stop_training = False
         self._step = 0
+        self._metric_rows = []
         self._seed = int(config.get('SEED', 42))
         self._loss_dev = torch.zeros(1, dtype=torch.float64, device=self.device)
-        self.dp = DataParallel(self.device)
+        # MirroredStrategy equivalent (Unets.py:70-75): on when torch.distributed is initialised with > 1 ranks.
+        # DATA_PARALLEL=False builds a rank-local model inside a multi-rank job (no collectives are ever issued).
+        self.dp = DataParallel(self.device, enabled=bool(config.get('DATA_PARALLEL', True)))
+        self.max_bindings = int(config.get('MAX_BINDINGS', 4))
+        self._metric_buf = None
         self.set_weights(self._initial_weights(self._seed))
 
     # ------------------------------------------------------------------ weights
@@ -334,18 +339,18 @@ class RvipUNet:
             if not isinstance(optimizer, (Adam, SGD)):
                 raise NotImplementedError('only the Adam and SGD optimizers are implemented on the device path')
             self.optimizer = optimizer
-        if isinstance(loss, dict):
-            loss = loss.get('unet', next(iter(loss.values())))
+        from ..models.Loss_and_metrics import resolve_loss
+        loss = resolve_loss(loss)
         if loss is not None:
-            kind = getattr(loss, 'rvip_kind', loss if isinstance(loss, str) else None)
-            if isinstance(kind, str):
-                kind = kind.lower().replace('mean_squared_error', 'mse')
-            if kind not in ffi.LOSS_KINDS:
-                raise NotImplementedError('loss %r is not implemented on the device path (MSE / masked / weighted '
-                                          'MSE and BCE+Dice are)' % (loss,))
-            self.loss_kind = kind
-            self.loss_args = dict(getattr(loss, 'rvip_args', {'mask_smaller_than': 0.01}))
-        self.metrics = list(metrics or [])
+            self.loss_kind = loss.rvip_kind
+            self.loss_args = dict(getattr(loss, 'rvip_args', None) or {'mask_smaller_than': 0.01})
+        self.metrics = []
+        for m in (metrics or []):
+            if not hasattr(m, 'rvip_channels'):
+                raise NotImplementedError('metric %r is not implemented on the device path (the dice_coef* family of '
+                                          'models/Loss_and_metrics.py is)' % (m,))
+            m.rvip_channels(self._cfg.classes)       # raises for a channel the model does not have
+            self.metrics.append(m)
         if self.loss_kind == 'weighted':
             H, W = self._cfg.H, self._cfg.W
             yy, xx = np.mgrid[0:H, 0:W]
@@ -359,10 +364,16 @@ class RvipUNet:
     # ------------------------------------------------------------------ plumbing
     def _binding(self, batch: int, training: bool) -> _Binding:
         key = (batch, training)
-        b = self._bindings.get(key)
+        b = self._bindings.pop(key, None)
         if b is None:
+            # every binding owns a full workspace (GBs at training sizes): keep the most recently used few
+            # (ragged last batches, volumes of varying depth) and release the rest
+            while len(self._bindings) >= max(self.max_bindings, 1):
+                old_key = next(iter(self._bindings))
+                torch.cuda.current_stream(self.device).synchronize()
+                self._bindings.pop(old_key).close()
             b = _Binding(self, batch, training)
-            self._bindings[key] = b
+        self._bindings[key] = b           # dict order = least recently used first
         if b.packed_version != self._version:
             ffi.check(ffi.lib().rvip_pack_weights(b.h, self._stream()))
             b.packed_version = self._version
@@ -379,15 +390,28 @@ class RvipUNet:
             self._pinned[key] = t
         return t
 
-    def _check_x(self, x: np.ndarray):
+    def _check_x(self, x):
         if x.ndim != 4 or tuple(x.shape[1:]) != (self._cfg.H, self._cfg.W, self._cfg.in_ch):
             raise ValueError('expected input [N,%d,%d,%d], got %s' % (self._cfg.H, self._cfg.W, self._cfg.in_ch,
                                                                         tuple(x.shape)))
+
+    def _check_y(self, y, n: int):
+        if y.ndim != 4 or tuple(y.shape) != (n, self._cfg.H, self._cfg.W, self._cfg.classes):
+            raise ValueError('expected target [%d,%d,%d,%d], got %s' % (n, self._cfg.H, self._cfg.W, self._cfg.classes,
+                                                                         tuple(y.shape)))
+
+    def _check_dev(self, t: torch.Tensor, what: str):
+        # raw pointers cross the C ABI: the kernels read dense fp32 NHWC on this model's device
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device:
+            raise ValueError('%s must be a contiguous float32 tensor on %s (got %s, %s, contiguous=%s)'
+                             % (what, self.device, t.dtype, t.device, t.is_contiguous()))
 
     # ------------------------------------------------------------------ inference
     def predict_device(self, x_dev: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """x_dev [B,H,W,in_ch] fp32 on the device -> heat [B,H,W,classes] fp32 (device)."""
         B = x_dev.shape[0]
+        self._check_x(x_dev)
+        self._check_dev(x_dev, 'x')
         b = self._binding(B, False)
         if out is None:
             out = torch.empty((B, self._cfg.H, self._cfg.W, self._cfg.classes), dtype=torch.float32, device=self.device)
@@ -431,9 +455,14 @@ class RvipUNet:
             raise RuntimeError('compile(optimizer=...) first')
         L = ffi.lib()
         B = x_dev.shape[0]
+        self._check_x(x_dev)
+        self._check_y(y_dev, B)
+        self._check_dev(x_dev, 'x')
+        self._check_dev(y_dev, 'y')
         b = self._binding(B, True)
         if heat is None:
             heat = self._heat_buf(B)
+        self._last_heat = heat
         self._step += 1
         seed = (self._seed * 1000003 + self._step) ^ (self.dp.rank << 40)
         thr = float(self.loss_args.get('mask_smaller_than', 0.01))
@@ -491,6 +520,7 @@ class RvipUNet:
         x = np.ascontiguousarray(x, dtype=np.float32)
         y = np.ascontiguousarray(y, dtype=np.float32)
         self._check_x(x)
+        self._check_y(y, len(x))
         with torch.cuda.device(self.device):
             hx = self._pin('tx', x.shape)
             hy = self._pin('ty', y.shape)
@@ -501,7 +531,7 @@ class RvipUNet:
             loss = self.train_step_device(xd, yd)
             return float(loss.item())
 
-    def _run_steps(self, batches) -> List[float]:
+    def _run_steps(self, batches, with_metrics: bool = False) -> List[float]:
         """Pipelined training steps over an iterable of host (x, y) batches -- the loop inside fit().
 
         Two staging slots: while the GPU runs step i, the host copies batch i+1 into pinned memory and a side
@@ -509,6 +539,8 @@ class RvipUNet:
         has been queued, so the device never waits for the host.  Every step still pays its own H2D copy of
         (x, y) and its own D2H read of the loss."""
         losses: List[float] = []
+        self._metric_rows: List[int] = []       # pixels per step whose heat statistics sit in self._metric_buf
+        nrow = 1 + 3 * self._cfg.classes
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream(self.device)
             if not hasattr(self, '_copy_stream'):
@@ -524,6 +556,7 @@ class RvipUNet:
                 x = np.ascontiguousarray(x, dtype=np.float32)
                 y = np.ascontiguousarray(y, dtype=np.float32)
                 self._check_x(x)
+                self._check_y(y, len(x))
                 s = i & 1
                 ev = self._slot_ev[s]
                 if used_once[s]:
@@ -545,6 +578,15 @@ class RvipUNet:
                     ev['ready'].record(cs)
                 main.wait_event(ev['ready'])
                 loss_dev = self.train_step_device(xd, yd)
+                if with_metrics:
+                    # training metrics: one reduction pass over this step's heat map and target, rows stay on the device
+                    if self._metric_buf is None or self._metric_buf.shape[0] <= i:
+                        grown = torch.zeros((max(256, 2 * (i + 1)), nrow), dtype=torch.float64, device=self.device)
+                        if self._metric_buf is not None:
+                            grown[:self._metric_buf.shape[0]] = self._metric_buf
+                        self._metric_buf = grown
+                    self._stats_row(self._last_heat, yd, self._metric_buf[i])
+                    self._metric_rows.append(len(x) * self._cfg.H * self._cfg.W)
                 ev['used'].record(main)
                 self._loss_pin[s].copy_(loss_dev.reshape(1), non_blocking=True)
                 ev['loss'].record(main)
@@ -558,43 +600,82 @@ class RvipUNet:
                 losses.append(float(self._loss_pin[pending][0]))
         return losses
 
-    def evaluate(self, x, y=None, batch_size=32, verbose=0) -> float:
-        """Validation loss (inference mode): device forward (rvip_predict), heat maps stay on the GPU and the scalar
-        reduction runs there with torch CUDA ops (validation bookkeeping, not the training hot path)."""
-        tot, n = 0.0, 0
+    # ------------------------------------------------------------------ loss / metric bookkeeping
+    def _metric_names(self) -> List[str]:
+        return [m.__name__ for m in self.metrics]
+
+    def _stats_row(self, heat: torch.Tensor, y_dev: torch.Tensor, out: torch.Tensor):
+        """rvip_heat_stats: out[0] = sum of the compiled loss's per-pixel terms, out[1 + 3c ..] = {sum t p, sum p, sum t}."""
+        thr = float(self.loss_args.get('mask_smaller_than', 0.01))
+        n_pix = heat.shape[0] * self._cfg.H * self._cfg.W
+        ffi.check(ffi.lib().rvip_heat_stats(ffi.ptr(heat), ffi.ptr(y_dev), ffi.ptr(self._inplane), n_pix,
+                                            self._cfg.H * self._cfg.W, self._cfg.classes,
+                                            ffi.LOSS_KINDS[self.loss_kind], thr, ffi.ptr(out), self._stream()))
+
+    def _finish_stats(self, row: np.ndarray, n_pix: int) -> Dict[str, float]:
+        """Host end of rvip_heat_stats for ONE batch: the loss value Keras logs and every compiled metric."""
+        C_ = self._cfg.classes
+        tp, sp, st = row[1::3][:C_], row[2::3][:C_], row[3::3][:C_]
+        out = {'loss': float(row[0]) / n_pix}
+        if self.loss_kind == 'bce_dice':
+            dice = (2.0 * tp.sum() + 1.0) / (st.sum() + sp.sum() + 1.0)
+            out['loss'] = float(self.loss_args.get('w_bce', 1.0)) * out['loss'] - float(self.loss_args.get('w_dice', 1.0)) * dice
+        for m in self.metrics:
+            ch = m.rvip_channels(C_)
+            out[m.__name__] = float((2.0 * tp[ch].sum() + 1.0) / (st[ch].sum() + sp[ch].sum() + 1.0))
+        return out
+
+    def _shard(self, x, y=None, per_replica: bool = False):
+        """MirroredStrategy shards every global batch over the replicas (Unets.py:70-75): rank r owns samples
+        [r * per, (r + 1) * per).  per_replica: the caller already hands out this rank's own batches."""
+        if self.dp.world == 1 or per_replica:
+            return (x, y)
+        from .dist import shard_range
+        lo, hi = shard_range(len(x), self.dp.rank, self.dp.world)
+        return (x[lo:hi], None if y is None else y[lo:hi])
+
+    def evaluate(self, x, y=None, batch_size=32, verbose=0, return_dict=False):
+        """Validation loss (+ compiled metrics) in inference mode, Keras' batch-size-weighted mean over batches: device
+        forward (rvip_predict), then ONE reduction kernel per batch over heat map and target (rvip_heat_stats); only the
+        1 + 3 C sums come back to the host."""
         if isinstance(x, np.ndarray):
             items = ((x[i:i + batch_size], y[i:i + batch_size]) for i in range(0, len(x), batch_size))
+            per_replica = False
         else:
-            items = (x[i] for i in range(len(x)))
-        for xb, yb in items:
-            xb = np.ascontiguousarray(xb, dtype=np.float32)
-            self._check_x(xb)
-            with torch.cuda.device(self.device):
-                p = self.predict_device(torch.from_numpy(xb).to(self.device)).clone()
-                t = torch.from_numpy(np.ascontiguousarray(yb, dtype=np.float32)).to(self.device)
-            if self.loss_kind == 'bce_dice':
-                e = 1e-7
-                pc = p.clamp(e, 1 - e)
-                bce = -(t * torch.log(pc + e) + (1 - t) * torch.log(1 - pc + e)).mean(dim=-1)
-                dice = (2 * (t * p).sum() + 1) / (t.sum() + p.sum() + 1)
-                per = float(self.loss_args.get('w_bce', 1.0)) * bce - float(self.loss_args.get('w_dice', 1.0)) * dice
-                tot += float(per.mean()) * len(xb)
+            items = (x[i][:2] for i in range(len(x)))
+            per_replica = bool(getattr(x, 'rvip_per_replica', False))
+        tot: Dict[str, float] = {}
+        n = 0
+        nrow = 1 + 3 * self._cfg.classes
+        with torch.cuda.device(self.device):
+            row_dev = torch.zeros(nrow, dtype=torch.float64, device=self.device)
+            for xb, yb in items:
+                xb, yb = self._shard(xb, yb, per_replica)
+                if len(xb) == 0:
+                    continue
+                xb = np.ascontiguousarray(xb, dtype=np.float32)
+                yb = np.ascontiguousarray(yb, dtype=np.float32)
+                self._check_x(xb)
+                self._check_y(yb, len(xb))
+                heat = self.predict_device(torch.from_numpy(xb).to(self.device))
+                self._stats_row(heat, torch.from_numpy(yb).to(self.device), row_dev)
+                vals = self._finish_stats(row_dev.cpu().numpy(), len(xb) * self._cfg.H * self._cfg.W)
+                for k, v in vals.items():
+                    tot[k] = tot.get(k, 0.0) + v * len(xb)
                 n += len(xb)
-                continue
-            per = ((p - t) ** 2).mean(dim=-1)
-            if self.loss_kind != 'mse':
-                per = per * (t > self.loss_args.get('mask_smaller_than', 0.01)).any(dim=-1).float()
-                if self.loss_kind == 'weighted':
-                    per = per * self._inplane[None] + 1e-7
-            tot += float(per.mean()) * len(xb)
-            n += len(xb)
-        return tot / max(n, 1)
+        keys = ['loss'] + self._metric_names()
+        vals = self.dp.mean_floats([tot.get(k, 0.0) for k in keys] + [float(n)])
+        res = {k: v / max(vals[-1], 1e-30) for k, v in zip(keys, vals[:-1])}
+        return res if return_dict else res['loss']
 
     def fit(self, x=None, y=None, batch_size=None, epochs=1, verbose=1, callbacks=None, validation_data=None,
             shuffle=True, initial_epoch=0, steps_per_epoch=None, max_queue_size=10, workers=1,
             use_multiprocessing=False, **kw) -> History:
         """Epoch/step loop with the Keras callback protocol (train_model.py:105-112). `x` is an ndarray
-        (with `y`) or a keras.utils.Sequence-like object (len / getitem -> (x, y) / on_epoch_end)."""
+        (with `y`) or a keras.utils.Sequence-like object (len / getitem -> (x, y) / on_epoch_end).
+        Data parallel (one process per GPU): every rank iterates the same global batches and trains on its shard;
+        the epoch logs are averaged over the ranks before any callback sees them, so checkpoint / learning-rate /
+        early-stopping decisions (and the collectives behind save_weights) are identical everywhere."""
         hist = History()
         callbacks = list(callbacks or [])
         for cb in callbacks:
@@ -605,28 +686,39 @@ class RvipUNet:
             if hasattr(cb, 'on_train_begin'):
                 cb.on_train_begin({})
         is_seq = not isinstance(x, np.ndarray)
+        per_replica = bool(getattr(x, 'rvip_per_replica', False)) if is_seq else False
         bs = int(batch_size or 32)
-        rng = np.random.default_rng(self._seed)
+        rng = np.random.default_rng(self._seed)        # same permutation on every rank: identical global batches
+        mnames = self._metric_names()
         for epoch in range(initial_epoch, epochs):
             for cb in callbacks:
                 if hasattr(cb, 'on_epoch_begin'):
                     cb.on_epoch_begin(epoch, {})
             t0 = time.time()
-            losses = []
             if is_seq:
                 n_steps = len(x) if steps_per_epoch is None else steps_per_epoch
-                losses = self._run_steps(tuple(x[i][:2]) for i in range(n_steps))
+                gen = (self._shard(*tuple(x[i][:2]), per_replica) for i in range(n_steps))
             else:
                 order = rng.permutation(len(x)) if shuffle else np.arange(len(x))
-                n_steps = len(x) // bs if steps_per_epoch is None else steps_per_epoch
-                losses = self._run_steps((x[order[i * bs:(i + 1) * bs]], y[order[i * bs:(i + 1) * bs]])
-                                         for i in range(max(n_steps, 1)))
-            logs = {'loss': float(np.mean(losses)) if losses else float('nan'), 'lr': self.optimizer.lr}
+                n_steps = -(-len(x) // bs) if steps_per_epoch is None else steps_per_epoch     # Keras: ceil
+                gen = (self._shard(x[order[i * bs:(i + 1) * bs]], y[order[i * bs:(i + 1) * bs]])
+                       for i in range(max(n_steps, 1)))
+            losses = self._run_steps(gen, with_metrics=bool(mnames))
+            logs = {'loss': float(np.mean(losses)) if losses else float('nan')}
+            for k, v in self._epoch_metrics().items():
+                logs[k] = v
             if validation_data is not None:
                 if isinstance(validation_data, (tuple, list)):
-                    logs['val_loss'] = self.evaluate(validation_data[0], validation_data[1], batch_size=bs)
+                    val = self.evaluate(validation_data[0], validation_data[1], batch_size=bs, return_dict=True)
                 else:
-                    logs['val_loss'] = self.evaluate(validation_data)
+                    val = self.evaluate(validation_data, return_dict=True)
+                for k, v in val.items():
+                    logs['val_' + k] = v
+            if self.dp.world > 1:
+                train_keys = [k for k in logs if not k.startswith('val_')]      # val_* are already global
+                for k, v in zip(train_keys, self.dp.mean_floats([logs[k] for k in train_keys])):
+                    logs[k] = v
+            logs['lr'] = self.optimizer.lr
             if is_seq and hasattr(x, 'on_epoch_end'):
                 x.on_epoch_end()
             hist.epoch.append(epoch)
@@ -645,6 +737,19 @@ class RvipUNet:
                 cb.on_train_end({})
         self.history = hist
         return hist
+
+    def _epoch_metrics(self) -> Dict[str, float]:
+        """Keras logs a compiled metric as the mean of its per-batch values: finish the rows rvip_heat_stats left on the
+        device during the epoch's training steps."""
+        if not self.metrics or not self._metric_rows:
+            return {}
+        rows = self._metric_buf[:len(self._metric_rows)].cpu().numpy()
+        acc: Dict[str, float] = {}
+        for row, n_pix in zip(rows, self._metric_rows):
+            for k, v in self._finish_stats(row, n_pix).items():
+                if k != 'loss':
+                    acc[k] = acc.get(k, 0.0) + v
+        return {k: v / len(rows) for k, v in acc.items()}
 
     # ------------------------------------------------------------------ introspection (tests / bench)
     def debug_buffer(self, layer: str, which: int, batch: int, training: bool) -> Optional[torch.Tensor]:

@@ -80,6 +80,15 @@ int rvip_train_step(rvip_handle* h, const float* x, const float* target, const f
 
 int rvip_set_loss_weights(rvip_handle* h, float w_bce, float w_dice);
 
+/* ---- validation loss and Dice metrics (model.evaluate / fit(validation_data=...), train_model.py:54-59, 105-112;
+ * src/models/Loss_and_metrics.py:124-171): one pass over heat and target [n_pixels][classes] fp32.
+ * out (device, 1 + 3 * classes doubles, zeroed by the call): out[0] = sum over pixels of the compiled loss's per-pixel
+ * term (MSE: mean_c (p - t)^2; masked / weighted: loss_with_zero_mask; BCE+Dice: mean_c binary cross-entropy),
+ * out[1 + 3c ..] = {sum t*p, sum p, sum t} of channel c, from which every dice_coef* metric follows.  hw = H * W
+ * (period of the in-plane weights, only read for RVIP_LOSS_WEIGHTED). */
+int rvip_heat_stats(const float* heat, const float* target, const float* inplane, long long n_pixels, int hw, int classes,
+                    int loss_kind, float mask_thr, double* out, void* stream);
+
 /* ---- Adam apply (ModelUtils.py:107; Keras epsilon-hat form) + operand re-pack.
  * grad_scale folds the data-parallel 1/world into the update. step counts from 1. */
 int rvip_adam_step(rvip_handle* h, float* m, float* v, float lr, float beta1, float beta2, float eps, long long step,

@@ -1,0 +1,121 @@
+"""Worker of tests/test_gpu_dp.py: one process per GPU under torchrun (NCCL).  Checks, on the CUDA path, what
+tf.distribute.MirroredStrategy guarantees for create_unet (src/models/Unets.py:70-75; SURVEY 8e "Equivalence test"):
+
+  grads   : every rank ends a step with the SUM over replicas of its local-mean-loss gradients; Adam's grad_scale 1/world
+            turns it into oracle.data_parallel_grads' mean
+  BN      : batch statistics stay per replica; moving statistics are averaged over replicas on read (get_weights)
+  fit     : with the reference's callback list every rank sees identical logs, so ModelCheckpoint / ReduceLROnPlateau /
+            EarlyStopping decide identically (no mismatched collectives), and replicas stay bit-identical
+Exit code 0 = all assertions held on this rank."""
+import os
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+def main():
+    from cmr_landmark_detection_b200 import synth
+    from cmr_landmark_detection_b200.models.Unets import create_unet
+    from cmr_landmark_detection_b200.runtime import dist as rdist
+    from cmr_landmark_detection_b200.utils.KerasCallbacks import get_callbacks
+    from oracle import unet_ref as R
+    rank, local, world = rdist.init_from_env()
+    assert world >= 2
+    torch.cuda.set_device(local)
+    precision = sys.argv[1] if len(sys.argv) > 1 else 'fp32'
+    config = {'DIM': [64, 64], 'DEPTH': 2, 'FILTERS': 32, 'IMG_CHANNELS': 1, 'MASK_CLASSES': 2,
+              'BATCH_NORMALISATION': True, 'BN_FIRST': False, 'ACTIVATION': 'relu', 'PAD': 'same', 'DROPOUT_MIN': 0.0,
+              'DROPOUT_MAX': 0.0, 'LEARNING_RATE': 1e-3, 'M_POOL': [2, 2], 'F_SIZE': [3, 3], 'SEED': 7,
+              'PRECISION': precision}
+    per = 3
+    model = create_unet(config)
+    assert model.dp.world == world and model.dp.enabled
+    cfg = R.cfg_from_config(config)
+    ws = R.init_weights(cfg, seed=11, randomize_bn=False)
+    model.set_weights(ws)
+    x, y = synth.make_batch(per * world, 64, 64, seed=5)          # the GLOBAL batch, identical on every rank
+    xs, ys = x[rank * per:(rank + 1) * per], y[rank * per:(rank + 1) * per]
+
+    # ---- one step: all-reduced gradients vs the oracle's replica mean
+    loss = float(model.train_step_device(torch.from_numpy(xs).cuda(), torch.from_numpy(ys).cuda(),
+                                         apply_optimizer=False).item())
+    torch.cuda.synchronize()
+    ref = R.data_parallel_grads(cfg, ws, x, y, world)
+    assert abs(loss - ref['per_rank'][rank]['loss']) <= (1e-5 if precision == 'fp32' else 1e-2) * abs(loss), (loss,)
+    g = model.grads.cpu().numpy() / world
+    lim = 3e-3 if precision == 'fp32' else 0.15
+    worst = 0.0
+    for (name, is_state, off, shape), rg in zip(model.tensors, ref['grads']):
+        if is_state or np.linalg.norm(rg) < 1e-12:
+            continue
+        mine = g[off:off + int(np.prod(shape))].reshape(shape).astype(np.float64)
+        e = float(np.linalg.norm(mine - rg) / np.linalg.norm(rg))
+        worst = max(worst, e)
+        if precision == 'fp32' or name.startswith(('head/', 'dec1.conv_b/kernel')):
+            assert e <= lim, (name, e)
+    # every rank holds the same reduced buffer
+    gsum = torch.tensor([float(np.abs(g).sum())], dtype=torch.float64, device='cuda')
+    gl = [torch.zeros_like(gsum) for _ in range(world)]
+    torch.distributed.all_gather(gl, gsum)
+    assert all(float(t) == float(gl[0]) for t in gl), gl
+
+    # ---- BN moving statistics: per replica on the device, replica mean on read
+    local_state = model.bn_state.cpu().numpy().copy()
+    mine = model.get_weights()
+    new = R.apply_new_stats(cfg, ws, ref['new_stats'])
+    own = R.apply_new_stats(cfg, ws, ref['per_rank'][rank]['new_stats'])
+    tol = dict(rtol=1e-4, atol=1e-6) if precision == 'fp32' else dict(rtol=5e-2, atol=1e-3)
+    for (name, is_state, off, shape), a, b, c in zip(model.tensors, mine, new, own):
+        if is_state:
+            assert np.allclose(a, b, **tol), name                                        # averaged on read
+            assert np.allclose(local_state[off:off + a.size].reshape(shape), c, **tol), name   # per replica underneath
+
+    # ---- Adam with grad_scale = 1 / world == oracle Adam on the mean gradient (fp32)
+    model.apply_gradients()
+    if precision == 'fp32':
+        gl_ = [None if st else (model.grads.cpu().numpy() / world)[off:off + int(np.prod(shp))].reshape(shp)
+               for (nm, st, off, shp) in model.tensors]
+        stepped = R.Adam(lr=1e-3).step(ws, gl_)
+        for (name, is_state, off, shape), a, b in zip(model.tensors, model.get_weights(), stepped):
+            if not is_state:
+                assert np.allclose(a, b, rtol=1e-5, atol=1e-7), name
+
+    # ---- fit() with the reference's callbacks: rank-local losses differ (different shards), decisions must not
+    tmp = tempfile.mkdtemp() if rank == 0 else None
+    box = [tmp]
+    torch.distributed.broadcast_object_list(box, src=0)
+    fcfg = dict(config, MODEL_PATH=os.path.join(box[0], 'model'), TENSORBOARD_PATH=os.path.join(box[0], 'tb'),
+                MONITOR_FUNCTION='val_loss', SAVE_MODEL_FUNCTION='val_loss', REDUCE_LR_ON_PLAEAU_PATIENCE=1,
+                EARLY_STOPPING_PATIENCE=3, LEARNING_RATE=5e-3)
+    from cmr_landmark_detection_b200.models import Loss_and_metrics as metr
+    m2 = create_unet(fcfg, metrics=[metr.dice_coef_labels, metr.dice_coef_upper])
+    xa, ya = synth.make_batch(4 * per * world, 64, 64, seed=9)
+    xv, yv = synth.make_batch(2 * per * world, 64, 64, seed=10)
+    h = m2.fit(xa, ya, batch_size=per * world, epochs=6, callbacks=get_callbacks(fcfg), validation_data=(xv, yv),
+               verbose=0)
+    keys = sorted(h.history)
+    assert 'val_loss' in keys and 'dice_coef_labels' in keys and 'val_dice_coef_upper' in keys, keys
+    flat = torch.tensor([v for k in keys for v in h.history[k]], dtype=torch.float64, device='cuda')
+    fl = [torch.zeros_like(flat) for _ in range(world)]
+    torch.distributed.all_gather(fl, flat)
+    assert all(torch.equal(t, fl[0]) for t in fl), 'epoch logs differ between ranks'
+    psum = m2.params.double().sum().reshape(1)
+    pl = [torch.zeros_like(psum) for _ in range(world)]
+    torch.distributed.all_gather(pl, psum)
+    assert all(float(t) == float(pl[0]) for t in pl), 'replicas diverged'
+    if rank == 0:
+        assert os.path.exists(os.path.join(fcfg['MODEL_PATH'], 'model.h5')) or \
+            os.path.exists(os.path.join(fcfg['MODEL_PATH'], 'model.h5.npz'))
+        print('dp_worker ok: world %d, %s, worst gradient rel-L2 %.3g, %d epochs' % (world, precision, worst,
+                                                                                      len(h.history['loss'])))
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -140,7 +140,11 @@ def test_first_layer_mappings_agree(precision, monkeypatch):
 
 
 @pytest.mark.parametrize('precision,dim,depth,batch', [('fp32', 32, 2, 3), ('bf16', 32, 2, 4), ('fp32', 64, 4, 2),
-                                                       ('bf16', 64, 4, 4), ('bf16', 128, 4, 2), ('bf16', 112, 3, 2)])
+                                                       ('bf16', 64, 4, 4), ('bf16', 128, 4, 2), ('bf16', 112, 3, 2),
+                                                       # BASELINE config C2's own shapes (256 x 256, depth 4, 32 filters):
+                                                       # two 128-pixel row tiles per image row, the row-merged level-0
+                                                       # weight gradient, the 256 x 256 BatchNorm passes
+                                                       ('fp32', 256, 4, 4), ('bf16', 256, 4, 4)])
 def test_train_step_matches_oracle(precision, dim, depth, batch):
     from oracle import unet_ref as R
     model, cfg, ws, x, y = _setup(precision, dim, depth, batch, randomize_bn=False)
@@ -561,3 +565,63 @@ def test_non_square_odd_batch_matches_oracle(dim, depth, batch):
             continue
         mine = g[off:off + int(np.prod(shape))].reshape(shape).astype(np.float64)
         assert np.linalg.norm(mine - rg) <= 7e-2 * np.linalg.norm(rg), name
+
+
+def test_bf16_training_trajectory_tracks_fp32_oracle():
+    """The bf16 device path must TRAIN like the fp32 oracle, not only match it at random init: 30 Adam steps on a small
+    net (cycling three fixed batches, dropout off) -- the two loss curves stay within a stated band of one another --
+    and then the per-tensor gradient check is repeated at the trained weights (BatchNorm gamma / beta away from 1 / 0,
+    non-zero biases), against SURVEY 8c's bf16 tolerance where the problem is well conditioned.  The measured numbers go
+    to gpurun_out/trajectory_grad_parity.json (DESIGN section 2 quotes them)."""
+    import json
+    from cmr_landmark_detection_b200 import synth
+    from oracle import unet_ref as R
+    model, cfg, ws, _, _ = _setup('bf16', 32, 2, 4, randomize_bn=False, seed=6)
+    batches = [synth.make_batch(4, 32, 32, seed=40 + i) for i in range(3)]
+    opt = R.Adam(lr=1e-3)
+    cur = [w.copy() for w in ws]
+    ref_curve, dev_curve = [], []
+    for i in range(30):
+        x, y = batches[i % 3]
+        out = R.train_grads(cfg, cur, x, y)
+        cur = opt.step(R.apply_new_stats(cfg, cur, out['new_stats']), out['grads'])
+        ref_curve.append(out['loss'])
+        dev_curve.append(model.train_on_batch(x, y))
+    ref_curve, dev_curve = np.array(ref_curve), np.array(dev_curve)
+    assert ref_curve[-3:].mean() < 0.7 * ref_curve[:3].mean()            # the oracle actually trained
+    band = np.abs(dev_curve - ref_curve) / ref_curve
+    assert band.max() <= 5e-2, (band.max(), dev_curve.tolist(), ref_curve.tolist())
+    # gradient parity at the device's trained weights
+    wt = model.get_weights()
+    x, y = batches[0]
+    ref = R.train_grads(cfg, wt, x, y)
+    cal = R.train_grads(cfg, wt, x, y, storage='bf16', phased_up=True)
+    model.train_step_device(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), apply_optimizer=False)
+    g = model.grads.cpu().numpy()
+    rows = {}
+    for (name, is_state, off, shape), rg, cg in zip(model.tensors, ref['grads'], cal['grads']):
+        if is_state or np.linalg.norm(rg) < 1e-12:
+            continue
+        mine = g[off:off + int(np.prod(shape))].reshape(shape).astype(np.float64)
+        rg = rg.astype(np.float64)
+        cos = float((mine * rg).sum() / (np.linalg.norm(mine) * np.linalg.norm(rg)))
+        rl2 = float(np.linalg.norm(mine - rg) / np.linalg.norm(rg))
+        e_cal = float(np.linalg.norm(cg.astype(np.float64) - rg) / np.linalg.norm(rg))
+        rows[name] = dict(cos=cos, rel_l2=rl2, cal_rel_l2=e_cal)
+    os.makedirs(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out'), exist_ok=True)
+    with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out',
+                           'trajectory_grad_parity.json'), 'w') as f:
+        json.dump(dict(loss_band_max=float(band.max()), ref_curve=ref_curve.tolist(), dev_curve=dev_curve.tolist(),
+                       grads=rows), f, indent=1)
+    kernels = {k: v for k, v in rows.items() if k.endswith('/kernel')}
+    # SURVEY 8c bf16 tolerance (cos >= 0.999, rel-L2 <= 3e-2) wherever bf16 STORAGE itself allows it (calibration run of
+    # the oracle with the same storage points within 1.5e-2 of its own fp32 self); elsewhere no worse than 2x calibration
+    n_strict = 0
+    for name, v in rows.items():
+        if v['cal_rel_l2'] <= 1.5e-2:
+            assert v['cos'] >= 0.999 and v['rel_l2'] <= 3e-2, (name, v)
+            n_strict += 1
+        else:
+            assert v['rel_l2'] <= 2.0 * v['cal_rel_l2'] + 0.03, (name, v)
+    assert min(v['cos'] for v in kernels.values()) >= 0.9, kernels
+    assert n_strict >= 1, rows
