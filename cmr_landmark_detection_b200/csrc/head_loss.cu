@@ -15,16 +15,20 @@ namespace rvip {
 
 constexpr int kMaxNC = 4;
 
-template <typename T, bool TRAIN, int NCT, int CPT>
-__global__ void __launch_bounds__(256, CPT == 16 ? 2 : 1) head_kernel(HeadArgs a) {
+// VAR: tuning variant of the software pipeline / occupancy (0 = default: depth 2 at 2 blocks/SM for CPT = 16)
+template <typename T, bool TRAIN, int NCT, int CPT, bool FOLD, int VAR = 0>
+__global__ void __launch_bounds__(256, (CPT == 16 && VAR != 2) ? 2 : 1) head_kernel(HeadArgs a) {
   constexpr int NV = CPT / 8;              // 8-channel vectors per thread
-  extern __shared__ float sm[];            // w [Cin*NC], b [NC], then (TRAIN) dw acc [Cin*NC], db acc [NC]
+  extern __shared__ float sm[];            // w [Cin*NC], b [NC], dw acc [Cin*NC], db acc [NC], (FOLD) scale, shift [Cin]
   pdl_wait();
-  const int NC = a.NC, Cin = a.Cin, G = Cin / CPT;
+  constexpr int NC = NCT;                  // the launcher instantiates the exact class count
+  const int Cin = a.Cin, G = Cin / CPT;
   float* w_s = sm;
   float* b_s = w_s + Cin * NC;
   float* dw_s = b_s + NC;
   float* db_s = dw_s + Cin * NC;
+  float* sc_s = db_s + NC;
+  float* sh_s = sc_s + Cin;
   __shared__ double loss_s;
   for (int k = threadIdx.x; k < Cin * NC; k += 256) {
     w_s[k] = a.w[k];
@@ -35,7 +39,36 @@ __global__ void __launch_bounds__(256, CPT == 16 ? 2 : 1) head_kernel(HeadArgs a
     if (TRAIN) db_s[threadIdx.x] = 0.f;
   }
   if (threadIdx.x == 0) loss_s = 0.0;
+  if (FOLD) {
+    // BatchNorm of the producing block, exactly as bn_apply_kernel's prologue derives it (same float expressions, so
+    // the backward pass sees the mean / rstd the forward used)
+    for (int k = threadIdx.x; k < Cin; k += 256) {
+      const double mean = a.bn_stats[k] * a.bn_inv_count;
+      double var = a.bn_stats[Cin + k] * a.bn_inv_count - mean * mean;
+      if (var < 0) var = 0;
+      const float m = (float)mean, r = rsqrtf((float)var + a.bn_eps);
+      if (blockIdx.x == 0 && a.bn_publish) {
+        a.bn_mean_out[k] = m;
+        a.bn_rstd_out[k] = r;
+        const double unb = a.bn_count > 1.0 ? var * a.bn_count / (a.bn_count - 1.0) : var;
+        a.bn_mov_mean[k] = a.bn_momentum * a.bn_mov_mean[k] + (1.f - a.bn_momentum) * m;
+        a.bn_mov_var[k] = a.bn_momentum * a.bn_mov_var[k] + (1.f - a.bn_momentum) * (float)unb;
+      }
+      const float sck = a.bn_gamma[k] * r;
+      sc_s[k] = sck;
+      sh_s[k] = fmaf(-m, sck, a.bn_beta[k]);
+    }
+  }
   __syncthreads();
+  if (FOLD) {
+    // logits = sum_c w[c][k] (sc[c] a[c] + sh[c]) + b[k]: the shift folds into the bias
+    if (threadIdx.x < NC) {
+      float s = b_s[threadIdx.x];
+      for (int c2 = 0; c2 < Cin; ++c2) s = fmaf(sh_s[c2], w_s[c2 * NC + threadIdx.x], s);
+      b_s[threadIdx.x] = s;
+    }
+    __syncthreads();
+  }
 
   const uint32_t P = (uint32_t)a.B * a.H * a.W;
   const uint32_t lg = 31 - __clz(G);
@@ -49,7 +82,7 @@ __global__ void __launch_bounds__(256, CPT == 16 ? 2 : 1) head_kernel(HeadArgs a
 #pragma unroll
   for (int j = 0; j < CPT; ++j)
 #pragma unroll
-    for (int k = 0; k < NCT; ++k) wreg[j][k] = k < NC ? w_s[(c + j) * NC + k] : 0.f;
+    for (int k = 0; k < NCT; ++k) wreg[j][k] = k < NC ? w_s[(c + j) * NC + k] * (FOLD ? sc_s[c + j] : 1.f) : 0.f;
   float dw_acc[CPT][NCT], db_acc[NCT];
 #pragma unroll
   for (int k = 0; k < NCT; ++k) {
@@ -72,7 +105,7 @@ __global__ void __launch_bounds__(256, CPT == 16 ? 2 : 1) head_kernel(HeadArgs a
   // Software pipeline: the loads of y and of the target for the item kDepth grid-strides ahead are in flight
   // while the current item is processed (ncu: with the loads issued at the point of use, 55 % of the stall
   // samples of this kernel were long-scoreboard waits on exactly those two loads).
-  constexpr int kDepth = CPT == 8 ? 4 : 2;
+  constexpr int kDepth = VAR == 1 ? 1 : (VAR == 2 ? 4 : (CPT == 8 ? 4 : 2));
   Raw8<T> ybuf[kDepth][NV];
   float tbuf[kDepth][NCT];
   auto issue = [&](int d, uint32_t i) {
@@ -169,12 +202,29 @@ __global__ void __launch_bounds__(256, CPT == 16 ? 2 : 1) head_kernel(HeadArgs a
 #pragma unroll
         for (int u = 0; u < NV; ++u) {
           float g[8];
+          // dy = dL/d(BN output) needs the PLAIN head weights; when folded wreg carries the BatchNorm scale, so they
+          // come from shared memory (vector loads, broadcast: all lanes of a channel group read the same address)
+          float wd[8][NCT];
+          if (FOLD) {
+            if constexpr (NC == 2) {
+#pragma unroll
+              for (int j = 0; j < 8; j += 2) {
+                const float4 t4 = *reinterpret_cast<const float4*>(w_s + (c + 8 * u + j) * 2);
+                wd[j][0] = t4.x; wd[j][1] = t4.y; wd[j + 1][0] = t4.z; wd[j + 1][1] = t4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int k = 0; k < NCT; ++k) wd[j][k] = w_s[(c + 8 * u + j) * NC + k];
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float s = 0.f;
 #pragma unroll
             for (int k = 0; k < NCT; ++k) {
-              s = fmaf(wreg[8 * u + j][k], dl[k], s);
+              s = fmaf(FOLD ? wd[j][k] : wreg[8 * u + j][k], dl[k], s);
               dw_acc[8 * u + j][k] = fmaf(v[8 * u + j], dl[k], dw_acc[8 * u + j][k]);
             }
             g[j] = s;
@@ -239,6 +289,36 @@ __global__ void __launch_bounds__(256) head_dice_sums_kernel(const float* __rest
 }
 int head_dice_sums_launch(const float* heat, const float* target, size_t n, double* sums, cudaStream_t st) {
   head_dice_sums_kernel<<<kNumSMs * 2, 256, 0, st>>>(heat, target, n, sums);
+  RVIP_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------- folded-BatchNorm finalize
+__global__ void head_bn_finalize_kernel(const float* __restrict__ dwa, const float* __restrict__ db,
+                                        const float* __restrict__ w, const float* __restrict__ gamma,
+                                        const float* __restrict__ beta, const float* __restrict__ mean,
+                                        const float* __restrict__ rstd, int Cin, int NC, float* __restrict__ dw,
+                                        double* __restrict__ red) {
+  pdl_wait();
+  for (int c = threadIdx.x; c < Cin; c += blockDim.x) {
+    const float sc = gamma[c] * rstd[c];
+    const float sh = fmaf(-mean[c], sc, beta[c]);
+    double s1 = 0.0, s2 = 0.0;
+    for (int k = 0; k < NC; ++k) {
+      const float g = dwa[c * NC + k];
+      dw[c * NC + k] = fmaf(sc, g, sh * db[k]);
+      s1 += (double)w[c * NC + k] * (double)db[k];
+      s2 += (double)w[c * NC + k] * (double)g;
+    }
+    red[c] = s1;
+    red[Cin + c] = s2;
+  }
+  pdl_launch_dependents();
+}
+int head_bn_finalize_launch(const float* dwa, const float* db, const float* w, const float* gamma, const float* beta,
+                            const float* mean, const float* rstd, int Cin, int NC, float* dw, double* red,
+                            cudaStream_t st) {
+  launch_kernel(head_bn_finalize_kernel, 1, 256, 0, st, dwa, db, w, gamma, beta, mean, rstd, Cin, NC, dw, red);
   RVIP_LAUNCH_CHECK();
   return 0;
 }
@@ -335,23 +415,31 @@ int head_launch(const HeadArgs& a, int training, int is_bf16, cudaStream_t st) {
   size_t g = (n + 255) / 256;
   const size_t cap = (size_t)kNumSMs * 2;   // 2 blocks/SM resident (122 registers); every block ends with Cin*NC + NC + 1 global atomics: keep them few
   const int grid = (int)(g < cap ? (g ? g : 1) : cap);
-  const size_t smem = (size_t)(2 * (a.Cin * a.NC + a.NC)) * sizeof(float);
-#define RVIP_HEAD(NCV, CPTV)                                                  \
-  if (a.NC == NCV && cpt == CPTV) {                                           \
-    if (training) {                                                           \
-      if (is_bf16)                                                            \
-        launch_kernel(head_kernel<__nv_bfloat16, true, NCV, CPTV>, grid, 256, smem, st, a);    \
-      else                                                                    \
-        launch_kernel(head_kernel<float, true, NCV, CPTV>, grid, 256, smem, st, a);            \
-    } else {                                                                  \
-      if (is_bf16)                                                            \
-        launch_kernel(head_kernel<__nv_bfloat16, false, NCV, CPTV>, grid, 256, smem, st, a);   \
-      else                                                                    \
-        launch_kernel(head_kernel<float, false, NCV, CPTV>, grid, 256, smem, st, a);           \
-    }                                                                         \
+  const size_t smem = (size_t)(2 * (a.Cin * a.NC + a.NC) + 2 * a.Cin) * sizeof(float);
+  const bool fold = a.bn_stats != nullptr;
+  // folded training head, 2 classes x 16 channels per thread: 128 registers spill (200 B) at 2 blocks/SM; one block per SM
+  // with a 4-deep load pipeline measured 108 us against 156 (depth 2, 2 blocks) and 128 (depth 1), profiles/r2d_headvar.jsonl
+  const int var = getenv("RVIP_HEAD_VAR") ? atoi(getenv("RVIP_HEAD_VAR")) : 2;
+  const int grid1 = (int)(g < (size_t)kNumSMs ? (g ? g : 1) : (size_t)kNumSMs);
+#define RVIP_HEAD_T(TT, NCV, CPTV)                                                             \
+  {                                                                                            \
+    if (training && fold && NCV == 2 && CPTV == 16 && var == 1)                                \
+      launch_kernel(head_kernel<TT, true, 2, 16, true, 1>, grid, 256, smem, st, a);            \
+    else if (training && fold && NCV == 2 && CPTV == 16 && var == 2)                           \
+      launch_kernel(head_kernel<TT, true, 2, 16, true, 2>, grid1, 256, smem, st, a);           \
+    else if (training && fold) launch_kernel(head_kernel<TT, true, NCV, CPTV, true>, grid, 256, smem, st, a);         \
+    else if (training) launch_kernel(head_kernel<TT, true, NCV, CPTV, false>, grid, 256, smem, st, a);           \
+    else if (fold) launch_kernel(head_kernel<TT, false, NCV, CPTV, true>, grid, 256, smem, st, a);               \
+    else launch_kernel(head_kernel<TT, false, NCV, CPTV, false>, grid, 256, smem, st, a);                        \
+  }
+#define RVIP_HEAD(NCV, CPTV)                          \
+  if (a.NC == NCV && cpt == CPTV) {                   \
+    if (is_bf16) RVIP_HEAD_T(__nv_bfloat16, NCV, CPTV) \
+    else RVIP_HEAD_T(float, NCV, CPTV)                \
   }
   RVIP_HEAD(1, 8) RVIP_HEAD(2, 8) RVIP_HEAD(3, 8) RVIP_HEAD(4, 8) RVIP_HEAD(1, 16) RVIP_HEAD(2, 16)
 #undef RVIP_HEAD
+#undef RVIP_HEAD_T
   RVIP_LAUNCH_CHECK();
   return 0;
 }

@@ -119,8 +119,30 @@ struct HeadArgs {
   // sums {sum t*p, sum p, sum t} before any gradient can be formed (head_dice_sums_launch)
   const double* dice_sums;
   float w_bce, w_dice;
+  // BatchNorm of the last decoder block folded into the head (training): `y` is then that block's relu(conv) output
+  // `a`, the head derives scale / shift from the conv epilogue's sum / sum^2 (bn_stats != nullptr) and normalises on the
+  // fly -- the block's bn_apply pass (read a, write y) disappears.  dw then accumulates sum_p a * dlogit, which
+  // head_bn_finalize_launch turns into the true head-kernel gradient AND into the BatchNorm-backward sums of that block
+  // (sum dy, sum dy * a): its bn_bwd_reduce pass disappears as well.
+  const double* bn_stats;  // [2][Cin] sum, sum of squares of `a`
+  double bn_count, bn_inv_count;
+  float bn_momentum, bn_eps;
+  const float* bn_gamma;
+  const float* bn_beta;
+  float* bn_mean_out;      // [Cin] published by block 0 when bn_publish (for the backward pass)
+  float* bn_rstd_out;
+  float* bn_mov_mean;
+  float* bn_mov_var;
+  int bn_publish;
 };
 int head_launch(const HeadArgs& a, int training, int is_bf16, cudaStream_t st);
+// dwa [Cin][NC] = sum_p a * dlogit, db [NC] = sum_p dlogit (both from the folded training head), w the head kernel:
+//   dw[c][k]  = sc[c] * dwa[c][k] + sh[c] * db[k]          (y = sc * a + sh)
+//   red[c]    = sum_p dy[c]     = sum_k w[c][k] * db[k]
+//   red[C+c]  = sum_p dy[c] a   = sum_k w[c][k] * dwa[c][k]      (dy = dlogit . w^T: exact, a 1x1 conv has no border)
+int head_bn_finalize_launch(const float* dwa, const float* db, const float* w, const float* gamma, const float* beta,
+                            const float* mean, const float* rstd, int Cin, int NC, float* dw, double* red,
+                            cudaStream_t st);
 // heat, target [n] fp32 -> sums[3] += {sum t*p, sum p, sum t} (double)
 int head_dice_sums_launch(const float* heat, const float* target, size_t n, double* sums, cudaStream_t st);
 

@@ -464,6 +464,8 @@ struct rvip_handle {
   std::vector<cudaEvent_t> ev_dz, ev_wg;    // per layer: dz ready (main) / wgrad done (side)
   int overlap_wgrad = 1;
   double* dice_sums = nullptr;              // {sum t*p, sum p, sum t} of the BCE+Dice loss
+  int head_fold = 0;                        // training: BatchNorm of the last block folded into the head (head_loss.cu)
+  float* head_dwa = nullptr;                // [Cin][classes] sum_p a * dlogit of the folded head
   float w_bce = 1.f, w_dice = 1.f;
   rvip::PackEntry* pack_table_dev = nullptr;
   int n_pack = 0;
@@ -683,6 +685,8 @@ static size_t carve(rvip_handle* h, uint8_t* base, int B, int training, bool ass
     if (assign) h->rstd = (float*)p;
     p = cv.take(sizeof(double) * 4);
     if (assign) h->dice_sums = (double*)p;
+    p = cv.take(sizeof(float) * 4096);
+    if (assign) h->head_dwa = (float*)p;
     p = cv.take(sizeof(float) * h->n_stat_ch);
     if (assign) h->aff_scale = (float*)p;
     p = cv.take(sizeof(float) * h->n_stat_ch);
@@ -924,7 +928,8 @@ static void fill_bn(const rvip_handle* h, const Layer& l, BnArgs* a, bool traini
   a->keep_scale = 1.f / (1.f - l.drop);
 }
 
-static int forward_body(rvip_handle* h, const float* x, bool training, uint64_t seed, cudaStream_t st) {
+static int forward_body(rvip_handle* h, const float* x, bool training, uint64_t seed, cudaStream_t st,
+                        bool fold_head = false) {
   if (training) {
     if (timed(h, KC_MISC, 1, st, [&] {
           RVIP_CUDA(cudaMemsetAsync(h->stats, 0, sizeof(double) * 2 * h->n_stat_ch, st));
@@ -955,6 +960,7 @@ static int forward_body(rvip_handle* h, const float* x, bool training, uint64_t 
     h->cur_tag = l.name + ":conv_fwd";
     if (conv_forward(h, l, x, training, st)) return 1;
     if (!l.bn) continue;
+    if (fold_head && &l == &h->L[h->head_in]) continue;   // normalised on the fly by the head kernel
     h->cur_tag = l.name + ":bn_fwd";
     BnArgs a;
     fill_bn(h, l, &a, training, seed);
@@ -992,6 +998,23 @@ static void fill_head(const rvip_handle* h, HeadArgs* a, float* heat) {
   a->b = h->params + h->head_b;
   a->heat = heat;
 }
+// training with the last block's BatchNorm folded into the head: read `a`, derive scale / shift from the conv epilogue's sums
+static void fold_head_bn(const rvip_handle* h, HeadArgs* a, int publish) {
+  const Layer& l = h->L[h->head_in];
+  a->y = l.a;
+  a->bn_stats = h->stats + 2 * l.off_stat;
+  a->bn_count = (double)h->batch * l.H * l.W;
+  a->bn_inv_count = 1.0 / a->bn_count;
+  a->bn_momentum = h->cfg.bn_momentum;
+  a->bn_eps = h->cfg.bn_eps;
+  a->bn_gamma = h->params + l.off_g;
+  a->bn_beta = h->params + l.off_be;
+  a->bn_mean_out = h->mean + l.off_stat;
+  a->bn_rstd_out = h->rstd + l.off_stat;
+  a->bn_mov_mean = h->bn_state + l.off_mm;
+  a->bn_mov_var = h->bn_state + l.off_mv;
+  a->bn_publish = publish;
+}
 
 // Backward pass.  Main chain per layer (reverse order):  BN/ReLU backward -> dz,  dgrad -> dx.  The weight gradient
 // of a layer only needs dz and the stored forward input, and nothing downstream needs it before the optimizer
@@ -1000,7 +1023,7 @@ static void fill_head(const rvip_handle* h, HeadArgs* a, float* heat) {
 // need almost no shared memory.  dz alternates between two scratch buffers; before a buffer is overwritten the
 // main stream waits for the wgrad that read it.  Measured 5.95 -> 5.68 ms/step.  (Serialising each wgrad behind
 // its layer's dgrad so that the two 200-KB-smem kernels never compete was slower: 5.82 ms.)
-static int backward_body(rvip_handle* h, const float* x, uint64_t seed, cudaStream_t st) {
+static int backward_body(rvip_handle* h, const float* x, uint64_t seed, cudaStream_t st, bool fold_head) {
   const int bf = is_bf16(h);
   const int nL = (int)h->L.size();
   const bool overlap = h->overlap_wgrad && !h->profile && h->side != nullptr;
@@ -1028,8 +1051,10 @@ static int backward_body(rvip_handle* h, const float* x, uint64_t seed, cudaStre
       a.dgamma = h->grads + l.off_g;
       a.dbeta = h->grads + l.off_be;
       a.dbias = h->grads + l.off_b;
-      if (timed(h, KC_BN_BWD, 2, st, [&] {
-            if (bn_bwd_reduce_launch(a, bf, st)) return 1;
+      // the folded head already left sum dy / sum dy * a of its input block in `red` (head_bn_finalize)
+      const bool have_sums = fold_head && i == h->head_in;
+      if (timed(h, KC_BN_BWD, have_sums ? 1 : 2, st, [&] {
+            if (!have_sums && bn_bwd_reduce_launch(a, bf, st)) return 1;
             return bn_bwd_apply_launch(a, bf, st);
           }))
         return 1;
@@ -1231,6 +1256,11 @@ int rvip_bind(rvip_handle* h, float* params, float* grads, float* bn_state, void
     RVIP_CUDA(cudaMemset(h->packed, 0, 2 * (size_t)std::max<long long>(h->n_packed, 1)));
     RVIP_CUDA(cudaStreamSynchronize(0));   // the packer runs on the caller's (possibly non-blocking) stream
   }
+  {
+    const Layer& hl = h->L[h->head_in];
+    h->head_fold = training && hl.bn && hl.post == POST_NONE && hl.Cout * h->cfg.classes <= 4096 &&
+                   getenv("RVIP_NO_HEAD_FOLD") == nullptr;
+  }
   if (build_descriptors(h)) return 1;
   if (training && !h->side) {
     h->overlap_wgrad = getenv("RVIP_NO_WGRAD_OVERLAP") == nullptr;
@@ -1275,12 +1305,18 @@ int rvip_train_step(rvip_handle* h, const float* x, const float* target, const f
         return 0;
       }))
     return 1;
-  if (forward_body(h, x, true, seed, st)) return 1;
+  const bool fold = h->head_fold != 0;
+  if (forward_body(h, x, true, seed, st, fold)) return 1;
   HeadArgs a;
   fill_head(h, &a, heat);
+  if (fold) {
+    fold_head_bn(h, &a, 1);
+    RVIP_CUDA(cudaMemsetAsync(h->head_dwa, 0, sizeof(float) * a.Cin * a.NC, st));
+  }
   a.target = target; a.inplane = inplane; a.loss_kind = loss_kind; a.mask_thr = mask_thr; a.eps = 1e-7f;
   a.dy = h->head_dy;
-  a.dw = h->grads + h->head_k; a.db = h->grads + h->head_b;
+  a.dw = fold ? h->head_dwa : h->grads + h->head_k;
+  a.db = h->grads + h->head_b;
   a.loss_acc = loss_out;
   a.dice_sums = h->dice_sums; a.w_bce = h->w_bce; a.w_dice = h->w_dice;
   h->cur_tag = "head:loss";
@@ -1290,13 +1326,21 @@ int rvip_train_step(rvip_handle* h, const float* x, const float* target, const f
     if (timed(h, KC_HEAD, 3, st, [&] {
           RVIP_CUDA(cudaMemsetAsync(h->dice_sums, 0, sizeof(double) * 4, st));
           if (head_launch(a, 0, is_bf16(h), st)) return 1;
+          a.bn_publish = 0;   // the inference-mode pass above already published mean / rstd and the moving statistics
           const Layer& hl = h->L[h->head_in];
           return head_dice_sums_launch(heat, target, (size_t)h->batch * hl.H * hl.W * h->cfg.classes, h->dice_sums, st);
         }))
       return 1;
   }
-  if (timed(h, KC_HEAD, 1, st, [&] { return head_launch(a, 1, is_bf16(h), st); })) return 1;
-  return backward_body(h, x, seed, st);
+  if (timed(h, KC_HEAD, fold ? 2 : 1, st, [&] {
+        if (head_launch(a, 1, is_bf16(h), st)) return 1;
+        if (!fold) return 0;
+        const Layer& hl = h->L[h->head_in];
+        return head_bn_finalize_launch(h->head_dwa, a.db, a.w, a.bn_gamma, a.bn_beta, a.bn_mean_out, a.bn_rstd_out, a.Cin,
+                                       a.NC, h->grads + h->head_k, h->red + 2 * kRedStripes * hl.off_stat, st);
+      }))
+    return 1;
+  return backward_body(h, x, seed, st, fold);
 }
 
 int rvip_set_loss_weights(rvip_handle* h, float w_bce, float w_dice) {

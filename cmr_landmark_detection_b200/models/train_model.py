@@ -68,9 +68,14 @@ def train_fold(config, in_memory=True):
         except ValueError as e:
             logging.warning('metric skipped: %s', e)
     # train_model.py:62 init_config: persist the UPPERCASE, serialisable keys
+    def _plain(v):
+        try:
+            json.dumps(v)
+            return True
+        except TypeError:
+            return False
     with open(os.path.join(config['CONFIG_PATH'], 'config.json'), 'w') as fh:
-        json.dump({k: v for k, v in config.items() if k.isupper() and isinstance(v, (str, int, float, bool, list, dict,
-                                                                                       type(None)))}, fh, indent=1)
+        json.dump({k: v for k, v in config.items() if k.isupper() and _plain(v)}, fh, indent=1)
     batch_generator, validation_generator = _generators(config, in_memory)
     logging.info('Create model')
     model = modelmanager.create_unet(config, metrics, supervision=False)
