@@ -31,26 +31,69 @@ BATCH_PER_GPU = 32
 WORKLOAD = 'C2: U-Net d4 f32 fwd+bwd+MSE+Adam, batch 32/GPU, 256x256x1 -> 2 RVIP heat maps, bf16 storage / fp32 accumulate'
 
 
-def conv_flops_per_slice(cfg=CONFIG):
-    """Algorithmic conv FLOPs (2*MACs) per slice: forward, and forward+dgrad+wgrad (first layer has no dgrad)."""
+def layer_table(cfg=CONFIG):
+    """The 3x3 conv layers of the reference graph (Unets.py:786-836) with what follows them:
+    (name, kind, cin, cout, h, w, post) -- kind 'block' = conv_layer_fn (BatchNorm), 'up' = decoder up-conv (ReLU only)."""
     H, W = cfg['DIM']
     f, cin, d = cfg['FILTERS'], cfg['IMG_CHANNELS'], cfg['DEPTH']
-    layers = []
+    out = []
     h, w = H, W
     for l in range(d):
-        layers += [(cin, f, h, w), (f, f, h, w)]
+        out += [('enc%d.conv_a' % l, 'block', cin, f, h, w, 'dropout'), ('enc%d.conv_b' % l, 'block', f, f, h, w, 'pool')]
         cin, f, h, w = f, f * 2, h // 2, w // 2
-    layers += [(cin, f, h, w), (f, f, h, w)]
+    out += [('mid.conv_a', 'block', cin, f, h, w, 'dropout'), ('mid.conv_b', 'block', f, f, h, w, 'upsample')]
     low = f
     for l in range(d):
         f //= 2
         h, w = h * 2, w * 2
-        layers += [(low, f, h, w), (2 * f, f, h, w), (f, f, h, w)]
+        out += [('dec%d.upconv' % l, 'up', low, f, h, w, 'none'), ('dec%d.conv_a' % l, 'block', 2 * f, f, h, w, 'dropout'),
+                ('dec%d.conv_b' % l, 'block', f, f, h, w, 'upsample' if l < d - 1 else 'head')]
         low = f
-    fwd = sum(2 * 9 * ci * co * hh * ww for ci, co, hh, ww in layers)
-    first = 2 * 9 * layers[0][0] * layers[0][1] * layers[0][2] * layers[0][3]
+    return out
+
+
+def bench_config(world):
+    """`config` of the JSON line: identical in the B200 arm and the CPU reference arm."""
+    return {'workload': WORKLOAD, 'global_batch': world * BATCH_PER_GPU, 'parallelism': 'dp%d' % world}
+
+
+def conv_flops_per_slice(cfg=CONFIG):
+    """Algorithmic conv FLOPs (2*MACs) per slice of the REFERENCE graph (3x3 convs on the up-sampled tensors): forward,
+    and forward+dgrad+wgrad (first layer has no dgrad).  `executed_*` = what the tensor pipe runs: the phase-decomposed
+    up-convolutions execute 16/36 of their forward / dgrad MMAs and 8/20 of their weight-gradient MMAs."""
+    layers = layer_table(cfg)
+    fl = [2 * 9 * ci * co * hh * ww for _, _, ci, co, hh, ww, _ in layers]
+    fwd, first = sum(fl), fl[0]
+    up = sum(v for v, l in zip(fl, layers) if l[1] == 'up')
     tc_fwd = fwd - first                  # tensor-core share (everything but the Cin=1 layer)
-    return dict(fwd=fwd, train=3 * fwd - first, tc_fwd=tc_fwd, tc_dgrad=tc_fwd, tc_wgrad=tc_fwd)
+    return dict(fwd=fwd, train=3 * fwd - first, tc_fwd=tc_fwd, tc_dgrad=tc_fwd, tc_wgrad=tc_fwd,
+                executed_fwd=tc_fwd - up + up * 16 / 36, executed_dgrad=tc_fwd - up + up * 16 / 36,
+                executed_wgrad=tc_fwd - up + up * 8 / 20)
+
+
+def algorithmic_bytes_per_slice(cfg=CONFIG, n_params=8635842, head_fold=True):
+    """Minimum HBM bytes per slice of every memory-bound kernel class (bf16 activations, fp32 image / heat maps): each
+    tensor a pass NEEDS is counted once -- BatchNorm forward = read relu(conv), write the block output (+ the pooled
+    quarter); BatchNorm backward = read dy, read relu(conv), write dz (3 passes; the separate statistics pass the kernels
+    run today is NOT algorithmic); the convs = read every input once (the up-conv its LOW-resolution input), write the output."""
+    layers = layer_table(cfg)
+    nc = cfg['MASK_CLASSES']
+    b = dict(conv=0.0, bn_forward=0.0, bn_backward=0.0, conv_cuda_core=0.0, head_loss=0.0)
+    for i, (name, kind, ci, co, h, w, post) in enumerate(layers):
+        px = h * w
+        if i == 0:
+            b['conv_cuda_core'] += px * (4 * ci + 2 * co) + px * (2 * co + 4 * ci)       # forward; weight gradient
+        else:
+            b['conv'] += (px // 4 if kind == 'up' else px) * ci * 2 + px * co * 2
+        if kind == 'block':
+            if not (post == 'head' and head_fold):
+                b['bn_forward'] += 2 * px * co * 2 + (px // 4 * co * 2 if post == 'pool' else 0)
+            b['bn_backward'] += 3 * px * co * 2 + (px // 4 * co * 2 if post == 'pool' else 0)
+        else:
+            b['bn_backward'] += 3 * px * co * 2                                          # ReLU backward of the up-conv
+    H, W = cfg['DIM']
+    b['head_loss'] = H * W * (2 * 2 * cfg['FILTERS'] + 2 * 4 * nc)                      # read a, write dy; target, heat
+    return b, 7 * 4 * n_params + 2 * 2 * 2 * n_params     # per STEP: Adam streams p, g, m, v in / p, m, v out + operand copies
 
 
 class ClockSampler:
@@ -138,8 +181,12 @@ def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get('bf16_tflops_sustained', 1377.3), d.get('hbm_gbs', 6548.2), 'measured (MEASURED_PEAKS.json, sustained bf16)'
+        PEAKS['burst_tflops'] = d.get('bf16_tflops', 1646.8)
+        return d.get('bf16_tflops_sustained', 1377.3), d.get('hbm_gbs', 6548.2), 'measured (MEASURED_PEAKS.json)'
     return 1400.0, 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+PEAKS = {'burst_tflops': 1646.8}
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
@@ -175,21 +222,26 @@ def oracle_train_rate(n_slices=4, steps=3, warmup=1, threads=None):
 
 
 def run_reference(args):
+    """CPU arm: the oracle restatement of the reference's TF2 path (TensorFlow is not installable here) on every host
+    thread, same metric / config / warm-up count as the B200 arm; every step is a bounded 4-slice sample of the
+    32-slice batch so that W + K steps end within minutes."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     n_slices = 4
-    rate, cores, spt = oracle_train_rate(n_slices=n_slices, steps=args.steps, warmup=min(args.warmup, 2))
+    W = max(args.warmup, 3)
+    rate, cores, spt = oracle_train_rate(n_slices=n_slices, steps=args.steps, warmup=W)
     line = {'impl': 'reference', 'metric': 'unet_train_slices_per_s_256', 'value': rate, 'unit': 'slices/s',
-            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': min(args.warmup, 2), 'ms_per_step': spt * 1e3,
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': W, 'ms_per_step': spt * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'note': 'CPU restatement (torch/oneDNN) of the reference TF2 path; TF is not '
-                       'installable here. Each step = %d slices (bounded sample of the 32-slice batch)' % n_slices},
+            'config': bench_config(args.gpus),
+            'notes': {'what': 'CPU restatement (torch/oneDNN, fp32) of the reference TF2 path; TF is not installable here',
+                      'sample': 'each step = %d slices of the 32-slice batch (bounded sample)' % n_slices},
             'cpu_baseline': {'value': rate, 'unit': 'slices/s', 'cores': cores, 'kind': 'port',
-                             'sample': '%d-slice fwd+bwd+Adam step x %d' % (n_slices, args.steps)},
+                             'sample': '%d-slice fwd+bwd+Adam step x %d (after %d warm-up steps)' % (n_slices, args.steps, W)},
             'e2e': {'value': rate, 'unit': 'slices/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------ B200 arm
@@ -275,36 +327,61 @@ def run_b200(args):
     line = None
     if rank == 0:
         peak_tf, peak_gbs, peak_src = peaks()
+        burst_tf = PEAKS['burst_tflops']
         fl = conv_flops_per_slice()
+        by, adam_bytes = algorithmic_bytes_per_slice(n_params=model.n_params)
         per_step = {k: v[0] / K for k, v in prof.items()}
         tot = sum(per_step.values())
+        # ALGORITHMIC work of every kernel class per step: conv FLOPs of the reference graph for the tensor-core classes,
+        # minimum HBM bytes (algorithmic_bytes_per_slice) for the streaming classes
         cls_flops = {'conv_fwd_tcgen05': fl['tc_fwd'] * B, 'conv_dgrad_tcgen05': fl['tc_dgrad'] * B,
                      'conv_wgrad_tcgen05': fl['tc_wgrad'] * B}
+        cls_exec = {'conv_fwd_tcgen05': fl['executed_fwd'] * B, 'conv_dgrad_tcgen05': fl['executed_dgrad'] * B,
+                    'conv_wgrad_tcgen05': fl['executed_wgrad'] * B}
+        cls_bytes = {'bn_forward': by['bn_forward'] * B, 'bn_backward': by['bn_backward'] * B,
+                     'conv_cuda_core': by['conv_cuda_core'] * B, 'head_loss': by['head_loss'] * B, 'adam_pack': adam_bytes}
         kern = {}
         for k, t in per_step.items():
             if t <= 0:
                 continue
-            kern[k] = {'ms_per_step': round(t, 4), 'share': round(t / tot, 4), 'launches_per_step': prof[k][1] // K}
+            e = {'ms_per_step': round(t, 4), 'share': round(t / tot, 4), 'launches_per_step': prof[k][1] // K}
             if k in cls_flops:
-                kern[k]['tflops'] = round(cls_flops[k] / (t * 1e-3) / 1e12, 1)
-        dom = max(cls_flops, key=lambda k: per_step.get(k, 0.0))
-        ach = cls_flops[dom] / (per_step[dom] * 1e-3) / 1e12
+                tf = cls_flops[k] / (t * 1e-3) / 1e12
+                e.update(bound='tensor', achieved=round(tf, 1), unit='TFLOP/s', frac=round(tf / peak_tf, 4),
+                         frac_of_burst=round(tf / burst_tf, 4),
+                         executed_tflops=round(cls_exec[k] / (t * 1e-3) / 1e12, 1),
+                         executed_over_algorithmic=round(cls_exec[k] / cls_flops[k], 4))
+            elif k in cls_bytes:
+                gbs = cls_bytes[k] / (t * 1e-3) / 1e9
+                e.update(bound='hbm', achieved=round(gbs, 1), unit='GB/s', frac=round(gbs / peak_gbs, 4),
+                         algorithmic_mbytes=round(cls_bytes[k] / 1e6, 1))
+            kern[k] = e
+        # the dominant class = the one with the largest share of the step (whatever roof binds it)
+        dom = max((k for k in kern if 'bound' in kern[k]), key=lambda k: per_step[k])
         conv_t = sum(per_step.get(k, 0.0) for k in cls_flops)
         conv_tf = sum(cls_flops.values()) / (conv_t * 1e-3) / 1e12
-        # DRAM traffic per launch of the dominant kernel class from the committed ncu --set full capture
-        traffic, traffic_src, ncu_pipe = None, None, None
-        tpath = os.path.join(ROOT, 'profiles', 'r1k_traffic.json')
+        # DRAM traffic per step of the dominant class from the committed ncu --set full capture of THIS code
+        # (profiles/capture.sh full -> profiles/r2_traffic.json); null when the capture does not cover it
+        traffic, traffic_src, ncu_extra = None, None, None
+        tpath = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
         if os.path.exists(tpath):
             tj = json.load(open(tpath)).get(dom)
             if tj:
-                traffic = int(tj['dram_mbytes_per_launch'] * 1e6)
-                traffic_src = '%s, mean of %d launches' % (tj['source'], tj['launches_captured'])
-                ncu_pipe = tj.get('tensor_pipe_active_pct')
-        roof = {'bound': 'tensor', 'kernel': dom, 'achieved': round(ach, 1), 'peak': peak_tf, 'unit': 'TFLOP/s',
-                'frac': round(ach / peak_tf, 4), 'traffic': traffic, 'traffic_source': traffic_src,
-                'ncu_tensor_pipe_active_pct': ncu_pipe, 'peak_source': peak_src,
+                traffic = int(tj['dram_mbytes_per_step'] * 1e6)
+                traffic_src = tj['source']
+                ncu_extra = {k: v for k, v in tj.items() if k not in ('dram_mbytes_per_step', 'source')}
+        step_tf = fl['train'] * B / (ms / K * 1e-3) / 1e12
+        roof = {'bound': kern[dom]['bound'], 'kernel': dom, 'achieved': kern[dom]['achieved'],
+                'peak': peak_tf if kern[dom]['bound'] == 'tensor' else peak_gbs, 'unit': kern[dom]['unit'],
+                'frac': kern[dom]['frac'], 'traffic': traffic, 'traffic_source': traffic_src, 'ncu': ncu_extra,
+                'peak_source': peak_src, 'peaks': {'hbm_gbs': peak_gbs, 'bf16_tflops_sustained': peak_tf,
+                                                   'bf16_tflops_burst': burst_tf},
                 'all_conv_tcgen05_tflops': round(conv_tf, 1), 'all_conv_frac': round(conv_tf / peak_tf, 4),
-                'step_tensor_frac': round(fl['train'] * B / (ms / K * 1e-3) / 1e12 / peak_tf, 4),
+                'step_tflops_algorithmic': round(step_tf, 1),
+                'step_tensor_frac': round(step_tf / peak_tf, 4), 'step_tensor_frac_of_burst': round(step_tf / burst_tf, 4),
+                'note': 'achieved = ALGORITHMIC work / device time per class (CUDA events around every launch group, '
+                        'weight gradients not overlapped in this profiling pass); the phase-decomposed up-convolutions '
+                        'execute fewer MMAs than the reference graph has (executed_over_algorithmic)',
                 'kernels': kern}
         # CPU baseline: rank 0 at N = 1 only (under torchrun OMP_NUM_THREADS=1 and N ranks share the host cores)
         cpu = None
@@ -315,9 +392,9 @@ def run_b200(args):
         line = {'metric': 'unet_train_slices_per_s_256', 'value': round(value, 1), 'unit': 'slices/s', 'n_gpus': world,
                 'steps': K, 'warmup': Wm, 'ms_per_step': round(ms / K, 4), 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-                'config': {'workload': WORKLOAD, 'global_batch': world * B, 'parallelism': 'dp%d' % world,
-                           'l2': 'per-step working set ~4.4 GB >> 126 MB L2; two input batches alternate',
-                           'final_loss': final_loss, 'gflop_per_slice_train': round(fl['train'] / 1e9, 2)},
+                'config': bench_config(world),
+                'notes': {'l2': 'per-step working set ~4.4 GB >> 126 MB L2; two input batches alternate',
+                          'final_loss': final_loss, 'gflop_per_slice_train': round(fl['train'] / 1e9, 2)},
                 'clocks': clocks, 'gpu_launches': int(launches),
                 'e2e': {'value': round(e2e, 1), 'unit': 'slices/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 8,
                         'ms_per_step': round(ms_e2e / K, 4), 'api': 'model.fit(Sequence of host batches)'},
@@ -327,7 +404,7 @@ def run_b200(args):
         # issues collectives the other ranks would never match)
         if not args.no_extra and world == 1:
             line['extra'] = extra_measurements(model, dev)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
@@ -353,6 +430,22 @@ def extra_measurements(model, dev):
     e1.record()
     torch.cuda.synchronize()
     out['infer_vols_per_s'] = round(n / (e0.elapsed_time(e1) * 1e-3), 1)
+    # the same through the public API with HOST buffers: model.predict(ndarray) -> ndarray (pinned staging, H2D of the
+    # slices, D2H of the heat maps inside the timed region), at one volume per call and at pred_fold's batch size 1
+    # (predict_model.py:89: one forward per slice)
+    for _ in range(2):
+        model.predict(x, batch_size=16)
+        model.predict(x, batch_size=1)
+    t0 = time.perf_counter()
+    for _ in range(n):
+        hp = model.predict(x, batch_size=16)
+    t1 = time.perf_counter()
+    for _ in range(3):
+        model.predict(x, batch_size=1)
+    t2 = time.perf_counter()
+    out['infer_e2e'] = {'api': 'model.predict(host ndarray [16,256,256,1]) -> host ndarray', 'vols_per_s': round(n / (t1 - t0), 1),
+                        'h2d_bytes_per_vol': int(x.nbytes), 'd2h_bytes_per_vol': int(hp.nbytes),
+                        'batch1_slices_per_s': round(3 * 16 / (t2 - t1), 1), 'batch1_ms_per_slice': round((t2 - t1) / 48 * 1e3, 3)}
     heat = torch.from_numpy(synth.make_volume_heat(16 * 64, 256, 256, seed=1)[:, :, :, :]).to(dev)   # 537 MB > L2
     for _ in range(3):
         extract_device(heat)
@@ -382,7 +475,7 @@ def extra_measurements(model, dev):
     # BASELINE config C5 (tensor-core stress): 5 levels, 64 base filters, 512 x 512, batch 8
     try:
         from cmr_landmark_detection_b200.models.Unets import create_unet
-        c5 = dict(CONFIG, DIM=[512, 512], DEPTH=5, FILTERS=64)
+        c5 = dict(CONFIG, DIM=[512, 512], DEPTH=5, FILTERS=64, DATA_PARALLEL=False)
         m5 = create_unet(c5)
         x5, y5 = synth.make_batch(8, 512, 512, seed=5)
         x5d, y5d = torch.from_numpy(x5).to(dev), torch.from_numpy(y5).to(dev)
@@ -405,7 +498,7 @@ def extra_measurements(model, dev):
     # the reference's own training resolution (DIM [224, 224], Train_tests.ipynb): 224 is off the 128-pixel row tiles and
     # only its 112-pixel level fits the 16-pixel halo blocks of the phase-decomposed up-conv
     try:
-        c224 = dict(CONFIG, DIM=[224, 224])
+        c224 = dict(CONFIG, DIM=[224, 224], DATA_PARALLEL=False)
         m2 = create_unet(c224)
         x2, y2 = synth.make_batch(32, 224, 224, seed=6)
         x2d, y2d = torch.from_numpy(x2).to(dev), torch.from_numpy(y2).to(dev)

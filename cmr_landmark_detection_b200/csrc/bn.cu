@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(BnArgs a) {
   T* y = static_cast<T*>(a.y) + c;
   T* y2 = static_cast<T*>(a.y2) + c;
   const DropKey key = dropout_key(a.seed, a.site);
+  const float lo = a.bn_first ? 0.f : -INFINITY;     // BN_FIRST: the ReLU follows the normalisation
   for (uint32_t i = i0; i < g.n_items; i += g.stride) {
     if (POST == POST_NONE || POST == POST_DROPOUT) {
       const size_t off = (size_t)(i >> g.lg) * a.C;
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(BnArgs a) {
       else
         Vec8<T>::load(av + off, v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), lo);
       if (POST == POST_DROPOUT) {
         bool keep[8];
         dropout_keep8(key, i, a.thr16, keep);
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(BnArgs a) {
         Vec8<T>::load(av + (size_t)p[k] * a.C, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          v[j] = fmaf(v[j], sc[j], sh[j]);
+          v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), lo);
           mx[j] = (k == 0) ? v[j] : fmaxf(mx[j], v[j]);
         }
         if (a.y) Vec8<T>::store(y + (size_t)p[k] * a.C, v);   // nullptr: pooling-only pass over an already normalised tensor
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(BnArgs a) {
       float v[8];
       Vec8<T>::load(av + (size_t)p * a.C, v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), lo);
       if (a.y2) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) Vec8<T>::store(y2 + (size_t)q[k] * a.C, v);
@@ -365,7 +366,8 @@ struct Gather {
       for (int k = 0; k < 4; ++k)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float yv = fmaf(av[k][j], sc[j], sh[j]);
+          float yv = fmaf(av[k][j], sc[j], sh[j]);
+          if (a.bn_first) yv = fmaxf(yv, 0.f);
           if (k == 0 || yv > best[j]) {
             best[j] = yv;
             arg[j] = k;
@@ -376,6 +378,14 @@ struct Gather {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           if (arg[j] == k) dy[k][j] += dp[j];
+    }
+    if (a.bn_first) {
+      // y = relu(BN(z)): the gradient passes where the normalised value was positive (same float expression as forward)
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (!(fmaf(av[k][j], sc[j], sh[j]) > 0.f)) dy[k][j] = 0.f;
     }
   }
 };
@@ -396,7 +406,7 @@ __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_reduce_
   if ((i0 & ~31u) < g.n_items) {   // warp-uniform: n_items is a multiple of 32 vectors or the warp is partial
     const int c = (int)(i0 & ((1u << g.lg) - 1)) * 8;
     float sc[8], sh[8], s1[8], s2[8];
-    if (POST == POST_POOL) scale_shift8(a, c, sc, sh);
+    if (POST == POST_POOL || a.bn_first) scale_shift8(a, c, sc, sh);
 #pragma unroll
     for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
     const DropKey key = dropout_key(a.seed, a.site);
@@ -434,6 +444,11 @@ __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_apply_k
   const double inv_P = 1.0 / ((double)a.B * a.H * a.W);
   for (int k = threadIdx.x; k < a.C; k += 256) {
     red_s[k] = 0.f;
+    if (a.identity) {      // no BatchNorm in this block: dz = [a > 0] * dy
+      coef_s[k] = 1.f;
+      coef_s[a.C + k] = coef_s[2 * a.C + k] = coef_s[3 * a.C + k] = 0.f;
+      continue;
+    }
     double s1 = 0.0, s2 = 0.0;
 #pragma unroll
     for (int s = 0; s < kRedStripes; ++s) {
@@ -463,10 +478,12 @@ __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_apply_k
       sc[j] = coef_s[c + j];
       k1[j] = coef_s[a.C + c + j];
       c0[j] = coef_s[2 * a.C + c + j];
-      if (POST == POST_POOL) {
-        // the pooling argmax replays the forward values: same float expressions as scale_shift8
+      if ((POST == POST_POOL || a.bn_first) && !a.identity) {
+        // the pooling argmax / BN_FIRST ReLU mask replay the forward values: same float expressions as scale_shift8
         sc[j] = a.gamma[c + j] * a.rstd[c + j];
         sh[j] = coef_s[3 * a.C + c + j];
+      } else {
+        sh[j] = 0.f;
       }
     }
 #pragma unroll
@@ -483,7 +500,7 @@ __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_apply_k
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float da = fmaf(sc[j], dy[k][j], fmaf(-k1[j], av[k][j], c0[j]));
-          dz[j] = av[k][j] > 0.f ? da : 0.f;
+          dz[j] = (a.bn_first || av[k][j] > 0.f) ? da : 0.f;
           db[j] += dz[j];
         }
         Vec8<T>::store(dzp + (size_t)pix[k] * a.C, dz);

@@ -285,10 +285,11 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
             if (a.mode != EPI_LINEAR) {
               const float4 b0 = *reinterpret_cast<const float4*>(s_bias + n0 + sl * 64 + hc * 32 + q * 8);
               const float4 b1 = *reinterpret_cast<const float4*>(s_bias + n0 + sl * 64 + hc * 32 + q * 8 + 4);
-              f[0] = fmaxf(f[0] + b0.x, 0.f); f[1] = fmaxf(f[1] + b0.y, 0.f);
-              f[2] = fmaxf(f[2] + b0.z, 0.f); f[3] = fmaxf(f[3] + b0.w, 0.f);
-              f[4] = fmaxf(f[4] + b1.x, 0.f); f[5] = fmaxf(f[5] + b1.y, 0.f);
-              f[6] = fmaxf(f[6] + b1.z, 0.f); f[7] = fmaxf(f[7] + b1.w, 0.f);
+              const float fl = a.floor;
+              f[0] = fmaxf(f[0] + b0.x, fl); f[1] = fmaxf(f[1] + b0.y, fl);
+              f[2] = fmaxf(f[2] + b0.z, fl); f[3] = fmaxf(f[3] + b0.w, fl);
+              f[4] = fmaxf(f[4] + b1.x, fl); f[5] = fmaxf(f[5] + b1.y, fl);
+              f[6] = fmaxf(f[6] + b1.z, fl); f[7] = fmaxf(f[7] + b1.w, fl);
             }
             if (oob) {
 #pragma unroll

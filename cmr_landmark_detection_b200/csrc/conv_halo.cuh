@@ -16,6 +16,7 @@ struct ConvHaloArgs {
   int C0, Ctot, Cout;
   int n_ntiles, tiles_x, tiles_y, total_tiles;
   int mode, out_split;     // ConvEpilogue; EPI_LINEAR: output channels >= out_split go to out1
+  float floor;             // activation floor of the EPI_RELU* modes: 0 = ReLU, -inf = none (BN_FIRST)
   const float* bias;
   double* stats;
   const float* scale;      // [Cout] (EPI_RELU_AFFINE)

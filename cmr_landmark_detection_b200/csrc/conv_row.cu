@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             f[j] = __uint_as_float(v[j]);
-            if (a.mode != EPI_LINEAR) f[j] = fmaxf(f[j] + bias[j], 0.f);
+            if (a.mode != EPI_LINEAR) f[j] = fmaxf(f[j] + bias[j], a.floor);
             if (oobx) f[j] = 0.f;            // pixel past the end of the image row: clipped by the store, not counted
             if (a.mode == EPI_RELU_STATS) {
               s1[j] += f[j];

@@ -17,6 +17,7 @@ struct ConvRowArgs {
   int C0, Ctot, Cout;
   int n_ntiles, tiles_x, tiles_y, total_tiles;
   int mode, out_split, wres;
+  float floor;             // activation floor of the EPI_RELU* modes: 0 = ReLU, -inf = none (BN_FIRST)
   int och;                 // channels per TMA store box: 64, or 32 when a dgrad's concat split falls on a 32-channel boundary
   int base_offset_mode;    // debug knob: 1 = encode (addr>>7)&3 in the descriptor base-offset field
   const float* bias;

@@ -44,8 +44,13 @@ __global__ void __launch_bounds__(256) conv3x3_simt_kernel(ConvSimtArgs a) {
         float v = 0.f;
         const int c = c0 + ci;
         if (ci < cw && yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) {
-          const size_t pidx = ((size_t)b * a.H + yy) * a.W + xx;
-          v = (c < a.C0) ? to_f32<Tin>(in0[pidx * a.C0 + c]) : to_f32<Tin>(in1[pidx * C1 + (c - a.C0)]);
+          if (a.in_stuffed) {
+            if ((yy & 1) && (xx & 1))
+              v = to_f32<Tin>(in0[(((size_t)b * (a.H >> 1) + (yy >> 1)) * (a.W >> 1) + (xx >> 1)) * a.C0 + c]);
+          } else {
+            const size_t pidx = ((size_t)b * a.H + yy) * a.W + xx;
+            v = (c < a.C0) ? to_f32<Tin>(in0[pidx * a.C0 + c]) : to_f32<Tin>(in1[pidx * C1 + (c - a.C0)]);
+          }
         }
         in_s[p][ci] = v;
       }
@@ -76,9 +81,13 @@ __global__ void __launch_bounds__(256) conv3x3_simt_kernel(ConvSimtArgs a) {
       const int n = n0 + tq * 8;
       if (a.mode != EPI_LINEAR) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j] + a.bias[n + j], 0.f);
+        for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j] + a.bias[n + j], a.floor);
       }
-      const size_t pidx = ((size_t)b * a.H + yy) * a.W + xx;
+      size_t pidx = ((size_t)b * a.H + yy) * a.W + xx;
+      if (a.out_stuffed) {
+        if (!((yy & 1) && (xx & 1))) continue;
+        pidx = ((size_t)b * (a.H >> 1) + (yy >> 1)) * (a.W >> 1) + (xx >> 1);
+      }
       if (a.mode == EPI_LINEAR && n >= a.out_split)
         Vec8<Tout>::store(static_cast<Tout*>(a.out1) + pidx * (a.Cout - a.out_split) + (n - a.out_split), acc);
       else
@@ -153,8 +162,13 @@ __global__ void __launch_bounds__(256) wgrad3x3_simt_kernel(WgradSimtArgs a) {
       float v = 0.f;
       const int c = c0 + cc;
       if (cc < cw && yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) {
-        const size_t pidx = ((size_t)b * a.H + yy) * a.W + xx;
-        v = (c < a.C0) ? to_f32<Tin>(in0[pidx * a.C0 + c]) : to_f32<Tin>(in1[pidx * C1 + (c - a.C0)]);
+        if (a.in_stuffed) {
+          if ((yy & 1) && (xx & 1))
+            v = to_f32<Tin>(in0[(((size_t)b * (a.H >> 1) + (yy >> 1)) * (a.W >> 1) + (xx >> 1)) * a.C0 + c]);
+        } else {
+          const size_t pidx = ((size_t)b * a.H + yy) * a.W + xx;
+          v = (c < a.C0) ? to_f32<Tin>(in0[pidx * a.C0 + c]) : to_f32<Tin>(in1[pidx * C1 + (c - a.C0)]);
+        }
       }
       in_s[p][cc] = v;
     }
@@ -181,6 +195,13 @@ __global__ void __launch_bounds__(256) wgrad3x3_simt_kernel(WgradSimtArgs a) {
   if (ci < cw) {
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
+      if (a.transposed_out) {
+        // dK[8 - tap][co][ci] of the Conv2DTranspose kernel (kh, kw, out, in)
+        float* dst = a.dw + ((size_t)(8 - tap) * a.Cout + n0 + co) * a.Ctot + c0 + ci;
+        atomicAdd(dst, acc[tap][0]);
+        atomicAdd(dst + a.Ctot, acc[tap][1]);
+        continue;
+      }
       float* dst = a.dw + ((size_t)tap * a.Ctot + c0 + ci) * a.Cout + n0 + co;
       atomicAdd(dst, acc[tap][0]);
       atomicAdd(dst + 1, acc[tap][1]);

@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(256, 1) conv3x3_tc_kernel(const __grid_constan
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             f[j] = __uint_as_float(v[q * 8 + j]);
-            if (a.mode != EPI_LINEAR) f[j] = fmaxf(f[j] + s_bias[n0 + ch * 32 + q * 8 + j], 0.f);
+            if (a.mode != EPI_LINEAR) f[j] = fmaxf(f[j] + s_bias[n0 + ch * 32 + q * 8 + j], a.floor);
           }
           if (a.mode == EPI_RELU_AFFINE) {   // inference only
             const float* sa = s_bias + a.Cout + n0 + ch * 32 + q * 8;

@@ -31,6 +31,7 @@ struct ConvTcArgs {
   int C0, Ctot, Cout;
   int n_ntiles, total_tiles;
   int mode, out_split;
+  float floor;        // activation floor of the EPI_RELU* modes: 0 = ReLU, -inf = none (BN_FIRST: Conv -> BN -> ReLU)
   const float* bias;  // [Cout] (EPI_RELU*)
   double* stats;      // [2][Cout] (EPI_RELU_STATS)
   const float* scale; // [Cout] (EPI_RELU_AFFINE)

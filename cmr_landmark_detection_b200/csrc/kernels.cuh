@@ -15,6 +15,13 @@ struct ConvSimtArgs {
   void* out1;           // EPI_LINEAR: channels >= out_split
   double* stats;        // [2][Cout]
   int B, H, W, C0, Ctot, Cout, mode, out_split;
+  float floor = 0.f;    // activation floor of the EPI_RELU* modes: 0 = ReLU, -inf = none (BN_FIRST)
+  // Conv2DTranspose(3, strides 2, 'same') in fp32 parity mode (KerasLayers.py:762-765) as a plain 3x3 convolution over the
+  // VIRTUAL zero-stuffed input xs[2i + 1][2j + 1] = x[i][j] (zero elsewhere) with the flipped kernel:
+  //   out[o] = sum_{2i + k = o} x[i] w[k]  ==  sum_{k'} xs[o + k' - 1] w[2 - k'].
+  int in_stuffed = 0;   // in0 is the LOW-resolution tensor [B, H/2, W/2, C0]; H, W are the output (high) resolution
+  int out_stuffed = 0;  // EPI_LINEAR: only the odd (y, x) outputs are kept, written to a low-resolution [B, H/2, W/2, .] tensor
+                        // (gradient of the zero-stuffing = gather)
 };
 int conv_simt_launch(const ConvSimtArgs& a, int in_is_bf16, int out_is_bf16, cudaStream_t st);
 
@@ -24,6 +31,8 @@ struct WgradSimtArgs {
   const void* dz;
   float* dw;            // [9][Ctot][Cout] fp32, accumulated
   int B, H, W, C0, Ctot, Cout;
+  int in_stuffed = 0;   // in0 is low-resolution and virtually zero-stuffed (see ConvSimtArgs)
+  int transposed_out = 0;   // accumulate into a Conv2DTranspose kernel gradient (kh, kw, Cout, Ctot), taps flipped
 };
 int wgrad_simt_launch(const WgradSimtArgs& a, int in_is_bf16, int dz_is_bf16, cudaStream_t st);
 
@@ -70,7 +79,10 @@ struct BnArgs {
   float* dgamma;
   float* dbeta;
   float* dbias;            // conv bias gradient = sum dz
-  int identity;            // forward: scale 1 / shift 0 (the affine already happened in the conv epilogue)
+  int identity;            // scale 1 / shift 0: the affine already happened in the conv epilogue (inference), or the block
+                           // has no BatchNorm at all (BATCH_NORMALISATION false: backward is then the ReLU mask alone)
+  int bn_first;            // BN_FIRST (KerasLayers.py:681-685): `a` holds z = conv + bias, y = relu(BN(z)); backward masks
+                           // dy with [BN(z) > 0] and dz is NOT masked by [a > 0]
   // first layer (Cin = 1, training): `a` = relu(conv(x) + b) is never stored -- K = 9, so every pass that needs it
   // recomputes it from the 1-channel image (saves a 134 MB write and three 134 MB reads per step at C2)
   const float* x0;         // [B,H,W] fp32 image, nullptr = read `a`

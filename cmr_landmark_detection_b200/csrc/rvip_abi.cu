@@ -115,6 +115,7 @@ static int setup_conv_row(ConvRowArgs* a, int BN, int R, int wres, const void* i
   a->mode = mode;
   a->out_split = (mode == EPI_LINEAR) ? out_split : Cout;
   a->wres = wres;
+  a->floor = 0.f;
   a->base_offset_mode = 0;
   a->bias = bias; a->stats = stats;
   a->dbg = nullptr;
@@ -167,6 +168,7 @@ static int setup_conv_halo(ConvHaloArgs* a, int BN, const void* in0, const void*
   a->out_split = (mode == EPI_LINEAR) ? out_split : Cout;
   a->bias = bias; a->stats = stats;
   a->dbg = nullptr;
+  a->floor = 0.f;
   a->up_ns = 0; a->up_dir = 0; a->up_nph = 1; a->up_cz = 64; a->bias_mod = Cout;
   if (make_act_map_box(&a->in0, in0, B, H, W, C0, 64, 18, 18, 1)) return 1;
   if (C1 > 0) {
@@ -315,6 +317,7 @@ static int setup_conv_tc(ConvTcArgs* a, int* KC, int* BN, const void* in0, const
   a->total_tiles = a->n_ntiles * a->g.tiles_x * a->g.tiles_y * a->g.tiles_b;
   a->mode = mode;
   a->out_split = (mode == EPI_LINEAR) ? out_split : Cout;
+  a->floor = 0.f;
   a->bias = bias;
   a->stats = stats;
   if (make_act_map(&a->in0, in0, B, H, W, C0, *KC, a->g)) return 1;
@@ -383,7 +386,8 @@ static const char* kClassNames[RVIP_NUM_KERNEL_CLASSES] = {"conv_fwd_tcgen05", "
 struct Layer {
   std::string name;
   int C0 = 0, C1 = 0, Cout = 0, H = 0, W = 0;
-  bool bn = false, first = false;
+  bool bn = false, first = false;      // bn: a conv_layer_fn block (conv -> [BN] -> dropout / pool / up-sample pass)
+  bool has_bn = false;                 // ... whose BatchNormalization layer exists (BATCH_NORMALISATION)
   int post = POST_NONE;
   float drop = 0.f;
   uint32_t site = 0;
@@ -414,6 +418,8 @@ struct Layer {
   int up_ns = 0, up_dgrad = 0;         // variant (0 = off); dgrad also phase-decomposed
   int up_wgrad = 0;                    // weight gradient from the low-resolution input (no up-sampled copy needed)
   int needs_y2 = 1;                    // POST_UPSAMPLE layers: some consumer still reads the up-sampled copy
+  int tr_simt = 0;                     // ... in fp32 parity mode: CUDA-core convolution over the virtually zero-stuffed low-resolution
+                                       // input (conv_simt.cu), forward weights = the fp32 rotated copy, dgrad = the raw kernel
   int transposed = 0;                  // decoder up-conv is a Conv2DTranspose(3, strides 2, 'same') (USE_UPSAMPLE falsy):
                                        // kernel layout (kh, kw, out, in); runs on the same phase kernels, other packing
   int feeds_up = 0;                    // this (POST_UPSAMPLE) layer's y feeds a phase-decomposed up-convolution
@@ -506,10 +512,6 @@ static int timed(rvip_handle* h, int cls, int n_launch, cudaStream_t st, F&& f) 
 static int build_plan(rvip_handle* h) {
   const rvip_cfg& c = h->cfg;
   RVIP_REQUIRE(c.depth >= 1 && c.depth <= RVIP_MAX_DEPTH, "DEPTH=%d not in [1,%d]", c.depth, RVIP_MAX_DEPTH);
-  RVIP_REQUIRE(c.batch_norm == 1, "BATCH_NORMALISATION=false is not implemented (every shipped config enables it)");
-  RVIP_REQUIRE(c.bn_first == 0, "BN_FIRST=true (Conv->BN->ReLU) is not implemented (SURVEY row N5)");
-  RVIP_REQUIRE(c.use_upsample == 1 || is_bf16(h), "USE_UPSAMPLE=false (Conv2DTranspose decoder, SURVEY row N5) is implemented "
-               "for PRECISION='bf16' only");
   RVIP_REQUIRE(c.H % (1 << c.depth) == 0 && c.W % (1 << c.depth) == 0, "DIM %dx%d must be divisible by 2^DEPTH=%d",
                c.H, c.W, 1 << c.depth);
   RVIP_REQUIRE(c.filters % 32 == 0 && c.filters >= 32, "FILTERS=%d must be a multiple of 32", c.filters);
@@ -519,6 +521,7 @@ static int build_plan(rvip_handle* h) {
   auto add = [&](const std::string& name, int C0, int C1, int Cout, int H, int W, bool bn, int post, float drop) {
     Layer l;
     l.name = name; l.C0 = C0; l.C1 = C1; l.Cout = Cout; l.H = H; l.W = W; l.bn = bn;
+    l.has_bn = bn && c.batch_norm != 0;
     l.post = post; l.drop = drop;
     if (post == POST_DROPOUT && !(drop > 0.f)) l.post = POST_NONE;
     l.site = (uint32_t)h->L.size();
@@ -584,6 +587,14 @@ static int build_plan(rvip_handle* h) {
     for (Layer& l : h->L) {
       if (l.bn || l.in0_layer < 0 || h->L[l.in0_layer].post != POST_UPSAMPLE) continue;
       l.transposed = 1;
+      if (!is_bf16(h)) {
+        // fp32 parity mode: the producer keeps its low-resolution y, its gradient arrives at low resolution
+        l.tr_simt = 1;
+        h->L[l.in0_layer].feeds_up = 1;
+        h->L[l.in0_layer].g0_lowres = 1;
+        h->L[l.in0_layer].needs_y2 = 0;
+        continue;
+      }
       RVIP_REQUIRE(l.up_ns && l.up_dgrad && l.up_wgrad,
                    "USE_UPSAMPLE=false: %s (%dx%d, %d -> %d channels) does not fit the phase-decomposed kernels (input "
                    "channels %% 64 == 0, FILTERS 32 or a multiple of 64)",
@@ -607,7 +618,7 @@ static int build_plan(rvip_handle* h) {
     else push(l.name + "/kernel", 0, po, {3, 3, Ct, l.Cout});
     po += 9LL * Ct * l.Cout;
     l.off_b = po; push(l.name + "/bias", 0, po, {l.Cout}); po += l.Cout;
-    if (l.bn) {
+    if (l.has_bn) {
       l.off_g = po; push(l.name + "/bn/gamma", 0, po, {l.Cout}); po += l.Cout;
       l.off_be = po; push(l.name + "/bn/beta", 0, po, {l.Cout}); po += l.Cout;
       l.off_mm = so; push(l.name + "/bn/moving_mean", 1, so, {l.Cout}); so += l.Cout;
@@ -720,7 +731,7 @@ static size_t carve(rvip_handle* h, uint8_t* base, int B, int training, bool ass
     if (training) {
       max_dz = std::max(max_dz, P * l.Cout);
       if (!l.first) {
-        T(assign ? &l.dx0 : sink, (l.up_dgrad ? P / 4 : P) * l.C0);
+        T(assign ? &l.dx0 : sink, ((l.up_dgrad || l.tr_simt) ? P / 4 : P) * l.C0);
         if (l.C1) T(assign ? &l.dx1 : sink, P * l.C1);
       }
     }
@@ -750,7 +761,11 @@ static const void* buffer_of(const rvip_handle* h, int layer, int which) {
 
 // Inference in bf16 mode folds BatchNorm (moving statistics) into the conv epilogue: the conv writes the block
 // output y directly (where the layer has one; up-sampling layers keep writing `a`, replicated by the pass after).
-static bool fused_inference(const rvip_handle* h, const Layer& l) { return !h->training && is_bf16(h) && l.bn; }
+static bool fused_inference(const rvip_handle* h, const Layer& l) {
+  return !h->training && is_bf16(h) && l.has_bn && !h->cfg.bn_first;   // BN_FIRST: relu(affine(z)) is not an epilogue affine
+}
+// activation floor of a block's conv epilogue: BN_FIRST stores the pre-activation z = conv + bias
+static float conv_floor(const rvip_handle* h, const Layer& l) { return (l.has_bn && h->cfg.bn_first) ? -INFINITY : 0.f; }
 static void* conv_output(const rvip_handle* h, const Layer& l) {
   return (fused_inference(h, l) && l.y) ? l.y : l.a;
 }
@@ -791,7 +806,7 @@ static int build_descriptors(rvip_handle* h) {
     const void* in0 = buffer_of(h, l.in0_layer, l.in0_which);
     const void* in1 = l.in1_layer >= 0 ? buffer_of(h, l.in1_layer, 1) : nullptr;
     const __nv_bfloat16* pk = static_cast<const __nv_bfloat16*>(h->packed);
-    const int mode = (l.bn && h->training) ? EPI_RELU_STATS : EPI_RELU;
+    const int mode = (l.has_bn && h->training) ? EPI_RELU_STATS : EPI_RELU;
     void* conv_out = conv_output(h, l);
     if (setup_conv_tc(&l.fwd, &l.fKC, &l.fBN, in0, in1, l.C0, l.C1, pk + l.pk_f, conv_out, nullptr, l.Cout, B, l.H, l.W,
                       l.Cout, mode, h->params + l.off_b, h->stats + 2 * l.off_stat))
@@ -813,10 +828,11 @@ static int build_descriptors(rvip_handle* h) {
     if (l.use_hfwd && setup_conv_halo(&l.hfwd, l.hfBN, in0, in1, l.C0, l.C1, pk + l.pk_f, conv_out, nullptr, l.Cout, B, l.H,
                                       l.W, l.Cout, mode, h->params + l.off_b, h->stats + 2 * l.off_stat))
       return 1;
-    if (l.bn) {
+    if (l.has_bn) {
       l.fwd.scale = l.rfwd.scale = l.hfwd.scale = h->aff_scale + l.off_stat;
       l.fwd.shift = l.rfwd.shift = l.hfwd.shift = h->aff_shift + l.off_stat;
     }
+    l.fwd.floor = l.rfwd.floor = l.hfwd.floor = conv_floor(h, l);
     if (h->training) {
       const int dsplit = l.C1 ? l.C0 : l.C0 + l.C1;
       l.use_rdgrad = allow_row && conv_row_plan(l.H, l.W, l.Cout, 0, l.C0 + l.C1, EPI_LINEAR, dsplit, &l.rdBN, &l.rdR,
@@ -861,7 +877,8 @@ static int build_descriptors(rvip_handle* h) {
 // SLOWER at C2 (forward 134 -> 199 us, BN backward 140 -> 274 us): 9 FMAs + 2.25 shared-memory weight loads per output
 // element make those HBM-bound passes issue-bound.  Kept as a tested variant (it saves the 134 MB buffer).
 static bool c1_recompute(const rvip_handle* h, const Layer& l) {
-  return l.first && l.bn && l.C0 == 1 && l.Cout <= 256 && l.W % 4 == 0 && getenv("RVIP_C1_RECOMPUTE") != nullptr &&
+  return l.first && l.has_bn && !h->cfg.bn_first && l.C0 == 1 && l.Cout <= 256 && l.W % 4 == 0 &&
+         getenv("RVIP_C1_RECOMPUTE") != nullptr &&
          (l.post == POST_NONE || l.post == POST_DROPOUT);
 }
 static void set_c1_source(const rvip_handle* h, const Layer& l, BnArgs* a, const float* x) {
@@ -871,7 +888,7 @@ static void set_c1_source(const rvip_handle* h, const Layer& l, BnArgs* a, const
 }
 
 static int conv_forward(rvip_handle* h, Layer& l, const float* x, bool training, cudaStream_t st) {
-  const int mode = (l.bn && training) ? EPI_RELU_STATS : (fused_inference(h, l) ? EPI_RELU_AFFINE : EPI_RELU);
+  const int mode = (l.has_bn && training) ? EPI_RELU_STATS : (fused_inference(h, l) ? EPI_RELU_AFFINE : EPI_RELU);
   if (is_bf16(h) && !l.first) {
     if (l.up_ns) return timed(h, KC_CONV_FWD_TC, 1, st, [&] { return conv_halo_launch(l.ufwd, l.ufBN, l.ufNb, st); });
     if (l.use_rfwd) {
@@ -891,7 +908,7 @@ static int conv_forward(rvip_handle* h, Layer& l, const float* x, bool training,
                              l.Cout, st);
     });
   }
-  if (l.first && l.C0 == 1 && l.Cout <= 256 && l.W % 4 == 0) {
+  if (l.first && l.C0 == 1 && l.Cout <= 256 && l.W % 4 == 0 && conv_floor(h, l) == 0.f) {
     return timed(h, KC_CONV_SIMT, 1, st, [&] {
       const bool aff = mode == EPI_RELU_AFFINE;
       return conv_c1_fwd_launch(x, h->params + l.off_k, h->params + l.off_b, conv_output(h, l), h->stats + 2 * l.off_stat,
@@ -903,11 +920,17 @@ static int conv_forward(rvip_handle* h, Layer& l, const float* x, bool training,
   a.in0 = l.first ? (const void*)x : buffer_of(h, l.in0_layer, l.in0_which);
   a.in1 = l.in1_layer >= 0 ? buffer_of(h, l.in1_layer, 1) : nullptr;
   a.w = h->params + l.off_k;
+  if (l.tr_simt) {   // Conv2DTranspose: low-resolution input, flipped + (out, in)-swapped kernel copy
+    a.in0 = buffer_of(h, l.in0_layer, 1);
+    a.in_stuffed = 1;
+    a.w = static_cast<const float*>(h->packed) + l.pk_d;
+  }
   a.bias = h->params + l.off_b;
   a.out0 = l.a; a.out1 = nullptr;
   a.stats = h->stats + 2 * l.off_stat;
   a.B = h->batch; a.H = l.H; a.W = l.W; a.C0 = l.C0; a.Ctot = l.C0 + l.C1; a.Cout = l.Cout;
   a.mode = mode; a.out_split = l.Cout;
+  a.floor = conv_floor(h, l);
   const int in_bf16 = l.first ? 0 : is_bf16(h);
   return timed(h, KC_CONV_SIMT, 1, st, [&] { return conv_simt_launch(a, in_bf16, is_bf16(h), st); });
 }
@@ -926,6 +949,8 @@ static void fill_bn(const rvip_handle* h, const Layer& l, BnArgs* a, bool traini
   a->seed = seed; a->site = l.site;
   a->thr16 = (uint32_t)std::lround((double)l.drop * 65536.0);
   a->keep_scale = 1.f / (1.f - l.drop);
+  a->identity = l.has_bn ? 0 : 1;          // BATCH_NORMALISATION false: only the dropout / pool / up-sample part remains
+  a->bn_first = (l.has_bn && h->cfg.bn_first) ? 1 : 0;
 }
 
 static int forward_body(rvip_handle* h, const float* x, bool training, uint64_t seed, cudaStream_t st,
@@ -936,7 +961,7 @@ static int forward_body(rvip_handle* h, const float* x, bool training, uint64_t 
           return 0;
         }))
       return 1;
-  } else if (is_bf16(h)) {
+  } else if (is_bf16(h) && !h->cfg.bn_first) {
     // one launch: scale / shift of every BatchNorm layer from the moving statistics
     if (timed(h, KC_BN_FWD, 1, st, [&] {
           return bn_eval_coef_launch(h->params, h->bn_state, h->bn_table_dev, h->n_bn, h->max_bn_c, h->cfg.bn_eps,
@@ -945,11 +970,11 @@ static int forward_body(rvip_handle* h, const float* x, bool training, uint64_t 
       return 1;
   } else {
     int n_bn = 0;
-    for (Layer& l : h->L) n_bn += l.bn ? 1 : 0;
+    for (Layer& l : h->L) n_bn += l.has_bn ? 1 : 0;
     if (timed(h, KC_BN_FWD, n_bn, st, [&] {
           // moving_mean / moving_variance are interleaved per layer in bn_state; prepare per layer
           for (Layer& l : h->L)
-            if (l.bn && bn_eval_prepare_launch(h->bn_state + l.off_mm, h->bn_state + l.off_mv, h->mean + l.off_stat,
+            if (l.has_bn && bn_eval_prepare_launch(h->bn_state + l.off_mm, h->bn_state + l.off_mv, h->mean + l.off_stat,
                                                h->rstd + l.off_stat, l.Cout, h->cfg.bn_eps, st))
               return 1;
           return 0;
@@ -973,7 +998,7 @@ static int forward_body(rvip_handle* h, const float* x, bool training, uint64_t 
       a.a = conv_output(h, l);
       if (a.post == POST_POOL) a.y = nullptr;
     }
-    if (training) {
+    if (training && l.has_bn) {
       a.stats = h->stats + 2 * l.off_stat;
       a.count = (double)h->batch * l.H * l.W;
       a.inv_count = 1.0 / a.count;
@@ -1052,7 +1077,7 @@ static int backward_body(rvip_handle* h, const float* x, uint64_t seed, cudaStre
       a.dbeta = h->grads + l.off_be;
       a.dbias = h->grads + l.off_b;
       // the folded head already left sum dy / sum dy * a of its input block in `red` (head_bn_finalize)
-      const bool have_sums = fold_head && i == h->head_in;
+      const bool have_sums = (fold_head && i == h->head_in) || a.identity;
       if (timed(h, KC_BN_BWD, have_sums ? 1 : 2, st, [&] {
             if (!have_sums && bn_bwd_reduce_launch(a, bf, st)) return 1;
             return bn_bwd_apply_launch(a, bf, st);
@@ -1095,12 +1120,21 @@ static int backward_body(rvip_handle* h, const float* x, uint64_t seed, cudaStre
       w.dz = l.dz;
       w.dw = h->grads + l.off_k;
       w.B = h->batch; w.H = l.H; w.W = l.W; w.C0 = l.C0; w.Ctot = l.C0 + l.C1; w.Cout = l.Cout;
+      if (l.tr_simt) {
+        w.in0 = buffer_of(h, l.in0_layer, 1);
+        w.in_stuffed = 1;
+        w.transposed_out = 1;
+      }
       const int in_bf16 = l.first ? 0 : bf;
       if (timed(h, KC_CONV_SIMT, 1, ws, [&] { return wgrad_simt_launch(w, in_bf16, bf, ws); })) return 1;
       if (!l.first) {
         ConvSimtArgs a;
         a.in0 = l.dz; a.in1 = nullptr;
         a.w = static_cast<const float*>(h->packed) + l.pk_d;
+        if (l.tr_simt) {   // the raw (kh, kw, out, in) kernel IS the rotated dgrad operand; keep the odd outputs only
+          a.w = h->params + l.off_k;
+          a.out_stuffed = 1;
+        }
         a.bias = nullptr;
         a.out0 = l.dx0; a.out1 = l.dx1;
         a.stats = nullptr;
@@ -1191,7 +1225,7 @@ size_t rvip_workspace_bytes(const rvip_handle* h, int batch, int training) {
 
 int rvip_bind(rvip_handle* h, float* params, float* grads, float* bn_state, void* workspace, size_t workspace_bytes,
               int batch, int training) {
-  RVIP_REQUIRE(h && params && bn_state && workspace && batch > 0, "rvip_bind: null/invalid argument");
+  RVIP_REQUIRE(h && params && workspace && batch > 0 && (bn_state || h->n_state == 0), "rvip_bind: null/invalid argument");
   RVIP_REQUIRE(!training || grads, "rvip_bind: training needs a gradient buffer");
   const size_t need = carve(h, nullptr, batch, training, false);
   RVIP_REQUIRE(workspace_bytes >= need, "rvip_bind: workspace too small (%zu < %zu)", workspace_bytes, need);
@@ -1216,6 +1250,10 @@ int rvip_bind(rvip_handle* h, float* params, float* grads, float* bn_state, void
     if (l.pk_d < 0) continue;
     PackEntry e;
     e.src = l.off_k; e.dst_f = l.pk_f; e.dst_d = l.pk_d; e.Ctot = l.C0 + l.C1; e.Cout = l.Cout;
+    if (l.tr_simt) {   // (kh, kw, out, in) read as HWIO with I = out, O = in: its rotated copy is the forward operand
+      e.Ctot = l.Cout;
+      e.Cout = l.C0;
+    }
     tab.push_back(e);
   }
   h->n_pack = (int)tab.size();
@@ -1238,7 +1276,7 @@ int rvip_bind(rvip_handle* h, float* params, float* grads, float* bn_state, void
     std::vector<BnEvalEntry> bt;
     h->max_bn_c = 0;
     for (const Layer& l : h->L) {
-      if (!l.bn) continue;
+      if (!l.has_bn) continue;
       BnEvalEntry e;
       e.off_g = l.off_g; e.off_be = l.off_be; e.off_mm = l.off_mm; e.off_mv = l.off_mv; e.off_stat = l.off_stat;
       e.C = l.Cout;
@@ -1258,7 +1296,7 @@ int rvip_bind(rvip_handle* h, float* params, float* grads, float* bn_state, void
   }
   {
     const Layer& hl = h->L[h->head_in];
-    h->head_fold = training && hl.bn && hl.post == POST_NONE && hl.Cout * h->cfg.classes <= 4096 &&
+    h->head_fold = training && hl.has_bn && !h->cfg.bn_first && hl.post == POST_NONE && hl.Cout * h->cfg.classes <= 4096 &&
                    getenv("RVIP_NO_HEAD_FOLD") == nullptr;
   }
   if (build_descriptors(h)) return 1;
@@ -1436,7 +1474,7 @@ int rvip_debug_buffer(const rvip_handle* h, const char* name, int which, void** 
       case 0: n = P * l.Cout; break;
       case 1: n = l.y ? P * l.Cout : 0; break;
       case 2: n = l.post == POST_POOL ? P / 4 * l.Cout : (l.post == POST_UPSAMPLE ? 4 * P * l.Cout : 0); break;
-      case 3: n = l.dx0 ? (l.up_dgrad ? P / 4 : P) * l.C0 : 0; break;
+      case 3: n = l.dx0 ? ((l.up_dgrad || l.tr_simt) ? P / 4 : P) * l.C0 : 0; break;
       case 4: n = l.dx1 ? P * l.C1 : 0; break;
       default: set_error("rvip_debug_buffer: bad selector %d", which); return 1;
     }

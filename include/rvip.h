@@ -28,10 +28,12 @@ typedef struct rvip_cfg {
   int classes;           /* MASK_CLASSES */
   int depth;             /* DEPTH */
   int filters;           /* FILTERS */
-  int batch_norm;        /* BATCH_NORMALISATION (only 1 is implemented) */
-  int bn_first;          /* BN_FIRST (only 0 is implemented: Conv -> ReLU -> BN, KerasLayers.py:687-691) */
+  int batch_norm;        /* BATCH_NORMALISATION: 0 = the blocks are Conv -> ReLU only (KerasLayers.py:684,691 skipped) */
+  int bn_first;          /* BN_FIRST: 0 = Conv -> ReLU -> BN (KerasLayers.py:687-691, every shipped config),
+                            1 = Conv -> BN -> ReLU (:681-685) */
   int use_upsample;      /* USE_UPSAMPLE truthiness: 1 = UpSampling2D + Conv (KerasLayers.py:753-759), 0 = Conv2DTranspose
-                            (:762-765; bf16 mode, shapes that fit the phase-decomposed kernels) */
+                            (:762-765; bf16: shapes that fit the phase-decomposed kernels; fp32: CUDA-core convolution
+                            over the zero-stuffed input) */
   int precision;         /* 0 = fp32 storage, CUDA-core convs; 1 = bf16 storage, tcgen05 convs */
   float dropout[RVIP_MAX_DEPTH]; /* encoder level l; decoder pops from the back (Unets.py:105-106, :832) */
   float dropout_mid;     /* DROPOUT_MAX at the bottleneck (Unets.py:813) */

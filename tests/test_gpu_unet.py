@@ -77,11 +77,28 @@ def test_conv2d_transpose_decoder_matches_oracle(dim, depth, batch):
             assert e_dev <= 2.5 * e_cal, (name, e_dev, e_cal)
 
 
-def test_conv2d_transpose_decoder_needs_bf16():
-    from cmr_landmark_detection_b200.models.Unets import create_unet
-    with pytest.raises(Exception, match='bf16'):
-        m = create_unet(dict(BASE, DIM=[64, 64], DEPTH=2, PRECISION='fp32', USE_UPSAMPLE=False))
-        m.predict(np.zeros((1, 64, 64, 1), np.float32), batch_size=1)
+@pytest.mark.parametrize('dim,depth,batch', [(32, 2, 3), (64, 3, 2)])
+def test_conv2d_transpose_decoder_fp32_matches_oracle(dim, depth, batch):
+    """USE_UPSAMPLE=False in fp32 parity mode: Conv2DTranspose as a CUDA-core convolution over the virtually zero-stuffed
+    low-resolution tensor (conv_simt.cu) -- heat maps, loss and EVERY gradient tensor against the fp32 oracle."""
+    from oracle import unet_ref as R
+    model, cfg, ws, x, y = _setup('fp32', dim, depth, batch, extra={'USE_UPSAMPLE': False})
+    assert [tuple(w.shape) for w in model.get_weights()] == [tuple(w.shape) for w in ws]
+    heat = model.predict(x, batch_size=batch)
+    ref = R.predict(cfg, ws, x)
+    assert np.abs(heat - ref).max() <= TOL['fp32']['heat'], np.abs(heat - ref).max()
+    model, cfg, ws, x, y = _setup('fp32', dim, depth, batch, randomize_bn=False, extra={'USE_UPSAMPLE': False})
+    out = R.train_grads(cfg, ws, x, y)
+    loss = float(model.train_step_device(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(),
+                                         apply_optimizer=False).item())
+    assert abs(loss - out['loss']) <= TOL['fp32']['loss'] * abs(out['loss']), (loss, out['loss'])
+    g = model.grads.cpu().numpy()
+    for (name, is_state, off, shape), rg in zip(model.tensors, out['grads']):
+        if is_state or np.linalg.norm(rg) < 1e-12:
+            continue
+        mine = g[off:off + int(np.prod(shape))].reshape(shape).astype(np.float64)
+        rl2 = float(np.linalg.norm(mine - rg) / np.linalg.norm(rg))
+        assert rl2 <= (1e-2 if name.endswith('/bias') else 3e-3), (name, rl2)
 
 
 @pytest.mark.parametrize('momentum,nesterov', [(0.0, False), (0.0, True), (0.9, True), (0.9, False)])
