@@ -168,7 +168,7 @@ __device__ __forceinline__ void upsampled_pixels(const BnArgs& a, uint32_t p, ui
 // (a.stats, double) into shared memory -- the former one-block bn_finalize launch, folded in; block 0 also
 // publishes mean / rstd for the backward pass and updates the moving statistics (momentum 0.99, unbiased
 // variance: TF fused batch norm).  Inference: mean / rstd were prepared from the moving statistics.
-template <typename T, int POST, bool FROMX>
+template <typename T, int POST, bool FROMX, bool BNF = false>
 __global__ void __launch_bounds__(256) bn_apply_kernel(BnArgs a) {
   extern __shared__ float coef_s[];   // [2][C]: scale, shift  (+ FROMX: first-layer w [9][C], b [C])
   pdl_wait();
@@ -212,12 +212,17 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(BnArgs a) {
   for (int j = 0; j < 8; ++j) {
     sc[j] = coef_s[c + j];
     sh[j] = coef_s[a.C + c + j];
+    // inverted dropout scales the kept values by 1 / (1 - rate): folded into the affine (ReLU commutes with a positive
+    // factor, so this also holds for BN_FIRST)
+    if (POST == POST_DROPOUT) {
+      sc[j] *= a.keep_scale;
+      sh[j] *= a.keep_scale;
+    }
   }
   const T* av = static_cast<const T*>(a.a) + c;
   T* y = static_cast<T*>(a.y) + c;
   T* y2 = static_cast<T*>(a.y2) + c;
   const DropKey key = dropout_key(a.seed, a.site);
-  const float lo = a.bn_first ? 0.f : -INFINITY;     // BN_FIRST: the ReLU follows the normalisation
   for (uint32_t i = i0; i < g.n_items; i += g.stride) {
     if (POST == POST_NONE || POST == POST_DROPOUT) {
       const size_t off = (size_t)(i >> g.lg) * a.C;
@@ -227,12 +232,15 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(BnArgs a) {
       else
         Vec8<T>::load(av + off, v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), lo);
+      for (int j = 0; j < 8; ++j) {
+        v[j] = fmaf(v[j], sc[j], sh[j]);
+        if (BNF) v[j] = fmaxf(v[j], 0.f);     // BN_FIRST: the ReLU follows the normalisation
+      }
       if (POST == POST_DROPOUT) {
         bool keep[8];
         dropout_keep8(key, i, a.thr16, keep);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = keep[j] ? v[j] * a.keep_scale : 0.f;
+        for (int j = 0; j < 8; ++j) v[j] = keep[j] ? v[j] : 0.f;
       }
       Vec8<T>::store(y + off, v);
     } else if (POST == POST_POOL) {
@@ -246,7 +254,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(BnArgs a) {
         Vec8<T>::load(av + (size_t)p[k] * a.C, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), lo);
+          v[j] = fmaf(v[j], sc[j], sh[j]);
+          if (BNF) v[j] = fmaxf(v[j], 0.f);
           mx[j] = (k == 0) ? v[j] : fmaxf(mx[j], v[j]);
         }
         if (a.y) Vec8<T>::store(y + (size_t)p[k] * a.C, v);   // nullptr: pooling-only pass over an already normalised tensor
@@ -259,7 +268,10 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(BnArgs a) {
       float v[8];
       Vec8<T>::load(av + (size_t)p * a.C, v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), lo);
+      for (int j = 0; j < 8; ++j) {
+        v[j] = fmaf(v[j], sc[j], sh[j]);
+        if (BNF) v[j] = fmaxf(v[j], 0.f);
+      }
       if (a.y2) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) Vec8<T>::store(y2 + (size_t)q[k] * a.C, v);
@@ -281,13 +293,26 @@ static int bn_apply_t(const BnArgs& a, cudaStream_t st) {
   const size_t P = (size_t)a.B * a.H * a.W;
   const int G = a.C / 8;
   const size_t n = (a.post == POST_POOL ? P / 4 : P) * G;
-  static const int fwd_per_sm = getenv("RVIP_BN_FWD_BLOCKS") ? atoi(getenv("RVIP_BN_FWD_BLOCKS")) : 6;
+  // 46 registers x 256 threads: five blocks fit an SM; a grid of six per SM ran its last 148 blocks as a second,
+  // nearly empty wave (bn_forward 0.481 -> 0.448 ms per step, profiles/r2j_sweep.jsonl)
+  static const int fwd_per_sm = getenv("RVIP_BN_FWD_BLOCKS") ? atoi(getenv("RVIP_BN_FWD_BLOCKS")) : 5;
   const int grid = ew_grid(n, fwd_per_sm);   // persistent blocks: the per-block coefficient prologue is amortised
   const size_t sm = (a.x0 ? 12 : 2) * a.C * sizeof(float);
   if (a.x0) {
     RVIP_REQUIRE(a.post == POST_NONE || a.post == POST_DROPOUT, "bn: first-layer recompute with post op %d", a.post);
+    RVIP_REQUIRE(!a.bn_first, "bn: first-layer recompute is not available with BN_FIRST");
     if (a.post == POST_NONE) launch_kernel(bn_apply_kernel<T, POST_NONE, true>, grid, 256, sm, st, a);
     else launch_kernel(bn_apply_kernel<T, POST_DROPOUT, true>, grid, 256, sm, st, a);
+    RVIP_LAUNCH_CHECK();
+    return 0;
+  }
+  if (a.bn_first) {
+    switch (a.post) {
+      case POST_NONE: launch_kernel(bn_apply_kernel<T, POST_NONE, false, true>, grid, 256, sm, st, a); break;
+      case POST_DROPOUT: launch_kernel(bn_apply_kernel<T, POST_DROPOUT, false, true>, grid, 256, sm, st, a); break;
+      case POST_POOL: launch_kernel(bn_apply_kernel<T, POST_POOL, false, true>, grid, 256, sm, st, a); break;
+      default: launch_kernel(bn_apply_kernel<T, POST_UPSAMPLE, false, true>, grid, 256, sm, st, a); break;
+    }
     RVIP_LAUNCH_CHECK();
     return 0;
   }
@@ -316,7 +341,7 @@ int bn_apply_launch(const BnArgs& a, int is_bf16, cudaStream_t st) {
 // ------------------------------------------------------------------------------------- backward
 // Work item -> K pixels (4 for a pooling window, else 1) with dy = dL/d(BN output) gathered from the
 // consumers' gradient buffers and the stored relu(conv) values.
-template <typename T, int POST, bool FROMX = false>
+template <typename T, int POST, bool FROMX = false, bool BNF = false>
 struct Gather {
   static constexpr int K = POST == POST_POOL ? 4 : 1;
   // w1_s: first-layer weights / bias staged in shared memory (FROMX only)
@@ -337,7 +362,7 @@ struct Gather {
         bool keep[8];
         dropout_keep8(key, i, a.thr16, keep);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dy[0][j] = keep[j] ? dy[0][j] * a.keep_scale : 0.f;
+        for (int j = 0; j < 8; ++j) dy[0][j] = keep[j] ? dy[0][j] : 0.f;   // x keep_scale: folded into the callers' coefficients
       }
     } else if constexpr (POST == POST_UPSAMPLE) {
       const uint32_t p = i >> g.lg;
@@ -367,7 +392,7 @@ struct Gather {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float yv = fmaf(av[k][j], sc[j], sh[j]);
-          if (a.bn_first) yv = fmaxf(yv, 0.f);
+          if (BNF) yv = fmaxf(yv, 0.f);
           if (k == 0 || yv > best[j]) {
             best[j] = yv;
             arg[j] = k;
@@ -379,7 +404,7 @@ struct Gather {
         for (int j = 0; j < 8; ++j)
           if (arg[j] == k) dy[k][j] += dp[j];
     }
-    if (a.bn_first) {
+    if (BNF) {
       // y = relu(BN(z)): the gradient passes where the normalised value was positive (same float expression as forward)
 #pragma unroll
       for (int k = 0; k < K; ++k)
@@ -393,7 +418,7 @@ struct Gather {
 // pass 1: red[stripe][c] += sum dy, red[stripe][C + c] += sum dy * a   (raw a; normalised by the finalize kernel).
 // Blocks spread their double atomics over kRedStripes copies: ~1200 blocks adding to ONE copy serialise in the L2
 // atomic unit for ~17 us (profiles/microbench/atomics.cu), 16 copies cost nothing measurable.
-template <typename T, int POST, bool FROMX>
+template <typename T, int POST, bool FROMX, bool BNF = false>
 __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_reduce_kernel(BnArgs a) {
   extern __shared__ float red_s[];  // [2][C]  (+ FROMX: first-layer w [9][C], b [C])
   pdl_wait();
@@ -406,14 +431,14 @@ __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_reduce_
   if ((i0 & ~31u) < g.n_items) {   // warp-uniform: n_items is a multiple of 32 vectors or the warp is partial
     const int c = (int)(i0 & ((1u << g.lg) - 1)) * 8;
     float sc[8], sh[8], s1[8], s2[8];
-    if (POST == POST_POOL || a.bn_first) scale_shift8(a, c, sc, sh);
+    if (POST == POST_POOL || BNF) scale_shift8(a, c, sc, sh);
 #pragma unroll
     for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
     const DropKey key = dropout_key(a.seed, a.site);
     for (uint32_t i = i0; i < g.n_items; i += g.stride) {
       uint32_t pix[K];
       float av[K][8], dy[K][8];
-      Gather<T, POST, FROMX>::run(a, g, key, i, c, sc, sh, pix, av, dy, red_s + 2 * a.C);
+      Gather<T, POST, FROMX, BNF>::run(a, g, key, i, c, sc, sh, pix, av, dy, red_s + 2 * a.C);
 #pragma unroll
       for (int k = 0; k < K; ++k)
 #pragma unroll
@@ -423,6 +448,13 @@ __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_reduce_
         }
     }
     pdl_launch_dependents();
+    if (POST == POST_DROPOUT) {   // dy of a kept element is keep_scale times the stored gradient
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] *= a.keep_scale;
+        s2[j] *= a.keep_scale;
+      }
+    }
     block_accumulate8(red_s, c, s1, 1u << g.lg);
     block_accumulate8(red_s + a.C, c, s2, 1u << g.lg);
   }
@@ -434,7 +466,7 @@ __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_reduce_
 // pass 2: dz and the conv-bias gradient.  Prologue (every block, one thread per channel): fold the stripes and
 // derive the coefficients of  dz = [a>0] * ( sc*dy - k1*a + c0 )  in double, once per channel; block 0 also
 // writes dgamma / dbeta.
-template <typename T, int POST, bool FROMX>
+template <typename T, int POST, bool FROMX, bool BNF = false>
 __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_apply_kernel(BnArgs a) {
   extern __shared__ float red_s[];  // [C] bias-gradient partials, then [4][C] sc, k1, c0, shift (+ FROMX: w [9][C], b [C])
   pdl_wait();
@@ -478,7 +510,7 @@ __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_apply_k
       sc[j] = coef_s[c + j];
       k1[j] = coef_s[a.C + c + j];
       c0[j] = coef_s[2 * a.C + c + j];
-      if ((POST == POST_POOL || a.bn_first) && !a.identity) {
+      if ((POST == POST_POOL || BNF) && !a.identity) {
         // the pooling argmax / BN_FIRST ReLU mask replay the forward values: same float expressions as scale_shift8
         sc[j] = a.gamma[c + j] * a.rstd[c + j];
         sh[j] = coef_s[3 * a.C + c + j];
@@ -486,21 +518,26 @@ __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_apply_k
         sh[j] = 0.f;
       }
     }
+    // coefficient of the gathered dy in dz: the dropout variant's gather leaves out the 1 / (1 - rate) factor
+    float scd[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) db[j] = 0.f;
+    for (int j = 0; j < 8; ++j) {
+      db[j] = 0.f;
+      scd[j] = POST == POST_DROPOUT ? coef_s[c + j] * a.keep_scale : coef_s[c + j];
+    }
     T* dzp = static_cast<T*>(a.dz) + c;
     const DropKey key = dropout_key(a.seed, a.site);
     for (uint32_t i = i0; i < g.n_items; i += g.stride) {
       uint32_t pix[K];
       float av[K][8], dy[K][8];
-      Gather<T, POST, FROMX>::run(a, g, key, i, c, sc, sh, pix, av, dy, red_s + 5 * a.C);
+      Gather<T, POST, FROMX, BNF>::run(a, g, key, i, c, sc, sh, pix, av, dy, red_s + 5 * a.C);
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         float dz[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float da = fmaf(sc[j], dy[k][j], fmaf(-k1[j], av[k][j], c0[j]));
-          dz[j] = (a.bn_first || av[k][j] > 0.f) ? da : 0.f;
+          const float da = fmaf(scd[j], dy[k][j], fmaf(-k1[j], av[k][j], c0[j]));
+          dz[j] = (BNF || av[k][j] > 0.f) ? da : 0.f;
           db[j] += dz[j];
         }
         Vec8<T>::store(dzp + (size_t)pix[k] * a.C, dz);
@@ -518,9 +555,11 @@ static int bn_bwd_t(const BnArgs& a, cudaStream_t st) {
   const size_t P = (size_t)a.B * a.H * a.W;
   const int G = a.C / 8;
   const size_t n = (a.post == POST_POOL ? P / 4 : P) * G;
-  // persistent grids: every block ends with C global atomics, so few, long-lived blocks; 3 (not 4) per SM leave
-  // registers for a co-resident weight-gradient CTA of the side stream (rvip_abi.cu:backward_body)
-  static const int per_sm = getenv("RVIP_BN_BWD_BLOCKS") ? atoi(getenv("RVIP_BN_BWD_BLOCKS")) : 3;
+  // persistent grids: every block ends with C global atomics, so few, long-lived blocks.  Four per SM (all the
+  // 64-register kernels allow): ncu shows these passes latency bound (long-scoreboard stalls 13-17 warps per issue, DRAM
+  // at 51-59 %), so occupancy buys bandwidth -- 1.388 -> 1.316 ms per step, and the overlapped step gains too
+  // (4.63 -> 4.54 ms) although a co-resident weight-gradient CTA of the side stream now finds fewer free registers
+  static const int per_sm = getenv("RVIP_BN_BWD_BLOCKS") ? atoi(getenv("RVIP_BN_BWD_BLOCKS")) : 4;
   const int grid = ew_grid(n, a.post == POST_POOL ? 2 : per_sm);
   const size_t sm = ((WHICH == 0 ? 2 : 5) + (a.x0 ? 10 : 0)) * a.C * sizeof(float);
   if (a.x0) {
@@ -535,10 +574,15 @@ static int bn_bwd_t(const BnArgs& a, cudaStream_t st) {
     RVIP_LAUNCH_CHECK();
     return 0;
   }
-#define RVIP_BWD(POSTV)                                                        \
-  if (WHICH == 0)                                                              \
-    launch_kernel(bn_bwd_reduce_kernel<T, POSTV, false>, grid, 256, sm, st, a); \
-  else                                                                         \
+#define RVIP_BWD(POSTV)                                                                \
+  if (a.bn_first) {                                                                    \
+    if (WHICH == 0)                                                                    \
+      launch_kernel(bn_bwd_reduce_kernel<T, POSTV, false, true>, grid, 256, sm, st, a); \
+    else                                                                               \
+      launch_kernel(bn_bwd_apply_kernel<T, POSTV, false, true>, grid, 256, sm, st, a);  \
+  } else if (WHICH == 0)                                                               \
+    launch_kernel(bn_bwd_reduce_kernel<T, POSTV, false>, grid, 256, sm, st, a);         \
+  else                                                                                 \
     launch_kernel(bn_bwd_apply_kernel<T, POSTV, false>, grid, 256, sm, st, a);
   switch (a.post) {
     case POST_NONE: RVIP_BWD(POST_NONE) break;
