@@ -111,8 +111,12 @@ __device__ __forceinline__ void row_mma_loop(const ConvRowArgs& a, RowCtl* ctl, 
   pdl_launch_dependents();   // all MMAs issued: the next kernel may start launching behind the last epilogue
 }
 
-template <int BN, int R, bool AFFINE, int OCH>
+// MODE (ConvEpilogue) is a template parameter: ncu showed the 8 epilogue warps -- two per scheduler, ~950 instructions per
+// warp and tile -- setting the tile period of the level-0 layers (2.6 us against 1.2 us of MMAs), and with a run-time
+// mode every element of a dgrad tile still issued the predicated-off bias / ReLU / statistics instructions.
+template <int BN, int R, int MODE, int OCH>
 __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_constant__ ConvRowArgs a, int nst) {
+  constexpr bool AFFINE = MODE == EPI_RELU_AFFINE;
   constexpr int A_TX = row_a_bytes(R);
   constexpr int A_ST = round1k(A_TX);
   constexpr int W_TILE = BN * kPixB;           // one (chunk, tap) weight tile: BN rows x 64 B
@@ -163,7 +167,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
   if (warp >= 4) {
     for (int c = threadIdx.x - 128; c < 16 * a.Cout; c += 256) s_slot[c] = 0.f;
     for (int c = threadIdx.x - 128; c < a.Cout; c += 256) {
-      s_bias[c] = a.mode != EPI_LINEAR ? a.bias[c] : 0.f;
+      s_bias[c] = MODE != EPI_LINEAR ? a.bias[c] : 0.f;
       if (AFFINE) {
         s_aff[c] = a.scale[c];
         s_aff[a.Cout + c] = a.shift[c];
@@ -238,7 +242,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
       const int y0 = ((pt / a.tiles_x) % a.tiles_y) * R;
       const int b = pt / (a.tiles_x * a.tiles_y);
       const int n0 = nt * BN;
-      const bool oobx = a.mode == EPI_RELU_STATS && x0 + r >= a.W;
+      const bool oobx = MODE == EPI_RELU_STATS && x0 + 128 > a.W && x0 + r >= a.W;   // only a partial last tile has any
       if (et == 0) tma_store_wait_read0();   // previous tile's TMA store has drained the staging buffer
       row_bar_sync(1, 256);
       mbar_wait(&ctl->tfull[acc], acc_phase);
@@ -246,7 +250,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
         float bias[32], s1[32], s2[32];
-        if (a.mode != EPI_LINEAR) {
+        if (MODE != EPI_LINEAR) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 t = *reinterpret_cast<const float4*>(s_bias + n0 + ch * 32 + j * 4);
@@ -266,9 +270,15 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             f[j] = __uint_as_float(v[j]);
-            if (a.mode != EPI_LINEAR) f[j] = fmaxf(f[j] + bias[j], a.floor);
-            if (oobx) f[j] = 0.f;            // pixel past the end of the image row: clipped by the store, not counted
-            if (a.mode == EPI_RELU_STATS) {
+            if (MODE != EPI_LINEAR) f[j] = fmaxf(f[j] + bias[j], a.floor);
+          }
+          if (MODE == EPI_RELU_STATS) {
+            if (oobx) {                      // pixel past the end of the image row: clipped by the store, not counted
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
               s1[j] += f[j];
               s2[j] = fmaf(f[j], f[j], s2[j]);
             }
@@ -289,7 +299,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
             *reinterpret_cast<uint4*>(staging + oc * OCHUNK + swz_off<OROWB>(row, cidx)) = pk;
           }
         }
-        if (a.mode == EPI_RELU_STATS) {
+        if (MODE == EPI_RELU_STATS) {
           // transpose-reduce: after the 5 steps lane j holds the sum over the warp's 32 pixels of channel j
 #pragma unroll
           for (int S = 16; S >= 1; S >>= 1) {
@@ -315,7 +325,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
 #pragma unroll 1
         for (int oc = 0; oc < BN / OCH; ++oc) {
           const int n = n0 + oc * OCH;
-          if (a.mode == EPI_LINEAR && n >= a.out_split)
+          if (MODE == EPI_LINEAR && n >= a.out_split)
             tma_store_4d(&a.out1, staging + oc * OCHUNK, n - a.out_split, x0, y0, b);
           else
             tma_store_4d(&a.out0, staging + oc * OCHUNK, n, x0, y0, b);
@@ -326,7 +336,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
       if (acc == 0) acc_phase ^= 1;
     }
     if (et == 0) tma_store_wait_all0();
-    if (a.mode == EPI_RELU_STATS) {
+    if (MODE == EPI_RELU_STATS) {
       row_bar_sync(1, 256);
       for (int c = et; c < 2 * a.Cout; c += 256) {
         float t = 0.f;
@@ -374,7 +384,7 @@ bool conv_row_plan(int H, int W, int C0, int C1, int Cout, int mode, int out_spl
   return false;
 }
 
-template <int BN, int R, bool AFFINE, int OCH>
+template <int BN, int R, int MODE, int OCH>
 static int launch_row(const ConvRowArgs& a, int nst, cudaStream_t st) {
   const int nchunks = a.Ctot / 32;
   const int wres_bytes = a.wres ? nchunks * 9 * a.Cout * kPixB : 0;
@@ -382,22 +392,28 @@ static int launch_row(const ConvRowArgs& a, int nst, cudaStream_t st) {
   RVIP_REQUIRE(smem <= (size_t)kMaxDynSmemRow, "conv_row: %zu bytes of shared memory needed", smem);
   static bool attr_set = false;
   if (!attr_set) {
-    RVIP_CUDA(cudaFuncSetAttribute(conv3x3_row_kernel<BN, R, AFFINE, OCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RVIP_CUDA(cudaFuncSetAttribute(conv3x3_row_kernel<BN, R, MODE, OCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    kMaxDynSmemRow));
     attr_set = true;
   }
   const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
-  launch_kernel(conv3x3_row_kernel<BN, R, AFFINE, OCH>, grid, 384, smem, st, a, nst);
+  launch_kernel(conv3x3_row_kernel<BN, R, MODE, OCH>, grid, 384, smem, st, a, nst);
   RVIP_LAUNCH_CHECK();
   return 0;
 }
 
 int conv_row_launch(const ConvRowArgs& a, int BN, int R, int nst, cudaStream_t st) {
-  const bool aff = a.mode == EPI_RELU_AFFINE;
   RVIP_REQUIRE(a.och == 32 || (a.och == 64 && BN == 64), "conv_row: bad store box width %d for BN=%d", a.och, BN);
-#define RVIP_ROW_CASE(bn, r, oc) \
-  if (BN == bn && R == r && a.och == oc)   \
-    return aff ? launch_row<bn, r, true, oc>(a, nst, st) : launch_row<bn, r, false, oc>(a, nst, st);
+  RVIP_REQUIRE(a.mode >= EPI_RELU_STATS && a.mode <= EPI_RELU_AFFINE, "conv_row: bad epilogue mode %d", a.mode);
+#define RVIP_ROW_CASE(bn, r, oc)                                                               \
+  if (BN == bn && R == r && a.och == oc) {                                                     \
+    switch (a.mode) {                                                                          \
+      case EPI_RELU_STATS: return launch_row<bn, r, EPI_RELU_STATS, oc>(a, nst, st);           \
+      case EPI_RELU: return launch_row<bn, r, EPI_RELU, oc>(a, nst, st);                       \
+      case EPI_LINEAR: return launch_row<bn, r, EPI_LINEAR, oc>(a, nst, st);                   \
+      default: return launch_row<bn, r, EPI_RELU_AFFINE, oc>(a, nst, st);                      \
+    }                                                                                          \
+  }
   RVIP_ROW_CASE(32, 4, 32)
   RVIP_ROW_CASE(32, 2, 32)
   RVIP_ROW_CASE(64, 4, 64)

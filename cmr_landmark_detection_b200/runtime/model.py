@@ -201,6 +201,8 @@ class RvipUNet:
         # DATA_PARALLEL=False builds a rank-local model inside a multi-rank job (no collectives are ever issued).
         self.dp = DataParallel(self.device, enabled=bool(config.get('DATA_PARALLEL', True)))
         self.max_bindings = int(config.get('MAX_BINDINGS', 4))
+        self._stage_threads = int(config.get('STAGING_THREADS', 4))
+        self._pool = None
         self._metric_buf = None
         self.set_weights(self._initial_weights(self._seed))
 
@@ -390,6 +392,32 @@ class RvipUNet:
             self._pinned[key] = t
         return t
 
+    def _stage(self, dst: torch.Tensor, src: np.ndarray) -> torch.Tensor:
+        """Host batch -> page-locked memory for the asynchronous H2D copy.  Already page-locked sources (cudaHostRegister /
+        pinned torch storage behind the ndarray) are used in place; anything else is copied into the pinned slot `dst` by a
+        few threads (numpy releases the GIL): one thread moves ~5 GB/s, i.e. 25 MB per step cost as much as the GPU step
+        itself once eight ranks share a host (round-1 finding: N = 8 end-to-end 12 % under the device-resident rate)."""
+        t = torch.from_numpy(src)
+        try:
+            if t.is_pinned():
+                return t
+        except RuntimeError:
+            pass
+        n = src.shape[0]
+        d = dst.numpy()
+        workers = min(self._stage_threads, n)
+        if workers <= 1 or src.nbytes < (1 << 20):
+            np.copyto(d, src)
+            return dst
+        if self._pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(max_workers=self._stage_threads)
+        bounds = [n * i // workers for i in range(workers + 1)]
+        futs = [self._pool.submit(np.copyto, d[bounds[i]:bounds[i + 1]], src[bounds[i]:bounds[i + 1]]) for i in range(workers)]
+        for f in futs:
+            f.result()
+        return dst
+
     def _check_x(self, x):
         if x.ndim != 4 or tuple(x.shape[1:]) != (self._cfg.H, self._cfg.W, self._cfg.in_ch):
             raise ValueError('expected input [N,%d,%d,%d], got %s' % (self._cfg.H, self._cfg.W, self._cfg.in_ch,
@@ -561,10 +589,8 @@ class RvipUNet:
                 ev = self._slot_ev[s]
                 if used_once[s]:
                     ev['ready'].synchronize()       # the pinned slot's previous H2D has completed (long ago)
-                hx = self._pin('fx%d' % s, x.shape)
-                hy = self._pin('fy%d' % s, y.shape)
-                hx.copy_(torch.from_numpy(x))
-                hy.copy_(torch.from_numpy(y))
+                hx = self._stage(self._pin('fx%d' % s, x.shape), x)
+                hy = self._stage(self._pin('fy%d' % s, y.shape), y)
                 key = (s, tuple(x.shape), tuple(y.shape))
                 if key not in dev_slots:
                     dev_slots[key] = (torch.empty(x.shape, dtype=torch.float32, device=self.device),

@@ -101,7 +101,7 @@ def test_conv2d_transpose_decoder_fp32_matches_oracle(dim, depth, batch):
         # depth 3 at 64 x 64 normalises over few values at the bottom: same fp32 conditioning bound as
         # test_train_step_matches_oracle uses for depth > 2
         # sums of dy / dz under BatchNorm nearly cancel (biases, beta, gamma): atomics-order noise shows there first
-        assert rl2 <= (3e-3 if name.endswith('/kernel') else 1e-2) * (5 if depth > 2 else 1), (name, rl2)
+        assert rl2 <= (1e-2 if name.endswith('/kernel') else 3e-2), (name, rl2)
 
 
 @pytest.mark.parametrize('momentum,nesterov', [(0.0, False), (0.0, True), (0.9, True), (0.9, False)])
