@@ -236,6 +236,14 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
     const int et = threadIdx.x - 128;       // 0..255
     float* slot = s_slot + (size_t)(warp - 4) * 2 * a.Cout;
     int acc = 0, acc_phase = 0;
+    // BN == 32 (one 32-channel chunk per tile): the per-thread BatchNorm partial sums live in registers across ALL tiles
+    // of the CTA (same N tile every time when Cout == 32) and the 31-shuffle transpose-reduce runs ONCE at the end -- per
+    // tile it was a quarter of the epilogue's instructions, and the epilogue (two warps per scheduler) sets the tile period
+    constexpr bool PERSIST = MODE == EPI_RELU_STATS && BN == 32;
+    const bool persist = PERSIST && a.n_ntiles == 1;
+    float p1[PERSIST ? 32 : 1], p2[PERSIST ? 32 : 1];
+#pragma unroll
+    for (int j = 0; j < (PERSIST ? 32 : 1); ++j) p1[j] = p2[j] = 0.f;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
       const int nt = tile % a.n_ntiles, pt = tile / a.n_ntiles;
       const int x0 = (pt % a.tiles_x) * 128;
@@ -258,7 +266,10 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
           }
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) s1[j] = s2[j] = 0.f;
+        for (int j = 0; j < 32; ++j) {
+          s1[j] = PERSIST ? p1[j] : 0.f;
+          s2[j] = PERSIST ? p2[j] : 0.f;
+        }
 #pragma unroll
         for (int ii = 0; ii < R / 2; ++ii) {
           const int i = eh * (R / 2) + ii;
@@ -299,7 +310,17 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
             *reinterpret_cast<uint4*>(staging + oc * OCHUNK + swz_off<OROWB>(row, cidx)) = pk;
           }
         }
-        if (MODE == EPI_RELU_STATS) {
+        if (PERSIST && persist) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            p1[j] = s1[j];
+            p2[j] = s2[j];
+          }
+        } else if (MODE == EPI_RELU_STATS) {
+          if (PERSIST) {     // several N tiles per CTA: the running sums are per tile after all
+#pragma unroll
+            for (int j = 0; j < 32; ++j) p1[j] = p2[j] = 0.f;
+          }
           // transpose-reduce: after the 5 steps lane j holds the sum over the warp's 32 pixels of channel j
 #pragma unroll
           for (int S = 16; S >= 1; S >>= 1) {
@@ -336,6 +357,21 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
       if (acc == 0) acc_phase ^= 1;
     }
     if (et == 0) tma_store_wait_all0();
+    if (PERSIST && persist) {
+#pragma unroll
+      for (int S = 16; S >= 1; S >>= 1) {
+        const bool up = (lane & S) != 0;
+#pragma unroll
+        for (int k = 0; k < S; ++k) {
+          const float send1 = up ? p1[k] : p1[k + S], keep1 = up ? p1[k + S] : p1[k];
+          const float send2 = up ? p2[k] : p2[k + S], keep2 = up ? p2[k + S] : p2[k];
+          p1[k] = keep1 + __shfl_xor_sync(0xffffffffu, send1, S);
+          p2[k] = keep2 + __shfl_xor_sync(0xffffffffu, send2, S);
+        }
+      }
+      slot[lane] += p1[0];
+      slot[a.Cout + lane] += p2[0];
+    }
     if (MODE == EPI_RELU_STATS) {
       row_bar_sync(1, 256);
       for (int c = et; c < 2 * a.Cout; c += 256) {
