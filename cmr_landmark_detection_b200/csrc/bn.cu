@@ -223,6 +223,40 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(BnArgs a) {
   T* y = static_cast<T*>(a.y) + c;
   T* y2 = static_cast<T*>(a.y2) + c;
   const DropKey key = dropout_key(a.seed, a.site);
+  if constexpr ((POST == POST_NONE || POST == POST_DROPOUT) && !FROMX) {
+    // kU independent 16-byte loads in flight per thread before the first dependent instruction (level-1 dropout layers
+    // 35 -> 27 us; profiles/r2p_sweep.jsonl).  The same pipelining of the BACKWARD passes (two items = four loads in
+    // flight) left their profile-mode time unchanged and slowed the overlapped step by 1.5 % (64 registers: no room
+    // beside a weight-gradient CTA of the side stream; profiles/r2r_bn_bwd_u2_sweep.jsonl) -- not kept.
+    constexpr int kU = 4;
+    for (uint32_t ib = i0; ib < g.n_items; ib += kU * g.stride) {
+      Raw8<T> raw[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const uint32_t i = ib + u * g.stride;
+        if (i < g.n_items) load_raw8(av + (size_t)(i >> g.lg) * a.C, raw[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const uint32_t i = ib + u * g.stride;
+        if (i >= g.n_items) break;
+        float v[8];
+        unpack_raw8(raw[u], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[j] = fmaf(v[j], sc[j], sh[j]);
+          if (BNF) v[j] = fmaxf(v[j], 0.f);     // BN_FIRST: the ReLU follows the normalisation
+        }
+        if (POST == POST_DROPOUT) {
+          bool keep[8];
+          dropout_keep8(key, i, a.thr16, keep);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = keep[j] ? v[j] : 0.f;
+        }
+        Vec8<T>::store(y + (size_t)(i >> g.lg) * a.C, v);
+      }
+    }
+  } else {
   for (uint32_t i = i0; i < g.n_items; i += g.stride) {
     if (POST == POST_NONE || POST == POST_DROPOUT) {
       const size_t off = (size_t)(i >> g.lg) * a.C;
@@ -279,6 +313,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(BnArgs a) {
       if (a.y) Vec8<T>::store(y + (size_t)p * a.C, v);   // low-resolution copy for the phase-decomposed up-conv
     }
   }
+  }
   pdl_launch_dependents();
 }
 
@@ -293,9 +328,10 @@ static int bn_apply_t(const BnArgs& a, cudaStream_t st) {
   const size_t P = (size_t)a.B * a.H * a.W;
   const int G = a.C / 8;
   const size_t n = (a.post == POST_POOL ? P / 4 : P) * G;
-  // 46 registers x 256 threads: five blocks fit an SM; a grid of six per SM ran its last 148 blocks as a second,
-  // nearly empty wave (bn_forward 0.481 -> 0.448 ms per step, profiles/r2j_sweep.jsonl)
-  static const int fwd_per_sm = getenv("RVIP_BN_FWD_BLOCKS") ? atoi(getenv("RVIP_BN_FWD_BLOCKS")) : 5;
+  // 56-60 registers x 256 threads (pooling variant; plain / dropout variants with four loads in flight): four blocks
+  // fit an SM.  Larger grids ran their surplus blocks as a second, nearly empty wave (six per SM: 0.481 ms per step,
+  // five: 0.448, four with the 4-deep loads: 0.410; profiles/r2j_sweep.jsonl, r2p_sweep.jsonl)
+  static const int fwd_per_sm = getenv("RVIP_BN_FWD_BLOCKS") ? atoi(getenv("RVIP_BN_FWD_BLOCKS")) : 4;
   const int grid = ew_grid(n, fwd_per_sm);   // persistent blocks: the per-block coefficient prologue is amortised
   const size_t sm = (a.x0 ? 12 : 2) * a.C * sizeof(float);
   if (a.x0) {
