@@ -293,6 +293,8 @@ def run_b200(args):
     # HOST numpy batches.  Every step stages (x, y) in pinned memory, copies them to the device and reads the loss
     # back, all inside the timed region; fit() pipelines batch i+1's staging / H2D behind step i's kernels.
     class _Seq:
+        rvip_per_replica = True      # weak scaling: every rank's generator hands out that rank's OWN 32-slice batches
+
         def __init__(self, n):
             self.n = n
 
