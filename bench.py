@@ -399,7 +399,8 @@ def run_b200(args):
                           'final_loss': final_loss, 'gflop_per_slice_train': round(fl['train'] / 1e9, 2)},
                 'clocks': clocks, 'gpu_launches': int(launches),
                 'e2e': {'value': round(e2e, 1), 'unit': 'slices/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 8,
-                        'ms_per_step': round(ms_e2e / K, 4), 'api': 'model.fit(Sequence of host batches)'},
+                        'ms_per_step': round(ms_e2e / K, 4), 'api': 'model.fit(Sequence of host batches)',
+                        'host_thread_ms_per_step': getattr(model, 'last_fit_timing', None)},
                 'roofline': roof,
                 'cpu_baseline': cpu}
         # secondary metrics build further models on this rank only: single-process runs only (a data-parallel model

@@ -562,68 +562,121 @@ class RvipUNet:
     def _run_steps(self, batches, with_metrics: bool = False) -> List[float]:
         """Pipelined training steps over an iterable of host (x, y) batches -- the loop inside fit().
 
-        Two staging slots: while the GPU runs step i, the host copies batch i+1 into pinned memory and a side
-        stream moves it to the device; the loss of step i is read back (async D2H + event) only after step i+1
-        has been queued, so the device never waits for the host.  Every step still pays its own H2D copy of
-        (x, y) and its own D2H read of the loss."""
+        Three pinned staging slots and a staging thread: while the GPU runs step i and this thread queues the launches of
+        step i + 1, the staging thread pulls batch i + 2 from the generator and copies it into page-locked memory; a copy
+        stream moves a staged batch to the device behind the running step; the loss of step i is read back (async D2H +
+        event) only after step i + 1 has been queued.  Every step still pays its own H2D copy of (x, y) and its own D2H
+        read of the loss; the device never waits for the host unless generator + staging alone exceed a step.
+        `self.last_fit_timing` holds where this thread's time went (ms per step): waiting for a staged batch, queueing
+        the step's launches, waiting for the previous step's loss."""
+        import queue
+        import threading
         losses: List[float] = []
         self._metric_rows: List[int] = []       # pixels per step whose heat statistics sit in self._metric_buf
         nrow = 1 + 3 * self._cfg.classes
+        NS = 3
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream(self.device)
             if not hasattr(self, '_copy_stream'):
                 self._copy_stream = torch.cuda.Stream(device=self.device)
-                self._slot_ev = [dict(ready=torch.cuda.Event(), used=torch.cuda.Event(), loss=torch.cuda.Event())
-                                 for _ in range(2)]
+                self._slot_ev = [dict(ready=torch.cuda.Event(), used=torch.cuda.Event()) for _ in range(NS)]
+                self._loss_ev = [torch.cuda.Event() for _ in range(2)]
                 self._loss_pin = [torch.zeros(1, dtype=torch.float64, pin_memory=True) for _ in range(2)]
             cs = self._copy_stream
+            staged: 'queue.Queue' = queue.Queue(maxsize=NS - 1)
+            free: 'queue.Queue' = queue.Queue()
+            for s in range(NS):
+                free.put((s, False))
+            stop = threading.Event()
+            dev = self.device
+
+            def producer():
+                try:
+                    torch.cuda.set_device(dev)
+                    for x, y in batches:
+                        x = np.ascontiguousarray(x, dtype=np.float32)
+                        y = np.ascontiguousarray(y, dtype=np.float32)
+                        self._check_x(x)
+                        self._check_y(y, len(x))
+                        s, used = free.get()
+                        if stop.is_set():
+                            return
+                        if used:
+                            self._slot_ev[s]['ready'].synchronize()   # the slot's previous H2D has left pinned memory
+                        hx = self._stage(self._pin('fx%d' % s, x.shape), x)
+                        hy = self._stage(self._pin('fy%d' % s, y.shape), y)
+                        staged.put((s, hx, hy))
+                    staged.put(None)
+                except BaseException as e:          # surface generator / validation errors in the training thread
+                    staged.put(e)
+
+            th = threading.Thread(target=producer, daemon=True)
+            th.start()
             dev_slots: Dict[Tuple[int, Tuple[int, ...], Tuple[int, ...]], Tuple[torch.Tensor, torch.Tensor]] = {}
-            pending = None       # slot whose loss has not been read yet
-            used_once = [False, False]
-            for i, (x, y) in enumerate(batches):
-                x = np.ascontiguousarray(x, dtype=np.float32)
-                y = np.ascontiguousarray(y, dtype=np.float32)
-                self._check_x(x)
-                self._check_y(y, len(x))
-                s = i & 1
-                ev = self._slot_ev[s]
-                if used_once[s]:
-                    ev['ready'].synchronize()       # the pinned slot's previous H2D has completed (long ago)
-                hx = self._stage(self._pin('fx%d' % s, x.shape), x)
-                hy = self._stage(self._pin('fy%d' % s, y.shape), y)
-                key = (s, tuple(x.shape), tuple(y.shape))
-                if key not in dev_slots:
-                    dev_slots[key] = (torch.empty(x.shape, dtype=torch.float32, device=self.device),
-                                      torch.empty(y.shape, dtype=torch.float32, device=self.device))
-                xd, yd = dev_slots[key]
-                if used_once[s]:
-                    cs.wait_event(ev['used'])       # step i-2 has finished reading this device slot
-                with torch.cuda.stream(cs):
-                    xd.copy_(hx, non_blocking=True)
-                    yd.copy_(hy, non_blocking=True)
-                    ev['ready'].record(cs)
-                main.wait_event(ev['ready'])
-                loss_dev = self.train_step_device(xd, yd)
-                if with_metrics:
-                    # training metrics: one reduction pass over this step's heat map and target, rows stay on the device
-                    if self._metric_buf is None or self._metric_buf.shape[0] <= i:
-                        grown = torch.zeros((max(256, 2 * (i + 1)), nrow), dtype=torch.float64, device=self.device)
-                        if self._metric_buf is not None:
-                            grown[:self._metric_buf.shape[0]] = self._metric_buf
-                        self._metric_buf = grown
-                    self._stats_row(self._last_heat, yd, self._metric_buf[i])
-                    self._metric_rows.append(len(x) * self._cfg.H * self._cfg.W)
-                ev['used'].record(main)
-                self._loss_pin[s].copy_(loss_dev.reshape(1), non_blocking=True)
-                ev['loss'].record(main)
-                used_once[s] = True
+            used_once = [False] * NS
+            pending = None       # loss slot whose value has not been read yet
+            t_wait = t_launch = t_loss = 0.0
+            i = 0
+            try:
+                while True:
+                    t0 = time.perf_counter()
+                    item = staged.get()
+                    t1 = time.perf_counter()
+                    if item is None:
+                        break
+                    if isinstance(item, BaseException):
+                        raise item
+                    s, hx, hy = item
+                    ev = self._slot_ev[s]
+                    key = (s, tuple(hx.shape), tuple(hy.shape))
+                    if key not in dev_slots:
+                        dev_slots[key] = (torch.empty(tuple(hx.shape), dtype=torch.float32, device=self.device),
+                                          torch.empty(tuple(hy.shape), dtype=torch.float32, device=self.device))
+                    xd, yd = dev_slots[key]
+                    if used_once[s]:
+                        cs.wait_event(ev['used'])       # the step that last read this device slot has finished
+                    with torch.cuda.stream(cs):
+                        xd.copy_(hx, non_blocking=True)
+                        yd.copy_(hy, non_blocking=True)
+                        ev['ready'].record(cs)
+                    free.put((s, True))                 # the staging thread may refill the slot once `ready` has fired
+                    main.wait_event(ev['ready'])
+                    loss_dev = self.train_step_device(xd, yd)
+                    if with_metrics:
+                        # training metrics: one reduction pass over this step's heat map and target, rows stay on the device
+                        if self._metric_buf is None or self._metric_buf.shape[0] <= i:
+                            grown = torch.zeros((max(256, 2 * (i + 1)), nrow), dtype=torch.float64, device=self.device)
+                            if self._metric_buf is not None:
+                                grown[:self._metric_buf.shape[0]] = self._metric_buf
+                            self._metric_buf = grown
+                        self._stats_row(self._last_heat, yd, self._metric_buf[i])
+                        self._metric_rows.append(int(hx.shape[0]) * self._cfg.H * self._cfg.W)
+                    ev['used'].record(main)
+                    ls = i & 1
+                    self._loss_pin[ls].copy_(loss_dev.reshape(1), non_blocking=True)
+                    self._loss_ev[ls].record(main)
+                    used_once[s] = True
+                    t2 = time.perf_counter()
+                    if pending is not None:
+                        self._loss_ev[pending].synchronize()
+                        losses.append(float(self._loss_pin[pending][0]))
+                    pending = ls
+                    t3 = time.perf_counter()
+                    t_wait += t1 - t0
+                    t_launch += t2 - t1
+                    t_loss += t3 - t2
+                    i += 1
                 if pending is not None:
-                    self._slot_ev[pending]['loss'].synchronize()
+                    self._loss_ev[pending].synchronize()
                     losses.append(float(self._loss_pin[pending][0]))
-                pending = s
-            if pending is not None:
-                self._slot_ev[pending]['loss'].synchronize()
-                losses.append(float(self._loss_pin[pending][0]))
+            finally:
+                stop.set()
+                free.put((0, False))       # unblock a producer waiting for a slot
+                th.join(timeout=5.0)
+        n = max(i, 1)
+        self.last_fit_timing = {'steps': i, 'wait_staged_ms': round(t_wait / n * 1e3, 3),
+                                'queue_launches_ms': round(t_launch / n * 1e3, 3),
+                                'wait_prev_loss_ms': round(t_loss / n * 1e3, 3)}
         return losses
 
     # ------------------------------------------------------------------ loss / metric bookkeeping
