@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
     for (int c = threadIdx.x - 128; c < 4 * auxc; c += 256) s_part[c] = 0.f;
     // the bias lives in shared memory: per-element __ldg in the epilogue exposed one L2 latency per 8 channels
     for (int c = threadIdx.x - 128; c < auxc; c += 256) {
-      s_bias[c] = a.mode != EPI_LINEAR ? a.bias[NS ? c % a.bias_mod : c] : 0.f;
+      s_bias[c] = (a.mode != EPI_LINEAR && a.mode != EPI_LINEAR_BNRED) ? a.bias[NS ? c % a.bias_mod : c] : 0.f;
       s_bias[a.Cout + c] = a.mode == EPI_RELU_AFFINE ? a.scale[c] : 1.f;
       s_bias[2 * a.Cout + c] = a.mode == EPI_RELU_AFFINE ? a.shift[c] : 0.f;
     }
@@ -249,6 +249,13 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
     uint8_t* stg = staging + (size_t)grp * Cfg::SB * Cfg::STG;
     int buf = 0, tphase = 0, sb = 0;
     long long t_epi = 0;
+    // EPI_LINEAR_BNRED (conv_tc.cuh): BatchNorm-backward sums of the block this gradient feeds, in the statistics mapping
+    // below (thread = 8 channels x 8 rows of a staged slice); its relu(conv) values come straight from global memory,
+    // requested before the accumulator slice is read so that their latency hides behind the TMEM loads and the packing
+    const bool red = a.mode == EPI_LINEAR_BNRED;
+    const bool lin = a.mode == EPI_LINEAR || red;
+    const bool sums = a.mode == EPI_RELU_STATS || red;
+    const DropKey dkey = {a.bnred.k0, a.bnred.k1};
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
       const int nt = tile % a.n_ntiles, pt = tile / n_eff;
       const int ph_t = (tile % n_eff) / a.n_ntiles;
@@ -272,6 +279,19 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
           else tma_store_wait_read0();
         }
         halo_bar_sync(1 + grp, 128);
+        uint4 auxv[8];
+        if (red) {
+          const int cg = gt & 7, rt = gt >> 3;
+          const __nv_bfloat16* A = static_cast<const __nv_bfloat16*>(a.bnred.a);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int row = rt + k * 16, yy = y0 + (row >> 3), xx = x0 + (row & 7);
+            const bool ok = yy < a.H && xx < a.W;
+            const size_t pix = ((size_t)b * a.H + yy) * a.W + xx;
+            auxv[k] = ok ? __ldg(reinterpret_cast<const uint4*>(A + pix * a.Cout + n0 + sl * 64 + cg * 8))
+                         : make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
 #pragma unroll
         for (int hc = 0; hc < 2; ++hc) {
           uint32_t v[32];
@@ -282,7 +302,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
             float f[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]);
-            if (a.mode != EPI_LINEAR) {
+            if (!lin) {
               const float4 b0 = *reinterpret_cast<const float4*>(s_bias + n0 + sl * 64 + hc * 32 + q * 8);
               const float4 b1 = *reinterpret_cast<const float4*>(s_bias + n0 + sl * 64 + hc * 32 + q * 8 + 4);
               const float fl = a.floor;
@@ -324,8 +344,9 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
             tma_store_4d(&a.out0, sbuf, n, x0, y0, b);
           tma_store_commit();
         }
-        if (a.mode == EPI_RELU_STATS) {
+        if (sums) {
           // per-channel sum / sum^2 of the slice from the bf16 values just staged: 8 column groups x 16 threads
+          // (EPI_LINEAR_BNRED: sum keep * dy / sum keep * dy * a instead, `a` from auxv, the dropout mask replayed)
           const int cg = gt & 7, rt = gt >> 3;
           float s[8], q2[8];
 #pragma unroll
@@ -335,6 +356,30 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
             const int row = rt + k * 16;
             const uint4 raw = *reinterpret_cast<const uint4*>(sbuf + swz_off<128>(row, cg));
             const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+            if (red) {
+              const int yy = y0 + (row >> 3), xx = x0 + (row & 7);
+              const bool ok = yy < a.H && xx < a.W;
+              const uint32_t pix = ((uint32_t)b * a.H + yy) * a.W + xx;
+              bool keep[8];
+              if (a.bnred.thr16) {
+                dropout_keep8(dkey, (pix << a.bnred.lg) | (uint32_t)((n0 + sl * 64) / 8 + cg), a.bnred.thr16, keep);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) keep[j] = true;
+              }
+              const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&auxv[k]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(h[j]);
+                const float2 av = __bfloat1622float2(ha[j]);
+                const float d0 = (ok && keep[2 * j]) ? f.x : 0.f, d1 = (ok && keep[2 * j + 1]) ? f.y : 0.f;
+                s[2 * j] += d0;
+                s[2 * j + 1] += d1;
+                q2[2 * j] = fmaf(d0, av.x, q2[2 * j]);
+                q2[2 * j + 1] = fmaf(d1, av.y, q2[2 * j + 1]);
+              }
+              continue;
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float2 f = __bfloat1622float2(h[j]);
@@ -384,10 +429,12 @@ __global__ void __launch_bounds__(384, 1) conv3x3_halo_kernel(const __grid_const
     }
     if (a.dbg && threadIdx.x == 128) a.dbg[blockIdx.x * 8 + 5] = t_epi;
     if (gt == 0) tma_store_wait_all0();
-    if (a.mode == EPI_RELU_STATS) {
+    if (sums) {
       halo_bar_sync(3, 256);
+      double* dst = red ? a.bnred.red + (size_t)(blockIdx.x % kBnRedStripes) * 2 * a.Cout : a.stats;
+      const double fac = red ? (double)a.bnred.keep_scale : 1.0;
       for (int c = threadIdx.x - 128; c < 2 * a.Cout; c += 256)
-        atomicAdd(&a.stats[c], (double)s_part[c] + (double)s_part[2 * a.Cout + c]);
+        atomicAdd(&dst[c], ((double)s_part[c] + (double)s_part[2 * a.Cout + c]) * fac);
     }
   }
   tc_fence_before();
@@ -453,7 +500,7 @@ int conv_halo_up_variant(int h, int w, int Cin, int Cout) {
 long long conv_halo_up_pack_elems(int Cin, int Cout) {
   return Cout % 64 == 0 ? 16LL * Cin * Cout : 2LL * 6 * 64 * Cin;
 }
-bool conv_halo_up_plan(int B, int h, int w, int Cin, int Cout, int dir, int* BN, int* nbst) {
+bool conv_halo_up_plan(int B, int h, int w, int Cin, int Cout, int dir, int* BN, int* nbst, bool bnred) {
   const int ns = conv_halo_up_variant(h, w, Cin, Cout);
   if (!ns) return false;
   const int nph = ns == 2 ? 4 : 2;
@@ -470,7 +517,7 @@ bool conv_halo_up_plan(int B, int h, int w, int Cin, int Cout, int dir, int* BN,
   // narrower N tiles need less shared memory (8 KB per weight-ring slot at BN = 64): fall back until one fits
   for (; bn >= 64; bn >>= 1) {
     if (N % bn != 0) continue;
-    const size_t fixed = halo_fixed_bytes(bn, N, dir == 0 ? EPI_RELU : EPI_LINEAR);
+    const size_t fixed = halo_fixed_bytes(bn, N, dir == 0 ? EPI_RELU : (bnred ? EPI_LINEAR_BNRED : EPI_LINEAR));
     if (fixed >= (size_t)kHaloMaxSmem) continue;
     int n = (int)((kHaloMaxSmem - fixed) / ((size_t)bn * 128));
     if (n > kHaloMaxB) n = kHaloMaxB;

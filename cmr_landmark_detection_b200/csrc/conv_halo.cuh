@@ -21,6 +21,7 @@ struct ConvHaloArgs {
   double* stats;
   const float* scale;      // [Cout] (EPI_RELU_AFFINE)
   const float* shift;
+  BnRedArgs bnred;         // EPI_LINEAR_BNRED
   long long* dbg;          // optional [grid][8]: issue-loop cycles, waits on TMEM / activation block / weight tile, kernel cycles, epilogue cycles
   // ---- phase-decomposed up-convolution (UpSampling2D(2) -> Conv3x3 folded into 2x2 / 2x3-tap convolutions on the
   // LOW-resolution tensor, one per output phase (row parity a, column parity b); conv_halo_up_* below).  H, W above are
@@ -45,7 +46,7 @@ int conv_halo_launch(const ConvHaloArgs& a, int BN, int nbst, cudaStream_t st);
 // (2 x 3 taps, structurally zero weights where a column phase does not see a tap).
 // Returns the variant (2 / 3) or 0 when the layer is not eligible (h, w = LOW-resolution size).
 int conv_halo_up_variant(int h, int w, int Cin, int Cout);
-bool conv_halo_up_plan(int B, int h, int w, int Cin, int Cout, int dir, int* BN, int* nbst);
+bool conv_halo_up_plan(int B, int h, int w, int Cin, int Cout, int dir, int* BN, int* nbst, bool bnred = false);
 // elements of one packed operand copy (forward and dgrad copies have the same size)
 long long conv_halo_up_pack_elems(int Cin, int Cout);
 

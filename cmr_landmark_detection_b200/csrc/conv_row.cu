@@ -117,6 +117,9 @@ __device__ __forceinline__ void row_mma_loop(const ConvRowArgs& a, RowCtl* ctl, 
 template <int BN, int R, int MODE, int OCH>
 __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_constant__ ConvRowArgs a, int nst) {
   constexpr bool AFFINE = MODE == EPI_RELU_AFFINE;
+  constexpr bool LIN = MODE == EPI_LINEAR || MODE == EPI_LINEAR_BNRED;   // no bias / activation in the epilogue
+  constexpr bool RED = MODE == EPI_LINEAR_BNRED;                        // ... plus the BatchNorm-backward sums
+  constexpr bool SUMS = MODE == EPI_RELU_STATS || RED;                   // per-channel partial sums of some kind
   constexpr int A_TX = row_a_bytes(R);
   constexpr int A_ST = round1k(A_TX);
   constexpr int W_TILE = BN * kPixB;           // one (chunk, tap) weight tile: BN rows x 64 B
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
   if (warp >= 4) {
     for (int c = threadIdx.x - 128; c < 16 * a.Cout; c += 256) s_slot[c] = 0.f;
     for (int c = threadIdx.x - 128; c < a.Cout; c += 256) {
-      s_bias[c] = MODE != EPI_LINEAR ? a.bias[c] : 0.f;
+      s_bias[c] = !LIN ? a.bias[c] : 0.f;
       if (AFFINE) {
         s_aff[c] = a.scale[c];
         s_aff[a.Cout + c] = a.shift[c];
@@ -239,7 +242,13 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
     // BN == 32 (one 32-channel chunk per tile): the per-thread BatchNorm partial sums live in registers across ALL tiles
     // of the CTA (same N tile every time when Cout == 32) and the 31-shuffle transpose-reduce runs ONCE at the end -- per
     // tile it was a quarter of the epilogue's instructions, and the epilogue (two warps per scheduler) sets the tile period
-    constexpr bool PERSIST = MODE == EPI_RELU_STATS && BN == 32;
+    constexpr bool PERSIST = SUMS && BN == 32;
+    // EPI_LINEAR_BNRED: the thread's items of a tile (rows x 32-channel chunks) of the BatchNorm block's stored relu(conv)
+    // tensor, fetched with plain coalesced loads BEFORE the accumulator is waited for (the latency hides behind the MMAs)
+    constexpr int NIT = (R / 2) * (BN / 32);
+    static_assert(!RED || NIT <= 2, "EPI_LINEAR_BNRED keeps at most two items of the aux tensor in registers");
+    uint4 aux[RED ? NIT * 4 : 1];
+    const DropKey dkey = {a.bnred.k0, a.bnred.k1};
     const bool persist = PERSIST && a.n_ntiles == 1;
     float p1[PERSIST ? 32 : 1], p2[PERSIST ? 32 : 1];
 #pragma unroll
@@ -250,7 +259,20 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
       const int y0 = ((pt / a.tiles_x) % a.tiles_y) * R;
       const int b = pt / (a.tiles_x * a.tiles_y);
       const int n0 = nt * BN;
-      const bool oobx = MODE == EPI_RELU_STATS && x0 + 128 > a.W && x0 + r >= a.W;   // only a partial last tile has any
+      const bool oobx = SUMS && x0 + 128 > a.W && x0 + r >= a.W;   // only a partial last tile has any
+      if (RED) {
+        const __nv_bfloat16* A = static_cast<const __nv_bfloat16*>(a.bnred.a);
+#pragma unroll
+        for (int ch = 0; ch < BN / 32; ++ch)
+#pragma unroll
+          for (int ii = 0; ii < R / 2; ++ii) {
+            const int i = eh * (R / 2) + ii;
+            const size_t pix = ((size_t)b * a.H + y0 + i) * a.W + x0 + r;
+            const uint4* src = reinterpret_cast<const uint4*>(A + pix * a.Cout + n0 + ch * 32);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) aux[(ch * (R / 2) + ii) * 4 + g] = oobx ? make_uint4(0u, 0u, 0u, 0u) : __ldg(src + g);
+          }
+      }
       if (et == 0) tma_store_wait_read0();   // previous tile's TMA store has drained the staging buffer
       row_bar_sync(1, 256);
       mbar_wait(&ctl->tfull[acc], acc_phase);
@@ -258,7 +280,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
         float bias[32], s1[32], s2[32];
-        if (MODE != EPI_LINEAR) {
+        if (!LIN) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 t = *reinterpret_cast<const float4*>(s_bias + n0 + ch * 32 + j * 4);
@@ -281,7 +303,33 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             f[j] = __uint_as_float(v[j]);
-            if (MODE != EPI_LINEAR) f[j] = fmaxf(f[j] + bias[j], a.floor);
+            if (!LIN) f[j] = fmaxf(f[j] + bias[j], a.floor);
+          }
+          if (RED) {
+            // sum keep * dy and sum keep * dy * a per channel (x keep_scale at the very end); dy = this accumulator
+            const uint32_t pix = ((uint32_t)b * a.H + y0 + i) * a.W + x0 + r;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint4 raw = aux[(ch * (R / 2) + ii) * 4 + g];
+              const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw);
+              bool keep[8];
+              if (a.bnred.thr16) {
+                dropout_keep8(dkey, (pix << a.bnred.lg) | (uint32_t)((n0 + ch * 32) / 8 + g), a.bnred.thr16, keep);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) keep[j] = true;
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 av = __bfloat1622float2(hh[j]);
+                const float d0 = (keep[2 * j] && !oobx) ? f[g * 8 + 2 * j] : 0.f;
+                const float d1 = (keep[2 * j + 1] && !oobx) ? f[g * 8 + 2 * j + 1] : 0.f;
+                s1[g * 8 + 2 * j] += d0;
+                s1[g * 8 + 2 * j + 1] += d1;
+                s2[g * 8 + 2 * j] = fmaf(d0, av.x, s2[g * 8 + 2 * j]);
+                s2[g * 8 + 2 * j + 1] = fmaf(d1, av.y, s2[g * 8 + 2 * j + 1]);
+              }
+            }
           }
           if (MODE == EPI_RELU_STATS) {
             if (oobx) {                      // pixel past the end of the image row: clipped by the store, not counted
@@ -316,7 +364,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
             p1[j] = s1[j];
             p2[j] = s2[j];
           }
-        } else if (MODE == EPI_RELU_STATS) {
+        } else if (SUMS) {
           if (PERSIST) {     // several N tiles per CTA: the running sums are per tile after all
 #pragma unroll
             for (int j = 0; j < 32; ++j) p1[j] = p2[j] = 0.f;
@@ -372,13 +420,16 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
       slot[lane] += p1[0];
       slot[a.Cout + lane] += p2[0];
     }
-    if (MODE == EPI_RELU_STATS) {
+    if (SUMS) {
       row_bar_sync(1, 256);
+      // EPI_LINEAR_BNRED: striped like bn_bwd_reduce_kernel's partial sums; the dropout factor 1 / (1 - rate) goes in here
+      double* dst = RED ? a.bnred.red + (size_t)(blockIdx.x % kBnRedStripes) * 2 * a.Cout : a.stats;
+      const float fac = RED ? a.bnred.keep_scale : 1.f;
       for (int c = et; c < 2 * a.Cout; c += 256) {
         float t = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) t += s_slot[(size_t)w * 2 * a.Cout + c];
-        atomicAdd(&a.stats[c], (double)t);
+        atomicAdd(&dst[c], (double)(t * fac));
       }
     }
   }
@@ -440,14 +491,26 @@ static int launch_row(const ConvRowArgs& a, int nst, cudaStream_t st) {
 
 int conv_row_launch(const ConvRowArgs& a, int BN, int R, int nst, cudaStream_t st) {
   RVIP_REQUIRE(a.och == 32 || (a.och == 64 && BN == 64), "conv_row: bad store box width %d for BN=%d", a.och, BN);
-  RVIP_REQUIRE(a.mode >= EPI_RELU_STATS && a.mode <= EPI_RELU_AFFINE, "conv_row: bad epilogue mode %d", a.mode);
+  RVIP_REQUIRE(a.mode >= EPI_RELU_STATS && a.mode <= EPI_LINEAR_BNRED, "conv_row: bad epilogue mode %d", a.mode);
+  if (a.mode == EPI_LINEAR_BNRED) {
+    RVIP_REQUIRE((R / 2) * (BN / 32) <= 2 && a.out_split == a.Cout && a.bnred.a && a.bnred.red,
+                 "conv_row: EPI_LINEAR_BNRED needs a single output and a tile of at most two items per thread (BN=%d R=%d)",
+                 BN, R);
+    // the instantiations that exist: (32, 4), (32, 2), (64, 2)
+    if (BN == 32 && R == 4 && a.och == 32) return launch_row<32, 4, EPI_LINEAR_BNRED, 32>(a, nst, st);
+    if (BN == 32 && R == 2 && a.och == 32) return launch_row<32, 2, EPI_LINEAR_BNRED, 32>(a, nst, st);
+    if (BN == 64 && R == 2 && a.och == 64) return launch_row<64, 2, EPI_LINEAR_BNRED, 64>(a, nst, st);
+    set_error("conv_row: no EPI_LINEAR_BNRED instantiation for BN=%d R=%d och=%d", BN, R, a.och);
+    return 1;
+  }
 #define RVIP_ROW_CASE(bn, r, oc)                                                               \
   if (BN == bn && R == r && a.och == oc) {                                                     \
     switch (a.mode) {                                                                          \
       case EPI_RELU_STATS: return launch_row<bn, r, EPI_RELU_STATS, oc>(a, nst, st);           \
       case EPI_RELU: return launch_row<bn, r, EPI_RELU, oc>(a, nst, st);                       \
       case EPI_LINEAR: return launch_row<bn, r, EPI_LINEAR, oc>(a, nst, st);                   \
-      default: return launch_row<bn, r, EPI_RELU_AFFINE, oc>(a, nst, st);                      \
+      case EPI_RELU_AFFINE: return launch_row<bn, r, EPI_RELU_AFFINE, oc>(a, nst, st);         \
+      default: break;                                                                          \
     }                                                                                          \
   }
   RVIP_ROW_CASE(32, 4, 32)

@@ -24,6 +24,7 @@ struct ConvRowArgs {
   double* stats;
   const float* scale;      // [Cout] (EPI_RELU_AFFINE)
   const float* shift;
+  BnRedArgs bnred;         // EPI_LINEAR_BNRED
   long long* dbg;          // optional [grid][8]: issue-loop cycles, waits on TMEM / input stage, -, kernel, epilogue cycles
 };
 // Chooses the tile (BN, R), weight residency and stage count; false if the layer does not fit this kernel.

@@ -19,6 +19,23 @@ enum ConvEpilogue {
   EPI_RELU = 1,        // a = relu(acc + bias), bf16 store (up-conv; inference)
   EPI_LINEAR = 2,      // acc, bf16 store (dgrad); output channels >= out_split go to out1
   EPI_RELU_AFFINE = 3, // y = scale * relu(acc + bias) + shift: inference, BatchNorm (moving statistics) folded in
+  EPI_LINEAR_BNRED = 4,  // dgrad whose output IS dL/dy of a BatchNorm block (row / halo kernels, single output): stores it like
+                         // EPI_LINEAR and also leaves that block's BatchNorm-backward sums (BnRedArgs) -- the separate
+                         // two-tensor statistics pass (bn_bwd_reduce) of that block disappears
+};
+
+// EPI_LINEAR_BNRED: the epilogue reads the block's stored relu(conv) tile `a` (plain coalesced loads issued before the
+// accumulator is waited for), replays the dropout keep-mask that sits between the block and this convolution, and adds
+//   red[stripe][c] += keep_scale * sum keep * dy,   red[stripe][C + c] += keep_scale * sum keep * dy * a
+// (the sums bn_bwd_reduce_kernel produces; striped like there).
+constexpr int kBnRedStripes = 4;
+struct BnRedArgs {
+  const void* a;          // [B, H, W, C] bf16: relu(conv) of the block whose output gradient this convolution produces
+  double* red;            // [kBnRedStripes][2][C]
+  uint32_t k0, k1;        // dropout key of the step (common.cuh: dropout_key(seed, site))
+  uint32_t thr16;         // 0 = no dropout between the block and this convolution
+  float keep_scale;       // 1 / (1 - rate)
+  int lg;                 // log2(C / 8): vector index of the mask generator = (pixel << lg) | (channel / 8)
 };
 
 // ---- forward / dgrad: out[p, n] = epi( sum_{tap, c} in[p + off(tap), c] * Wp[n][tap][c] )

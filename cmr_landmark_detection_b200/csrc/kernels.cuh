@@ -45,7 +45,7 @@ int wgrad_c1_launch(const float* x, const void* dz, float* dw, int B, int H, int
                     cudaStream_t st);
 
 // ------------------------------------------------------------------ BatchNorm passes (bn.cu)
-constexpr int kRedStripes = 4;   // copies of the BN-backward partial sums (blocks add to copy blockIdx % 4)
+constexpr int kRedStripes = kBnRedStripes;   // copies of the BN-backward partial sums (blocks add to copy blockIdx % 4)
 enum PostOp { POST_NONE = 0, POST_DROPOUT = 1, POST_POOL = 2, POST_UPSAMPLE = 3 };
 
 struct BnArgs {

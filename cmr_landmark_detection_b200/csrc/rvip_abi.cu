@@ -116,6 +116,7 @@ static int setup_conv_row(ConvRowArgs* a, int BN, int R, int wres, const void* i
   a->out_split = (mode == EPI_LINEAR) ? out_split : Cout;
   a->wres = wres;
   a->floor = 0.f;
+  memset(&a->bnred, 0, sizeof(a->bnred));
   a->base_offset_mode = 0;
   a->bias = bias; a->stats = stats;
   a->dbg = nullptr;
@@ -169,6 +170,7 @@ static int setup_conv_halo(ConvHaloArgs* a, int BN, const void* in0, const void*
   a->bias = bias; a->stats = stats;
   a->dbg = nullptr;
   a->floor = 0.f;
+  memset(&a->bnred, 0, sizeof(a->bnred));
   a->up_ns = 0; a->up_dir = 0; a->up_nph = 1; a->up_cz = 64; a->bias_mod = Cout;
   if (make_act_map_box(&a->in0, in0, B, H, W, C0, 64, 18, 18, 1)) return 1;
   if (C1 > 0) {
@@ -422,6 +424,8 @@ struct Layer {
                                        // input (conv_simt.cu), forward weights = the fp32 rotated copy, dgrad = the raw kernel
   int transposed = 0;                  // decoder up-conv is a Conv2DTranspose(3, strides 2, 'same') (USE_UPSAMPLE falsy):
                                        // kernel layout (kh, kw, out, in); runs on the same phase kernels, other packing
+  int red_fused = 0;                   // this block's BatchNorm-backward sums come out of the dgrad that produces its output
+                                       // gradient (EPI_LINEAR_BNRED): no bn_bwd_reduce pass
   int feeds_up = 0;                    // this (POST_UPSAMPLE) layer's y feeds a phase-decomposed up-convolution
   int g0_lowres = 0;                   // ... and its gradient arrives at its own (low) resolution
   long long pk_uf = -1, pk_ud = -1;    // packed up-convolution operands
@@ -489,6 +493,20 @@ struct rvip_handle {
 };
 
 namespace rvip {
+
+// host restatement of common.cuh: mix32 / dropout_key (the dgrad epilogues of EPI_LINEAR_BNRED take the key by value)
+static uint32_t host_mix32(uint32_t v) {
+  v ^= v >> 16;
+  v *= 0x85ebca6bu;
+  v ^= v >> 13;
+  v *= 0xc2b2ae35u;
+  v ^= v >> 16;
+  return v;
+}
+static void host_dropout_key(uint64_t seed, uint32_t site, uint32_t* k0, uint32_t* k1) {
+  *k0 = host_mix32((uint32_t)seed ^ (site * 0x9E3779B9u) ^ 0xa511e9b3u);
+  *k1 = host_mix32((uint32_t)(seed >> 32) + site * 0x85ebca6bu + 0x6a09e667u);
+}
 
 static bool is_bf16(const rvip_handle* h) { return h->cfg.precision == 1; }
 static size_t esize(const rvip_handle* h) { return is_bf16(h) ? 2 : 4; }
@@ -770,9 +788,32 @@ static void* conv_output(const rvip_handle* h, const Layer& l) {
   return (fused_inference(h, l) && l.y) ? l.y : l.a;
 }
 
+// Can the dgrad of layer i also produce the BatchNorm-backward sums of the block it feeds (EPI_LINEAR_BNRED)?  That block
+// must take its whole output gradient from this one tensor (no pooling / skip sum), through at most a dropout mask.
+// OPT-IN (RVIP_BNRED_FUSION=all | halo): measured at C2 it LOSES -- the level-0/1 row-kernel epilogues (8 warps, two per
+// scheduler) already set the tile period, so the extra mask replay + multiply-adds cost more there (dgrad 51 -> 138 us)
+// than the streaming pass they replace (52 us); at the deep levels the halo epilogues hide it better but still add
+// 8-14 us against 12-15 us saved.  bn_backward 1.31 -> 1.01 ms, dgrad 0.96 -> 1.32 ms per step
+// (profiles/r2u_bnred_fusion_*).  Kept as a tested variant; DESIGN section 7.
+static bool bnred_candidate(const rvip_handle* h, int i) {
+  const char* mode = getenv("RVIP_BNRED_FUSION");
+  if (!h->training || !is_bf16(h) || h->cfg.bn_first || !mode || !(strcmp(mode, "all") == 0 || strcmp(mode, "halo") == 0))
+    return false;
+  const Layer& l = h->L[i];
+  if (l.first || l.in0_layer < 0 || l.C1 != 0) return false;
+  const Layer& c = h->L[l.in0_layer];
+  if (!c.has_bn || c.g0_layer != i || c.g0_which != 3 || c.Cout != l.C0 || c.Cout % 64 != 0 && c.Cout != 32) return false;
+  if (c.first && getenv("RVIP_C1_RECOMPUTE")) return false;
+  if (c.post == POST_NONE || c.post == POST_DROPOUT) return c.H == l.H && c.W == l.W;
+  return c.post == POST_UPSAMPLE && c.g0_lowres && l.up_dgrad;     // low-resolution gradient straight from the up-conv dgrad
+}
+
 static int build_descriptors(rvip_handle* h) {
   const int B = h->batch;
-  for (size_t i = 0; i < h->L.size(); ++i) h->L[i].dz = h->training ? h->dz2[i & 1] : nullptr;
+  for (size_t i = 0; i < h->L.size(); ++i) {
+    h->L[i].dz = h->training ? h->dz2[i & 1] : nullptr;
+    h->L[i].red_fused = 0;
+  }
   for (size_t i = 0; i < h->L.size(); ++i) {
     Layer& l = h->L[i];
     if (l.first || !is_bf16(h)) continue;
@@ -784,6 +825,10 @@ static int build_descriptors(rvip_handle* h) {
         return 1;
       if (h->training) {
         if (l.up_dgrad) {
+          // with room for the per-channel arrays of EPI_LINEAR_BNRED where this gradient feeds a BatchNorm block directly
+          if (bnred_candidate(h, (int)i) && conv_halo_up_plan(B, lo.H, lo.W, l.C0, l.Cout, 1, &l.udBN, &l.udNb, true))
+            h->L[l.in0_layer].red_fused = 1;
+          else
           RVIP_REQUIRE(conv_halo_up_plan(B, lo.H, lo.W, l.C0, l.Cout, 1, &l.udBN, &l.udNb), "%s: no up-conv dgrad plan",
                        l.name.c_str());
           if (setup_conv_halo_up(&l.udgrad, 1, l.udBN, l.dx0, l.dz, pk + l.pk_ud, nullptr, B, lo.H, lo.W, l.C0, l.Cout))
@@ -840,12 +885,18 @@ static int build_descriptors(rvip_handle* h) {
       if (l.use_rdgrad && setup_conv_row(&l.rdgrad, l.rdBN, l.rdR, wres, l.dz, nullptr, l.Cout, 0, pk + l.pk_d, l.dx0,
                                          l.dx1, dsplit, B, l.H, l.W, l.C0 + l.C1, EPI_LINEAR, nullptr, nullptr))
         return 1;
-      l.use_hdgrad = allow_halo &&
-                     conv_halo_plan(B, l.H, l.W, l.Cout, 0, l.C0 + l.C1, EPI_LINEAR, dsplit, &l.hdBN, &l.hdNb);
+      const bool cand = bnred_candidate(h, (int)i);
+      l.use_hdgrad = allow_halo && conv_halo_plan(B, l.H, l.W, l.Cout, 0, l.C0 + l.C1, cand ? EPI_LINEAR_BNRED : EPI_LINEAR,
+                                                  dsplit, &l.hdBN, &l.hdNb);
       if (l.use_hdgrad && l.use_rdgrad) {
         if (l.hdBN >= 128 && getenv("RVIP_PREFER_ROW") == nullptr) l.use_rdgrad = 0;
         else l.use_hdgrad = 0;
       }
+      // the row kernel keeps at most two (row, 32-channel chunk) items of the aux tensor per thread
+      const bool row_too = cand && strcmp(getenv("RVIP_BNRED_FUSION"), "all") == 0;
+      if (cand && (l.use_hdgrad ||
+                   (row_too && l.use_rdgrad && (l.rdR / 2) * (l.rdBN / 32) <= 2 && (l.rdBN == 32 || l.rdR == 2))))
+        h->L[l.in0_layer].red_fused = 1;
       if (l.use_hdgrad && setup_conv_halo(&l.hdgrad, l.hdBN, l.dz, nullptr, l.Cout, 0, pk + l.pk_d, l.dx0, l.dx1, dsplit,
                                           B, l.H, l.W, l.C0 + l.C1, EPI_LINEAR, nullptr, nullptr))
         return 1;
@@ -1077,7 +1128,7 @@ static int backward_body(rvip_handle* h, const float* x, uint64_t seed, cudaStre
       a.dbeta = h->grads + l.off_be;
       a.dbias = h->grads + l.off_b;
       // the folded head already left sum dy / sum dy * a of its input block in `red` (head_bn_finalize)
-      const bool have_sums = (fold_head && i == h->head_in) || a.identity;
+      const bool have_sums = (fold_head && i == h->head_in) || a.identity || l.red_fused;
       if (timed(h, KC_BN_BWD, have_sums ? 1 : 2, st, [&] {
             if (!have_sums && bn_bwd_reduce_launch(a, bf, st)) return 1;
             return bn_bwd_apply_launch(a, bf, st);
@@ -1101,6 +1152,27 @@ static int backward_body(rvip_handle* h, const float* x, uint64_t seed, cudaStre
             return wgrad_tc_launch(l.wg, l.wCBA, l.wCBB, ws);
           }))
         return 1;
+      if (l.in0_layer >= 0 && h->L[l.in0_layer].red_fused) {
+        // this gradient is dL/dy of the BatchNorm block below: its epilogue also leaves that block's backward sums
+        const Layer& c = h->L[l.in0_layer];
+        BnRedArgs r;
+        r.a = c.a;
+        r.red = h->red + 2 * kRedStripes * c.off_stat;
+        const bool drop = c.post == POST_DROPOUT;
+        host_dropout_key(seed, c.site, &r.k0, &r.k1);
+        r.thr16 = drop ? (uint32_t)std::lround((double)c.drop * 65536.0) : 0u;
+        r.keep_scale = drop ? 1.f / (1.f - c.drop) : 1.f;
+        r.lg = 0;
+        while ((8 << r.lg) < c.Cout) ++r.lg;
+        ConvHaloArgs* ha = l.up_dgrad ? &l.udgrad : (l.use_hdgrad ? &l.hdgrad : nullptr);
+        if (ha) {
+          ha->mode = EPI_LINEAR_BNRED;
+          ha->bnred = r;
+        } else {
+          l.rdgrad.mode = EPI_LINEAR_BNRED;
+          l.rdgrad.bnred = r;
+        }
+      }
       if (timed(h, KC_CONV_DGRAD_TC, 1, st, [&] {
             if (l.up_dgrad) return conv_halo_launch(l.udgrad, l.udBN, l.udNb, st);
             if (l.use_rdgrad) return conv_row_launch(l.rdgrad, l.rdBN, l.rdR, l.rdNst, st);

@@ -643,3 +643,42 @@ def test_bf16_training_trajectory_tracks_fp32_oracle():
         else:
             assert v['rel_l2'] <= 2.0 * v['cal_rel_l2'] + 0.03, (name, v)
     assert n_strict >= 1, rows
+
+
+@pytest.mark.parametrize('dim,depth', [(128, 2), (128, 3)])
+def test_fused_bn_backward_sums_variant_matches_default(dim, depth, monkeypatch):
+    """RVIP_BNRED_FUSION=all (opt-in: the dgrad epilogues also produce the BatchNorm-backward sums of the block they feed,
+    replaying the dropout mask -- measured slower) must give the same gradients as the default path with
+    its separate statistics pass.  Dropout ON, same seed, bf16: both row (128 px wide) and halo kernels take part."""
+    from cmr_landmark_detection_b200 import synth
+    from cmr_landmark_detection_b200.models.Unets import create_unet
+    res = {}
+    for flag in (None, 'all'):
+        if flag:
+            monkeypatch.setenv('RVIP_BNRED_FUSION', flag)
+        else:
+            monkeypatch.delenv('RVIP_BNRED_FUSION', raising=False)
+        model = create_unet(dict(BASE, DIM=[dim, dim], DEPTH=depth, PRECISION='bf16', DROPOUT_MIN=0.3, DROPOUT_MAX=0.5))
+        x, y = synth.make_batch(4, dim, dim, seed=14)
+        loss = float(model.train_step_device(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(),
+                                             apply_optimizer=False).item())
+        res[flag] = (loss, model.grads.cpu().numpy().astype(np.float64), model.tensors)
+    assert res[None][0] == res['all'][0]            # the forward pass is untouched
+    g0, g1, tensors = res[None][1], res['all'][1], res[None][2]
+    worst = 1.0
+    for name, is_state, off, shape in tensors:
+        if is_state:
+            continue
+        n = int(np.prod(shape))
+        a, b = g0[off:off + n], g1[off:off + n]
+        if np.linalg.norm(a) < 1e-12:
+            continue
+        # the fused sums see the fp32 accumulator where the separate pass sees its bf16 rounding, and the atomics order
+        # differs: BatchNorm's cancelling sums turn that into a few per cent on the deepest-path tensors
+        cos = float((a * b).sum() / (np.linalg.norm(a) * np.linalg.norm(b)))
+        worst = min(worst, cos)
+        if name.startswith(('head/', 'dec%d.' % (depth - 1))):
+            assert cos >= 0.999, (name, cos)
+    # run-to-run, two bf16 steps of the DEFAULT path already differ by a few per cent on the deepest-path tensors (atomics
+    # order under BatchNorm's cancelling sums, test_first_layer_mappings_agree); a wrong mask or a missed tile would be O(1)
+    assert worst >= 0.97, worst
