@@ -114,8 +114,13 @@ __device__ __forceinline__ void row_mma_loop(const ConvRowArgs& a, RowCtl* ctl, 
 // MODE (ConvEpilogue) is a template parameter: ncu showed the 8 epilogue warps -- two per scheduler, ~950 instructions per
 // warp and tile -- setting the tile period of the level-0 layers (2.6 us against 1.2 us of MMAs), and with a run-time
 // mode every element of a dgrad tile still issued the predicated-off bias / ReLU / statistics instructions.
-template <int BN, int R, int MODE, int OCH>
-__global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_constant__ ConvRowArgs a, int nst) {
+// NEW = epilogue warps (8 or 16).  With 8, two warps share a scheduler and each walks ~700-950 dependent instructions per
+// tile: the epilogue, not the MMAs (1.2 us) or HBM, set the tile period of the level-0 layers (2.6 us).  With 16 every
+// warp owns ONE 16-channel sub-chunk of the N tile (fixed for the whole kernel when the layer has a single N tile), half
+// the instructions per tile, four warps per scheduler; bias and the BatchNorm partial sums of its 16 channels stay in
+// registers across all tiles.
+template <int BN, int R, int MODE, int OCH, int NEW = 8>
+__global__ void __launch_bounds__(128 + 32 * NEW, 1) conv3x3_row_kernel(const __grid_constant__ ConvRowArgs a, int nst) {
   constexpr bool AFFINE = MODE == EPI_RELU_AFFINE;
   constexpr bool LIN = MODE == EPI_LINEAR || MODE == EPI_LINEAR_BNRED;   // no bias / activation in the epilogue
   constexpr bool RED = MODE == EPI_LINEAR_BNRED;                        // ... plus the BatchNorm-backward sums
@@ -157,7 +162,7 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ctl->tfull[i], 1);
-      mbar_init(&ctl->tempty[i], 8);
+      mbar_init(&ctl->tempty[i], NEW);
     }
     mbar_init(&ctl->wfull, 1);
     fence_barrier_init();
@@ -168,8 +173,8 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
   }
   pdl_wait();   // everything above is independent of the previous kernel's output
   if (warp >= 4) {
-    for (int c = threadIdx.x - 128; c < 16 * a.Cout; c += 256) s_slot[c] = 0.f;
-    for (int c = threadIdx.x - 128; c < a.Cout; c += 256) {
+    for (int c = threadIdx.x - 128; c < 16 * a.Cout; c += 32 * NEW) s_slot[c] = 0.f;
+    for (int c = threadIdx.x - 128; c < a.Cout; c += 32 * NEW) {
       s_bias[c] = !LIN ? a.bias[c] : 0.f;
       if (AFFINE) {
         s_aff[c] = a.scale[c];
@@ -227,6 +232,130 @@ __global__ void __launch_bounds__(384, 1) conv3x3_row_kernel(const __grid_consta
         row_mma_loop<BN, R, true>(a, ctl, stages, wres, stage_bytes, nst, nchunks, 0u);
       else
         row_mma_loop<BN, R, false>(a, ctl, stages, wres, stage_bytes, nst, nchunks, tmem_base);
+    }
+  } else if (warp >= 4 && NEW == 16) {
+    // ------------------------------------------------------------------ epilogue (16 warps; modes without BNRED; the
+    // statistics mode only for layers with one N tile, conv_row_launch)
+    constexpr int NSUB = BN / 16;              // 16-channel sub-chunks of the N tile
+    constexpr int RSTEP = 4 / NSUB;            // warp groups per sub-chunk: rows of a tile are dealt round-robin to them
+    constexpr int NU = R / RSTEP;              // (row, sub-chunk) units per thread and tile
+    static_assert(RSTEP >= 1 && NU >= 1, "row kernel: 16-warp epilogue geometry");
+    const int q = (warp - 4) & 3, eg = (warp - 4) >> 2;
+    const int sub = eg % NSUB, rbase = eg / NSUB;
+    const int r = q * 32 + lane;              // pixel column inside the tile == TMEM lane
+    const int et = threadIdx.x - 128;         // 0..511
+    int acc = 0, acc_phase = 0;
+    float p1[16], p2[16], bias[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) p1[j] = p2[j] = bias[j] = 0.f;
+    for (int tile_i = blockIdx.x; tile_i < a.total_tiles; tile_i += gridDim.x) {
+      const int tile = tile_i;
+      const int nt = tile % a.n_ntiles, pt = tile / a.n_ntiles;
+      const int x0 = (pt % a.tiles_x) * 128;
+      const int y0 = ((pt / a.tiles_x) % a.tiles_y) * R;
+      const int b = pt / (a.tiles_x * a.tiles_y);
+      const int n0 = nt * BN, c0 = n0 + sub * 16;
+      const bool oobx = MODE == EPI_RELU_STATS && x0 + 128 > a.W && x0 + r >= a.W;
+      if (et == 0) tma_store_wait_read0();   // previous tile's TMA store has drained the staging buffer
+      row_bar_sync(1, 32 * NEW);
+      if (!LIN) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 t = *reinterpret_cast<const float4*>(s_bias + c0 + j * 4);
+          bias[4 * j] = t.x; bias[4 * j + 1] = t.y; bias[4 * j + 2] = t.z; bias[4 * j + 3] = t.w;
+        }
+      }
+      mbar_wait(&ctl->tfull[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < NU; ++k) {
+        const int i = rbase + k * RSTEP;
+        const uint32_t row = i * 128 + r;
+        uint32_t v[16];
+        tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS + i * BN + sub * 16, v);
+        tmem_ld_wait();
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          f[j] = __uint_as_float(v[j]);
+          if (!LIN) f[j] = fmaxf(f[j] + bias[j], a.floor);
+        }
+        if (MODE == EPI_RELU_STATS) {
+          if (oobx) {                      // pixel past the end of the image row: clipped by the store, not counted
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            p1[j] += f[j];
+            p2[j] = fmaf(f[j], f[j], p2[j]);
+          }
+        }
+        if (AFFINE) {
+          const float* sa = s_aff + c0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaf(f[j], sa[j], sa[a.Cout + j]);
+        }
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          uint4 pk;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[g * 8 + 2 * j], f[g * 8 + 2 * j + 1]);
+          const int col = sub * 16 + g * 8;
+          const int oc = col / OCH, cidx = (col % OCH) / 8;
+          *reinterpret_cast<uint4*>(staging + oc * OCHUNK + swz_off<OROWB>(row, cidx)) = pk;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->tempty[acc]);
+      fence_proxy_async_smem();
+      row_bar_sync(1, 32 * NEW);
+      if (et == 0) {
+#pragma unroll 1
+        for (int oc = 0; oc < BN / OCH; ++oc) {
+          const int n = n0 + oc * OCH;
+          if (MODE == EPI_LINEAR && n >= a.out_split)
+            tma_store_4d(&a.out1, staging + oc * OCHUNK, n - a.out_split, x0, y0, b);
+          else
+            tma_store_4d(&a.out0, staging + oc * OCHUNK, n, x0, y0, b);
+        }
+        tma_store_commit();
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (et == 0) tma_store_wait_all0();
+    if (MODE == EPI_RELU_STATS) {
+      // transpose-reduce of the 16 per-pixel sums: after four steps lane l holds channel (l & 15) over its half warp
+#pragma unroll
+      for (int S = 8; S >= 1; S >>= 1) {
+        const bool up = (lane & S) != 0;
+#pragma unroll
+        for (int k = 0; k < S; ++k) {
+          const float send1 = up ? p1[k] : p1[k + S], keep1 = up ? p1[k + S] : p1[k];
+          const float send2 = up ? p2[k] : p2[k + S], keep2 = up ? p2[k + S] : p2[k];
+          p1[k] = keep1 + __shfl_xor_sync(0xffffffffu, send1, S);
+          p2[k] = keep2 + __shfl_xor_sync(0xffffffffu, send2, S);
+        }
+      }
+      p1[0] += __shfl_xor_sync(0xffffffffu, p1[0], 16);
+      p2[0] += __shfl_xor_sync(0xffffffffu, p2[0], 16);
+      float* slot = s_slot + (size_t)(warp - 4) * 32;       // [16 warps][2][16]
+      if (lane < 16) {
+        slot[lane] = p1[0];
+        slot[16 + lane] = p2[0];
+      }
+      row_bar_sync(1, 32 * NEW);
+      // single N tile (Cout == BN): channel c lives in sub-chunk c / 16, held by the warps with eg % NSUB == c / 16
+      for (int c = et; c < 2 * a.Cout; c += 32 * NEW) {
+        const int which = c / a.Cout, ch = c % a.Cout;
+        float t = 0.f;
+        for (int w = 0; w < 16; ++w)
+          if (((w >> 2) % NSUB) == ch / 16) t += s_slot[(size_t)w * 32 + which * 16 + (ch & 15)];
+        atomicAdd(&a.stats[c], (double)t);
+      }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (8 warps)
@@ -471,7 +600,7 @@ bool conv_row_plan(int H, int W, int C0, int C1, int Cout, int mode, int out_spl
   return false;
 }
 
-template <int BN, int R, int MODE, int OCH>
+template <int BN, int R, int MODE, int OCH, int NEW = 8>
 static int launch_row(const ConvRowArgs& a, int nst, cudaStream_t st) {
   const int nchunks = a.Ctot / 32;
   const int wres_bytes = a.wres ? nchunks * 9 * a.Cout * kPixB : 0;
@@ -479,12 +608,12 @@ static int launch_row(const ConvRowArgs& a, int nst, cudaStream_t st) {
   RVIP_REQUIRE(smem <= (size_t)kMaxDynSmemRow, "conv_row: %zu bytes of shared memory needed", smem);
   static bool attr_set = false;
   if (!attr_set) {
-    RVIP_CUDA(cudaFuncSetAttribute(conv3x3_row_kernel<BN, R, MODE, OCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RVIP_CUDA(cudaFuncSetAttribute(conv3x3_row_kernel<BN, R, MODE, OCH, NEW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    kMaxDynSmemRow));
     attr_set = true;
   }
   const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
-  launch_kernel(conv3x3_row_kernel<BN, R, MODE, OCH>, grid, 384, smem, st, a, nst);
+  launch_kernel(conv3x3_row_kernel<BN, R, MODE, OCH, NEW>, grid, 128 + 32 * NEW, smem, st, a, nst);
   RVIP_LAUNCH_CHECK();
   return 0;
 }
@@ -503,7 +632,19 @@ int conv_row_launch(const ConvRowArgs& a, int BN, int R, int nst, cudaStream_t s
     set_error("conv_row: no EPI_LINEAR_BNRED instantiation for BN=%d R=%d och=%d", BN, R, a.och);
     return 1;
   }
+  // 16 epilogue warps wherever the geometry allows (the statistics mode needs the layer's single N tile: every warp keeps
+  // the sums of its 16 channels in registers for the whole kernel); RVIP_ROW_EPI8=1 = the 8-warp epilogue everywhere
+  const bool wide = getenv("RVIP_ROW_EPI8") == nullptr && (a.mode != EPI_RELU_STATS || a.n_ntiles == 1);
 #define RVIP_ROW_CASE(bn, r, oc)                                                               \
+  if (BN == bn && R == r && a.och == oc && wide) {                                             \
+    switch (a.mode) {                                                                          \
+      case EPI_RELU_STATS: return launch_row<bn, r, EPI_RELU_STATS, oc, 16>(a, nst, st);       \
+      case EPI_RELU: return launch_row<bn, r, EPI_RELU, oc, 16>(a, nst, st);                   \
+      case EPI_LINEAR: return launch_row<bn, r, EPI_LINEAR, oc, 16>(a, nst, st);               \
+      case EPI_RELU_AFFINE: return launch_row<bn, r, EPI_RELU_AFFINE, oc, 16>(a, nst, st);     \
+      default: break;                                                                          \
+    }                                                                                          \
+  }                                                                                            \
   if (BN == bn && R == r && a.och == oc) {                                                     \
     switch (a.mode) {                                                                          \
       case EPI_RELU_STATS: return launch_row<bn, r, EPI_RELU_STATS, oc>(a, nst, st);           \
