@@ -559,7 +559,8 @@ __global__ void __launch_bounds__(256, POST == POST_POOL ? 2 : 4) bn_bwd_apply_k
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       db[j] = 0.f;
-      scd[j] = POST == POST_DROPOUT ? coef_s[c + j] * a.keep_scale : coef_s[c + j];
+      // (the pooling variant keeps ONE copy -- the float product its argmax replay uses: it runs at the 128-register cap)
+      scd[j] = POST == POST_DROPOUT ? coef_s[c + j] * a.keep_scale : (POST == POST_POOL ? sc[j] : coef_s[c + j]);
     }
     T* dzp = static_cast<T*>(a.dz) + c;
     const DropKey key = dropout_key(a.seed, a.site);
