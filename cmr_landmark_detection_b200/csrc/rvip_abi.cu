@@ -484,6 +484,17 @@ struct rvip_handle {
   std::vector<std::pair<long long, long long>> buckets;   // (offset, count) in grads
   std::vector<int> bucket_after_layer;                    // bucket i completes after backward of this layer index
   std::vector<cudaEvent_t> bucket_events;
+  // per bucket: slices of the two pack tables (entries are in layer order, a bucket is a contiguous run of layers)
+  std::vector<int> bucket_pack0, bucket_packn, bucket_up0, bucket_upn;
+  // one-shot request (rvip_set_inline_adam): rvip_train_step applies Adam + the operand re-pack bucket by bucket on the
+  // weight-gradient stream as soon as a bucket's gradients are complete, hidden behind the rest of backward
+  struct {
+    int armed = 0;
+    float *m = nullptr, *v = nullptr;
+    float lr_t = 0.f, b1 = 0.f, b2 = 0.f, eps = 0.f, gs = 1.f;
+  } inline_adam;
+  cudaStream_t opt = nullptr;               // third stream: the inline optimizer (behind neither chain's kernels)
+  cudaEvent_t ev_opt = nullptr, ev_grad = nullptr;   // optimizer work complete / main-chain gradients of a bucket final
   // profiling
   int profile = 0;
   std::vector<rvip::ProfRec> prof;
@@ -1218,12 +1229,42 @@ static int backward_body(rvip_handle* h, const float* x, uint64_t seed, cudaStre
     }
     if (overlap) RVIP_CUDA(cudaEventRecord(h->ev_wg[i], ws));
     const bool bucket_end = next_bucket < h->buckets.size() && h->bucket_after_layer[next_bucket] == i;
-    if (overlap && (bucket_end || i == 0)) RVIP_CUDA(cudaStreamWaitEvent(st, h->ev_wg[i], 0));   // join
+    const bool inline_opt = bucket_end && h->inline_adam.armed;
+    if (inline_opt) {
+      // every gradient of this bucket is final: its BatchNorm / bias gradients were written by the main chain, its weight
+      // gradients by the side stream.  Adam + the re-pack of exactly these layers run on a third stream behind both,
+      // hidden behind the backward pass of the layers below; the main stream only waits for it at the end of the step.
+      const size_t b = next_bucket;
+      cudaStream_t os = overlap ? h->opt : st;
+      if (overlap) {
+        RVIP_CUDA(cudaEventRecord(h->ev_grad, st));
+        RVIP_CUDA(cudaStreamWaitEvent(os, h->ev_grad, 0));
+        RVIP_CUDA(cudaStreamWaitEvent(os, h->ev_wg[i], 0));
+      }
+      h->cur_tag = "step:adam";
+      const auto& ia = h->inline_adam;
+      const long long off = h->buckets[b].first, cnt = h->buckets[b].second;
+      if (timed(h, KC_OPTIM, 3, os, [&] {
+            if (adam_launch(h->params + off, h->grads + off, ia.m + off, ia.v + off, (size_t)cnt, ia.lr_t, ia.b1, ia.b2, ia.eps,
+                            ia.gs, os))
+              return 1;
+            if (pack_weights_launch(h->params, h->packed, h->pack_table_dev + h->bucket_pack0[b], h->bucket_packn[b], is_bf16(h),
+                                    os))
+              return 1;
+            return pack_up_launch(h->params, h->packed, h->up_pack_table_dev + h->bucket_up0[b], h->bucket_upn[b], os);
+          }))
+        return 1;
+      if (overlap) RVIP_CUDA(cudaEventRecord(h->ev_opt, os));
+    }
+    // join: a gradient bucket handed to the caller (all-reduce) must be complete; so must the whole step at its end
+    if (overlap && ((bucket_end && !inline_opt) || i == 0)) RVIP_CUDA(cudaStreamWaitEvent(st, h->ev_wg[i], 0));
+    if (overlap && inline_opt && i == 0) RVIP_CUDA(cudaStreamWaitEvent(st, h->ev_opt, 0));
     if (bucket_end) {
       if (h->bucket_events[next_bucket]) RVIP_CUDA(cudaEventRecord(h->bucket_events[next_bucket], st));
       ++next_bucket;
     }
   }
+  h->inline_adam.armed = 0;
   return 0;
 }
 
@@ -1265,6 +1306,9 @@ void rvip_destroy(rvip_handle* h) {
   if (h->bn_table_dev) cudaFree(h->bn_table_dev);
   for (cudaEvent_t e : h->ev_dz) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_wg) if (e) cudaEventDestroy(e);
+  if (h->ev_opt) cudaEventDestroy(h->ev_opt);
+  if (h->ev_grad) cudaEventDestroy(h->ev_grad);
+  if (h->opt) cudaStreamDestroy(h->opt);
   if (h->side) cudaStreamDestroy(h->side);
   for (auto& r : h->prof) {
     cudaEventDestroy(r.e0);
@@ -1311,13 +1355,16 @@ int rvip_bind(rvip_handle* h, float* params, float* grads, float* bn_state, void
   // pack table
   std::vector<PackEntry> tab;
   std::vector<UpPackEntry> utab;
-  for (const Layer& l : h->L) {
+  std::vector<int> tab_layer, utab_layer;      // layer index of every entry
+  for (size_t li = 0; li < h->L.size(); ++li) {
+    const Layer& l = h->L[li];
     if (l.first) continue;
     if (l.up_ns) {
       UpPackEntry u;
       u.src = l.off_k; u.dst_f = l.pk_uf; u.dst_d = l.pk_ud; u.Cin = l.C0; u.C = l.Cout; u.ns = l.up_ns;
       u.transposed = l.transposed;
       utab.push_back(u);
+      utab_layer.push_back((int)li);
     }
     if (l.pk_d < 0) continue;
     PackEntry e;
@@ -1327,6 +1374,28 @@ int rvip_bind(rvip_handle* h, float* params, float* grads, float* bn_state, void
       e.Cout = l.C0;
     }
     tab.push_back(e);
+    tab_layer.push_back((int)li);
+  }
+  {
+    const size_t nb = h->buckets.size();
+    h->bucket_pack0.assign(nb, 0); h->bucket_packn.assign(nb, 0);
+    h->bucket_up0.assign(nb, 0); h->bucket_upn.assign(nb, 0);
+    int hi = (int)h->L.size();                 // bucket b covers layers [bucket_after_layer[b], hi)
+    for (size_t b = 0; b < nb; ++b) {
+      const int lo = h->bucket_after_layer[b];
+      auto slice = [&](const std::vector<int>& layers, int* first, int* count) {
+        *first = -1; *count = 0;
+        for (size_t k = 0; k < layers.size(); ++k)
+          if (layers[k] >= lo && layers[k] < hi) {
+            if (*first < 0) *first = (int)k;
+            ++*count;
+          }
+        if (*first < 0) *first = 0;
+      };
+      slice(tab_layer, &h->bucket_pack0[b], &h->bucket_packn[b]);
+      slice(utab_layer, &h->bucket_up0[b], &h->bucket_upn[b]);
+      hi = lo;
+    }
   }
   h->n_pack = (int)tab.size();
   if (h->pack_table_dev) cudaFree(h->pack_table_dev);
@@ -1379,6 +1448,9 @@ int rvip_bind(rvip_handle* h, float* params, float* grads, float* bn_state, void
     int lo = 0, hi = 0;
     RVIP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = least priority
     RVIP_CUDA(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, getenv("RVIP_SIDE_PRIO_HIGH") ? hi : lo));
+    RVIP_CUDA(cudaEventCreateWithFlags(&h->ev_opt, cudaEventDisableTiming));
+    RVIP_CUDA(cudaEventCreateWithFlags(&h->ev_grad, cudaEventDisableTiming));
+    RVIP_CUDA(cudaStreamCreateWithPriority(&h->opt, cudaStreamNonBlocking, lo));
     h->ev_dz.assign(h->L.size(), nullptr);
     h->ev_wg.assign(h->L.size(), nullptr);
     for (size_t i = 0; i < h->L.size(); ++i) {
@@ -1475,6 +1547,17 @@ int rvip_adam_step(rvip_handle* h, float* m, float* v, float lr, float beta1, fl
       }))
     return 1;
   return pack_weights(h, st);
+}
+
+int rvip_set_inline_adam(rvip_handle* h, float* m, float* v, float lr, float beta1, float beta2, float eps, long long step,
+                         float grad_scale) {
+  RVIP_REQUIRE(h && h->bound && h->training && m && v && step >= 1, "rvip_set_inline_adam: handle not bound for training");
+  h->inline_adam.m = m; h->inline_adam.v = v;
+  h->inline_adam.lr_t = (float)((double)lr * std::sqrt(1.0 - std::pow((double)beta2, (double)step)) /
+                                (1.0 - std::pow((double)beta1, (double)step)));
+  h->inline_adam.b1 = beta1; h->inline_adam.b2 = beta2; h->inline_adam.eps = eps; h->inline_adam.gs = grad_scale;
+  h->inline_adam.armed = 1;
+  return 0;
 }
 
 int rvip_sgd_step(rvip_handle* h, float* velocity, float lr, float momentum, int nesterov, float grad_scale, void* stream) {

@@ -521,9 +521,24 @@ class RvipUNet:
         if self.loss_kind == 'bce_dice':
             ffi.check(L.rvip_set_loss_weights(b.h, float(self.loss_args.get('w_bce', 1.0)),
                                               float(self.loss_args.get('w_dice', 1.0))))
+        # single replica + Adam: the step applies the optimizer itself, bucket by bucket behind the backward pass
+        inline = (apply_optimizer and self.dp.world == 1 and isinstance(self.optimizer, Adam)
+                  and not os.environ.get('RVIP_NO_INLINE_ADAM'))
+        if inline:
+            opt = self.optimizer
+            if opt.m is None:
+                opt.m = torch.zeros_like(self.params)
+                opt.v = torch.zeros_like(self.params)
+            opt.iterations += 1
+            ffi.check(L.rvip_set_inline_adam(b.h, ffi.ptr(opt.m), ffi.ptr(opt.v), opt.lr, opt.beta_1, opt.beta_2,
+                                             opt.epsilon, opt.iterations, 1.0))
         ffi.check(L.rvip_train_step(b.h, ffi.ptr(x_dev), ffi.ptr(y_dev), ffi.ptr(self._inplane),
                                     ffi.LOSS_KINDS[self.loss_kind], thr, C.c_uint64(seed & (2 ** 64 - 1)),
                                     ffi.ptr(heat), ffi.ptr(self._loss_dev), self._stream()))
+        if inline:
+            self._version += 1
+            b.packed_version = self._version      # the step re-packed this binding's operand copies
+            return self._loss_dev
         if self.dp.world > 1:
             self.dp.allreduce_buckets(self.grads, self._buckets(b), b.events)
         if apply_optimizer:

@@ -95,6 +95,12 @@ int rvip_heat_stats(const float* heat, const float* target, const float* inplane
  * grad_scale folds the data-parallel 1/world into the update. step counts from 1. */
 int rvip_adam_step(rvip_handle* h, float* m, float* v, float lr, float beta1, float beta2, float eps, long long step,
                    float grad_scale, void* stream);
+/* Arms the NEXT rvip_train_step to apply Adam itself (same update as rvip_adam_step): every gradient bucket is stepped and
+ * its tensor-core operand copies re-packed on the weight-gradient stream as soon as the bucket's gradients are final, so
+ * the optimizer hides behind the rest of the backward pass.  Single-replica training only (under data parallelism the
+ * all-reduce sits between backward and the optimizer: use rvip_adam_step).  One-shot: cleared by that train step. */
+int rvip_set_inline_adam(rvip_handle* h, float* m, float* v, float lr, float beta1, float beta2, float eps, long long step,
+                         float grad_scale);
 /* tf.keras.optimizers.SGD apply (OPTIMIZER='sgd', ModelUtils.py:109-111, and the Adam -> SGD switch of
  * utils/KerasCallbacks.py:280-306) + operand re-pack: v = momentum v - lr g; w += nesterov ? momentum v - lr g : v.
  * velocity [n_params] may be NULL when momentum == 0. */
