@@ -1560,6 +1560,25 @@ int rvip_set_inline_adam(rvip_handle* h, float* m, float* v, float lr, float bet
   return 0;
 }
 
+int rvip_adam_bucket(rvip_handle* h, int bucket, float* m, float* v, float lr, float beta1, float beta2, float eps,
+                     long long step, float grad_scale, void* stream) {
+  RVIP_REQUIRE(h && h->bound && h->training && m && v && step >= 1, "rvip_adam_bucket: handle not bound for training");
+  RVIP_REQUIRE(bucket >= 0 && bucket < (int)h->buckets.size(), "rvip_adam_bucket: bucket %d out of range", bucket);
+  cudaStream_t st = (cudaStream_t)stream;
+  const float lr_t = (float)((double)lr * std::sqrt(1.0 - std::pow((double)beta2, (double)step)) /
+                             (1.0 - std::pow((double)beta1, (double)step)));
+  const long long off = h->buckets[bucket].first, cnt = h->buckets[bucket].second;
+  h->cur_tag = "step:adam";
+  return timed(h, KC_OPTIM, 3, st, [&] {
+    if (adam_launch(h->params + off, h->grads + off, m + off, v + off, (size_t)cnt, lr_t, beta1, beta2, eps, grad_scale, st))
+      return 1;
+    if (pack_weights_launch(h->params, h->packed, h->pack_table_dev + h->bucket_pack0[bucket], h->bucket_packn[bucket],
+                            is_bf16(h), st))
+      return 1;
+    return pack_up_launch(h->params, h->packed, h->up_pack_table_dev + h->bucket_up0[bucket], h->bucket_upn[bucket], st);
+  });
+}
+
 int rvip_sgd_step(rvip_handle* h, float* velocity, float lr, float momentum, int nesterov, float grad_scale, void* stream) {
   RVIP_REQUIRE(h && h->bound && h->training, "rvip_sgd_step: handle not bound for training");
   RVIP_REQUIRE(momentum == 0.f || velocity, "rvip_sgd_step: momentum needs a velocity buffer");

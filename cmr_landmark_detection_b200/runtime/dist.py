@@ -64,17 +64,22 @@ class DataParallel:
             self._comm_stream = torch.cuda.Stream(device=self.device)
         return self._comm_stream
 
-    def allreduce_buckets(self, grads: torch.Tensor, ranges: Sequence[Tuple[int, int]], events: Sequence) -> None:
+    def allreduce_buckets(self, grads: torch.Tensor, ranges: Sequence[Tuple[int, int]], events: Sequence,
+                          after_bucket=None) -> None:
         """Sum-all-reduce every bucket on the communication stream once its event has fired; the compute
-        stream then waits for the communication stream. The 1/world factor is folded into Adam."""
+        stream then waits for the communication stream. The 1/world factor is folded into Adam.
+        after_bucket(i, stream_ptr): called with the communication stream current right behind bucket i's all-reduce
+        (the optimizer step of that bucket: it then overlaps the rest of backward and the later all-reduces)."""
         if not self.enabled:
             return
         cur = torch.cuda.current_stream(self.device)
         cs = self.comm_stream()
-        for (off, cnt), ev in zip(ranges, events):
+        for i, ((off, cnt), ev) in enumerate(zip(ranges, events)):
             cs.wait_event(ev)
             with torch.cuda.stream(cs):
                 dist.all_reduce(grads[off:off + cnt], op=dist.ReduceOp.SUM)
+                if after_bucket is not None:
+                    after_bucket(i, cs.cuda_stream)
         cur.wait_stream(cs)
 
     def allreduce_flat(self, grads: torch.Tensor, ranges: Sequence[Tuple[int, int]]) -> None:

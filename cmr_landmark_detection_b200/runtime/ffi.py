@@ -58,6 +58,7 @@ _SIGS = {
     'rvip_heat_stats': (_I, [_VP, _VP, _VP, _LL, _I, _I, _I, _F, _VP, _VP]),
     'rvip_adam_step': (_I, [_VP, _VP, _VP, _F, _F, _F, _F, _LL, _F, _VP]),
     'rvip_set_inline_adam': (_I, [_VP, _VP, _VP, _F, _F, _F, _F, _LL, _F]),
+    'rvip_adam_bucket': (_I, [_VP, _I, _VP, _VP, _F, _F, _F, _F, _LL, _F, _VP]),
     'rvip_sgd_step': (_I, [_VP, _VP, _F, _F, _I, _F, _VP]),
     'rvip_num_buckets': (_I, [_VP]),
     'rvip_bucket': (_I, [_VP, _I, C.POINTER(_LL), C.POINTER(_LL)]),

@@ -540,6 +540,21 @@ class RvipUNet:
             b.packed_version = self._version      # the step re-packed this binding's operand copies
             return self._loss_dev
         if self.dp.world > 1:
+            if (apply_optimizer and isinstance(self.optimizer, Adam) and not os.environ.get('RVIP_NO_INLINE_ADAM')):
+                # data parallel: every bucket is stepped on the communication stream right behind its all-reduce
+                opt = self.optimizer
+                if opt.m is None:
+                    opt.m = torch.zeros_like(self.params)
+                    opt.v = torch.zeros_like(self.params)
+                opt.iterations += 1
+
+                def step_bucket(i, stream_ptr):
+                    ffi.check(L.rvip_adam_bucket(b.h, i, ffi.ptr(opt.m), ffi.ptr(opt.v), opt.lr, opt.beta_1, opt.beta_2,
+                                                 opt.epsilon, opt.iterations, 1.0 / self.dp.world, C.c_void_p(stream_ptr)))
+                self.dp.allreduce_buckets(self.grads, self._buckets(b), b.events, after_bucket=step_bucket)
+                self._version += 1
+                b.packed_version = self._version
+                return self._loss_dev
             self.dp.allreduce_buckets(self.grads, self._buckets(b), b.events)
         if apply_optimizer:
             self.apply_gradients(b)

@@ -101,6 +101,11 @@ int rvip_adam_step(rvip_handle* h, float* m, float* v, float lr, float beta1, fl
  * all-reduce sits between backward and the optimizer: use rvip_adam_step).  One-shot: cleared by that train step. */
 int rvip_set_inline_adam(rvip_handle* h, float* m, float* v, float lr, float beta1, float beta2, float eps, long long step,
                          float grad_scale);
+/* Data-parallel counterpart: Adam + operand re-pack of ONE gradient bucket (rvip_bucket) on the caller's stream -- issued on
+ * the communication stream right behind that bucket's all-reduce, so the optimizer of early buckets overlaps the backward
+ * pass and the all-reduce of later ones. */
+int rvip_adam_bucket(rvip_handle* h, int bucket, float* m, float* v, float lr, float beta1, float beta2, float eps,
+                     long long step, float grad_scale, void* stream);
 /* tf.keras.optimizers.SGD apply (OPTIMIZER='sgd', ModelUtils.py:109-111, and the Adam -> SGD switch of
  * utils/KerasCallbacks.py:280-306) + operand re-pack: v = momentum v - lr g; w += nesterov ? momentum v - lr g : v.
  * velocity [n_params] may be NULL when momentum == 0. */
