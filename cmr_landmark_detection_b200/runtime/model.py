@@ -642,11 +642,9 @@ class RvipUNet:
             for s in range(NS):
                 free.put((s, False))
             stop = threading.Event()
-            dev = self.device
 
             def producer():
                 try:
-                    torch.cuda.set_device(dev)
                     for x, y in batches:
                         x = np.ascontiguousarray(x, dtype=np.float32)
                         y = np.ascontiguousarray(y, dtype=np.float32)
