@@ -522,13 +522,15 @@ class RvipUNet:
             ffi.check(L.rvip_set_loss_weights(b.h, float(self.loss_args.get('w_bce', 1.0)),
                                               float(self.loss_args.get('w_dice', 1.0))))
         # single replica + Adam: the step applies the optimizer itself, bucket by bucket behind the backward pass
-        inline = (apply_optimizer and self.dp.world == 1 and isinstance(self.optimizer, Adam)
-                  and not os.environ.get('RVIP_NO_INLINE_ADAM'))
+        bucketed = (apply_optimizer and isinstance(self.optimizer, Adam) and not os.environ.get('RVIP_NO_INLINE_ADAM'))
+        inline = bucketed and self.dp.world == 1
+        if bucketed and self.optimizer.m is None:
+            # the moments are zero-filled on THIS stream before the step is queued: the per-bucket optimizer work runs on
+            # other streams that are only ordered behind the step's own events
+            self.optimizer.m = torch.zeros_like(self.params)
+            self.optimizer.v = torch.zeros_like(self.params)
         if inline:
             opt = self.optimizer
-            if opt.m is None:
-                opt.m = torch.zeros_like(self.params)
-                opt.v = torch.zeros_like(self.params)
             opt.iterations += 1
             ffi.check(L.rvip_set_inline_adam(b.h, ffi.ptr(opt.m), ffi.ptr(opt.v), opt.lr, opt.beta_1, opt.beta_2,
                                              opt.epsilon, opt.iterations, 1.0))
@@ -540,12 +542,9 @@ class RvipUNet:
             b.packed_version = self._version      # the step re-packed this binding's operand copies
             return self._loss_dev
         if self.dp.world > 1:
-            if (apply_optimizer and isinstance(self.optimizer, Adam) and not os.environ.get('RVIP_NO_INLINE_ADAM')):
+            if bucketed:
                 # data parallel: every bucket is stepped on the communication stream right behind its all-reduce
                 opt = self.optimizer
-                if opt.m is None:
-                    opt.m = torch.zeros_like(self.params)
-                    opt.v = torch.zeros_like(self.params)
                 opt.iterations += 1
 
                 def step_bucket(i, stream_ptr):
