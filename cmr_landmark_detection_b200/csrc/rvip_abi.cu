@@ -405,6 +405,10 @@ struct Layer {
   // bound buffers
   void *a = nullptr, *y = nullptr, *y2 = nullptr, *dx0 = nullptr, *dx1 = nullptr;
   void* dz = nullptr;                  // this layer's dz scratch buffer (one of two, alternating by layer index)
+  void* dz_own = nullptr;              // ... or its own, when its weight gradient is deferred (defer_wgrad)
+  int defer_wgrad = 0;                 // weight gradient queued late, behind the wide encoder levels' BatchNorm passes
+  int flush_deferred = 0;              // the deferred weight gradients are queued right behind this layer's own
+  int dz_prev_user = -1;               // layer whose weight gradient last read this layer's dz scratch buffer
   // tensor-core launch descriptors (bf16 mode, non-first layers)
   ConvTcArgs fwd, dgrad;
   WgradTcArgs wg;
@@ -536,6 +540,47 @@ static int timed(rvip_handle* h, int cls, int n_launch, cudaStream_t st, F&& f) 
   RVIP_CUDA(cudaEventRecord(r.e1, st));
   h->prof.push_back(r);
   return rc;
+}
+
+// Deferred weight gradients.  A weight gradient needs the tensor pipe for 30-75 us at the deep levels, where the BatchNorm
+// passes it is meant to hide behind last ~30 us: the rest of it holds the SMs (whole TMEM, ~200 KB shared memory) against
+// the next dgrad.  The wide encoder levels at the END of the backward pass have the opposite imbalance (BatchNorm passes of
+// 70-140 us over weight gradients of 35-70 us).  So the largest deep-level weight gradients keep their dz in a buffer of
+// their own and are queued on the side stream when the backward pass reaches the first wide encoder layer.
+// RVIP_DEFER_WGRAD = comma-separated layer names | "none" | unset (default rule below); RVIP_DEFER_FLUSH = layer name.
+static void plan_deferred_wgrads(rvip_handle* h) {
+  if (h->cfg.precision != 1 || h->L.size() < 6) return;
+  const char* env = getenv("RVIP_DEFER_WGRAD");
+  const char* flush_env = getenv("RVIP_DEFER_FLUSH");
+  if (env && strcmp(env, "none") == 0) return;
+  const int nL = (int)h->L.size();
+  // flush point: the first layer of the encoder half (in backward order) on a level at least as wide as H / 2
+  int flush = -1;
+  for (int i = nL - 1; i >= 0; --i) {
+    Layer& l = h->L[i];
+    if (flush_env ? l.name == flush_env : (l.name.rfind("enc", 0) == 0 && l.H * 2 >= h->cfg.H && !l.first)) {
+      flush = i;
+      break;
+    }
+  }
+  if (flush < 0) return;
+  int n = 0;
+  for (int i = nL - 1; i > flush; --i) {
+    Layer& l = h->L[i];
+    if (l.first) continue;
+    bool pick;
+    if (env) {
+      const std::string list = std::string(",") + env + ",";
+      pick = list.find("," + l.name + ",") != std::string::npos;
+    } else {
+      pick = false;
+    }
+    if (pick) {
+      l.defer_wgrad = 1;
+      ++n;
+    }
+  }
+  if (n) h->L[flush].flush_deferred = 1;
 }
 
 static int build_plan(rvip_handle* h) {
@@ -693,6 +738,7 @@ static int build_plan(rvip_handle* h) {
     }
   }
   h->bucket_events.assign(h->buckets.size(), nullptr);
+  plan_deferred_wgrads(h);
   return 0;
 }
 
@@ -758,7 +804,8 @@ static size_t carve(rvip_handle* h, uint8_t* base, int B, int training, bool ass
       l.y = l.a;   // conv + ReLU without BN: the conv output is the block output
     }
     if (training) {
-      max_dz = std::max(max_dz, P * l.Cout);
+      if (l.defer_wgrad) T(assign ? &l.dz_own : sink, P * l.Cout);
+      else max_dz = std::max(max_dz, P * l.Cout);
       if (!l.first) {
         T(assign ? &l.dx0 : sink, ((l.up_dgrad || l.tr_simt) ? P / 4 : P) * l.C0);
         if (l.C1) T(assign ? &l.dx1 : sink, P * l.C1);
@@ -824,6 +871,23 @@ static int build_descriptors(rvip_handle* h) {
   for (size_t i = 0; i < h->L.size(); ++i) {
     h->L[i].dz = h->training ? h->dz2[i & 1] : nullptr;
     h->L[i].red_fused = 0;
+  }
+  if (h->training) {
+    // layers with a deferred weight gradient keep dz to themselves; the others alternate between the two shared buffers
+    int last_user[2] = {-1, -1};
+    int slot = 0;
+    for (int i = (int)h->L.size() - 1; i >= 0; --i) {
+      Layer& l = h->L[i];
+      if (l.defer_wgrad) {
+        l.dz = l.dz_own;
+        l.dz_prev_user = -1;
+        continue;
+      }
+      l.dz = h->dz2[slot];
+      l.dz_prev_user = last_user[slot];
+      last_user[slot] = i;
+      slot ^= 1;
+    }
   }
   for (size_t i = 0; i < h->L.size(); ++i) {
     Layer& l = h->L[i];
@@ -1116,11 +1180,70 @@ static int backward_body(rvip_handle* h, const float* x, uint64_t seed, cudaStre
   const bool overlap = h->overlap_wgrad && !h->profile && h->side != nullptr;
   cudaStream_t ws = overlap ? h->side : st;      // stream of the weight-gradient kernels
   size_t next_bucket = 0;
+  std::vector<int> deferred;          // layers whose weight gradient has not been queued yet (Layer::defer_wgrad)
+  cudaEvent_t last_ws_ev = nullptr;   // most recent event on the side stream: covers every weight gradient queued so far
+  auto launch_wgrad_tc = [&](Layer& l) -> int {
+    return timed(h, KC_CONV_WGRAD_TC, 1, ws, [&] {
+      if (l.use_hwg) return wgrad_halo_launch(l.hwg, l.hwp.CIC, l.hwp.BN, ws);
+      if (l.use_rwg) return wgrad_row_launch(l.rwg, l.rwBN, l.rwR, l.rwNst, ws);
+      return wgrad_tc_launch(l.wg, l.wCBA, l.wCBB, ws);
+    });
+  };
+  // Hands gradient bucket `b` on: every gradient in it is final once the main chain has reached this point and the side
+  // stream has finished what is queued on it.  Single replica + Adam: optimizer + operand re-pack of exactly these layers
+  // on a third stream behind both.  Otherwise the caller's bucket event is recorded on the SIDE stream behind the main
+  // chain's position, so the main chain itself never waits for a weight gradient here.
+  auto close_bucket = [&](size_t b) -> int {
+    if (!overlap) {
+      if (h->inline_adam.armed) {
+        h->cur_tag = "step:adam";
+        const auto& ia = h->inline_adam;
+        const long long off = h->buckets[b].first, cnt = h->buckets[b].second;
+        if (timed(h, KC_OPTIM, 3, st, [&] {
+              if (adam_launch(h->params + off, h->grads + off, ia.m + off, ia.v + off, (size_t)cnt, ia.lr_t, ia.b1, ia.b2,
+                              ia.eps, ia.gs, st))
+                return 1;
+              if (pack_weights_launch(h->params, h->packed, h->pack_table_dev + h->bucket_pack0[b], h->bucket_packn[b],
+                                      is_bf16(h), st))
+                return 1;
+              return pack_up_launch(h->params, h->packed, h->up_pack_table_dev + h->bucket_up0[b], h->bucket_upn[b], st);
+            }))
+          return 1;
+      }
+      if (h->bucket_events[b]) RVIP_CUDA(cudaEventRecord(h->bucket_events[b], st));
+      return 0;
+    }
+    RVIP_CUDA(cudaEventRecord(h->ev_grad, st));
+    if (h->inline_adam.armed) {
+      cudaStream_t os = h->opt;
+      RVIP_CUDA(cudaStreamWaitEvent(os, h->ev_grad, 0));
+      if (last_ws_ev) RVIP_CUDA(cudaStreamWaitEvent(os, last_ws_ev, 0));
+      h->cur_tag = "step:adam";
+      const auto& ia = h->inline_adam;
+      const long long off = h->buckets[b].first, cnt = h->buckets[b].second;
+      if (timed(h, KC_OPTIM, 3, os, [&] {
+            if (adam_launch(h->params + off, h->grads + off, ia.m + off, ia.v + off, (size_t)cnt, ia.lr_t, ia.b1, ia.b2,
+                            ia.eps, ia.gs, os))
+              return 1;
+            if (pack_weights_launch(h->params, h->packed, h->pack_table_dev + h->bucket_pack0[b], h->bucket_packn[b],
+                                    is_bf16(h), os))
+              return 1;
+            return pack_up_launch(h->params, h->packed, h->up_pack_table_dev + h->bucket_up0[b], h->bucket_upn[b], os);
+          }))
+        return 1;
+      RVIP_CUDA(cudaEventRecord(h->ev_opt, os));
+      if (h->bucket_events[b]) RVIP_CUDA(cudaEventRecord(h->bucket_events[b], os));
+    } else if (h->bucket_events[b]) {
+      RVIP_CUDA(cudaStreamWaitEvent(ws, h->ev_grad, 0));
+      RVIP_CUDA(cudaEventRecord(h->bucket_events[b], ws));
+    }
+    return 0;
+  };
   for (int i = nL - 1; i >= 0; --i) {
     Layer& l = h->L[i];
     const size_t P = (size_t)h->batch * l.H * l.W;
-    // the wgrad of layer i + 2 read the dz buffer this layer is about to overwrite
-    if (overlap && i + 2 < nL) RVIP_CUDA(cudaStreamWaitEvent(st, h->ev_wg[i + 2], 0));
+    // the weight gradient that last read the dz buffer this layer is about to overwrite must have finished
+    if (overlap && l.dz_prev_user >= 0) RVIP_CUDA(cudaStreamWaitEvent(st, h->ev_wg[l.dz_prev_user], 0));
     h->cur_tag = l.name + ":bn_bwd";
     if (l.bn) {
       BnArgs a;
@@ -1156,13 +1279,14 @@ static int backward_body(rvip_handle* h, const float* x, uint64_t seed, cudaStre
       RVIP_CUDA(cudaStreamWaitEvent(ws, h->ev_dz[i], 0));
     }
     h->cur_tag = l.name + ":conv_bwd";
+    bool queued_now = true;
     if (bf && !l.first) {
-      if (timed(h, KC_CONV_WGRAD_TC, 1, ws, [&] {
-            if (l.use_hwg) return wgrad_halo_launch(l.hwg, l.hwp.CIC, l.hwp.BN, ws);
-            if (l.use_rwg) return wgrad_row_launch(l.rwg, l.rwBN, l.rwR, l.rwNst, ws);
-            return wgrad_tc_launch(l.wg, l.wCBA, l.wCBB, ws);
-          }))
+      if (overlap && l.defer_wgrad) {
+        deferred.push_back(i);
+        queued_now = false;
+      } else if (launch_wgrad_tc(l)) {
         return 1;
+      }
       if (l.in0_layer >= 0 && h->L[l.in0_layer].red_fused) {
         // this gradient is dL/dy of the BatchNorm block below: its epilogue also leaves that block's backward sums
         const Layer& c = h->L[l.in0_layer];
@@ -1227,41 +1351,33 @@ static int backward_body(rvip_handle* h, const float* x, uint64_t seed, cudaStre
         if (timed(h, KC_CONV_SIMT, 1, st, [&] { return conv_simt_launch(a, bf, bf, st); })) return 1;
       }
     }
-    if (overlap) RVIP_CUDA(cudaEventRecord(h->ev_wg[i], ws));
-    const bool bucket_end = next_bucket < h->buckets.size() && h->bucket_after_layer[next_bucket] == i;
-    const bool inline_opt = bucket_end && h->inline_adam.armed;
-    if (inline_opt) {
-      // every gradient of this bucket is final: its BatchNorm / bias gradients were written by the main chain, its weight
-      // gradients by the side stream.  Adam + the re-pack of exactly these layers run on a third stream behind both,
-      // hidden behind the backward pass of the layers below; the main stream only waits for it at the end of the step.
-      const size_t b = next_bucket;
-      cudaStream_t os = overlap ? h->opt : st;
-      if (overlap) {
-        RVIP_CUDA(cudaEventRecord(h->ev_grad, st));
-        RVIP_CUDA(cudaStreamWaitEvent(os, h->ev_grad, 0));
-        RVIP_CUDA(cudaStreamWaitEvent(os, h->ev_wg[i], 0));
-      }
-      h->cur_tag = "step:adam";
-      const auto& ia = h->inline_adam;
-      const long long off = h->buckets[b].first, cnt = h->buckets[b].second;
-      if (timed(h, KC_OPTIM, 3, os, [&] {
-            if (adam_launch(h->params + off, h->grads + off, ia.m + off, ia.v + off, (size_t)cnt, ia.lr_t, ia.b1, ia.b2, ia.eps,
-                            ia.gs, os))
-              return 1;
-            if (pack_weights_launch(h->params, h->packed, h->pack_table_dev + h->bucket_pack0[b], h->bucket_packn[b], is_bf16(h),
-                                    os))
-              return 1;
-            return pack_up_launch(h->params, h->packed, h->up_pack_table_dev + h->bucket_up0[b], h->bucket_upn[b], os);
-          }))
-        return 1;
-      if (overlap) RVIP_CUDA(cudaEventRecord(h->ev_opt, os));
+    if (overlap && queued_now) {
+      RVIP_CUDA(cudaEventRecord(h->ev_wg[i], ws));
+      last_ws_ev = h->ev_wg[i];
     }
-    // join: a gradient bucket handed to the caller (all-reduce) must be complete; so must the whole step at its end
-    if (overlap && ((bucket_end && !inline_opt) || i == 0)) RVIP_CUDA(cudaStreamWaitEvent(st, h->ev_wg[i], 0));
-    if (overlap && inline_opt && i == 0) RVIP_CUDA(cudaStreamWaitEvent(st, h->ev_opt, 0));
-    if (bucket_end) {
-      if (h->bucket_events[next_bucket]) RVIP_CUDA(cudaEventRecord(h->bucket_events[next_bucket], st));
+    if (overlap && (l.flush_deferred || i == 0) && !deferred.empty()) {
+      // the wide encoder levels start here: their long BatchNorm passes hide the weight gradients held back so far
+      for (int j : deferred) {
+        h->cur_tag = h->L[j].name + ":conv_bwd";
+        if (launch_wgrad_tc(h->L[j])) return 1;
+        RVIP_CUDA(cudaEventRecord(h->ev_wg[j], ws));
+        last_ws_ev = h->ev_wg[j];
+      }
+      deferred.clear();
+    }
+    // a bucket is handed on once none of its layers still holds a weight gradient back
+    while (next_bucket < h->buckets.size() && h->bucket_after_layer[next_bucket] >= i) {
+      const int lo = h->bucket_after_layer[next_bucket];
+      bool pending = false;
+      for (int j : deferred) pending = pending || j >= lo;
+      if (pending) break;
+      if (close_bucket(next_bucket)) return 1;
       ++next_bucket;
+    }
+    // join at the end of the step: the side stream and the optimizer stream
+    if (overlap && i == 0) {
+      if (last_ws_ev) RVIP_CUDA(cudaStreamWaitEvent(st, last_ws_ev, 0));
+      if (h->inline_adam.armed) RVIP_CUDA(cudaStreamWaitEvent(st, h->ev_opt, 0));
     }
   }
   h->inline_adam.armed = 0;
