@@ -8,6 +8,7 @@
 // pixel repeats the sigmoid / loss / dlogit arithmetic, so CPT = 16 (two lanes per pixel at 32 channels) halves that
 // redundancy and the logit shuffles.
 #include "kernels.cuh"
+#include "tc_prims.cuh"
 
 #include <stdlib.h>
 
@@ -17,7 +18,8 @@ constexpr int kMaxNC = 4;
 
 // VAR: tuning variant of the software pipeline / occupancy (0 = default: depth 2 at 2 blocks/SM for CPT = 16)
 template <typename T, bool TRAIN, int NCT, int CPT, bool FOLD, int VAR = 0>
-__global__ void __launch_bounds__(256, (CPT == 16 && VAR != 2) ? 2 : 1) head_kernel(HeadArgs a) {
+__global__ void __launch_bounds__(VAR == 3 ? 384 : 256, (CPT == 16 && VAR < 2) ? 2 : 1) head_kernel(HeadArgs a) {
+  constexpr int NT = VAR == 3 ? 384 : 256;   // threads per block = items per tile
   constexpr int NV = CPT / 8;              // 8-channel vectors per thread
   extern __shared__ float sm[];            // w [Cin*NC], b [NC], dw acc [Cin*NC], db acc [NC], (FOLD) scale, shift [Cin]
   pdl_wait();
@@ -30,7 +32,7 @@ __global__ void __launch_bounds__(256, (CPT == 16 && VAR != 2) ? 2 : 1) head_ker
   float* sc_s = db_s + NC;
   float* sh_s = sc_s + Cin;
   __shared__ double loss_s;
-  for (int k = threadIdx.x; k < Cin * NC; k += 256) {
+  for (int k = threadIdx.x; k < Cin * NC; k += NT) {
     w_s[k] = a.w[k];
     if (TRAIN) dw_s[k] = 0.f;
   }
@@ -42,7 +44,7 @@ __global__ void __launch_bounds__(256, (CPT == 16 && VAR != 2) ? 2 : 1) head_ker
   if (FOLD) {
     // BatchNorm of the producing block, exactly as bn_apply_kernel's prologue derives it (same float expressions, so
     // the backward pass sees the mean / rstd the forward used)
-    for (int k = threadIdx.x; k < Cin; k += 256) {
+    for (int k = threadIdx.x; k < Cin; k += NT) {
       const double mean = a.bn_stats[k] * a.bn_inv_count;
       double var = a.bn_stats[Cin + k] * a.bn_inv_count - mean * mean;
       if (var < 0) var = 0;
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(256, (CPT == 16 && VAR != 2) ? 2 : 1) head_ker
   const uint32_t P = (uint32_t)a.B * a.H * a.W;
   const uint32_t lg = 31 - __clz(G);
   const uint32_t n_items = P << lg;
-  const uint32_t i0 = blockIdx.x * 256 + threadIdx.x;
+  const uint32_t i0 = blockIdx.x * NT + threadIdx.x;
   const int cg = (int)(i0 & (G - 1)), c = cg * CPT;
   const uint32_t HW = (uint32_t)a.H * a.W;
   const T* y = static_cast<const T*>(a.y);
@@ -101,11 +103,11 @@ __global__ void __launch_bounds__(256, (CPT == 16 && VAR != 2) ? 2 : 1) head_ker
   }
   // all lanes of a warp run the same trip count (n_items and the stride are multiples of 32)
   const uint32_t n_round = (n_items + 31) / 32 * 32;
-  const uint32_t stride = gridDim.x * 256;
+  const uint32_t stride = gridDim.x * NT;
   // Software pipeline: the loads of y and of the target for the item kDepth grid-strides ahead are in flight
   // while the current item is processed (ncu: with the loads issued at the point of use, 55 % of the stall
   // samples of this kernel were long-scoreboard waits on exactly those two loads).
-  constexpr int kDepth = VAR == 1 ? 1 : (VAR == 2 ? 4 : (CPT == 8 ? 4 : 2));
+  constexpr int kDepth = VAR == 1 ? 1 : (VAR == 2 ? 4 : (VAR == 3 ? 1 : (CPT == 8 ? 4 : 2)));
   Raw8<T> ybuf[kDepth][NV];
   float tbuf[kDepth][NCT];
   auto issue = [&](int d, uint32_t i) {
@@ -124,26 +126,8 @@ __global__ void __launch_bounds__(256, (CPT == 16 && VAR != 2) ? 2 : 1) head_ker
       for (int k = 0; k < NCT; ++k) tbuf[d][k] = 0.f;
     }
   };
-#pragma unroll
-  for (int d = 0; d < kDepth; ++d) issue(d, i0 + d * stride);
-  for (uint32_t ib = i0; ib < n_round; ib += kDepth * stride) {
-#pragma unroll
-    for (int d = 0; d < kDepth; ++d) {
-      const uint32_t i = ib + d * stride;
-      if (i >= n_round) break;           // warp-uniform
-      const bool live = i < n_items;
-      const size_t p = live ? (i >> lg) : 0;
-      float v[CPT], tgt[NCT];
-#pragma unroll
-      for (int u = 0; u < NV; ++u) {
-        float t8[8];
-        unpack_raw8(ybuf[d][u], t8);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[8 * u + j] = t8[j];
-      }
-#pragma unroll
-      for (int k = 0; k < NCT; ++k) tgt[k] = tbuf[d][k];
-      issue(d, i + kDepth * stride);
+  // one item: logits (lanes of a pixel combine by shuffle), sigmoid, heat map, loss terms, dL/dy, dW / db partials
+  auto process = [&](bool live, size_t p, const float (&v)[CPT], const float (&tgt)[NCT]) {
       float logit[NCT];
 #pragma unroll
       for (int k = 0; k < NCT; ++k) {
@@ -153,7 +137,7 @@ __global__ void __launch_bounds__(256, (CPT == 16 && VAR != 2) ? 2 : 1) head_ker
         for (int o = 1; o < G; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         logit[k] = s + (k < NC ? b_s[k] : 0.f);
       }
-      if (!live) continue;
+      if (!live) return;
       float prob[NCT];
 #pragma unroll
       for (int k = 0; k < NCT; ++k) prob[k] = 1.f / (1.f + expf(-logit[k]));
@@ -232,7 +216,94 @@ __global__ void __launch_bounds__(256, (CPT == 16 && VAR != 2) ? 2 : 1) head_ker
           Vec8<T>::store(dy + p * Cin + c + 8 * u, g);
         }
       }
+  };
+  if constexpr (VAR == 3) {
+    using namespace tc;
+    // Shared-memory staged variant: one thread keeps kSlots tiles (NT items = NT / G consecutive pixels: 12 KB of y and
+    // their targets, both contiguous) in flight with 1-D bulk copies, so no register holds a prefetch: 160 registers
+    // instead of 233, which buys 12 warps per SM instead of 8 (the kernel is bound by instruction latency at this
+    // occupancy, not by its loads: staging alone, at 8 warps, measured no change).
+    constexpr int kSlots = 6;
+    constexpr uint32_t kYBytes = (uint32_t)NT * CPT * sizeof(T);
+    const uint32_t tile_px = (uint32_t)NT >> lg;
+    const uint32_t t_full = TRAIN ? tile_px * NC * (uint32_t)sizeof(float) : 0u;
+    const uint32_t slot_bytes = kYBytes + ((t_full + 127u) & ~127u);
+    __shared__ uint64_t full_bar[kSlots];
+    uint8_t* ring = reinterpret_cast<uint8_t*>(sh_s + Cin);
+    ring += (128u - (smem_u32(ring) & 127u)) & 127u;
+    const uint32_t n_tiles = (n_items + NT - 1) / NT;
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int s2 = 0; s2 < kSlots; ++s2) mbar_init(&full_bar[s2], 1);
+      fence_barrier_init();
     }
+    __syncthreads();
+    auto fill = [&](uint32_t k) {
+      const uint32_t tile = blockIdx.x + k * gridDim.x;
+      if (tile >= n_tiles) return;
+      const uint32_t s2 = k % kSlots;
+      uint8_t* dst = ring + s2 * slot_bytes;
+      // the last tile may be partial: whole pixels (the launcher checks that their bytes are 16-byte multiples)
+      const uint32_t px = min(tile_px, P - tile * tile_px);
+      const uint32_t yb = px * Cin * (uint32_t)sizeof(T), tb = TRAIN ? px * NC * (uint32_t)sizeof(float) : 0u;
+      mbar_expect_tx(&full_bar[s2], yb + tb);
+      bulk_load_1d(dst, y + (size_t)tile * tile_px * Cin, yb, &full_bar[s2]);
+      if (TRAIN) bulk_load_1d(dst + kYBytes, a.target + (size_t)tile * tile_px * NC, tb, &full_bar[s2]);
+    };
+    if (threadIdx.x == 0) {
+      for (uint32_t k = 0; k < kSlots; ++k) fill(k);
+    }
+    for (uint32_t k = 0;; ++k) {
+      const uint32_t tile = blockIdx.x + k * gridDim.x;
+      if (tile >= n_tiles) break;
+      const uint32_t s2 = k % kSlots;
+      mbar_wait(&full_bar[s2], (k / kSlots) & 1u);
+      const uint8_t* src = ring + s2 * slot_bytes;
+      const uint32_t item = tile * NT + threadIdx.x;
+      const bool live = item < n_items;
+      const size_t p = live ? (item >> lg) : 0;
+      float v[CPT], tgt[NCT];
+#pragma unroll
+      for (int u = 0; u < NV; ++u) {
+        Raw8<T> r8;
+        if (live) load_raw8(reinterpret_cast<const T*>(src) + threadIdx.x * CPT + 8 * u, r8);
+        else zero_raw8(r8);
+        float t8[8];
+        unpack_raw8(r8, t8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[8 * u + j] = t8[j];
+      }
+#pragma unroll
+      for (int k2 = 0; k2 < NCT; ++k2)
+        tgt[k2] = (TRAIN && live && k2 < NC) ? reinterpret_cast<const float*>(src + kYBytes)[(threadIdx.x >> lg) * NC + k2] : 0.f;
+      __syncthreads();                       // every thread has its values: the slot may be refilled
+      if (threadIdx.x == 0) fill(k + kSlots);
+      process(live, p, v, tgt);
+    }
+  } else {
+#pragma unroll
+  for (int d = 0; d < kDepth; ++d) issue(d, i0 + d * stride);
+  for (uint32_t ib = i0; ib < n_round; ib += kDepth * stride) {
+#pragma unroll
+    for (int d = 0; d < kDepth; ++d) {
+      const uint32_t i = ib + d * stride;
+      if (i >= n_round) break;           // warp-uniform
+      const bool live = i < n_items;
+      const size_t p = live ? (i >> lg) : 0;
+      float v[CPT], tgt[NCT];
+#pragma unroll
+      for (int u = 0; u < NV; ++u) {
+        float t8[8];
+        unpack_raw8(ybuf[d][u], t8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[8 * u + j] = t8[j];
+      }
+#pragma unroll
+      for (int k = 0; k < NCT; ++k) tgt[k] = tbuf[d][k];
+      issue(d, i + kDepth * stride);
+      process(live, p, v, tgt);
+    }
+  }
   }
   pdl_launch_dependents();
   if (TRAIN) {
@@ -255,7 +326,7 @@ __global__ void __launch_bounds__(256, (CPT == 16 && VAR != 2) ? 2 : 1) head_ker
     float l = warp_sum(loss_acc);
     if ((threadIdx.x & 31) == 0) atomicAdd(&loss_s, (double)l);
     __syncthreads();
-    for (int k = threadIdx.x; k < Cin * NC; k += 256) atomicAdd(&a.dw[k], dw_s[k]);
+    for (int k = threadIdx.x; k < Cin * NC; k += NT) atomicAdd(&a.dw[k], dw_s[k]);
     if (threadIdx.x < NC) atomicAdd(&a.db[threadIdx.x], db_s[threadIdx.x]);
     if (threadIdx.x == 0) {
       double l = loss_s / (double)P;                                  // mean over B*H*W
@@ -419,14 +490,31 @@ int head_launch(const HeadArgs& a, int training, int is_bf16, cudaStream_t st) {
   const bool fold = a.bn_stats != nullptr;
   // folded training head, 2 classes x 16 channels per thread: 128 registers spill (200 B) at 2 blocks/SM; one block per SM
   // with a 4-deep load pipeline measured 108 us against 156 (depth 2, 2 blocks) and 128 (depth 1), profiles/r2d_headvar.jsonl
-  const int var = getenv("RVIP_HEAD_VAR") ? atoi(getenv("RVIP_HEAD_VAR")) : 2;
+  // (variant 3: shared-memory staged loads, 384 threads at 156 registers: 96 us, profiles/r2zc_head_sweep.jsonl)
+  int var = getenv("RVIP_HEAD_VAR") ? atoi(getenv("RVIP_HEAD_VAR")) : 3;
   const int grid1 = (int)(g < (size_t)kNumSMs ? (g ? g : 1) : (size_t)kNumSMs);
+  // variant 3 stages whole 384-item tiles in shared memory with bulk copies (16-byte granules, whole pixels)
+  const size_t tile_px3 = 384 / G;
+  const size_t g3 = (n + 383) / 384;
+  const int grid3 = (int)(g3 < (size_t)kNumSMs ? (g3 ? g3 : 1) : (size_t)kNumSMs);
+  if (var == 3 && (!is_bf16 || 384 % G != 0 || (a.NC * sizeof(float)) % 16 != 0 && ((size_t)a.B * a.H * a.W) % 2 != 0)) var = 2;
+  const size_t smem3 = smem + 128 + 6 * (384 * 16 * 2 + ((tile_px3 * a.NC * sizeof(float) + 127) & ~size_t(127)));
+  if (var == 3) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      RVIP_CUDA(cudaFuncSetAttribute(head_kernel<__nv_bfloat16, true, 2, 16, true, 3>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      attr_set = true;
+    }
+  }
 #define RVIP_HEAD_T(TT, NCV, CPTV)                                                             \
   {                                                                                            \
     if (training && fold && NCV == 2 && CPTV == 16 && var == 1)                                \
       launch_kernel(head_kernel<TT, true, 2, 16, true, 1>, grid, 256, smem, st, a);            \
     else if (training && fold && NCV == 2 && CPTV == 16 && var == 2)                           \
       launch_kernel(head_kernel<TT, true, 2, 16, true, 2>, grid1, 256, smem, st, a);           \
+    else if (training && fold && NCV == 2 && CPTV == 16 && var == 3)                           \
+      launch_kernel(head_kernel<TT, true, 2, 16, true, 3>, grid3, 384, smem3, st, a);           \
     else if (training && fold) launch_kernel(head_kernel<TT, true, NCV, CPTV, true>, grid, 256, smem, st, a);         \
     else if (training) launch_kernel(head_kernel<TT, true, NCV, CPTV, false>, grid, 256, smem, st, a);           \
     else if (fold) launch_kernel(head_kernel<TT, false, NCV, CPTV, true>, grid, 256, smem, st, a);               \
