@@ -242,6 +242,28 @@ __device__ __forceinline__ void block_accumulate8(float* smem_acc, int c, const 
   }
 }
 
+// Packed fp32 pairs (Blackwell FFMA2 / FADD2): two IEEE fp32 operations per issued instruction, each lane rounded exactly
+// like the scalar instruction; a pair built from one value twice compiles to the broadcast operand form (no packing move).
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2_t r, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r));
+}
+__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2_t f2_add(f32x2_t a, f32x2_t b) {
+  f32x2_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
