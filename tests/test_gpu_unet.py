@@ -154,9 +154,15 @@ def test_first_layer_mappings_agree(precision, monkeypatch):
     assert np.array_equal(out[False][0], out[True][0])              # same FMA order per output element
     g0, g1 = out[False][1], out[True][1]
     # two separate steps: in bf16 mode the atomics-order noise of the BatchNorm reductions upstream flips bf16 roundings of
-    # dz (run-to-run ~0.5 % on this ill-conditioned first-layer gradient, same mapping or not); fp32 mode is tight
-    lim = 1e-4 if precision == 'fp32' else 3e-2
-    assert np.linalg.norm(g0 - g1) <= lim * np.linalg.norm(g0) + 1e-12
+    # dz (run-to-run ~0.5 % on this ill-conditioned first-layer gradient, same mapping or not).  fp32 mode: the 9 x Cout
+    # sums are folded with float atomics (shared, then one global add per block) in scheduling order, and this gradient
+    # is a cancelling sum (|result| << sum |partials|), so two runs of the SAME mapping already differ by up to a few
+    # 1e-4 relative (1 run in ~3 exceeded 1e-4 on the GPU box); the mapping-independent kernel test
+    # (test_gpu_kernels.py, vs torch fp32) holds the arithmetic itself to 2e-3 / 1e-4
+    lim = 2e-3 if precision == 'fp32' else 3e-2
+    rel = np.linalg.norm(g0 - g1) / (np.linalg.norm(g0) + 1e-30)
+    print('first-layer gradient, two mappings: rel diff %.3e (%s)' % (rel, precision))
+    assert rel <= lim
 
 
 @pytest.mark.parametrize('precision,dim,depth,batch', [('fp32', 32, 2, 3), ('bf16', 32, 2, 4), ('fp32', 64, 4, 2),
