@@ -114,7 +114,10 @@ int rvip_sgd_step(rvip_handle* h, float* velocity, float lr, float momentum, int
 
 /* ---- data-parallel plumbing (MirroredStrategy, Unets.py:70-75): gradient buckets are contiguous
  * ranges of `grads` in backward-completion order; each records a cudaEvent_t when complete so the
- * caller can start that bucket's all-reduce while the rest of backward still runs. */
+ * caller can start that bucket's all-reduce while the rest of backward still runs.  The event is
+ * recorded on the handle's weight-gradient stream once every gradient of the bucket is final (the
+ * main chain is never made to wait for a weight gradient at a bucket boundary); the step's own
+ * stream has joined that stream by the time rvip_train_step's launches end. */
 int rvip_num_buckets(const rvip_handle* h);
 int rvip_bucket(const rvip_handle* h, int index, long long* offset, long long* count);
 int rvip_set_bucket_event(rvip_handle* h, int index, void* cuda_event);
