@@ -692,3 +692,42 @@ def test_fused_bn_backward_sums_variant_matches_default(dim, depth, monkeypatch)
     # run-to-run, two bf16 steps of the DEFAULT path already differ by a few per cent on the deepest-path tensors (atomics
     # order under BatchNorm's cancelling sums, test_first_layer_mappings_agree); a wrong mask or a missed tile would be O(1)
     assert worst >= 0.97, worst
+
+
+def test_deferred_weight_gradients_variant_matches_default(monkeypatch):
+    """RVIP_DEFER_WGRAD (opt-in schedule: deep-level weight gradients keep dz in buffers of their own and are queued when
+    backward reaches the wide encoder levels; measured neutral) changes WHEN kernels run, never what they
+    compute: same loss, same gradients up to the run-to-run atomics-order noise, and the optimizer step still sees every
+    bucket complete (two Adam steps give the same weights)."""
+    from cmr_landmark_detection_b200 import synth
+    from cmr_landmark_detection_b200.models.Unets import create_unet
+    res = {}
+    for flag in (None, 'dec0.conv_a,dec1.conv_a,mid.conv_b,enc3.conv_b,enc2.conv_a'):
+        if flag:
+            monkeypatch.setenv('RVIP_DEFER_WGRAD', flag)
+        else:
+            monkeypatch.delenv('RVIP_DEFER_WGRAD', raising=False)
+        model = create_unet(dict(BASE, DIM=[64, 64], DEPTH=4, PRECISION='bf16'))
+        x, y = synth.make_batch(4, 64, 64, seed=21)
+        xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+        loss = float(model.train_step_device(xd, yd, apply_optimizer=False).item())
+        g = model.grads.cpu().numpy().astype(np.float64)
+        for _ in range(2):
+            model.train_step_device(xd, yd)
+        res[flag] = (loss, g, model.params.cpu().numpy().astype(np.float64), model.tensors)
+    (l0, g0, p0, tensors), (l1, g1, p1, _) = res[None], res[[k for k in res if k][0]]
+    assert abs(l0 - l1) <= 2e-3 * abs(l0), (l0, l1)      # the forward pass is untouched; its statistics atomics reorder
+    for name, is_state, off, shape in tensors:
+        if is_state:
+            continue
+        n = int(np.prod(shape))
+        a, b = g0[off:off + n], g1[off:off + n]
+        if np.linalg.norm(a) < 1e-12:
+            continue
+        cos = float((a * b).sum() / (np.linalg.norm(a) * np.linalg.norm(b)))
+        assert cos >= 0.97, (name, cos)                      # same bound as two runs of the default path
+        if name.endswith('/kernel'):
+            # a weight gradient that was never queued (or an optimizer that ran before it) would leave the kernel unchanged
+            # or far off: Adam moves every element by ~lr per step
+            wa, wb = p0[off:off + n], p1[off:off + n]
+            assert np.abs(wa - wb).max() <= 4.1e-3, (name, float(np.abs(wa - wb).max()))
