@@ -467,6 +467,9 @@ bool conv_halo_plan(int B, int H, int W, int C0, int C1, int Cout, int mode, int
   if (bn == 256 && waves_eff(256) < 0.67 && waves_eff(128) > waves_eff(256)) bn = 128;
   // BN = 256 fills TMEM with one tile (no double buffering): with several tiles per CTA every epilogue is exposed
   if (bn == 256 && mtiles * (Cout / 256) > kNumSMs && getenv("RVIP_HALO_BN256") == nullptr) bn = 128;
+  // ... and once more: 64 units of N = 128 on 148 SMs (the 256-channel dgrad at the bottom of the depth-4 net, ncu: 36 us
+  // at 26 % SM throughput) become 128 units of N = 64
+  if (bn == 128 && waves_eff(128) < 0.67 && waves_eff(64) > waves_eff(128) && getenv("RVIP_HALO_NO_BN64") == nullptr) bn = 64;
   const size_t fixed = halo_fixed_bytes(bn, Cout, mode);
   if (fixed >= (size_t)kHaloMaxSmem) return false;
   int n = (int)((kHaloMaxSmem - fixed) / ((size_t)bn * 128));
