@@ -202,7 +202,7 @@ class RvipUNet:
         self.dp = DataParallel(self.device, enabled=bool(config.get('DATA_PARALLEL', True)))
         self.max_bindings = int(config.get('MAX_BINDINGS', 4))
         # host threads that copy one batch into page-locked memory.  Measured at 8 ranks on one 32-core host
-        # (profiles/r2zk_8gpu_*.json): 4 threads per rank 52 590 slices/s end to end, 2 threads 50 186, 1 thread 37 906 --
+        # (profiles/r2zk_8gpu_staging*.json): 4 threads per rank 52 590 slices/s end to end, 2 threads 50 186, 1 thread 37 906 --
         # the copy (8 x 25 MB per 4.6 ms step) is bound by per-thread memory bandwidth, not by core count
         self._stage_threads = int(os.environ.get('RVIP_STAGING_THREADS') or config.get('STAGING_THREADS', 4))
         self._pool = None
