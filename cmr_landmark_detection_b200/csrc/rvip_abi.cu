@@ -1167,6 +1167,19 @@ static void fold_head_bn(const rvip_handle* h, HeadArgs* a, int publish) {
   a->bn_publish = publish;
 }
 
+// Adam on gradient bucket `b` plus the re-pack of exactly the operand copies its layers own, on `st`
+static int adam_pack_bucket(rvip_handle* h, size_t b, float* m, float* v, float lr_t, float b1, float b2, float eps, float gs,
+                            cudaStream_t st) {
+  const long long off = h->buckets[b].first, cnt = h->buckets[b].second;
+  h->cur_tag = "step:adam";
+  return timed(h, KC_OPTIM, 3, st, [&] {
+    if (adam_launch(h->params + off, h->grads + off, m + off, v + off, (size_t)cnt, lr_t, b1, b2, eps, gs, st)) return 1;
+    if (pack_weights_launch(h->params, h->packed, h->pack_table_dev + h->bucket_pack0[b], h->bucket_packn[b], is_bf16(h), st))
+      return 1;
+    return pack_up_launch(h->params, h->packed, h->up_pack_table_dev + h->bucket_up0[b], h->bucket_upn[b], st);
+  });
+}
+
 // Backward pass.  Main chain per layer (reverse order):  BN/ReLU backward -> dz,  dgrad -> dx.  The weight gradient
 // of a layer only needs dz and the stored forward input, and nothing downstream needs it before the optimizer
 // (or the layer's gradient bucket): it runs on a low-priority side stream, so wgrad CTAs fill SMs the main chain
@@ -1194,43 +1207,18 @@ static int backward_body(rvip_handle* h, const float* x, uint64_t seed, cudaStre
   // on a third stream behind both.  Otherwise the caller's bucket event is recorded on the SIDE stream behind the main
   // chain's position, so the main chain itself never waits for a weight gradient here.
   auto close_bucket = [&](size_t b) -> int {
+    const auto& ia = h->inline_adam;
     if (!overlap) {
-      if (h->inline_adam.armed) {
-        h->cur_tag = "step:adam";
-        const auto& ia = h->inline_adam;
-        const long long off = h->buckets[b].first, cnt = h->buckets[b].second;
-        if (timed(h, KC_OPTIM, 3, st, [&] {
-              if (adam_launch(h->params + off, h->grads + off, ia.m + off, ia.v + off, (size_t)cnt, ia.lr_t, ia.b1, ia.b2,
-                              ia.eps, ia.gs, st))
-                return 1;
-              if (pack_weights_launch(h->params, h->packed, h->pack_table_dev + h->bucket_pack0[b], h->bucket_packn[b],
-                                      is_bf16(h), st))
-                return 1;
-              return pack_up_launch(h->params, h->packed, h->up_pack_table_dev + h->bucket_up0[b], h->bucket_upn[b], st);
-            }))
-          return 1;
-      }
+      if (ia.armed && adam_pack_bucket(h, b, ia.m, ia.v, ia.lr_t, ia.b1, ia.b2, ia.eps, ia.gs, st)) return 1;
       if (h->bucket_events[b]) RVIP_CUDA(cudaEventRecord(h->bucket_events[b], st));
       return 0;
     }
     RVIP_CUDA(cudaEventRecord(h->ev_grad, st));
-    if (h->inline_adam.armed) {
+    if (ia.armed) {
       cudaStream_t os = h->opt;
       RVIP_CUDA(cudaStreamWaitEvent(os, h->ev_grad, 0));
       if (last_ws_ev) RVIP_CUDA(cudaStreamWaitEvent(os, last_ws_ev, 0));
-      h->cur_tag = "step:adam";
-      const auto& ia = h->inline_adam;
-      const long long off = h->buckets[b].first, cnt = h->buckets[b].second;
-      if (timed(h, KC_OPTIM, 3, os, [&] {
-            if (adam_launch(h->params + off, h->grads + off, ia.m + off, ia.v + off, (size_t)cnt, ia.lr_t, ia.b1, ia.b2,
-                            ia.eps, ia.gs, os))
-              return 1;
-            if (pack_weights_launch(h->params, h->packed, h->pack_table_dev + h->bucket_pack0[b], h->bucket_packn[b],
-                                    is_bf16(h), os))
-              return 1;
-            return pack_up_launch(h->params, h->packed, h->up_pack_table_dev + h->bucket_up0[b], h->bucket_upn[b], os);
-          }))
-        return 1;
+      if (adam_pack_bucket(h, b, ia.m, ia.v, ia.lr_t, ia.b1, ia.b2, ia.eps, ia.gs, os)) return 1;
       RVIP_CUDA(cudaEventRecord(h->ev_opt, os));
       if (h->bucket_events[b]) RVIP_CUDA(cudaEventRecord(h->bucket_events[b], os));
     } else if (h->bucket_events[b]) {
@@ -1683,16 +1671,7 @@ int rvip_adam_bucket(rvip_handle* h, int bucket, float* m, float* v, float lr, f
   cudaStream_t st = (cudaStream_t)stream;
   const float lr_t = (float)((double)lr * std::sqrt(1.0 - std::pow((double)beta2, (double)step)) /
                              (1.0 - std::pow((double)beta1, (double)step)));
-  const long long off = h->buckets[bucket].first, cnt = h->buckets[bucket].second;
-  h->cur_tag = "step:adam";
-  return timed(h, KC_OPTIM, 3, st, [&] {
-    if (adam_launch(h->params + off, h->grads + off, m + off, v + off, (size_t)cnt, lr_t, beta1, beta2, eps, grad_scale, st))
-      return 1;
-    if (pack_weights_launch(h->params, h->packed, h->pack_table_dev + h->bucket_pack0[bucket], h->bucket_packn[bucket],
-                            is_bf16(h), st))
-      return 1;
-    return pack_up_launch(h->params, h->packed, h->up_pack_table_dev + h->bucket_up0[bucket], h->bucket_upn[bucket], st);
-  });
+  return adam_pack_bucket(h, (size_t)bucket, m, v, lr_t, beta1, beta2, eps, grad_scale, st);
 }
 
 int rvip_sgd_step(rvip_handle* h, float* velocity, float lr, float momentum, int nesterov, float grad_scale, void* stream) {
