@@ -104,3 +104,27 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith('.py'):
                 src = open(os.path.join(dp, f)).read()
                 assert 'oracle' not in src.replace('the oracle', ''), os.path.join(dp, f)
+
+
+def test_deferred_weight_gradient_plan(monkeypatch):
+    """RVIP_DEFER_WGRAD (opt-in backward schedule): the named deep-level layers get dz buffers of their own, so the
+    training workspace grows by exactly those tensors (rounded to the carver's 1 KB granules); inference is untouched."""
+    L = ffi.lib()
+    base = dict(H=256, W=256, in_ch=1, classes=2, depth=4, filters=32, batch_norm=1, bn_first=0, use_upsample=1,
+                precision=1, dropout_mid=0.5, bn_momentum=0.99, bn_eps=1e-3)
+
+    def sizes():
+        h = C.c_void_p()
+        ffi.check(L.rvip_create(C.byref(ffi.rvip_cfg(**base)), C.byref(h)))
+        out = (L.rvip_workspace_bytes(h, 32, 1), L.rvip_workspace_bytes(h, 32, 0))
+        L.rvip_destroy(h)
+        return out
+
+    monkeypatch.delenv('RVIP_DEFER_WGRAD', raising=False)
+    t0, i0 = sizes()
+    monkeypatch.setenv('RVIP_DEFER_WGRAD', 'mid.conv_b,dec0.conv_a')
+    t1, i1 = sizes()
+    extra = 32 * 16 * 16 * 512 * 2 + 32 * 32 * 32 * 256 * 2          # bf16 dz of mid.conv_b and dec0.conv_a at batch 32
+    assert i1 == i0 and extra <= t1 - t0 <= extra + 4096
+    monkeypatch.setenv('RVIP_DEFER_WGRAD', 'none')
+    assert sizes() == (t0, i0)
