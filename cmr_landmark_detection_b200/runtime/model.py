@@ -290,38 +290,61 @@ class RvipUNet:
              'moving_mean': 'moving_mean:0', 'moving_variance': 'moving_variance:0'}
 
     def save_weights(self, filepath: str, overwrite: bool = True):
-        """Weights keyed like Keras' HDF5 layout (<layer>/<layer>/<var>:0). h5py is not available in
-        this image, so the container is .npz; a path ending in .h5 is written as <path>.npz."""
-        ws = self.get_weights()
-        blob = {}
-        names = []
+        """model.save_weights (ModelCheckpoint(save_weights_only=True), KerasCallbacks.py:54-61).  A path ending in .h5 /
+        .hdf5 is written as a Keras HDF5 weight file (tf.keras hdf5_format layout: root attributes layer_names / backend /
+        keras_version, one group per layer with weight_names and <layer>/<var>:0 datasets) by utils/hdf5_lite.py -- h5py is
+        not needed.  Any other path is written as <path>.npz with the same keys."""
+        ws = self.get_weights()               # a collective under data parallelism (moving statistics): every rank calls it
+        layers = []
         for lname, idxs in self.keras_layer_names():
-            names.append(lname)
-            for i in idxs:
-                leaf = self._LEAF[self.tensors[i][0].rsplit('/', 1)[-1]]
-                blob['%s/%s/%s' % (lname, lname, leaf)] = ws[i]
-        blob['layer_names'] = np.array(names)
-        path = filepath if filepath.endswith('.npz') else filepath + '.npz'
-        if self.dp.rank == 0:
-            os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
-            np.savez(path, **blob)
+            layers.append((lname, [('%s/%s' % (lname, self._LEAF[self.tensors[i][0].rsplit('/', 1)[-1]]), ws[i]) for i in idxs]))
+        if self.dp.rank != 0:
+            return
+        os.makedirs(os.path.dirname(os.path.abspath(filepath)), exist_ok=True)
+        if filepath.endswith(('.h5', '.hdf5')):
+            from ..utils import hdf5_lite
+            hdf5_lite.save_keras_weights(filepath, layers)
+            return
+        blob = {'%s/%s' % (lname, wn): arr for lname, weights in layers for wn, arr in weights}
+        blob['layer_names'] = np.array([lname for lname, _ in layers])
+        np.savez(filepath if filepath.endswith('.npz') else filepath + '.npz', **blob)
 
     def load_weights(self, filepath: str):
-        path = filepath if filepath.endswith('.npz') else filepath + '.npz'
-        if not os.path.exists(path) and filepath.endswith(('.h5', '.hdf5')) and os.path.exists(filepath):
-            raise NotImplementedError('HDF5 weight files need h5py, which is not installed in this image '
-                                      '(SURVEY row N1); convert to .npz with the same keys')
-        z = np.load(path, allow_pickle=False)
-        ws = [None] * len(self.tensors)
-        # key by position (Keras auto-numbering depends on process history), verify shapes
-        file_layers = [str(s) for s in z['layer_names']]
+        """model.load_weights (predict_model.py:76): a Keras HDF5 weight file (read by utils/hdf5_lite.py; files written
+        with h5py's default settings, no compression) or the .npz container save_weights writes.  Like Keras' topological
+        loading, layers are matched by POSITION among the layers that have weights (auto-numbered layer names depend on
+        the process history) and every shape is checked."""
+        from ..utils import hdf5_lite
+        path = filepath
+        if not os.path.exists(path) and os.path.exists(filepath + '.npz'):
+            path = filepath + '.npz'
+        with open(path, 'rb') as fh:
+            head = fh.read(8)
         mine = self.keras_layer_names()
+        if head == hdf5_lite.SIGNATURE or path.endswith(('.h5', '.hdf5')):
+            file_layers = hdf5_lite.load_keras_weights(path)
+        else:
+            z = np.load(path, allow_pickle=False)
+            file_layers = []
+            for fl in [str(s) for s in z['layer_names']]:
+                prefix = fl + '/'
+                # this layer's arrays, in the order the model lists its own (kernel, bias | gamma, beta, moving_*)
+                file_layers.append((fl, [(k[len(prefix):], z[k]) for k in z.files if k.startswith(prefix)]))
         if len(file_layers) != len(mine):
-            raise ValueError('weight file has %d layers, model has %d' % (len(file_layers), len(mine)))
-        for fl, (lname, idxs) in zip(file_layers, mine):
+            raise ValueError('weight file has %d layers with weights, model has %d' % (len(file_layers), len(mine)))
+        ws = [None] * len(self.tensors)
+        for (fl, weights), (lname, idxs) in zip(file_layers, mine):
+            by_leaf = {wn.rsplit('/', 1)[-1]: arr for wn, arr in weights}
+            if len(weights) != len(idxs):
+                raise ValueError('layer %s: file has %d weight arrays, model layer %s has %d' % (fl, len(weights), lname, len(idxs)))
             for i in idxs:
                 leaf = self._LEAF[self.tensors[i][0].rsplit('/', 1)[-1]]
-                ws[i] = z['%s/%s/%s' % (fl, fl, leaf)]
+                if leaf not in by_leaf:
+                    raise ValueError('layer %s in the weight file has no %s' % (fl, leaf))
+                arr = np.asarray(by_leaf[leaf], dtype=np.float32)
+                if tuple(arr.shape) != tuple(self.tensors[i][3]):
+                    raise ValueError('%s/%s: shape %s in the file, %s in the model' % (fl, leaf, arr.shape, tuple(self.tensors[i][3])))
+                ws[i] = arr
         self.set_weights(ws)
 
     def count_params(self) -> int:

@@ -352,10 +352,21 @@ def test_weights_roundtrip_and_summary(tmp_path):
     assert len(ws) == 118
     p = str(tmp_path / 'model.h5')
     model.save_weights(p)
+    assert open(p, 'rb').read(8) == b'\x89HDF\r\n\x1a\n'          # a Keras HDF5 weight file (utils/hdf5_lite.py), not a renamed .npz
     m2 = create_unet(dict(BASE, DIM=[128, 128], DEPTH=4, PRECISION='bf16', SEED=99))
     m2.load_weights(p)
     for a, b in zip(ws, m2.get_weights()):
         assert np.array_equal(a, b)
+    # the .npz container (any other extension) still works, and a file of another architecture is refused
+    q = str(tmp_path / 'weights')
+    model.save_weights(q)
+    m3 = create_unet(dict(BASE, DIM=[128, 128], DEPTH=4, PRECISION='bf16', SEED=5))
+    m3.load_weights(q)
+    for a, b in zip(ws, m3.get_weights()):
+        assert np.array_equal(a, b)
+    small = create_unet(dict(BASE, DIM=[64, 64], DEPTH=2, PRECISION='bf16'))
+    with pytest.raises(ValueError):
+        small.load_weights(p)
     lines = []
     model.summary(print_fn=lines.append)
     assert any('8,641,730' in l for l in lines)

@@ -1,0 +1,136 @@
+"""utils/hdf5_lite.py: the reader against a file written by the HDF5 library itself, the writer by round trip, and the
+Keras weight-file layout on top (tf.keras hdf5_format: layer_names / weight_names attributes, <layer>/<weight name>)."""
+import glob
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from cmr_landmark_detection_b200.utils import hdf5_lite as H
+
+
+def _library_written_file():
+    try:
+        import scipy.io
+    except Exception:
+        return None
+    hits = glob.glob(os.path.join(os.path.dirname(scipy.io.__file__), 'matlab', 'tests', 'data', 'testhdf5_7.4_GLNX86.mat'))
+    return hits[0] if hits else None
+
+
+def test_reader_on_a_library_written_file():
+    """MATLAB v7.3 files are HDF5 files (512-byte user block, superblock 0, symbol-table groups, version-1 object
+    headers): the one scipy ships holds testdouble = 0 : pi/4 : 2 pi as a 9 x 1 float64 dataset with a string attribute."""
+    path = _library_written_file()
+    if path is None:
+        pytest.skip('scipy test data not installed')
+    f = H.File(path)
+    assert f.keys() == ['testdouble']
+    d = f['testdouble']
+    assert not d.is_group and d.shape == (9, 1)
+    assert np.allclose(d.read().reshape(-1), np.arange(9) * np.pi / 4, rtol=0, atol=1e-15)
+    assert bytes(d.attrs['MATLAB_class']) == b'double'
+    with pytest.raises(KeyError):
+        f['nope']
+
+
+def _layers(rng):
+    return [('conv2d', [('conv2d/kernel:0', rng.standard_normal((3, 3, 1, 32)).astype(np.float32)),
+                        ('conv2d/bias:0', rng.standard_normal(32).astype(np.float32))]),
+            ('batch_normalization', [('batch_normalization/%s:0' % n, rng.standard_normal(32).astype(np.float32))
+                                     for n in ('gamma', 'beta', 'moving_mean', 'moving_variance')]),
+            ('max_pooling2d', []),
+            ('unet', [('unet/kernel:0', rng.standard_normal((1, 1, 32, 2)).astype(np.float32)),
+                      ('unet/bias:0', np.zeros(2, np.float32))])]
+
+
+def test_keras_layout_round_trip(tmp_path):
+    layers = _layers(np.random.default_rng(0))
+    path = str(tmp_path / 'model.h5')
+    H.save_keras_weights(path, layers)
+    f = H.File(path)
+    assert [bytes(x).decode() for x in f.attrs['layer_names']] == [n for n, _ in layers]
+    assert bytes(f.attrs['backend']) == b'tensorflow'
+    assert sorted(f.keys()) == sorted(n for n, _ in layers)
+    assert f['conv2d'].keys() == ['conv2d'] and sorted(f['conv2d/conv2d'].keys()) == ['bias:0', 'kernel:0']
+    assert f['max_pooling2d'].keys() == [] and np.asarray(f['max_pooling2d'].attrs['weight_names']).size == 0
+    back = H.load_keras_weights(path)
+    assert [n for n, _ in back] == [n for n, w in layers if w]          # weightless layers are dropped, as Keras does
+    for (n0, w0), (n1, w1) in zip([l for l in layers if l[1]], back):
+        assert [a for a, _ in w0] == [a for a, _ in w1]
+        for (_, a), (_, b) in zip(w0, w1):
+            assert a.dtype == b.dtype == np.float32 and a.shape == b.shape and np.array_equal(a, b)
+
+
+def test_written_file_structure(tmp_path):
+    """The bytes the HDF5 library looks at first: signature, superblock 0 with 8-byte offsets, end-of-file address,
+    root symbol-table entry -> version-1 object header whose first message is the symbol table; every group's members
+    fit one symbol node (leaf K is sized for the widest group)."""
+    w = H.Writer()
+    for i in range(45):
+        w.dataset('/g/d%02d' % i, np.full((2, 3), i, np.float32))
+    w.attr('/', 'note', b'hello')
+    path = str(tmp_path / 'wide.h5')
+    w.save(path)
+    raw = open(path, 'rb').read()
+    assert raw[:8] == H.SIGNATURE and raw[8] == 0 and raw[13] == 8 and raw[14] == 8
+    leaf_k, internal_k = struct.unpack_from('<HH', raw, 16)
+    assert 2 * leaf_k >= 45 and internal_k == 16
+    base, free, eof, drv = struct.unpack_from('<QQQQ', raw, 24)
+    assert base == 0 and eof == len(raw) and free == drv == H.UNDEF
+    name_off, root_hdr, cache = struct.unpack_from('<QQI', raw, 56)
+    assert cache == 1 and raw[root_hdr] == 1 and struct.unpack_from('<H', raw, root_hdr + 16)[0] == 0x0011
+    f = H.File(path)
+    assert bytes(f.attrs['note']) == b'hello'
+    assert f['g'].keys() == ['d%02d' % i for i in range(45)]              # sorted, as a symbol node must be
+    assert all(float(f['g/d%02d' % i].read()[1, 2]) == i for i in range(45))
+
+
+def test_unsupported_files_fail_loudly(tmp_path):
+    p = tmp_path / 'x.h5'
+    p.write_bytes(b'not an hdf5 file' * 64)
+    with pytest.raises(H.Hdf5Error):
+        H.File(str(p))
+    p.write_bytes(H.SIGNATURE + bytes([2]) + b'\x00' * 200)              # superblock version 2 (libver='latest')
+    with pytest.raises(H.Hdf5Error):
+        H.File(str(p))
+
+
+def test_c2_model_sized_weight_file(tmp_path):
+    """The whole C2 network's weight table (118 arrays, 8.64 M floats, names and shapes from the C plan) through the
+    writer and back: what ModelCheckpoint('model.h5') writes and pred_fold's load_weights reads."""
+    import ctypes as C
+    from cmr_landmark_detection_b200.runtime import ffi
+    L = ffi.lib()
+    cfg = ffi.rvip_cfg(H=256, W=256, in_ch=1, classes=2, depth=4, filters=32, batch_norm=1, bn_first=0, use_upsample=1,
+                       precision=1, dropout_mid=0.5, bn_momentum=0.99, bn_eps=1e-3)
+    h = C.c_void_p()
+    ffi.check(L.rvip_create(C.byref(cfg), C.byref(h)))
+    rng = np.random.default_rng(3)
+    layers, n_conv, n_bn = [], 0, 0
+    for i in range(L.rvip_num_tensors(h)):
+        nm = C.create_string_buffer(128)
+        st, off, nd, dims = C.c_int(), C.c_longlong(), C.c_int(), (C.c_int * 4)()
+        ffi.check(L.rvip_tensor_info(h, i, nm, 128, C.byref(st), C.byref(off), C.byref(nd), C.byref(dims)))
+        name, shape = nm.value.decode(), tuple(dims[:nd.value])
+        leaf = name.rsplit('/', 1)[-1]
+        if leaf == 'kernel':
+            lname = 'unet' if name.startswith('head/') else ('conv2d' if n_conv == 0 else 'conv2d_%d' % n_conv)
+            n_conv += 0 if name.startswith('head/') else 1
+            layers.append((lname, []))
+        elif leaf == 'gamma':
+            lname = 'batch_normalization' if n_bn == 0 else 'batch_normalization_%d' % n_bn
+            n_bn += 1
+            layers.append((lname, []))
+        layers[-1][1].append(('%s/%s:0' % (layers[-1][0], leaf), rng.standard_normal(shape).astype(np.float32)))
+    L.rvip_destroy(h)
+    assert len(layers) == 41 and sum(len(w) for _, w in layers) == 118
+    path = str(tmp_path / 'model.h5')
+    H.save_keras_weights(path, layers)
+    assert 8641730 * 4 < os.path.getsize(path) < 8641730 * 4 + 400000      # payload + ~2.6 KB of group structure per group
+    back = H.load_keras_weights(path)
+    assert [n for n, _ in back] == [n for n, _ in layers]
+    for (_, w0), (_, w1) in zip(layers, back):
+        for (n0, a), (n1, b) in zip(w0, w1):
+            assert n0 == n1 and np.array_equal(a, b)
