@@ -134,3 +134,22 @@ def test_c2_model_sized_weight_file(tmp_path):
     for (_, w0), (_, w1) in zip(layers, back):
         for (n0, a), (n1, b) in zip(w0, w1):
             assert n0 == n1 and np.array_equal(a, b)
+
+
+def test_convert_tool_round_trip(tmp_path):
+    """tools/keras_h5_convert.py: HDF5 -> .npz -> HDF5 keeps every layer, name and array."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('keras_h5_convert', os.path.join(root, 'tools', 'keras_h5_convert.py'))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    layers = [l for l in _layers(np.random.default_rng(1)) if l[1]]
+    a, z, b = str(tmp_path / 'a.h5'), str(tmp_path / 'w.npz'), str(tmp_path / 'b.h5')
+    H.save_keras_weights(a, layers)
+    tool.to_npz(a, z)
+    tool.to_h5(z, b)
+    back = H.load_keras_weights(b)
+    assert [n for n, _ in back] == [n for n, _ in layers]
+    for (_, w0), (_, w1) in zip(layers, back):
+        assert [n for n, _ in w0] == [n for n, _ in w1]
+        assert all(np.array_equal(x, y) for (_, x), (_, y) in zip(w0, w1))
