@@ -469,13 +469,8 @@ class Writer:
 
     def save(self, path: str):
         buf = bytearray()
-        # leaf K: every group's symbols fit ONE symbol node (capacity 2 K), so every group B-tree is a single leaf entry
-        def widest(g: _Group) -> int:
-            return max([len(g.children)] + [widest(c) for c in g.children.values() if isinstance(c, _Group)])
-        leaf_k = max(4, (widest(self.root) + 1) // 2)
-        internal_k = 16
-        if leaf_k > 0x7FFF:
-            raise Hdf5Error('too many members in one group')
+        # the library's default group B-tree geometry: symbol nodes of up to 2 * 4 entries, tree nodes of up to 2 * 16 children
+        leaf_k, internal_k = 4, 16
 
         def alloc(data: bytes) -> int:
             buf.extend(b'\x00' * (-len(buf) % 8))
@@ -521,17 +516,47 @@ class Writer:
             seg.extend(struct.pack('<QQ', 1, 16))          # one free block: next = 1 (last), size 16 (minimum heap free block)
             seg_addr = alloc(bytes(seg))
             heap_addr = alloc(b'HEAP' + struct.pack('<B3xQQQ', 0, len(seg), free_off, seg_addr))
-            snod = bytearray(b'SNOD' + struct.pack('<BxH', 1, len(entries)))
-            for name, hdr, ctype, bt, hp in entries:
-                scratch = struct.pack('<QQ', bt, hp) if ctype == 1 else b'\x00' * 16
-                snod.extend(struct.pack('<QQI4x', offs[name], hdr, ctype) + scratch)
-            snod.extend(b'\x00' * (8 + 2 * leaf_k * 40 - len(snod)))
-            tree = bytearray(b'TREE' + struct.pack('<BBHQQ', 0, 0, 1 if entries else 0, UNDEF, UNDEF))
-            if entries:
-                snod_addr = alloc(bytes(snod))
-                tree.extend(struct.pack('<QQQ', 0, snod_addr, offs[entries[-1][0]]))
-            tree.extend(b'\x00' * (24 + (2 * internal_k + 1) * 8 + 2 * internal_k * 8 - len(tree)))
-            tree_addr = alloc(bytes(tree))
+            def tree_node(level: int, keys: List[int], children: List[int], left: int, right: int) -> bytes:
+                node = bytearray(b'TREE' + struct.pack('<BBHQQ', 0, level, len(children), left, right))
+                for k, c in zip(keys, children):
+                    node.extend(struct.pack('<QQ', k, c))
+                if children:
+                    node.extend(struct.pack('<Q', keys[-1]))
+                node.extend(b'\x00' * (24 + (2 * internal_k + 1) * 8 + 2 * internal_k * 8 - len(node)))
+                return bytes(node)
+
+            # level 0: symbol nodes of <= 2 * leaf_k entries (sorted by name); a key is the heap offset of the largest name
+            # of the child to its left, the very first key the empty string at heap offset 0
+            nodes: List[Tuple[int, int]] = []            # (address, heap offset of the largest name below)
+            for i in range(0, len(entries), 2 * leaf_k):
+                part = entries[i:i + 2 * leaf_k]
+                snod = bytearray(b'SNOD' + struct.pack('<BxH', 1, len(part)))
+                for name, hdr, ctype, bt, hp in part:
+                    scratch = struct.pack('<QQ', bt, hp) if ctype == 1 else b'\x00' * 16
+                    snod.extend(struct.pack('<QQI4x', offs[name], hdr, ctype) + scratch)
+                snod.extend(b'\x00' * (8 + 2 * leaf_k * 40 - len(snod)))
+                nodes.append((alloc(bytes(snod)), offs[part[-1][0]]))
+            level = 0
+            while True:
+                groups = [nodes[i:i + 2 * internal_k] for i in range(0, len(nodes), 2 * internal_k)] or [[]]
+                # reserve the addresses first: siblings of one level point at each other
+                size = 24 + (2 * internal_k + 1) * 8 + 2 * internal_k * 8
+                buf.extend(b'\x00' * (-len(buf) % 8))
+                addrs = [len(buf) + k * size for k in range(len(groups))]
+                first_key = 0
+                parents = []
+                for k, grp in enumerate(groups):
+                    keys = [first_key] + [mx for _, mx in grp]
+                    node = tree_node(level, keys, [a for a, _ in grp],
+                                     addrs[k - 1] if k > 0 else UNDEF, addrs[k + 1] if k + 1 < len(groups) else UNDEF)
+                    assert alloc(node) == addrs[k]
+                    if grp:
+                        first_key = grp[-1][1]
+                        parents.append((addrs[k], grp[-1][1]))
+                if len(groups) == 1:
+                    tree_addr = addrs[0]
+                    break
+                nodes, level = parents, level + 1
             msgs = [_msg(0x0011, struct.pack('<QQ', tree_addr, heap_addr), flags=1)] + [_attribute(k, v) for k, v in g.attrs]
             return header(msgs), tree_addr, heap_addr
 

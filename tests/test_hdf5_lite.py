@@ -64,27 +64,38 @@ def test_keras_layout_round_trip(tmp_path):
 
 
 def test_written_file_structure(tmp_path):
-    """The bytes the HDF5 library looks at first: signature, superblock 0 with 8-byte offsets, end-of-file address,
-    root symbol-table entry -> version-1 object header whose first message is the symbol table; every group's members
-    fit one symbol node (leaf K is sized for the widest group)."""
+    """The bytes the HDF5 library looks at first: signature, superblock 0 with 8-byte offsets and the library's default
+    B-tree geometry (symbol nodes of 2 x 4 entries, tree nodes of 2 x 16 children), end-of-file address, root symbol-table
+    entry -> version-1 object header whose first message is the symbol table.  45 members need six symbol nodes under one
+    tree node; 300 members need 38 symbol nodes under two level-0 nodes under a level-1 root."""
     w = H.Writer()
     for i in range(45):
         w.dataset('/g/d%02d' % i, np.full((2, 3), i, np.float32))
+    for i in range(300):
+        w.dataset('/big/x%03d' % i, np.full((1,), i, np.float32))
+    w.group('/empty')
     w.attr('/', 'note', b'hello')
     path = str(tmp_path / 'wide.h5')
     w.save(path)
     raw = open(path, 'rb').read()
     assert raw[:8] == H.SIGNATURE and raw[8] == 0 and raw[13] == 8 and raw[14] == 8
-    leaf_k, internal_k = struct.unpack_from('<HH', raw, 16)
-    assert 2 * leaf_k >= 45 and internal_k == 16
+    assert struct.unpack_from('<HH', raw, 16) == (4, 16)
     base, free, eof, drv = struct.unpack_from('<QQQQ', raw, 24)
     assert base == 0 and eof == len(raw) and free == drv == H.UNDEF
     name_off, root_hdr, cache = struct.unpack_from('<QQI', raw, 56)
     assert cache == 1 and raw[root_hdr] == 1 and struct.unpack_from('<H', raw, root_hdr + 16)[0] == 0x0011
     f = H.File(path)
     assert bytes(f.attrs['note']) == b'hello'
-    assert f['g'].keys() == ['d%02d' % i for i in range(45)]              # sorted, as a symbol node must be
+    assert f.keys() == ['big', 'empty', 'g'] and f['empty'].keys() == []
+    assert f['g'].keys() == ['d%02d' % i for i in range(45)]              # in name order, as the B-tree must be
     assert all(float(f['g/d%02d' % i].read()[1, 2]) == i for i in range(45))
+    assert f['big'].keys() == ['x%03d' % i for i in range(300)]
+    assert all(float(f['big/x%03d' % i].read()[0]) == i for i in (0, 7, 8, 255, 256, 299))
+    # the big group's tree really has two levels, and every node's keys ascend (heap offsets follow name order here)
+    bt = struct.unpack_from('<Q', [b for t, b in f['big']._msgs if t == 0x0011][0], 0)[0]
+    assert raw[bt:bt + 4] == b'TREE' and raw[bt + 5] == 1 and struct.unpack_from('<H', raw, bt + 6)[0] == 2
+    keys = [struct.unpack_from('<Q', raw, bt + 24 + 16 * i)[0] for i in range(3)]
+    assert keys[0] == 0 and keys == sorted(keys)
 
 
 def test_unsupported_files_fail_loudly(tmp_path):
