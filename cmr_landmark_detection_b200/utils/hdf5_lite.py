@@ -44,10 +44,15 @@ class Node:
         self._f, self._addr, self.name = f, addr, name
         self._msgs = f._read_object_header(addr)
         self.attrs: Dict[str, Union[np.ndarray, bytes, str, float, int]] = {}
+        self.unreadable_attrs: Dict[str, str] = {}       # attribute name (or '?') -> why it could not be decoded
         for t, body in self._msgs:
             if t == 0x000C:
-                k, v = f._parse_attribute(body)
-                self.attrs[k] = v
+                try:
+                    k, v = f._parse_attribute(body)
+                    self.attrs[k] = v
+                except (Hdf5Error, struct.error, IndexError, ValueError) as e:
+                    # an exotic attribute must not make the weights unreadable; asking for it later says why
+                    self.unreadable_attrs[f._attribute_name(body)] = str(e)
         self._children: Optional[Dict[str, int]] = None
 
     # ---- groups
@@ -347,6 +352,16 @@ class File(Node):
             return a
         raise Hdf5Error('cannot decode datatype %s' % typ.kind)
 
+    @staticmethod
+    def _attribute_name(body: bytes) -> str:
+        try:
+            ver = body[0]
+            name_size = struct.unpack_from('<H', body, 2)[0]
+            p = 9 if ver == 3 else 8
+            return body[p:p + name_size].split(b'\x00')[0].decode('utf-8', 'replace')
+        except Exception:
+            return '?'
+
     def _parse_attribute(self, body: bytes):
         ver = body[0]
         name_size, type_size, space_size = struct.unpack_from('<HHH', body, 2)
@@ -597,7 +612,8 @@ def load_keras_weights(path: str) -> List[Tuple[str, List[Tuple[str, np.ndarray]
     if 'layer_names' not in g.attrs and 'model_weights' in g:
         g = g['model_weights']
     if 'layer_names' not in g.attrs:
-        raise Hdf5Error('%s is not a Keras weight file (no layer_names attribute)' % path)
+        why = g.unreadable_attrs.get('layer_names')
+        raise Hdf5Error('%s is not a Keras weight file (%s)' % (path, 'layer_names: ' + why if why else 'no layer_names attribute'))
 
     def names(v) -> List[str]:
         out = []

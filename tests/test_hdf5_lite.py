@@ -164,3 +164,73 @@ def test_convert_tool_round_trip(tmp_path):
     for (_, w0), (_, w1) in zip(layers, back):
         assert [n for n, _ in w0] == [n for n, _ in w1]
         assert all(np.array_equal(x, y) for (_, x), (_, y) in zip(w0, w1))
+
+
+def test_reader_variable_length_string_attribute(tmp_path):
+    """h5py 3 stores str attributes (`backend`, `keras_version` of newer Keras) as variable-length UTF-8 strings: a
+    version-3 attribute message whose 16-byte element points into a global heap collection.  Hand-assembled here from the
+    format specification (the writer itself only emits fixed-length strings); an attribute of a datatype the reader does
+    not know is skipped with a reason instead of making the file unreadable."""
+    w = H.Writer()
+    w.dataset('/d', np.arange(4, dtype=np.float32))
+    path = str(tmp_path / 'v.h5')
+    w.save(path)
+    raw = bytearray(open(path, 'rb').read())
+    # global heap collection: object 1 = b'tensorflow', then the free-space object 0
+    text = b'tensorflow'
+    gcol_addr = len(raw)
+    obj = struct.pack('<HHIQ', 1, 0, 0, len(text)) + text + b'\x00' * (-len(text) % 8)
+    body = obj + struct.pack('<HHIQ', 0, 0, 0, 0)
+    raw += b'GCOL' + struct.pack('<B3xQ', 1, 16 + len(body)) + body
+    # attribute message version 3: vlen string (class 9, type = string, UTF-8) of base type 1-byte string, scalar space v2
+    base = struct.pack('<B3BI', 0x13, 0x00, 0, 0, 1)
+    vtype = struct.pack('<B3BI', 0x19, 0x01 | (1 << 4), 0x01, 0, 16) + base
+    space = struct.pack('<BBBB', 2, 0, 0, 0)
+    name = b'backend\x00'
+    att = struct.pack('<BBHHHB', 3, 0, len(name), len(vtype), len(space), 1) + name + vtype + space
+    att += struct.pack('<IQI', len(text), gcol_addr, 1)
+    weird = struct.pack('<BBHHHB', 3, 0, 6, 8, len(space), 0) + b'weird\x00' + struct.pack('<B3BI', 0x16, 0, 0, 0, 4) + space + b'\x00' * 4
+    # a new object header for the root group: its symbol-table message copied over, plus the two attributes
+    f = H.File(path)
+    symtab = [b for t, b in f._msgs if t == 0x0011][0]
+    msgs = [H._msg(0x0011, symtab, flags=1), H._msg(0x000C, att), H._msg(0x000C, weird)]
+    blob = b''.join(msgs)
+    raw += b'\x00' * (-len(raw) % 8)
+    hdr_addr = len(raw)
+    raw += struct.pack('<BxHII4x', 1, len(msgs), 1, len(blob)) + blob
+    struct.pack_into('<Q', raw, 56 + 8, hdr_addr)                       # root symbol-table entry -> the new header
+    struct.pack_into('<Q', raw, 24 + 16, len(raw))                      # end-of-file address
+    open(path, 'wb').write(bytes(raw))
+    g = H.File(path)
+    assert bytes(g.attrs['backend']) == text
+    assert 'weird' in g.unreadable_attrs and 'weird' not in g.attrs
+    assert np.array_equal(g['d'].read(), np.arange(4, dtype=np.float32))
+
+
+def test_reader_follows_object_header_continuations(tmp_path):
+    """A root group whose attributes did not fit the first header chunk: the library appends a continuation message
+    (0x0010: address, length) and stores the rest there.  Assembled by hand around a file the writer produced."""
+    layers = [l for l in _layers(np.random.default_rng(2)) if l[1]]
+    path = str(tmp_path / 'c.h5')
+    H.save_keras_weights(path, layers)
+    f = H.File(path)
+    raw = bytearray(open(path, 'rb').read())
+    symtab = [b for t, b in f._msgs if t == 0x0011][0]
+    attrs = [H._attribute('layer_names', np.array([n.encode() for n, _ in layers])), H._attribute('backend', b'tensorflow'),
+             H._attribute('keras_version', b'2.4.0')]
+    raw += b'\x00' * (-len(raw) % 8)
+    cont_addr = len(raw)
+    cont = attrs[1] + attrs[2] + H._msg(0x0000, b'\x00' * 24)            # two attributes and a NIL filler
+    raw += cont
+    first = [H._msg(0x0011, symtab, flags=1), attrs[0], H._msg(0x0010, struct.pack('<QQ', cont_addr, len(cont)))]
+    blob = b''.join(first)
+    hdr_addr = len(raw)
+    raw += struct.pack('<BxHII4x', 1, 6, 1, len(blob)) + blob
+    struct.pack_into('<Q', raw, 56 + 8, hdr_addr)
+    struct.pack_into('<Q', raw, 24 + 16, len(raw))
+    open(path, 'wb').write(bytes(raw))
+    g = H.File(path)
+    assert bytes(g.attrs['keras_version']) == b'2.4.0' and bytes(g.attrs['backend']) == b'tensorflow'
+    back = H.load_keras_weights(path)
+    assert [n for n, _ in back] == [n for n, _ in layers]
+    assert all(np.array_equal(a, b) for (_, w0), (_, w1) in zip(layers, back) for (_, a), (_, b) in zip(w0, w1))
