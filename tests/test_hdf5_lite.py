@@ -234,3 +234,47 @@ def test_reader_follows_object_header_continuations(tmp_path):
     back = H.load_keras_weights(path)
     assert [n for n, _ in back] == [n for n, _ in layers]
     assert all(np.array_equal(a, b) for (_, w0), (_, w1) in zip(layers, back) for (_, a), (_, b) in zip(w0, w1))
+
+
+def test_reader_unfiltered_chunked_dataset(tmp_path):
+    """create_dataset(..., chunks=...) without compression: data layout class 2 -> version-1 B-tree of raw-data chunks.
+    A 5 x 7 float32 array in 2 x 3 chunks (edge chunks stick out of the array), assembled by hand from the specification."""
+    arr = np.arange(35, dtype=np.float32).reshape(5, 7)
+    w = H.Writer()
+    w.dataset('/plain', arr)
+    path = str(tmp_path / 'k.h5')
+    w.save(path)
+    raw = bytearray(open(path, 'rb').read())
+    ch = (2, 3)
+    keys, kids = [], []
+    for i in range(0, 5, ch[0]):
+        for j in range(0, 7, ch[1]):
+            block = np.zeros(ch, np.float32)
+            part = arr[i:i + ch[0], j:j + ch[1]]
+            block[:part.shape[0], :part.shape[1]] = part
+            raw += b'\x00' * (-len(raw) % 8)
+            kids.append(len(raw))
+            raw += block.tobytes()
+            keys.append(struct.pack('<II3Q', block.nbytes, 0, i, j, 0))
+    raw += b'\x00' * (-len(raw) % 8)
+    tree_addr = len(raw)
+    node = b'TREE' + struct.pack('<BBHQQ', 1, 0, len(kids), H.UNDEF, H.UNDEF)
+    for k, c in zip(keys, kids):
+        node += k + struct.pack('<Q', c)
+    node += struct.pack('<II3Q', 0, 0, 6, 9, 0)                         # final key: one chunk past the end
+    raw += node
+    layout = struct.pack('<BBBQ3I', 3, 2, 3, tree_addr, ch[0], ch[1], 4)
+    msgs = [H._msg(0x0001, H._dataspace(arr.shape)), H._msg(0x0003, H._datatype_f32(), flags=1), H._msg(0x0008, layout)]
+    blob = b''.join(msgs)
+    raw += b'\x00' * (-len(raw) % 8)
+    hdr = len(raw)
+    raw += struct.pack('<BxHII4x', 1, len(msgs), 1, len(blob)) + blob
+    # point the symbol-table entry of '/plain' at the chunked dataset's header
+    f = H.File(path)
+    old = f._links()['plain']
+    snod = raw.find(b'SNOD')
+    assert struct.unpack_from('<Q', raw, snod + 8 + 8)[0] == old
+    struct.pack_into('<Q', raw, snod + 8 + 8, hdr)
+    struct.pack_into('<Q', raw, 24 + 16, len(raw))
+    open(path, 'wb').write(bytes(raw))
+    assert np.array_equal(H.File(path)['plain'].read(), arr)
