@@ -278,3 +278,22 @@ def test_reader_unfiltered_chunked_dataset(tmp_path):
     struct.pack_into('<Q', raw, 24 + 16, len(raw))
     open(path, 'wb').write(bytes(raw))
     assert np.array_equal(H.File(path)['plain'].read(), arr)
+
+
+def test_golden_file_is_reproduced_byte_for_byte(tmp_path):
+    """tests/golden/keras_weights_tiny.h5 is the file a maintainer can open with h5py (tools/keras_h5_convert.py verify);
+    the writer must keep producing exactly those bytes, and the reader must return exactly the arrays of the .npz twin."""
+    import importlib.util
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    spec = importlib.util.spec_from_file_location('make_hdf5_golden', os.path.join(here, 'make_hdf5_golden.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    path = str(tmp_path / 't.h5')
+    H.save_keras_weights(path, mod.layers())
+    assert open(path, 'rb').read() == open(os.path.join(here, 'keras_weights_tiny.h5'), 'rb').read()
+    z = np.load(os.path.join(here, 'keras_weights_tiny.npz'))
+    back = H.load_keras_weights(os.path.join(here, 'keras_weights_tiny.h5'))
+    assert [n for n, _ in back] == ['conv2d', 'batch_normalization', 'unet']
+    for lname, ws in back:
+        for wn, arr in ws:
+            assert np.array_equal(arr, z['%s|%s' % (lname, wn)])
