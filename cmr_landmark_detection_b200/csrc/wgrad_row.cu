@@ -91,7 +91,6 @@ __global__ void __launch_bounds__(256, 1) wgrad3x3_row_kernel(const __grid_const
   constexpr int X_ST = wg_round1k(X_TX);
   constexpr int DZ_ROWB = BN * 2;                      // 64 B (SW64) or 128 B (SW128) per pixel
   constexpr int DZ_BYTES = R * 128 * DZ_ROWB;
-  constexpr uint64_t LAYB = BN == 64 ? kLayoutSW128 : kLayoutSW64;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* dzbuf = smem;                               // 2 x DZ_BYTES
